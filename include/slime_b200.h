@@ -1,0 +1,186 @@
+/*
+ * slime_b200.h -- C ABI of the B200-native slime-mold step engine.
+ *
+ * Drop-in boundary for the simulation half of Velfi/slime-mold: these entry
+ * points replace what the reference does through wgpu in
+ *   src/pipeline_manager.rs:20-75   (compute / decay / diffuse pipelines)
+ *   src/bind_group_manager.rs:13-65 (compute bind group: agents, trail, uniform)
+ * and the call sites of src/main.rs listed beside each function.  Plain C types
+ * only; the engine owns all device memory, host pointers are borrowed for the
+ * duration of a call.  Every function returns 0 on success or a negative
+ * sm_status; sm_last_error() returns the message of the calling thread's last
+ * failure.  There is NO CPU fallback: without an sm_100 device every call that
+ * needs one fails with SM_ERR_NO_DEVICE.
+ *
+ * A handle is not thread safe (one caller thread at a time, like the
+ * reference's single winit thread).  sm_step()/sm_diffuse_only() are
+ * asynchronous with respect to the host until sm_sync() or a download.
+ */
+#ifndef SLIME_B200_H
+#define SLIME_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SM_VERSION_MAJOR 0
+#define SM_VERSION_MINOR 1
+
+typedef enum sm_status {
+    SM_OK = 0,
+    SM_ERR_BAD_ARG = -1,
+    SM_ERR_CUDA = -2,
+    SM_ERR_NCCL = -3,
+    SM_ERR_OOM = -4,
+    SM_ERR_NO_DEVICE = -5,
+    SM_ERR_STATE = -6
+} sm_status;
+
+/* The reference's uniform block, byte for byte:
+ * `#[repr(C)] struct SimSizeUniform`, src/main.rs:29-46 (56 bytes; the WGSL view
+ * in src/compute.wgsl:37-50 stops at offset 44).  width/height are the GLOBAL
+ * map size.  blur_radius / blur_sigma are ignored by the reference's shader and
+ * by the engine unless SM_FLAG_GAUSSIAN_BLUR is set (extension). */
+typedef struct sm_params {
+    uint32_t width;
+    uint32_t height;
+    float decay_factor;
+    float agent_jitter;
+    float agent_speed_min;
+    float agent_speed_max;
+    float agent_turn_speed;
+    float agent_sensor_angle;
+    float agent_sensor_distance;
+    float diffusion_rate;
+    float pheromone_deposition_amount;
+    float blur_radius;
+    float blur_sigma;
+    uint32_t _pad;
+} sm_params;
+
+enum {
+    /* Replace the 3x3 mean of compute.wgsl:181-194 by a separable Gaussian of
+     * radius round(blur_radius) (1..8) and sigma blur_sigma.  Extension with no
+     * reference semantics ("parity unpinned"). */
+    SM_FLAG_GAUSSIAN_BLUR = 1u << 0,
+    /* Never re-order agents in memory (disables the periodic cell sort). */
+    SM_FLAG_NO_SORT = 1u << 1
+};
+
+typedef struct sm_config {
+    uint32_t width;          /* global map width  (cells) */
+    uint32_t height;         /* global map height (cells) */
+    uint64_t agent_count;    /* GLOBAL number of agents (src/settings.rs:9) */
+    int32_t device;          /* CUDA device ordinal of this rank */
+    int32_t rank;            /* strip index 0..world_size-1 (0 for a single GPU) */
+    int32_t world_size;      /* number of horizontal strips == GPUs (1 = whole map) */
+    uint32_t flags;          /* SM_FLAG_* */
+    uint32_t sort_interval;  /* steps between agent cell sorts; 0 = engine default */
+    uint32_t reserved;
+} sm_config;
+
+typedef struct sm_timing {       /* CUDA-event totals since sm_reset_timing() */
+    double agents_ms;            /* agent kernel (compute.wgsl `main`) */
+    double trail_ms;             /* fused decay+blur (`decay_trail` + `diffuse_trail`) */
+    double sort_ms;              /* periodic cell sort */
+    double exchange_ms;          /* halo exchange + migration (multi-GPU) */
+    uint64_t agent_launches, trail_launches, sort_launches, exchange_launches;
+    uint64_t steps;
+} sm_timing;
+
+typedef struct sm_trail_stats {  /* computed on the device over the owned strip */
+    double sum;
+    double sum_sq;
+    float max;
+    uint32_t _pad;
+    uint64_t nonzero;
+} sm_trail_stats;
+
+typedef struct sm_engine sm_engine;
+
+const char *sm_last_error(void);
+void sm_version(int *major, int *minor);
+/* Number of CUDA devices with compute capability 10.x (0 => nothing can run). */
+int sm_device_count(void);
+
+/* Construction = PipelineManager::new + BindGroupManager::new + the buffer
+ * creation of src/main.rs:263-293 (agents uninitialised, trail zeroed). */
+int sm_create(sm_engine **out, const sm_config *cfg);
+int sm_destroy(sm_engine *e);
+
+/* Multi-GPU (one process per GPU).  Rank 0 obtains an id with
+ * sm_comm_unique_id(), the host distributes the 128 bytes out of band (bench.py
+ * uses torch.distributed), every rank then calls sm_comm_init().  The engine
+ * exchanges halo rows and migrating agents with its two ring neighbours over
+ * NCCL (NVLink). */
+#define SM_COMM_ID_BYTES 128
+int sm_comm_unique_id(uint8_t id[SM_COMM_ID_BYTES]);
+int sm_comm_init(sm_engine *e, const uint8_t id[SM_COMM_ID_BYTES]);
+
+/* queue.write_buffer(&sim_size_buffer, ..) -- src/main.rs:98, 827-831, 1056.
+ * params->width/height must equal the engine's map size. */
+int sm_set_params(sm_engine *e, const sm_params *params);
+int sm_get_params(sm_engine *e, sm_params *params);
+
+/* Agents are (x, y, angle, speed) f32x4, src/main.rs:263-282, indexed by their
+ * persistent GLOBAL index (the `agent_index` of compute.wgsl:60, which also
+ * seeds the jitter hash at :117).  Single GPU: any [first, first+n) range.
+ * Multi GPU: every rank passes the same global array slice; each rank keeps the
+ * agents whose row falls in its strip. */
+int sm_upload_agents(sm_engine *e, const float *xyas, uint64_t first, uint64_t n);
+/* Writes the agents this rank currently owns into xyas[4*global_index..];
+ * entries of agents owned by other ranks are left untouched.  *n_owned (may be
+ * NULL) receives the number written. */
+int sm_download_agents(sm_engine *e, float *xyas, uint64_t first, uint64_t n, uint64_t *n_owned);
+/* Seeded version of the start-up fill of src/main.rs:269-282, generated on the
+ * device: x~U[0,W) y~U[0,H) angle~U[0,2pi) speed~U[min,max), counter-based RNG
+ * keyed by (seed, agent index). */
+int sm_init_agents(sm_engine *e, uint64_t seed);
+/* N key, src/main.rs:682-791: new agent count, all agents re-randomised. */
+int sm_set_agent_count(sm_engine *e, uint64_t n, uint64_t seed);
+/* reassign_agent_speeds, src/main.rs:101-145 (on the device, seeded). */
+int sm_reassign_speeds(sm_engine *e, uint64_t seed);
+uint64_t sm_agent_count(sm_engine *e);        /* global */
+uint64_t sm_local_agent_count(sm_engine *e);  /* owned by this rank */
+
+/* C key, src/main.rs:909-913 */
+int sm_clear_trail(sm_engine *e);
+/* Rectangle (x0,y0,w,h) in GLOBAL coordinates, row-major f32 with `pitch`
+ * floats per host row; only the rows this rank owns are touched. */
+int sm_upload_trail(sm_engine *e, const float *src, uint32_t x0, uint32_t y0,
+                    uint32_t w, uint32_t h, size_t pitch);
+int sm_download_trail(sm_engine *e, float *dst, uint32_t x0, uint32_t y0,
+                      uint32_t w, uint32_t h, size_t pitch);
+int sm_trail_statistics(sm_engine *e, sm_trail_stats *out);
+
+/* Window resize, src/main.rs:954-1015: agent positions scaled by new/old size,
+ * trail replaced by a zeroed map of the new size.  Single GPU only. */
+int sm_resize(sm_engine *e, uint32_t width, uint32_t height);
+
+/* One frame of src/main.rs:1163-1235 per step: agents -> decay -> diffuse. */
+int sm_step(sm_engine *e, uint32_t n_steps);
+/* decay + diffuse only (BASELINE config 5). */
+int sm_diffuse_only(sm_engine *e, uint32_t n_passes);
+int sm_sync(sm_engine *e);
+
+int sm_get_timing(sm_engine *e, sm_timing *out);
+int sm_reset_timing(sm_engine *e);
+/* 0 = no per-kernel events (fastest), 1 = CUDA events around every kernel. */
+int sm_set_timing_enabled(sm_engine *e, int enabled);
+
+/* Raw stream handle (cudaStream_t) the engine launches on, so a host harness can
+ * record its own CUDA events on it. */
+void *sm_stream(sm_engine *e);
+
+/* Test hooks for the arithmetic spec (device evaluation of sin/cos, fmod, the
+ * jitter hash and x/9): out arrays are host pointers of n floats. */
+int sm_test_math(int device, int what, const float *a, const float *b, const int32_t *i,
+                 float *out0, float *out1, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLIME_B200_H */

@@ -1,0 +1,112 @@
+// agent_core.cuh -- per-agent update of /root/reference/src/compute.wgsl:65-144
+// (sense -> rotate -> jitter -> move -> wrap -> deposit cell), written once as a
+// __host__ __device__ function so the CUDA kernels and the CPU-side hostcheck
+// test (tests/hostcheck, test-only) share the exact statement sequence.
+#pragma once
+#include "device_math.cuh"
+
+namespace smd {
+
+// Uniform, per-launch constants derived on the host from sm_params
+// (SimSizeUniform, /root/reference/src/main.rs:29-46).
+struct AgentConsts {
+    uint32_t W, H;             // global map size
+    float Wf, Hf;              // f32(W), f32(H)
+    float rcpW, rcpH;          // ~1/W, ~1/H (quotient estimates for fmod_exact)
+    float xmax, ymax;          // f32(W) - 2, f32(H) - 2: last valid x0 / y0 of a bilinear tap
+    float speed_min, speed_max;
+    float turn_speed;
+    float sensor_angle, sensor_distance;
+    float jitter;
+    // strip of the trail this kernel may read (multi-GPU): global rows
+    // [row0 - halo, row0 + rows + halo) live at trail + (row - row_base) * W
+    int64_t row_base;
+};
+
+constexpr float kTau = 6.28318530718f;             // compute.wgsl:4
+constexpr float kTwoPi = 2.0f * 3.14159265359f;    // compute.wgsl:121
+constexpr float kRcpTwoPi = 0.15915494f;
+constexpr float kTimeStep = 0.016f;                // compute.wgsl:55
+
+// sample_trail_map, compute.wgsl:7-29.  LD(ptr) loads one f32 of the trail.
+template <class LD>
+SM_HD float sample_trail(const float* __restrict__ trail, const AgentConsts& c, float px, float py, LD ld)
+{
+    float fx = ::floorf(px), fy = ::floorf(py);
+    // x0 < 0 || x1 >= W || y0 < 0 || y1 >= H -> 0 (sensing is NOT toroidal); NaN -> outside
+    if (!(fx >= 0.0f && fx <= c.xmax && fy >= 0.0f && fy <= c.ymax)) return 0.0f;
+    int64_t x0 = (int64_t)(int32_t)fx;
+    int64_t y0 = (int64_t)(int32_t)fy;
+    float dx = sub(px, fx), dy = sub(py, fy);
+    const float* r0 = trail + (y0 - c.row_base) * (int64_t)c.W + x0;
+    const float* r1 = r0 + c.W;
+    float v00 = ld(r0), v10 = ld(r0 + 1), v01 = ld(r1), v11 = ld(r1 + 1);
+    float omdx = sub(1.0f, dx);
+    float v0 = mixf_pre(v00, v10, dx, omdx);
+    float v1 = mixf_pre(v01, v11, dx, omdx);
+    return mixf(v0, v1, dy);
+}
+
+// Returns the deposit cell as (cx, cy) with cx < 0 when the deposit is skipped
+// (compute.wgsl:138: x == W can occur by rounding).
+template <class LD>
+SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t agent_index,
+                        const float* __restrict__ trail, const AgentConsts& c, LD ld,
+                        int32_t& cx, int32_t& cy)
+{
+    speed = clampf(speed, c.speed_min, c.speed_max);                       // :72
+
+    float sL, cL, sR, cR, sC, cC;
+    sincos(sub(angle, c.sensor_angle), sL, cL);                            // :75
+    sincos(add(angle, c.sensor_angle), sR, cR);                            // :76
+    sincos(angle, sC, cC);                                                 // :77
+    const float sd = c.sensor_distance;
+    float vL = sample_trail(trail, c, add(x, mul(sd, cL)), add(y, mul(sd, sL)), ld);   // :79-82,93
+    float vR = sample_trail(trail, c, add(x, mul(sd, cR)), add(y, mul(sd, sR)), ld);   // :83-86,94
+    float vC = sample_trail(trail, c, add(x, mul(sd, cC)), add(y, mul(sd, sC)), ld);   // :87-90,95
+
+    if (vC > vL && vC > vR) {                                              // :98
+    } else if (vL > vR) {                                                  // :100-104
+        float diff = sub(sub(angle, kTau), angle);
+        angle = add(angle, mul(::fminf(c.turn_speed, ::fabsf(diff)), signf(diff)));
+    } else if (vR > vL) {                                                  // :105-109
+        float diff = sub(add(angle, kTau), angle);
+        angle = add(angle, mul(::fminf(c.turn_speed, ::fabsf(diff)), signf(diff)));
+    }
+
+    float rnd = hash01(agent_index, x, y);                                 // :117 (pre-move x, y)
+    angle = add(angle, mul(sub(mul(rnd, 2.0f), 1.0f), c.jitter));          // :118
+
+    angle = fmod_exact(angle, kTwoPi, kRcpTwoPi);                          // :121
+    if (angle < 0.0f) angle = add(angle, kTwoPi);                          // :122
+
+    float move = mul(speed, kTimeStep);                                    // :125
+    float sM, cM;
+    sincos(angle, sM, cM);
+    x = add(x, mul(move, cM));                                             // :126
+    y = add(y, mul(move, sM));                                             // :127
+
+    x = fmod_exact(x, c.Wf, c.rcpW);                                       // :130
+    if (x < 0.0f) x = add(x, c.Wf);                                        // :131
+    y = fmod_exact(y, c.Hf, c.rcpH);                                       // :132
+    if (y < 0.0f) y = add(y, c.Hf);                                        // :133
+
+    if (x >= 0.0f && x < c.Wf && y >= 0.0f && y < c.Hf) {                  // :136-138
+        cx = (int32_t)x; cy = (int32_t)y;
+    } else {
+        cx = -1; cy = -1;
+    }
+}
+
+// seeded start-up fill, /root/reference/src/main.rs:269-282
+SM_HD void agent_init(uint64_t seed, uint64_t id, float Wf, float Hf, float speed_min, float speed_max,
+                      float& x, float& y, float& angle, float& speed)
+{
+    const float kPi = 3.14159274101257324f;   // std::f32::consts::PI
+    x = mul(rand01(seed, id, 0), Wf);
+    y = mul(rand01(seed, id, 1), Hf);
+    angle = mul(mul(rand01(seed, id, 2), 2.0f), kPi);
+    speed = add(speed_min, mul(rand01(seed, id, 3), sub(speed_max, speed_min)));
+}
+
+}  // namespace smd

@@ -1,0 +1,210 @@
+// device_math.cuh -- the engine's implementation of the arithmetic spec
+// (DESIGN.md "Arithmetic spec"): bit-defined f32 sin/cos, exact fmod, exact x/9,
+// WGSL mix/clamp/fract/sign as used by /root/reference/src/compute.wgsl.
+//
+// Written independently of oracle/sm_oracle_math.h (the CPU checker); the two are
+// compared bit for bit by tests/test_math_parity.py on the GPU and by
+// tests/test_hostcheck.py on the CPU (these functions are __host__ __device__ so
+// the same source can be exercised without a GPU -- the host instantiation is
+// test-only and never linked into the product library's compute path).
+//
+// Device build flags that this file relies on: --fmad=false (no contraction),
+// default -prec-div=true -prec-sqrt=true -ftz=false.
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define SM_HD __host__ __device__ __forceinline__
+#else
+#define SM_HD inline
+#endif
+
+namespace smd {
+
+// ---- rounding-explicit primitives (never contracted) -----------------------
+SM_HD float mul(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;   // volatile: forbid host-side contraction regardless of flags
+    return r;
+#endif
+}
+SM_HD float add(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
+}
+SM_HD float sub(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    volatile float r = a - b;
+    return r;
+#endif
+}
+SM_HD float fma(float a, float b, float c)
+{
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return ::fmaf(a, b, c);
+#endif
+}
+SM_HD uint32_t f2u(float f)
+{
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; std::memcpy(&u, &f, 4); return u;
+#endif
+}
+SM_HD float u2f(uint32_t u)
+{
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; std::memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// ---- SPEC-SINCOS -------------------------------------------------------------
+// x = k*(pi/2) + r by the round-to-integer magic constant; q = k mod 4 read from
+// the low mantissa bits.  Fast path: three f32 FMAs against a 3-way split of pi/2
+// (exact first step for |k| < 2^13).  Slow path (|x| > 8192: the jitter hash of
+// compute.wgsl:117, whose argument reaches 1e7..1e10): the same in f64.
+SM_HD void reduce_pio2(float x, float& r, uint32_t& q)
+{
+    if (::fabsf(x) <= 8192.0f) {
+        const float magic = 12582912.0f;                        // 1.5 * 2^23
+        float t = fma(x, 0x1.45f306p-1f /* fl32(2/pi) */, magic);
+        q = f2u(t) & 3u;
+        float k = sub(t, magic);
+        float nk = -k;
+        r = fma(nk, 0x1.921fb6p+0f /* fl32(pi/2) */, x);
+        r = fma(nk, -0x1.777a5cp-25f, r);
+        r = fma(nk, -0x1.ee59dap-50f, r);
+    } else {
+        const double magic = 6755399441055744.0;                // 1.5 * 2^52
+        double xd = (double)x;
+        if (!(::fabs(xd) < 0x1p50))
+            xd = ::fmod(xd, 0x1.921fb54442d18p+2);
+#ifdef __CUDA_ARCH__
+        double t = __fma_rn(xd, 0x1.45f306dc9c883p-1, magic);
+        q = (uint32_t)__double2loint(t) & 3u;
+        double k = __dsub_rn(t, magic);
+        double rd = __fma_rn(-k, 0x1.921fb54442d18p+0, xd);
+        rd = __fma_rn(-k, 0x1.1a62633145c07p-54, rd);
+#else
+        double t = ::fma(xd, 0x1.45f306dc9c883p-1, magic);
+        uint64_t tb; std::memcpy(&tb, &t, 8);
+        q = (uint32_t)tb & 3u;
+        volatile double kv = t - magic;
+        double k = kv;
+        double rd = ::fma(-k, 0x1.921fb54442d18p+0, xd);
+        rd = ::fma(-k, 0x1.1a62633145c07p-54, rd);
+#endif
+        r = (float)rd;
+    }
+}
+
+SM_HD void sincos(float x, float& sn, float& cs)
+{
+    float r; uint32_t q;
+    reduce_pio2(x, r, q);
+    float s2 = mul(r, r);
+    float p = fma(-1.9515295891e-4f, s2, 8.3321608736e-3f);
+    p = fma(p, s2, -1.6666654611e-1f);
+    p = mul(p, s2);
+    float sinr = fma(p, r, r);
+    float c = fma(2.443315711809948e-5f, s2, -1.388731625493765e-3f);
+    c = fma(c, s2, 4.166664568298827e-2f);
+    c = fma(c, s2, -0.5f);
+    float cosr = fma(c, s2, 1.0f);
+    float so = (q & 1u) ? cosr : sinr;
+    float co = (q & 1u) ? sinr : cosr;
+    // sign flips as XOR on the sign bit (q&2 -> sin, (q+1)&2 -> cos)
+    sn = u2f(f2u(so) ^ ((q & 2u) << 30));
+    cs = u2f(f2u(co) ^ (((q + 1u) & 2u) << 30));
+}
+
+// ---- exact truncated remainder (WGSL float %, == IEEE fmodf) ----------------
+// b > 0, finite, normal; rcp_b ~ 1/b (any rounding: the quotient is corrected).
+SM_HD float fmod_exact(float a, float b, float rcp_b)
+{
+    float aa = ::fabsf(a);
+    float r;
+    if (aa < b) {
+        r = aa;
+    } else if (aa <= mul(b, 4194304.0f)) {          // quotient < 2^22: estimate off by at most 1
+        float qf = ::truncf(mul(aa, rcp_b));
+        r = fma(-qf, b, aa);
+        if (r < 0.0f) { qf = sub(qf, 1.0f); r = fma(-qf, b, aa); }
+        else if (r >= b) { qf = add(qf, 1.0f); r = fma(-qf, b, aa); }
+    } else {
+        r = ::fmodf(aa, b);                           // huge / inf / NaN: library routine (exact)
+    }
+    return ::copysignf(r, a);
+}
+
+// ---- exact s / 9.0f for finite s (Markstein correction; verified against IEEE
+// division for every non-negative binary32 value, tests/exhaustive_div9.c) -----
+SM_HD float div9(float s)
+{
+    const float c = 0x1.c71c72p-4f;   // fl32(1/9)
+    float q = mul(s, c);
+    float r = fma(-q, 9.0f, s);
+    float q2 = fma(r, c, q);
+    return (::fabsf(s) <= 3.402823466e38f) ? q2 : s / 9.0f;   // inf/NaN: true division
+}
+
+// ---- WGSL builtins ----------------------------------------------------------
+SM_HD float clampf(float x, float lo, float hi) { return ::fminf(::fmaxf(x, lo), hi); }
+SM_HD float mixf(float a, float b, float t)
+{
+    return add(mul(a, sub(1.0f, t)), mul(b, t));
+}
+SM_HD float mixf_pre(float a, float b, float t, float one_minus_t)
+{
+    return add(mul(a, one_minus_t), mul(b, t));
+}
+SM_HD float fractf(float v) { return sub(v, ::floorf(v)); }
+SM_HD float signf(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+
+// compute.wgsl:117  fract(sin(f32(idx)*12.9898 + x*78.233 + y*37.719) * 43758.5453)
+SM_HD float hash01(int32_t idx, float x, float y)
+{
+    float a = mul((float)idx, 12.9898f);
+    float b = mul(x, 78.233f);
+    float c = mul(y, 37.719f);
+    float arg = add(add(a, b), c);
+    float s, cc;
+    sincos(arg, s, cc);
+    return fractf(mul(s, 43758.5453f));
+}
+
+// ---- SPEC-RNG (seeded initial state) ----------------------------------------
+SM_HD uint64_t mix64(uint64_t z)
+{
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return z;
+}
+SM_HD float rand01(uint64_t seed, uint64_t id, uint32_t stream)
+{
+    uint64_t z = (id * 4ull + (uint64_t)stream) * 0x9E3779B97F4A7C15ull
+               + seed * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
+    z = mix64(z);
+    return mul((float)(uint32_t)(z >> 40), 0x1p-24f);
+}
+
+}  // namespace smd

@@ -1,0 +1,820 @@
+// engine.cu -- C ABI (include/slime_b200.h) over the sm_100a kernels in kernels.cuh.
+//
+// Replaces, for the simulation half of the reference, what
+// /root/reference/src/pipeline_manager.rs and src/bind_group_manager.rs set up and
+// what src/main.rs:1163-1235 dispatches every frame.  No CPU fallback: every entry
+// point that needs the device fails with SM_ERR_NO_DEVICE / SM_ERR_CUDA otherwise.
+#include "../../include/slime_b200.h"
+#include "kernels.cuh"
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+thread_local std::string g_sm_err;
+
+int sm_fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_sm_err = buf;
+    return code;
+}
+
+#define SM_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t err__ = (call);                                                            \
+        if (err__ != cudaSuccess)                                                              \
+            return sm_fail(err__ == cudaErrorMemoryAllocation ? SM_ERR_OOM : SM_ERR_CUDA,     \
+                           "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                \
+                           cudaGetErrorString(err__));                                         \
+    } while (0)
+
+#define SM_TRY(expr)                    \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != SM_OK) return rc__; \
+    } while (0)
+
+static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// ---------------------------------------------------------------------------
+// derived constants
+// ---------------------------------------------------------------------------
+smd::AgentConsts sm_engine::agent_consts() const
+{
+    smd::AgentConsts c{};
+    c.W = W; c.H = H;
+    c.Wf = (float)W; c.Hf = (float)H;
+    c.rcpW = 1.0f / c.Wf; c.rcpH = 1.0f / c.Hf;
+    c.xmax = (float)W - 2.0f; c.ymax = (float)H - 2.0f;
+    c.speed_min = params.agent_speed_min; c.speed_max = params.agent_speed_max;
+    c.turn_speed = params.agent_turn_speed;
+    c.sensor_angle = params.agent_sensor_angle;
+    c.sensor_distance = params.agent_sensor_distance;
+    c.jitter = params.agent_jitter;
+    c.row_base = (int64_t)row0;
+    return c;
+}
+
+smd::TrailConsts sm_engine::trail_consts() const
+{
+    smd::TrailConsts t{};
+    t.dep = params.pheromone_deposition_amount;
+    volatile float d = params.decay_factor * 0.001f;            // compute.wgsl:159 (f32 product)
+    t.decay_sub = d;
+    t.rate = fminf(fmaxf(params.diffusion_rate, 0.0f), 1.0f);   // compute.wgsl:173
+    volatile float om = 1.0f - t.rate;
+    t.one_minus_rate = om;
+    return t;
+}
+
+// ---------------------------------------------------------------------------
+// timing helpers
+// ---------------------------------------------------------------------------
+int sm_engine::tic(int kind)
+{
+    if (!timing_enabled) return SM_OK;
+    if (ev_used == ev_pool.size()) {
+        if (ev_pool.size() >= 4096) SM_TRY(resolve_timing());
+        else {
+            EvPair p{};
+            SM_CUDA(cudaEventCreate(&p.a));
+            SM_CUDA(cudaEventCreate(&p.b));
+            ev_pool.push_back(p);
+        }
+    }
+    ev_pool[ev_used].kind = kind;
+    SM_CUDA(cudaEventRecord(ev_pool[ev_used].a, stream));
+    return SM_OK;
+}
+int sm_engine::toc()
+{
+    if (!timing_enabled) return SM_OK;
+    SM_CUDA(cudaEventRecord(ev_pool[ev_used].b, stream));
+    ev_used++;
+    return SM_OK;
+}
+int sm_engine::resolve_timing()
+{
+    if (ev_used == 0) return SM_OK;
+    SM_CUDA(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < ev_used; ++i) {
+        float ms = 0.f;
+        SM_CUDA(cudaEventElapsedTime(&ms, ev_pool[i].a, ev_pool[i].b));
+        switch (ev_pool[i].kind) {
+        case 0: timing.agents_ms += ms; timing.agent_launches++; break;
+        case 1: timing.trail_ms += ms; timing.trail_launches++; break;
+        case 2: timing.sort_ms += ms; timing.sort_launches++; break;
+        default: timing.exchange_ms += ms; timing.exchange_launches++; break;
+        }
+    }
+    ev_used = 0;
+    return SM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// allocation
+// ---------------------------------------------------------------------------
+int sm_engine::alloc_trail()
+{
+    const size_t cells = (size_t)(rows + 2 * (size_t)ghost) * W;
+    for (int i = 0; i < 2; ++i) {
+        SM_CUDA(cudaMalloc(&trail_base[i], cells * sizeof(float)));
+        SM_CUDA(cudaMemsetAsync(trail_base[i], 0, cells * sizeof(float), stream));
+        SM_CUDA(cudaMalloc(&counts_base[i], cells * sizeof(uint32_t)));
+        SM_CUDA(cudaMemsetAsync(counts_base[i], 0, cells * sizeof(uint32_t), stream));
+    }
+    cur = 0; ccur = 0;
+    return SM_OK;
+}
+void sm_engine::free_trail()
+{
+    for (int i = 0; i < 2; ++i) {
+        if (trail_base[i]) cudaFree(trail_base[i]);
+        if (counts_base[i]) cudaFree(counts_base[i]);
+        trail_base[i] = nullptr; counts_base[i] = nullptr;
+    }
+    if (gauss_dec) cudaFree(gauss_dec);
+    if (gauss_hb) cudaFree(gauss_hb);
+    gauss_dec = gauss_hb = nullptr;
+}
+int sm_engine::alloc_agents(uint64_t capacity)
+{
+    free_agents();
+    cap_local = std::max<uint64_t>(capacity, 1);
+    for (int i = 0; i < 2; ++i) {
+        SM_CUDA(cudaMalloc(&agents[i], cap_local * sizeof(float4)));
+        SM_CUDA(cudaMalloc(&ids[i], cap_local * sizeof(uint32_t)));
+    }
+    acur = 0;
+    return SM_OK;
+}
+void sm_engine::free_agents()
+{
+    for (int i = 0; i < 2; ++i) {
+        if (agents[i]) cudaFree(agents[i]);
+        if (ids[i]) cudaFree(ids[i]);
+        agents[i] = nullptr; ids[i] = nullptr;
+    }
+}
+int sm_engine::setup_tiles()
+{
+    if (tile_hist) { cudaFree(tile_hist); tile_hist = nullptr; }
+    if (tile_sums) { cudaFree(tile_sums); tile_sums = nullptr; }
+    tiles.shift_x = (uint32_t)env_int("SM_TILE_SHIFT_X", 4);
+    tiles.shift_y = (uint32_t)env_int("SM_TILE_SHIFT_Y", 4);
+    tiles.W = W;
+    tiles.rows = rows;
+    tiles.row_base = (int64_t)row0;
+    tiles.tiles_x = (W + (1u << tiles.shift_x) - 1) >> tiles.shift_x;
+    tiles.tiles_y = (rows + (1u << tiles.shift_y) - 1) >> tiles.shift_y;
+    n_tiles = (uint64_t)tiles.tiles_x * tiles.tiles_y;
+    if (n_tiles >= (1ull << 31)) return sm_fail(SM_ERR_BAD_ARG, "too many sort tiles");
+    n_scan_blocks = (uint32_t)((n_tiles + smk::kScanBlock * smk::kScanItems - 1) / (smk::kScanBlock * smk::kScanItems));
+    SM_CUDA(cudaMalloc(&tile_hist, n_tiles * sizeof(uint32_t)));
+    SM_CUDA(cudaMalloc(&tile_sums, (size_t)n_scan_blocks * sizeof(uint32_t)));
+    return SM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernels: launch helpers
+// ---------------------------------------------------------------------------
+int sm_engine::sort_agents()
+{
+    if (n_local == 0) return SM_OK;
+    SM_TRY(tic(2));
+    SM_CUDA(cudaMemsetAsync(tile_hist, 0, n_tiles * sizeof(uint32_t), stream));
+    smk::k_tile_hist<<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], n_local, tile_hist, tiles);
+    smk::k_scan_block<<<n_scan_blocks, smk::kScanBlock, 0, stream>>>(tile_hist, tile_hist, tile_sums, (uint32_t)n_tiles);
+    smk::k_scan_sums<<<1, 1024, 0, stream>>>(tile_sums, n_scan_blocks);
+    smk::k_scan_add<<<n_scan_blocks, smk::kScanBlock, 0, stream>>>(tile_hist, tile_sums, (uint32_t)n_tiles);
+    smk::k_tile_scatter<<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, tile_hist,
+                                                                      agents[1 - acur], ids[1 - acur], tiles);
+    SM_CUDA(cudaGetLastError());
+    acur = 1 - acur;
+    identity_order = false;
+    SM_TRY(toc());
+    return SM_OK;
+}
+
+int sm_engine::launch_agents()
+{
+    if (n_local == 0) return SM_OK;
+    SM_TRY(tic(0));
+    smk::k_agents<<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, trail_ptr(cur),
+                                                                counts_ptr(ccur), agent_consts());
+    SM_CUDA(cudaGetLastError());
+    SM_TRY(toc());
+    return SM_OK;
+}
+
+int sm_engine::launch_trail(bool has_counts)
+{
+    const smd::TrailConsts tc = trail_consts();
+    smk::TrailGeom g{};
+    g.W = W; g.rows = rows; g.wrap_y = (world == 1) ? 1 : 0;
+    const float* tin = trail_ptr(cur);
+    float* tout = trail_ptr(1 - cur);
+    const uint32_t* cin = counts_ptr(ccur);
+    uint32_t* czero = counts_ptr(1 - ccur);
+    SM_TRY(tic(1));
+    if (cfg.flags & SM_FLAG_GAUSSIAN_BLUR) {
+        SM_TRY(launch_gauss(has_counts, g, tc));
+    } else if (W % 4 == 0 && W >= 8 && !force_generic) {
+        const unsigned bs = 128;
+        const unsigned bx = blocks_for(W / 4, bs);
+        // aim for >= 8 resident CTAs per SM; 2/rows_per_chunk of the reads are halo re-reads
+        uint64_t want_blocks = (uint64_t)num_sms * 16;
+        uint64_t rpc = ((uint64_t)rows * bx + want_blocks - 1) / want_blocks;
+        rpc = std::min<uint64_t>(std::max<uint64_t>(rpc, 8), 64);
+        if (rpc_override > 0) rpc = rpc_override;
+        g.rows_per_chunk = (uint32_t)rpc;
+        dim3 grid(bx, (unsigned)((rows + rpc - 1) / rpc));
+        if (has_counts) smk::k_trail_rows<true, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
+        else smk::k_trail_rows<false, 4><<<grid, bs, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc);
+    } else {
+        g.rows_per_chunk = 1;
+        for (uint32_t y0 = 0; y0 < rows; y0 += 32768) {
+            uint32_t ny = std::min<uint32_t>(32768, rows - y0);
+            dim3 grid(blocks_for(W, 256), ny);
+            if (has_counts) smk::k_trail_generic<true><<<grid, 256, 0, stream>>>(tin, cin, czero, tout, g, tc, (int64_t)y0);
+            else smk::k_trail_generic<false><<<grid, 256, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc, (int64_t)y0);
+        }
+    }
+    SM_CUDA(cudaGetLastError());
+    SM_TRY(toc());
+    cur = 1 - cur;
+    if (has_counts) ccur = 1 - ccur;
+    return SM_OK;
+}
+
+int sm_engine::launch_gauss(bool has_counts, const smk::TrailGeom& g, const smd::TrailConsts& tc)
+{
+    if (world != 1) return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR is single-GPU only");
+    int R = (int)lroundf(params.blur_radius);
+    if (R < 1 || R > 8) return sm_fail(SM_ERR_BAD_ARG, "gaussian blur radius must round to 1..8 (got %g)", params.blur_radius);
+    if (!(params.blur_sigma > 0.0f)) return sm_fail(SM_ERR_BAD_ARG, "gaussian blur sigma must be > 0");
+    smk::GaussConsts gc{};
+    gc.R = R;
+    {   // weights: exp(-d^2 / 2 sigma^2) in f64, normalised in f64, rounded to f32 (oracle: so_gauss_weights)
+        double tmp[17], s = 0.0;
+        for (int d = -R; d <= R; ++d) {
+            tmp[d + R] = exp(-(double)(d * d) / (2.0 * (double)params.blur_sigma * (double)params.blur_sigma));
+            s += tmp[d + R];
+        }
+        for (int d = 0; d <= 2 * R; ++d) gc.w[d] = (float)(tmp[d] / s);
+    }
+    const size_t cells = (size_t)rows * W;
+    if (!gauss_dec) SM_CUDA(cudaMalloc(&gauss_dec, cells * sizeof(float)));
+    if (!gauss_hb) SM_CUDA(cudaMalloc(&gauss_hb, cells * sizeof(float)));
+    const float* tin = trail_ptr(cur);
+    float* tout = trail_ptr(1 - cur);
+    const uint32_t* cin = counts_ptr(ccur);
+    uint32_t* czero = counts_ptr(1 - ccur);
+    const unsigned bs = 256;
+    const size_t smem = (bs + 2 * R) * sizeof(float);
+    for (uint32_t y0 = 0; y0 < rows; y0 += 32768) {
+        uint32_t ny = std::min<uint32_t>(32768, rows - y0);
+        dim3 grid(blocks_for(W, bs), ny);
+        if (has_counts) smk::k_gauss_h<true><<<grid, bs, smem, stream>>>(tin, cin, czero, gauss_dec, gauss_hb, g, tc, gc, (int64_t)y0);
+        else smk::k_gauss_h<false><<<grid, bs, smem, stream>>>(tin, nullptr, nullptr, gauss_dec, gauss_hb, g, tc, gc, (int64_t)y0);
+    }
+    for (uint32_t y0 = 0; y0 < rows; y0 += 32768) {
+        uint32_t ny = std::min<uint32_t>(32768, rows - y0);
+        dim3 grid(blocks_for(W, bs), ny);
+        smk::k_gauss_v<<<grid, bs, 0, stream>>>(gauss_dec, gauss_hb, tout, czero, has_counts ? 1 : 0, g, tc, gc, (int64_t)y0);
+    }
+    return SM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* sm_last_error(void) { return g_sm_err.c_str(); }
+
+void sm_version(int* major, int* minor)
+{
+    if (major) *major = SM_VERSION_MAJOR;
+    if (minor) *minor = SM_VERSION_MINOR;
+}
+
+int sm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+static int check_device(int device, int* num_sms)
+{
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return sm_fail(SM_ERR_NO_DEVICE, "no CUDA device available (%s); this engine has no CPU fallback",
+                       err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+    }
+    if (device < 0 || device >= n) return sm_fail(SM_ERR_BAD_ARG, "device %d out of range (0..%d)", device, n - 1);
+    int major = 0, minor = 0;
+    SM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    SM_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (major != 10)
+        return sm_fail(SM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", device, major, minor);
+    SM_CUDA(cudaSetDevice(device));
+    if (num_sms) SM_CUDA(cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, device));
+    return SM_OK;
+}
+
+int sm_create(sm_engine** out, const sm_config* cfg)
+{
+    if (!out || !cfg) return sm_fail(SM_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->width == 0 || cfg->height == 0) return sm_fail(SM_ERR_BAD_ARG, "map size must be non-zero");
+    if (cfg->width > 65536 || cfg->height > 65536) return sm_fail(SM_ERR_BAD_ARG, "map size above 65536 is not supported");
+    if (cfg->agent_count >= (1ull << 31)) return sm_fail(SM_ERR_BAD_ARG, "agent_count must be < 2^31 (i32 index of compute.wgsl:60)");
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+        return sm_fail(SM_ERR_BAD_ARG, "bad rank/world_size %d/%d", cfg->rank, cfg->world_size);
+    if ((uint32_t)cfg->world_size > cfg->height) return sm_fail(SM_ERR_BAD_ARG, "more strips than rows");
+    int num_sms = 0;
+    SM_TRY(check_device(cfg->device, &num_sms));
+
+    sm_engine* e = new sm_engine();
+    e->cfg = *cfg;
+    e->device = cfg->device;
+    e->num_sms = num_sms;
+    e->W = cfg->width; e->H = cfg->height;
+    e->rank = cfg->rank; e->world = cfg->world_size;
+    // strip r owns rows [r*H/G, (r+1)*H/G)
+    e->row0 = (uint32_t)(((uint64_t)e->rank * e->H) / e->world);
+    uint32_t row1 = (uint32_t)(((uint64_t)(e->rank + 1) * e->H) / e->world);
+    e->rows = row1 - e->row0;
+    e->ghost = 0;
+    if (e->world > 1) {
+        uint32_t want = cfg->reserved ? cfg->reserved : 232u;   // >= ceil(225)+2 (Snake/Mesh presets) + slack
+        uint32_t min_rows = e->H / e->world;                    // thinnest strip
+        e->ghost = std::min(want, min_rows);
+    }
+    e->n_global = cfg->agent_count;
+    e->sort_interval = cfg->sort_interval ? cfg->sort_interval : (uint32_t)env_int("SM_SORT_INTERVAL", 16);
+    if (cfg->flags & SM_FLAG_NO_SORT) e->sort_interval = 0;
+    e->force_generic = env_int("SM_FORCE_GENERIC_TRAIL", 0) != 0;
+    e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
+
+    // defaults = Settings::default(), /root/reference/src/settings.rs:8-27
+    sm_params p{};
+    p.width = e->W; p.height = e->H;
+    p.decay_factor = 10.0f; p.agent_jitter = 0.0f;
+    p.agent_speed_min = 30.0f; p.agent_speed_max = 50.0f;
+    p.agent_turn_speed = 0.43f; p.agent_sensor_angle = 0.3f; p.agent_sensor_distance = 20.0f;
+    p.diffusion_rate = 1.0f; p.pheromone_deposition_amount = 1.0f;
+    p.blur_radius = 2.0f; p.blur_sigma = 1.0f;
+    e->params = p;
+
+    auto fail = [&](int rc) { sm_destroy(e); return rc; };
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(sm_fail(SM_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
+    int rc;
+    if ((rc = e->alloc_trail()) != SM_OK) return fail(rc);
+    uint64_t cap = e->n_global;
+    if (e->world > 1) cap = std::min<uint64_t>(e->n_global, 2 * ((e->n_global + e->world - 1) / e->world) + (1u << 20));
+    if ((rc = e->alloc_agents(cap)) != SM_OK) return fail(rc);
+    if ((rc = e->setup_tiles()) != SM_OK) return fail(rc);
+    if (cudaMalloc(&e->stats_dev, sizeof(smk::StatsAcc)) != cudaSuccess)
+        return fail(sm_fail(SM_ERR_OOM, "cudaMalloc(stats) failed"));
+    e->n_local = 0;
+    e->agents_valid = false;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess)
+        return fail(sm_fail(SM_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = e;
+    return SM_OK;
+}
+
+int sm_destroy(sm_engine* e)
+{
+    if (!e) return SM_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    e->comm_destroy();
+    e->free_trail();
+    e->free_agents();
+    if (e->tile_hist) cudaFree(e->tile_hist);
+    if (e->tile_sums) cudaFree(e->tile_sums);
+    if (e->stats_dev) cudaFree(e->stats_dev);
+    for (auto& p : e->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return SM_OK;
+}
+
+#define SM_ENTER(e)                                                    \
+    if (!(e)) return sm_fail(SM_ERR_BAD_ARG, "null engine handle");    \
+    SM_CUDA(cudaSetDevice((e)->device))
+
+int sm_set_params(sm_engine* e, const sm_params* p)
+{
+    SM_ENTER(e);
+    if (!p) return sm_fail(SM_ERR_BAD_ARG, "null params");
+    if (p->width != e->W || p->height != e->H)
+        return sm_fail(SM_ERR_BAD_ARG, "params size %ux%u does not match the engine's map %ux%u (use sm_resize)",
+                       p->width, p->height, e->W, e->H);
+    if (e->world > 1) {
+        // ghost depth needed for sensing: taps reach floor(x + sd*cos) + 1
+        float sd = fabsf(p->agent_sensor_distance);
+        if (!(sd + 3.0f <= (float)e->ghost))
+            return sm_fail(SM_ERR_BAD_ARG, "sensor distance %g needs %d ghost rows; strips provide %u", sd, (int)ceilf(sd) + 3, e->ghost);
+    }
+    e->params = *p;
+    return SM_OK;
+}
+
+int sm_get_params(sm_engine* e, sm_params* p)
+{
+    SM_ENTER(e);
+    if (!p) return sm_fail(SM_ERR_BAD_ARG, "null params");
+    *p = e->params;
+    return SM_OK;
+}
+
+uint64_t sm_agent_count(sm_engine* e) { return e ? e->n_global : 0; }
+uint64_t sm_local_agent_count(sm_engine* e) { return e ? e->n_local : 0; }
+
+static inline uint32_t owner_row(float y, uint32_t H)
+{
+    if (!(y >= 0.0f)) return 0;                 // negative / NaN
+    if (y >= (float)H) return H - 1;
+    return (uint32_t)y;
+}
+
+int sm_upload_agents(sm_engine* e, const float* xyas, uint64_t first, uint64_t n)
+{
+    SM_ENTER(e);
+    if (!xyas && n) return sm_fail(SM_ERR_BAD_ARG, "null agent array");
+    if (first + n > e->n_global) return sm_fail(SM_ERR_BAD_ARG, "agent range [%llu, %llu) exceeds agent_count %llu",
+                                                (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)e->n_global);
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->world == 1) {
+        if (!e->agents_valid && !(first == 0 && n == e->n_global)) {
+            // first partial upload into uninitialised storage: zero-fill the rest deterministically
+            SM_CUDA(cudaMemsetAsync(e->agents[e->acur], 0, e->n_global * sizeof(float4), e->stream));
+            e->identity_order = false;
+        }
+        if (!e->identity_order) {
+            if (e->agents_valid) SM_TRY(e->restore_identity_order());
+            else SM_TRY(e->fill_identity_ids());
+        }
+        SM_CUDA(cudaMemcpyAsync(e->agents[e->acur] + first, xyas, n * sizeof(float4), cudaMemcpyHostToDevice, e->stream));
+        SM_CUDA(cudaStreamSynchronize(e->stream));
+        e->n_local = e->n_global;
+        e->agents_valid = true;
+        e->steps_since_sort = e->sort_interval;   // force a sort before the next step
+        return SM_OK;
+    }
+    if (!(first == 0 && n == e->n_global))
+        return sm_fail(SM_ERR_BAD_ARG, "multi-GPU upload must cover all agents (first=0, n=agent_count)");
+    std::vector<float> keep;
+    std::vector<uint32_t> keep_ids;
+    keep.reserve((size_t)(n / e->world) * 4 + 1024);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t r = owner_row(xyas[4 * i + 1], e->H);
+        if (r >= e->row0 && r < e->row0 + e->rows) {
+            keep.insert(keep.end(), xyas + 4 * i, xyas + 4 * i + 4);
+            keep_ids.push_back((uint32_t)(first + i));
+        }
+    }
+    uint64_t m = keep_ids.size();
+    if (m > e->cap_local) return sm_fail(SM_ERR_OOM, "strip %d would own %llu agents, capacity %llu", e->rank,
+                                         (unsigned long long)m, (unsigned long long)e->cap_local);
+    SM_CUDA(cudaMemcpy(e->agents[e->acur], keep.data(), m * sizeof(float4), cudaMemcpyHostToDevice));
+    SM_CUDA(cudaMemcpy(e->ids[e->acur], keep_ids.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    e->n_local = m;
+    e->agents_valid = true;
+    e->identity_order = false;
+    e->steps_since_sort = e->sort_interval;
+    return SM_OK;
+}
+
+int sm_download_agents(sm_engine* e, float* xyas, uint64_t first, uint64_t n, uint64_t* n_owned)
+{
+    SM_ENTER(e);
+    if (!xyas && n) return sm_fail(SM_ERR_BAD_ARG, "null agent array");
+    if (first + n > e->n_global) return sm_fail(SM_ERR_BAD_ARG, "agent range exceeds agent_count");
+    if (!e->agents_valid) return sm_fail(SM_ERR_STATE, "agents were never initialised or uploaded");
+    if (e->world == 1) {
+        if (!e->identity_order) SM_TRY(e->restore_identity_order());
+        SM_CUDA(cudaMemcpyAsync(xyas, e->agents[e->acur] + first, n * sizeof(float4), cudaMemcpyDeviceToHost, e->stream));
+        SM_CUDA(cudaStreamSynchronize(e->stream));
+        if (n_owned) *n_owned = n;
+        return SM_OK;
+    }
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    std::vector<float> a((size_t)e->n_local * 4);
+    std::vector<uint32_t> id((size_t)e->n_local);
+    SM_CUDA(cudaMemcpy(a.data(), e->agents[e->acur], e->n_local * sizeof(float4), cudaMemcpyDeviceToHost));
+    SM_CUDA(cudaMemcpy(id.data(), e->ids[e->acur], e->n_local * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    uint64_t cnt = 0;
+    for (uint64_t i = 0; i < e->n_local; ++i) {
+        uint64_t g = id[i];
+        if (g >= first && g < first + n) {
+            memcpy(xyas + 4 * (g - first), a.data() + 4 * i, 16);
+            cnt++;
+        }
+    }
+    if (n_owned) *n_owned = cnt;
+    return SM_OK;
+}
+
+int sm_init_agents(sm_engine* e, uint64_t seed)
+{
+    SM_ENTER(e);
+    const float Wf = (float)e->W, Hf = (float)e->H;
+    if (e->world == 1) {
+        if (e->n_global)
+            smk::k_init_agents<<<blocks_for(e->n_global, 256), 256, 0, e->stream>>>(
+                e->agents[e->acur], e->ids[e->acur], e->n_global, 0, seed, Wf, Hf,
+                e->params.agent_speed_min, e->params.agent_speed_max);
+        SM_CUDA(cudaGetLastError());
+        e->n_local = e->n_global;
+        e->identity_order = true;
+    } else {
+        SM_TRY(e->init_agents_strip(seed));
+    }
+    e->agents_valid = true;
+    e->steps_since_sort = e->sort_interval;
+    return SM_OK;
+}
+
+int sm_set_agent_count(sm_engine* e, uint64_t n, uint64_t seed)
+{
+    SM_ENTER(e);
+    if (n == 0) return sm_fail(SM_ERR_BAD_ARG, "agent_count must be >= 1 (src/main.rs:738-739)");
+    if (n >= (1ull << 31)) return sm_fail(SM_ERR_BAD_ARG, "agent_count must be < 2^31");
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    e->n_global = n;
+    e->cfg.agent_count = n;
+    uint64_t cap = n;
+    if (e->world > 1) cap = std::min<uint64_t>(n, 2 * ((n + e->world - 1) / e->world) + (1u << 20));
+    if (cap > e->cap_local) SM_TRY(e->alloc_agents(cap));
+    e->agents_valid = false;
+    return sm_init_agents(e, seed);
+}
+
+int sm_reassign_speeds(sm_engine* e, uint64_t seed)
+{
+    SM_ENTER(e);
+    if (!e->agents_valid) return sm_fail(SM_ERR_STATE, "agents were never initialised or uploaded");
+    if (e->n_local)
+        smk::k_reassign_speeds<<<blocks_for(e->n_local, 256), 256, 0, e->stream>>>(
+            e->agents[e->acur], e->ids[e->acur], e->n_local, seed, e->params.agent_speed_min, e->params.agent_speed_max);
+    SM_CUDA(cudaGetLastError());
+    return SM_OK;
+}
+
+int sm_clear_trail(sm_engine* e)
+{
+    SM_ENTER(e);
+    const size_t cells = (size_t)(e->rows + 2 * (size_t)e->ghost) * e->W;
+    SM_CUDA(cudaMemsetAsync(e->trail_base[e->cur], 0, cells * sizeof(float), e->stream));
+    return SM_OK;
+}
+
+static int clip_rows(sm_engine* e, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, size_t pitch,
+                     uint32_t* ya, uint32_t* yb)
+{
+    if ((uint64_t)x0 + w > e->W || (uint64_t)y0 + h > e->H) return sm_fail(SM_ERR_BAD_ARG, "rectangle outside the map");
+    if (pitch < w) return sm_fail(SM_ERR_BAD_ARG, "pitch smaller than the rectangle width");
+    *ya = std::max(y0, e->row0);
+    *yb = std::min(y0 + h, e->row0 + e->rows);
+    return SM_OK;
+}
+
+int sm_upload_trail(sm_engine* e, const float* src, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, size_t pitch)
+{
+    SM_ENTER(e);
+    if (!src) return sm_fail(SM_ERR_BAD_ARG, "null source");
+    uint32_t ya = 0, yb = 0;
+    SM_TRY(clip_rows(e, x0, y0, w, h, pitch, &ya, &yb));
+    if (ya < yb && w) {
+        float* dst = e->trail_ptr(e->cur) + (size_t)(ya - e->row0) * e->W + x0;
+        SM_CUDA(cudaMemcpy2DAsync(dst, (size_t)e->W * 4, src + (size_t)(ya - y0) * pitch, pitch * 4, (size_t)w * 4,
+                                  yb - ya, cudaMemcpyHostToDevice, e->stream));
+        SM_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    e->ghost_stale = true;
+    return SM_OK;
+}
+
+int sm_download_trail(sm_engine* e, float* dst, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, size_t pitch)
+{
+    SM_ENTER(e);
+    if (!dst) return sm_fail(SM_ERR_BAD_ARG, "null destination");
+    uint32_t ya = 0, yb = 0;
+    SM_TRY(clip_rows(e, x0, y0, w, h, pitch, &ya, &yb));
+    if (ya < yb && w) {
+        const float* src = e->trail_ptr(e->cur) + (size_t)(ya - e->row0) * e->W + x0;
+        SM_CUDA(cudaMemcpy2DAsync(dst + (size_t)(ya - y0) * pitch, pitch * 4, src, (size_t)e->W * 4, (size_t)w * 4,
+                                  yb - ya, cudaMemcpyDeviceToHost, e->stream));
+    }
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    return SM_OK;
+}
+
+int sm_trail_statistics(sm_engine* e, sm_trail_stats* out)
+{
+    SM_ENTER(e);
+    if (!out) return sm_fail(SM_ERR_BAD_ARG, "null output");
+    SM_CUDA(cudaMemsetAsync(e->stats_dev, 0, sizeof(smk::StatsAcc), e->stream));
+    const uint64_t cells = (uint64_t)e->rows * e->W;
+    unsigned nb = (unsigned)std::min<uint64_t>((cells + 255) / 256, (uint64_t)e->num_sms * 8);
+    smk::k_trail_stats<<<nb, 256, 0, e->stream>>>(e->trail_ptr(e->cur), cells, (smk::StatsAcc*)e->stats_dev);
+    SM_CUDA(cudaGetLastError());
+    smk::StatsAcc h{};
+    SM_CUDA(cudaMemcpyAsync(&h, e->stats_dev, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    out->sum = h.sum; out->sum_sq = h.sum_sq; out->nonzero = h.nonzero;
+    memcpy(&out->max, &h.max_bits, 4);
+    out->_pad = 0;
+    return SM_OK;
+}
+
+int sm_resize(sm_engine* e, uint32_t width, uint32_t height)
+{
+    SM_ENTER(e);
+    if (e->world != 1) return sm_fail(SM_ERR_STATE, "sm_resize is single-GPU only");
+    if (width == 0 || height == 0 || width > 65536 || height > 65536) return sm_fail(SM_ERR_BAD_ARG, "bad map size");
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    // src/main.rs:985-989: x *= new_w as f32 / old_w as f32
+    volatile float fx = (float)width / (float)e->W;
+    volatile float fy = (float)height / (float)e->H;
+    if (e->agents_valid && e->n_local)
+        smk::k_rescale_agents<<<blocks_for(e->n_local, 256), 256, 0, e->stream>>>(e->agents[e->acur], e->n_local, fx, fy);
+    SM_CUDA(cudaGetLastError());
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    e->free_trail();                                   // src/main.rs:999-1015: new zeroed trail
+    e->W = width; e->H = height;
+    e->rows = height; e->row0 = 0;
+    e->cfg.width = width; e->cfg.height = height;
+    e->params.width = width; e->params.height = height;
+    SM_TRY(e->alloc_trail());
+    SM_TRY(e->setup_tiles());
+    e->steps_since_sort = e->sort_interval;
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    return SM_OK;
+}
+
+int sm_step(sm_engine* e, uint32_t n_steps)
+{
+    SM_ENTER(e);
+    if (!e->agents_valid) return sm_fail(SM_ERR_STATE, "agents were never initialised or uploaded");
+    if (e->world > 1 && !e->comm_ready) return sm_fail(SM_ERR_STATE, "multi-GPU engine: call sm_comm_init first");
+    for (uint32_t s = 0; s < n_steps; ++s) {
+        if (e->world > 1 && e->ghost_stale) SM_TRY(e->exchange_trail_ghosts());
+        if (e->sort_interval && e->steps_since_sort >= e->sort_interval) {
+            SM_TRY(e->sort_agents());
+            e->steps_since_sort = 0;
+        }
+        SM_TRY(e->launch_agents());                      // src/main.rs:1164-1181
+        if (e->world > 1) SM_TRY(e->exchange_counts());
+        SM_TRY(e->launch_trail(true));                   // src/main.rs:1184-1199 + 1220-1235
+        if (e->world > 1) {
+            SM_TRY(e->exchange_trail_ghosts());
+            SM_TRY(e->migrate_agents());
+        }
+        e->steps_since_sort++;
+        e->timing.steps++;
+    }
+    return SM_OK;
+}
+
+int sm_diffuse_only(sm_engine* e, uint32_t n_passes)
+{
+    SM_ENTER(e);
+    if (e->world > 1 && !e->comm_ready) return sm_fail(SM_ERR_STATE, "multi-GPU engine: call sm_comm_init first");
+    for (uint32_t s = 0; s < n_passes; ++s) {
+        if (e->world > 1 && e->ghost_stale) SM_TRY(e->exchange_trail_ghosts());
+        SM_TRY(e->launch_trail(false));
+        if (e->world > 1) SM_TRY(e->exchange_trail_ghosts());
+    }
+    return SM_OK;
+}
+
+int sm_sync(sm_engine* e)
+{
+    SM_ENTER(e);
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    return SM_OK;
+}
+
+int sm_get_timing(sm_engine* e, sm_timing* out)
+{
+    SM_ENTER(e);
+    if (!out) return sm_fail(SM_ERR_BAD_ARG, "null output");
+    SM_TRY(e->resolve_timing());
+    *out = e->timing;
+    return SM_OK;
+}
+int sm_reset_timing(sm_engine* e)
+{
+    SM_ENTER(e);
+    SM_TRY(e->resolve_timing());
+    e->timing = sm_timing{};
+    return SM_OK;
+}
+int sm_set_timing_enabled(sm_engine* e, int enabled)
+{
+    SM_ENTER(e);
+    SM_TRY(e->resolve_timing());
+    e->timing_enabled = enabled != 0;
+    return SM_OK;
+}
+
+void* sm_stream(sm_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int sm_test_math(int device, int what, const float* a, const float* b, const int32_t* iv, float* o0, float* o1, uint64_t n)
+{
+    SM_TRY(check_device(device, nullptr));
+    if (what < 0 || what > 3 || !a || !o0) return sm_fail(SM_ERR_BAD_ARG, "bad sm_test_math arguments");
+    float *da = nullptr, *db = nullptr, *d0 = nullptr, *d1 = nullptr;
+    int32_t* di = nullptr;
+    int rc = SM_OK;
+    auto cleanup = [&]() { cudaFree(da); cudaFree(db); cudaFree(d0); cudaFree(d1); cudaFree(di); };
+#define TM(call) do { cudaError_t er = (call); if (er != cudaSuccess) { rc = sm_fail(SM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(er)); cleanup(); return rc; } } while (0)
+    TM(cudaMalloc(&da, n * 4)); TM(cudaMalloc(&d0, n * 4)); TM(cudaMalloc(&d1, n * 4));
+    TM(cudaMemcpy(da, a, n * 4, cudaMemcpyHostToDevice));
+    if (b) { TM(cudaMalloc(&db, n * 4)); TM(cudaMemcpy(db, b, n * 4, cudaMemcpyHostToDevice)); }
+    if (iv) { TM(cudaMalloc(&di, n * 4)); TM(cudaMemcpy(di, iv, n * 4, cudaMemcpyHostToDevice)); }
+    if ((what == 1 || what == 3) && !b) { cleanup(); return sm_fail(SM_ERR_BAD_ARG, "second operand required"); }
+    if (what == 3 && !iv) { cleanup(); return sm_fail(SM_ERR_BAD_ARG, "index operand required"); }
+    smk::k_test_math<<<blocks_for(n, 256), 256>>>(what, da, db, di, d0, d1, n);
+    TM(cudaGetLastError());
+    TM(cudaDeviceSynchronize());
+    TM(cudaMemcpy(o0, d0, n * 4, cudaMemcpyDeviceToHost));
+    if (o1) TM(cudaMemcpy(o1, d1, n * 4, cudaMemcpyDeviceToHost));
+#undef TM
+    cleanup();
+    return SM_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// order restoration (single GPU): agents back to index order
+// ---------------------------------------------------------------------------
+namespace smk {
+__global__ void __launch_bounds__(256)
+k_unsort(const float4* __restrict__ agents, const uint32_t* __restrict__ ids, uint64_t n,
+         float4* __restrict__ agents_out, uint32_t* __restrict__ ids_out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t id = ids[i];
+    agents_out[id] = agents[i];
+    ids_out[id] = id;
+}
+__global__ void __launch_bounds__(256)
+k_iota(uint32_t* __restrict__ ids, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = (uint32_t)i;
+}
+}  // namespace smk
+
+int sm_engine::restore_identity_order()
+{
+    if (n_local) {
+        smk::k_unsort<<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, agents[1 - acur], ids[1 - acur]);
+        SM_CUDA(cudaGetLastError());
+        acur = 1 - acur;
+    }
+    identity_order = true;
+    return SM_OK;
+}
+int sm_engine::fill_identity_ids()
+{
+    if (n_global) smk::k_iota<<<blocks_for(n_global, 256), 256, 0, stream>>>(ids[acur], n_global);
+    SM_CUDA(cudaGetLastError());
+    identity_order = true;
+    return SM_OK;
+}

@@ -1,0 +1,110 @@
+// engine.h -- internal state behind the opaque sm_engine handle of include/slime_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/slime_b200.h"
+#include "kernels.cuh"
+
+int sm_fail(int code, const char* fmt, ...);
+
+struct EvPair { cudaEvent_t a, b; int kind; };
+
+// Per-direction migration staging (multi-GPU): agents leaving towards a ring neighbour.
+struct MigrateBuf {
+    float4* send_a = nullptr;
+    uint32_t* send_id = nullptr;
+    uint64_t cap = 0;
+};
+
+struct sm_engine {
+    sm_config cfg{};
+    sm_params params{};
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+
+    // geometry: this rank owns global rows [row0, row0 + rows) of a W x H map and keeps
+    // `ghost` extra rows above and below (0 on a single GPU, where rows wrap toroidally)
+    uint32_t W = 0, H = 0;
+    int rank = 0, world = 1;
+    uint32_t row0 = 0, rows = 0, ghost = 0;
+
+    // trail: two ping-pong f32 fields, two alternating u32 deposit-count fields
+    float* trail_base[2] = {nullptr, nullptr};
+    uint32_t* counts_base[2] = {nullptr, nullptr};
+    int cur = 0, ccur = 0;
+    bool ghost_stale = true;          // ghost rows of trail[cur] need a (re-)exchange
+    float* gauss_dec = nullptr;       // extension scratch
+    float* gauss_hb = nullptr;
+    float* trail_ptr(int i) const { return trail_base[i] + (size_t)ghost * W; }        // owned row 0
+    uint32_t* counts_ptr(int i) const { return counts_base[i] + (size_t)ghost * W; }
+
+    // agents: float4 state + u32 persistent index, double buffered for the cell sort
+    float4* agents[2] = {nullptr, nullptr};
+    uint32_t* ids[2] = {nullptr, nullptr};
+    int acur = 0;
+    uint64_t n_global = 0, n_local = 0, cap_local = 0;
+    uint64_t n_live = 0;              // multi-GPU: n_local minus dead (migrated-away) slots
+    bool agents_valid = false;
+    bool identity_order = false;      // single GPU: agents[i] is agent i
+
+    // periodic cell sort
+    smk::TileGeom tiles{};
+    uint64_t n_tiles = 0;
+    uint32_t n_scan_blocks = 0;
+    uint32_t* tile_hist = nullptr;
+    uint32_t* tile_sums = nullptr;
+    uint32_t sort_interval = 16, steps_since_sort = 0;
+
+    // tuning overrides (environment, read at sm_create)
+    bool force_generic = false;
+    int rpc_override = 0;
+
+    // statistics scratch
+    void* stats_dev = nullptr;
+
+    // timing
+    bool timing_enabled = false;
+    std::vector<EvPair> ev_pool;
+    size_t ev_used = 0;
+    sm_timing timing{};
+
+    // multi-GPU (exchange.cu)
+    bool comm_ready = false;
+    void* comm = nullptr;             // ncclComm_t
+    uint32_t* counts_xchg = nullptr;  // recv staging for the deposit-count exchange
+    uint64_t counts_xchg_rows = 0;
+    MigrateBuf mig[2];                // 0: towards rank-1 (up), 1: towards rank+1 (down)
+    unsigned long long* mig_counters = nullptr;   // device: [leave_up, leave_down, arrive_from_down, arrive_from_up]
+    unsigned long long* mig_counters_host = nullptr;  // pinned mirror
+
+    smd::AgentConsts agent_consts() const;
+    smd::TrailConsts trail_consts() const;
+
+    int tic(int kind);
+    int toc();
+    int resolve_timing();
+
+    int alloc_trail();
+    void free_trail();
+    int alloc_agents(uint64_t capacity);
+    void free_agents();
+    int setup_tiles();
+
+    int sort_agents();
+    int launch_agents();
+    int launch_trail(bool has_counts);
+    int launch_gauss(bool has_counts, const smk::TrailGeom& g, const smd::TrailConsts& tc);
+    int restore_identity_order();
+    int fill_identity_ids();
+
+    // exchange.cu
+    int init_agents_strip(uint64_t seed);
+    int exchange_counts();
+    int exchange_trail_ghosts();
+    int migrate_agents();
+    void comm_destroy();
+};

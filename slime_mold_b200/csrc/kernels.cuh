@@ -1,0 +1,469 @@
+// kernels.cuh -- sm_100a CUDA kernels of the slime-mold step loop.
+//
+//   k_agents        compute.wgsl `main`          (:57-145)  one agent per thread
+//   k_trail_rows    `decay_trail`+`diffuse_trail` (:148-195) fused with the deposit
+//                   merge, register sliding window, float4 row streaming
+//   k_trail_generic same arithmetic, one cell per thread, any W (ragged sizes)
+//   k_tile_*        periodic counting sort of agents by map tile (gather locality)
+//
+// HBM layout (DESIGN.md "Data layout"): agents are SoA-of-vectors -- one float4
+// (x, y, angle, speed) array plus a u32 persistent-index array, so one LDG.128 /
+// STG.128 per agent, coalesced; the trail is row-major f32 with `ghost` rows above
+// and below the owned strip (0 on a single GPU); deposits are u32 per-cell counts in
+// two alternating buffers (the trail pass zeroes the one the next step will use).
+#pragma once
+#include <cuda_runtime.h>
+#include "agent_core.cuh"
+#include "trail_core.cuh"
+
+namespace smk {
+
+using smd::AgentConsts;
+using smd::TrailConsts;
+
+struct LdgF32 {
+    __device__ __forceinline__ float operator()(const float* p) const { return __ldg(p); }
+};
+
+// ---------------------------------------------------------------------------
+// agents
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+k_init_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n, uint64_t first_id,
+              uint64_t seed, float Wf, float Hf, float speed_min, float speed_max)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t id = first_id + i;
+    float4 a;
+    smd::agent_init(seed, id, Wf, Hf, speed_min, speed_max, a.x, a.y, a.z, a.w);
+    agents[i] = a;
+    ids[i] = (uint32_t)id;
+}
+
+static __global__ void __launch_bounds__(256)
+k_reassign_speeds(float4* __restrict__ agents, const uint32_t* __restrict__ ids, uint64_t n,
+                  uint64_t seed, float speed_min, float speed_max)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r = smd::rand01(seed, (uint64_t)ids[i], 3);
+    agents[i].w = smd::add(speed_min, smd::mul(r, smd::sub(speed_max, speed_min)));
+}
+
+static __global__ void __launch_bounds__(256)
+k_rescale_agents(float4* __restrict__ agents, uint64_t n, float fx, float fy)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = agents[i];
+    a.x = smd::mul(a.x, fx);
+    a.y = smd::mul(a.y, fy);
+    agents[i] = a;
+}
+
+// One agent per thread.  `trail` and `counts` point at owned row 0 of this rank's
+// strip (global row c.row_base); ghost rows sit at negative / >= rows offsets.
+static __global__ void __launch_bounds__(256)
+k_agents(float4* __restrict__ agents, const uint32_t* __restrict__ ids, uint64_t n,
+         const float* __restrict__ trail, uint32_t* __restrict__ counts, const AgentConsts c)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = agents[i];
+    int32_t idx = (int32_t)ids[i];
+    int32_t cx, cy;
+    smd::agent_update(a.x, a.y, a.z, a.w, idx, trail, c, LdgF32(), cx, cy);
+    agents[i] = a;
+    if (cx >= 0) {
+        // deposit: integer count, order-free (phase_split form of compute.wgsl:140)
+        atomicAdd(counts + ((int64_t)cy - c.row_base) * (int64_t)c.W + cx, 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// trail: merge deposits -> decay -> 3x3 toroidal mean -> mix, out of place
+// ---------------------------------------------------------------------------
+struct TrailGeom {
+    uint32_t W;          // row length (cells); fast kernel requires W % 4 == 0
+    uint32_t rows;       // owned rows
+    uint32_t rows_per_chunk;
+    int wrap_y;          // 1: rows wrap toroidally inside the buffer (single GPU); 0: ghost rows
+};
+
+__device__ __forceinline__ int64_t row_index(int64_t y, const TrailGeom& g)
+{
+    if (g.wrap_y) {
+        if (y < 0) y += g.rows;
+        else if (y >= (int64_t)g.rows) y -= g.rows;
+    }
+    return y;
+}
+
+template <bool HAS_COUNTS>
+struct RawRow {
+    float4 t;
+    uint4 k;
+    float tl, tr;
+    uint32_t kl, kr;
+};
+
+// Each thread owns 4 consecutive columns and walks down `rows_per_chunk` rows with a
+// 3-row register window of decayed values; the horizontal neighbours come from the
+// adjacent lanes by shuffle (warp-edge lanes fetch one extra cell).  Loads for
+// UNROLL rows are issued before any of them is consumed.
+template <bool HAS_COUNTS, int UNROLL>
+static __global__ void __launch_bounds__(128)
+k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
+             uint32_t* __restrict__ czero, float* __restrict__ tout,
+             const TrailGeom g, const TrailConsts tc)
+{
+    const uint32_t grp = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t x0 = grp * 4u;
+    const bool active = x0 < g.W;
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool left_edge = active && (lane == 0u);
+    const bool right_edge = active && (lane == 31u || x0 + 4u >= g.W);
+    const uint32_t xl = (x0 == 0u) ? g.W - 1u : x0 - 1u;
+    const uint32_t xr = (x0 + 4u >= g.W) ? 0u : x0 + 4u;
+
+    const int64_t y_begin = (int64_t)blockIdx.y * g.rows_per_chunk;
+    int64_t y_end = y_begin + g.rows_per_chunk;
+    if (y_end > (int64_t)g.rows) y_end = g.rows;
+
+    auto issue = [&](int64_t y, RawRow<HAS_COUNTS>& r) {
+        const int64_t off = row_index(y, g) * (int64_t)g.W;
+        r.t = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.k = make_uint4(0u, 0u, 0u, 0u);
+        r.tl = r.tr = 0.f;
+        r.kl = r.kr = 0u;
+        if (active) {
+            r.t = __ldg(reinterpret_cast<const float4*>(tin + off + x0));
+            if (HAS_COUNTS) r.k = __ldg(reinterpret_cast<const uint4*>(cin + off + x0));
+        }
+        if (left_edge) {
+            r.tl = __ldg(tin + off + xl);
+            if (HAS_COUNTS) r.kl = __ldg(cin + off + xl);
+        }
+        if (right_edge) {
+            r.tr = __ldg(tin + off + xr);
+            if (HAS_COUNTS) r.kr = __ldg(cin + off + xr);
+        }
+    };
+    auto cell = [&](float t, uint32_t k) {
+        if (HAS_COUNTS) t = smd::merge_deposit(t, k, tc.dep);
+        return smd::decay_cell(t, tc.decay_sub);
+    };
+    // d[0] = column x0-1, d[1..4] = own columns, d[5] = column x0+4 (all decayed)
+    auto finish = [&](const RawRow<HAS_COUNTS>& r, float (&d)[6]) {
+        d[1] = cell(r.t.x, r.k.x);
+        d[2] = cell(r.t.y, r.k.y);
+        d[3] = cell(r.t.z, r.k.z);
+        d[4] = cell(r.t.w, r.k.w);
+        float from_left = __shfl_up_sync(0xffffffffu, d[4], 1);
+        float from_right = __shfl_down_sync(0xffffffffu, d[1], 1);
+        d[0] = left_edge ? cell(r.tl, r.kl) : from_left;
+        d[5] = right_edge ? cell(r.tr, r.kr) : from_right;
+    };
+
+    float prev[6], cur[6], next[6];
+    {
+        RawRow<HAS_COUNTS> r0, r1;
+        issue(y_begin - 1, r0);
+        issue(y_begin, r1);
+        finish(r0, prev);
+        finish(r1, cur);
+    }
+    for (int64_t y = y_begin; y < y_end; y += UNROLL) {
+        RawRow<HAS_COUNTS> raw[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            int64_t yy = y + u + 1;
+            if (yy > y_end) yy = y_end;          // past the chunk: harmless re-load of the halo row
+            issue(yy, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            finish(raw[u], next);
+            if (y + u < y_end && active) {
+                float4 o;
+                o.x = smd::box9_mix(prev[0], prev[1], prev[2], cur[0], cur[1], cur[2], next[0], next[1], next[2], tc);
+                o.y = smd::box9_mix(prev[1], prev[2], prev[3], cur[1], cur[2], cur[3], next[1], next[2], next[3], tc);
+                o.z = smd::box9_mix(prev[2], prev[3], prev[4], cur[2], cur[3], cur[4], next[2], next[3], next[4], tc);
+                o.w = smd::box9_mix(prev[3], prev[4], prev[5], cur[3], cur[4], cur[5], next[3], next[4], next[5], tc);
+                const int64_t off = (y + u) * (int64_t)g.W + x0;
+                *reinterpret_cast<float4*>(tout + off) = o;
+                if (HAS_COUNTS) *reinterpret_cast<uint4*>(czero + off) = make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { prev[j] = cur[j]; cur[j] = next[j]; }
+        }
+    }
+}
+
+// Any W, H >= 1 (ragged sizes, W % 4 != 0): one cell per thread, nine direct loads.
+template <bool HAS_COUNTS>
+static __global__ void __launch_bounds__(256)
+k_trail_generic(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
+                uint32_t* __restrict__ czero, float* __restrict__ tout,
+                const TrailGeom g, const TrailConsts tc, int64_t y_first)
+{
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t y = y_first + blockIdx.y;
+    if (x >= (int64_t)g.W) return;
+    float v[9];
+    int j = 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+        int64_t ry = y + dy;
+        if (g.wrap_y) ry = (ry + g.rows) % (int64_t)g.rows;
+        for (int dx = -1; dx <= 1; ++dx) {
+            int64_t nx = (x + dx + g.W) % (int64_t)g.W;
+            int64_t off = ry * (int64_t)g.W + nx;
+            float t = __ldg(tin + off);
+            if (HAS_COUNTS) t = smd::merge_deposit(t, __ldg(cin + off), tc.dep);
+            v[j++] = smd::decay_cell(t, tc.decay_sub);
+        }
+    }
+    const int64_t off = y * (int64_t)g.W + x;
+    tout[off] = smd::box9_mix(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], tc);
+    if (HAS_COUNTS) czero[off] = 0u;
+}
+
+// ---------------------------------------------------------------------------
+// EXTENSION: separable Gaussian blur (no reference semantics, "parity unpinned").
+// Pass 1 (horizontal) fuses merge + decay and writes the decayed field D and the
+// row-blurred field Hb; pass 2 (vertical) mixes D with the column blur of Hb.
+// ---------------------------------------------------------------------------
+struct GaussConsts { int R; float w[17]; };
+
+template <bool HAS_COUNTS>
+static __global__ void __launch_bounds__(256)
+k_gauss_h(const float* __restrict__ tin, const uint32_t* __restrict__ cin, uint32_t* __restrict__ czero,
+          float* __restrict__ dec, float* __restrict__ hb, const TrailGeom g, const TrailConsts tc,
+          const GaussConsts gc, int64_t y_first)
+{
+    extern __shared__ float srow[];                    // blockDim.x + 2R decayed values
+    const int64_t y = y_first + blockIdx.y;
+    const int64_t off = y * (int64_t)g.W;
+    const int64_t xb = (int64_t)blockIdx.x * blockDim.x;
+    const int R = gc.R;
+    for (int j = threadIdx.x; j < (int)blockDim.x + 2 * R; j += blockDim.x) {
+        int64_t x = xb + j - R;
+        x = ((x % (int64_t)g.W) + g.W) % (int64_t)g.W;
+        float t = __ldg(tin + off + x);
+        if (HAS_COUNTS) t = smd::merge_deposit(t, __ldg(cin + off + x), tc.dep);
+        srow[j] = smd::decay_cell(t, tc.decay_sub);
+    }
+    __syncthreads();
+    const int64_t x = xb + threadIdx.x;
+    if (x >= (int64_t)g.W) return;
+    float acc = 0.0f;
+    for (int d = 0; d <= 2 * R; ++d) acc = smd::fma(gc.w[d], srow[threadIdx.x + d], acc);
+    dec[off + x] = srow[threadIdx.x + R];
+    hb[off + x] = acc;
+}
+
+static __global__ void __launch_bounds__(256)
+k_gauss_v(const float* __restrict__ dec, const float* __restrict__ hb, float* __restrict__ tout,
+          uint32_t* __restrict__ czero, int has_counts, const TrailGeom g, const TrailConsts tc,
+          const GaussConsts gc, int64_t y_first)
+{
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t y = y_first + blockIdx.y;
+    if (x >= (int64_t)g.W) return;
+    float acc = 0.0f;
+    for (int d = -gc.R; d <= gc.R; ++d) {
+        int64_t ry = y + d;
+        if (g.wrap_y) ry = ((ry % (int64_t)g.rows) + g.rows) % (int64_t)g.rows;
+        acc = smd::fma(gc.w[d + gc.R], __ldg(hb + ry * (int64_t)g.W + x), acc);
+    }
+    const int64_t off = y * (int64_t)g.W + x;
+    tout[off] = smd::mixf_pre(dec[off], acc, tc.rate, tc.one_minus_rate);
+    if (has_counts) czero[off] = 0u;
+}
+
+// ---------------------------------------------------------------------------
+// periodic cell sort (counting sort by tile key), carries the persistent index
+// ---------------------------------------------------------------------------
+struct TileGeom {
+    uint32_t shift_x, shift_y;   // tile = 2^shift_x x 2^shift_y cells
+    uint32_t tiles_x, tiles_y;   // over the strip
+    uint32_t W;
+    int64_t row_base;            // global row of local row 0
+    uint32_t rows;               // owned rows
+};
+
+__device__ __forceinline__ uint32_t tile_key(float x, float y, const TileGeom& t)
+{
+    int32_t cx = (int32_t)x;                                   // x in [0, W] (W by rounding)
+    int64_t cy = (int64_t)(int32_t)y - t.row_base;
+    if (cx < 0) cx = 0;
+    if (cx >= (int32_t)t.W) cx = t.W - 1;
+    if (cy < 0) cy = 0;
+    if (cy >= (int64_t)t.rows) cy = t.rows - 1;
+    return ((uint32_t)cy >> t.shift_y) * t.tiles_x + ((uint32_t)cx >> t.shift_x);
+}
+
+static __global__ void __launch_bounds__(256)
+k_tile_hist(const float4* __restrict__ agents, uint64_t n, uint32_t* __restrict__ hist, const TileGeom t)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = agents[i];
+    atomicAdd(hist + tile_key(a.x, a.y, t), 1u);
+}
+
+// exclusive scan of `n` u32 in three phases (block sums -> scan of sums -> add).
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;    // per thread
+static __global__ void __launch_bounds__(kScanBlock)
+k_scan_block(const uint32_t* in, uint32_t* out, uint32_t* __restrict__ block_sums, uint32_t n)
+{
+    __shared__ uint32_t warp_sums[kScanBlock / 32];
+    const uint32_t base = (blockIdx.x * kScanBlock + threadIdx.x) * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        v[j] = (base + j < n) ? in[base + j] : 0u;
+        tsum += v[j];
+    }
+    // inclusive scan of tsum across the block
+    uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += up;
+    }
+    if (lane == 31u) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t ws = (lane < kScanBlock / 32) ? warp_sums[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t up = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= (uint32_t)o) ws += up;
+        }
+        if (lane < kScanBlock / 32) warp_sums[lane] = ws;   // inclusive warp totals
+    }
+    __syncthreads();
+    uint32_t excl = inc - tsum + (warp ? warp_sums[warp - 1] : 0u);
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        if (base + j < n) out[base + j] = excl;
+        excl += v[j];
+    }
+    if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = excl;
+}
+static __global__ void __launch_bounds__(1024)
+k_scan_sums(uint32_t* __restrict__ sums, uint32_t n)   // single block, in-place exclusive scan
+{
+    __shared__ uint32_t carry;
+    __shared__ uint32_t warp_sums[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = (i < n) ? sums[i] : 0u;
+        uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += up;
+        }
+        if (lane == 31u) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t up = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= (uint32_t)o) ws += up;
+            }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        uint32_t excl = inc - v + (warp ? warp_sums[warp - 1] : 0u) + carry;
+        if (i < n) sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+static __global__ void __launch_bounds__(kScanBlock)
+k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ block_sums, uint32_t n)
+{
+    const uint32_t base = (blockIdx.x * kScanBlock + threadIdx.x) * kScanItems;
+    const uint32_t add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+        if (base + j < n) out[base + j] += add;
+}
+
+static __global__ void __launch_bounds__(256)
+k_tile_scatter(const float4* __restrict__ agents, const uint32_t* __restrict__ ids, uint64_t n,
+               uint32_t* __restrict__ cursor, float4* __restrict__ agents_out, uint32_t* __restrict__ ids_out,
+               const TileGeom t)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = agents[i];
+    uint32_t pos = atomicAdd(cursor + tile_key(a.x, a.y, t), 1u);
+    agents_out[pos] = a;
+    ids_out[pos] = ids[i];
+}
+
+// ---------------------------------------------------------------------------
+// field statistics (the per-step "result" a host harness reads back)
+// ---------------------------------------------------------------------------
+struct StatsAcc { double sum, sum_sq; unsigned long long nonzero; unsigned int max_bits; unsigned int pad; };
+
+static __global__ void __launch_bounds__(256)
+k_trail_stats(const float* __restrict__ t, uint64_t cells, StatsAcc* __restrict__ acc)
+{
+    double s = 0.0, s2 = 0.0;
+    unsigned long long nz = 0;
+    float m = 0.0f;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        float v = t[i];
+        s += (double)v;
+        s2 += (double)v * (double)v;
+        nz += (v != 0.0f);
+        m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        nz += __shfl_down_sync(0xffffffffu, nz, o);
+        m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicAdd(&acc->sum, s);
+        atomicAdd(&acc->sum_sq, s2);
+        atomicAdd(&acc->nonzero, nz);
+        atomicMax(&acc->max_bits, __float_as_uint(m));   // valid ordering for m >= 0
+    }
+}
+
+// ---------------------------------------------------------------------------
+// arithmetic-spec probes (sm_test_math)
+// ---------------------------------------------------------------------------
+static __global__ void k_test_math(int what, const float* a, const float* b, const int32_t* iv,
+                            float* o0, float* o1, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (what) {
+    case 0: { float s, c; smd::sincos(a[i], s, c); o0[i] = s; o1[i] = c; break; }
+    case 1: { float bb = b[i]; o0[i] = smd::fmod_exact(a[i], bb, __frcp_rn(bb)); break; }
+    case 2: o0[i] = smd::div9(a[i]); break;
+    case 3: o0[i] = smd::hash01(iv[i], a[i], b[i]); break;
+    default: break;
+    }
+}
+
+}  // namespace smk
