@@ -155,8 +155,10 @@ SM_HD float fmod_exact(float a, float b, float rcp_b)
     return ::copysignf(r, a);
 }
 
-// ---- exact s / 9.0f for finite s (Markstein correction; verified against IEEE
-// division for every non-negative binary32 value, tests/exhaustive_div9.c) -----
+// ---- exact s / 9.0f (Markstein correction; verified against IEEE division for EVERY
+// non-negative binary32 value incl. subnormals by tests/exhaustive_div9.c; negative
+// values follow by symmetry except -0.0, which the 9-tap sum can never produce because
+// it starts from +0.0) ------------------------------------------------------------
 SM_HD float div9(float s)
 {
     const float c = 0x1.c71c72p-4f;   // fl32(1/9)

@@ -1,0 +1,89 @@
+"""C ABI checks that need no GPU: libslime_b200.so loads, exports every symbol that
+include/slime_b200.h declares, struct layouts match the header, and the product path
+fails loudly (no CPU fallback) when no sm_100 device is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "slime_b200.h")
+
+
+def declared_functions():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sm_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported(engine_lib):
+    from slime_mold_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(engine_lib, n), f"{n} declared in slime_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+
+
+def test_struct_layouts_match_header():
+    from slime_mold_b200 import SimSizeUniform
+    from slime_mold_b200._lib import SmConfig, SmTiming, SmTrailStats
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "slime_b200.h"
+    int main(void) {
+        printf("%zu %zu %zu %zu\n", sizeof(sm_params), sizeof(sm_config), sizeof(sm_timing), sizeof(sm_trail_stats));
+        printf("%zu %zu %zu %zu %zu\n", offsetof(sm_params, decay_factor), offsetof(sm_params, diffusion_rate),
+               offsetof(sm_params, pheromone_deposition_amount), offsetof(sm_params, blur_radius), offsetof(sm_params, _pad));
+        printf("%zu %zu %zu\n", offsetof(sm_config, agent_count), offsetof(sm_config, device), offsetof(sm_config, sort_interval));
+        return 0;
+    }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "p.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "p")
+        cc = "/usr/bin/gcc-13" if os.path.exists("/usr/bin/gcc-13") else "gcc"
+        subprocess.run([cc, "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split("\n")
+    sizes = list(map(int, out[0].split()))
+    assert sizes == [C.sizeof(SimSizeUniform), C.sizeof(SmConfig), C.sizeof(SmTiming), C.sizeof(SmTrailStats)]
+    assert sizes[0] == 56                                   # SimSizeUniform, src/main.rs:29-46
+    # offsets of SURVEY.md 8(a) a6
+    assert list(map(int, out[1].split())) == [8, 36, 40, 44, 52]
+    assert list(map(int, out[2].split())) == [SmConfig.agent_count.offset, SmConfig.device.offset, SmConfig.sort_interval.offset]
+
+
+def test_version(engine_lib):
+    ma, mi = C.c_int(-1), C.c_int(-1)
+    engine_lib.sm_version(C.byref(ma), C.byref(mi))
+    assert (ma.value, mi.value) == (0, 1)
+
+
+def test_no_cpu_fallback(engine_lib):
+    """Without an sm_100 device every compute entry point must fail loudly."""
+    import slime_mold_b200 as sm
+    if sm.device_count() > 0:
+        pytest.skip("a B200 is present: the loud-failure path is not reachable here")
+    with pytest.raises(sm.SlimeError) as ei:
+        sm.CudaBackend.new(64, 64, agent_count=16)
+    assert ei.value.code == -5 and "no CPU fallback" in str(ei.value)
+    import numpy as np
+    from slime_mold_b200.backend import test_math
+    with pytest.raises(sm.SlimeError):
+        test_math("div9", np.ones(4, np.float32))
+
+
+def test_product_does_not_import_oracle():
+    """The package must not reference oracle/ (the checker) anywhere."""
+    pkg = os.path.join(ROOT, "slime_mold_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "slime_oracle" not in txt and "libslime_oracle" not in txt, f
+                assert not re.search(r"#include\s+\"[^\"]*oracle", txt), f

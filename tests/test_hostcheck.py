@@ -1,0 +1,91 @@
+"""The engine's __host__ __device__ arithmetic (device_math.cuh / agent_core.cuh /
+trail_core.cuh), instantiated for the host by tests/hostcheck (TEST ONLY), against the
+oracle -- bit for bit.  This is how kernel arithmetic is debugged without a GPU; the
+device instantiation is checked by the -m gpu tests."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+from presets_util import PRESET_NAMES, preset_uniform, to_oracle_params
+
+
+def P(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def special_values():
+    return np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 8192.0, -8192.0, 8192.001, 1e15, 2e15, 3e38, 1e-40,
+                     6.2831855, -6.2831855, 12.566371], dtype=np.float32)
+
+
+def test_sincos_bits(oracle, hostcheck):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([
+        rng.integers(0, 2**32, 1_000_000, dtype=np.uint64).astype(np.uint32).view(np.float32),
+        rng.uniform(-10, 10, 500_000).astype(np.float32), rng.uniform(-9000, 9000, 300_000).astype(np.float32),
+        rng.uniform(-2e10, 2e10, 300_000).astype(np.float32), special_values()])
+    s0, c0 = oracle.sincos(x)
+    s1, c1 = np.empty_like(x), np.empty_like(x)
+    hostcheck.hc_sincos_array(P(x, C.c_float), P(s1, C.c_float), P(c1, C.c_float), C.c_uint64(x.size))
+    assert bits_equal(s0, s1) and bits_equal(c0, c1)
+
+
+@pytest.mark.parametrize("b", [6.2831855, 1920.0, 1080.0, 4096.0, 65536.0, 1.0, 7.0, 37.0])
+def test_fmod_exact_bits(oracle, hostcheck, b):
+    rng = np.random.default_rng(1)
+    a = np.concatenate([rng.uniform(-3 * b, 3 * b, 400_000), rng.uniform(-1e7, 1e7, 200_000), rng.uniform(-1e12, 1e12, 50_000)]).astype(np.float32)
+    a = np.concatenate([a, rng.integers(0, 2**32, 400_000, dtype=np.uint64).astype(np.uint32).view(np.float32), special_values(),
+                        np.float32(b) * np.arange(-5, 6, dtype=np.float32)])
+    bb = np.full_like(a, np.float32(b))
+    r1 = np.empty_like(a)
+    hostcheck.hc_fmod_array(P(a, C.c_float), P(bb, C.c_float), P(r1, C.c_float), C.c_uint64(a.size))
+    assert bits_equal(oracle.fmod(a, bb), r1)
+
+
+def test_div9_bits(oracle, hostcheck):
+    rng = np.random.default_rng(2)
+    d = np.concatenate([rng.integers(0, 2**32, 1_000_000, dtype=np.uint64).astype(np.uint32).view(np.float32),
+                        rng.uniform(0, 9, 500_000).astype(np.float32), special_values()])
+    # domain of the fast path: the 9-tap sum starts from +0.0 and adds values >= +0, so it is never -0.0
+    d = d[~((d == 0) & np.signbit(d))]
+    r1 = np.empty_like(d)
+    hostcheck.hc_div9_array(P(d, C.c_float), P(r1, C.c_float), C.c_uint64(d.size))
+    assert bits_equal(oracle.div9(d), r1)
+
+
+def test_hash_and_init_bits(oracle, hostcheck):
+    rng = np.random.default_rng(3)
+    n = 500_000
+    idx = rng.integers(0, 2**31 - 1, n).astype(np.int32)
+    x = rng.uniform(0, 32768, n).astype(np.float32)
+    y = rng.uniform(0, 32768, n).astype(np.float32)
+    r1 = np.empty_like(x)
+    hostcheck.hc_hash01_array(P(idx, C.c_int32), P(x, C.c_float), P(y, C.c_float), P(r1, C.c_float), C.c_uint64(n))
+    assert bits_equal(oracle.hash01(idx, x, y), r1)
+    a0 = oracle.init_agents(50_000, 1920, 1080, 30, 50, 7, first_id=123)
+    a1 = np.empty_like(a0)
+    hostcheck.hc_init_agents(P(a1, C.c_float), C.c_uint64(123), C.c_uint64(50_000), C.c_uint32(1920), C.c_uint32(1080),
+                             C.c_float(30), C.c_float(50), C.c_uint64(7))
+    assert bits_equal(a0, a1)
+
+
+@pytest.mark.parametrize("name", PRESET_NAMES)
+def test_step_loop_bits(oracle, hostcheck, name):
+    W, H, N, steps = 320, 256, 20000, 12
+    u = preset_uniform(name, W, H)
+    p = to_oracle_params(oracle, u)
+    ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 3)
+    sim = oracle.Sim(p, ag)
+    a = ag.copy()
+    tr = np.zeros((H, W), np.float32)
+    cn = np.zeros((H, W), np.uint32)
+    out = np.empty_like(tr)
+    for step in range(steps):
+        sim.step(1)
+        hostcheck.hc_agents_phase_split(P(a, C.c_float), None, C.c_uint64(N), P(tr, C.c_float), P(cn, C.c_uint32), C.byref(p))
+        hostcheck.hc_trail_pass(P(tr, C.c_float), P(cn, C.c_uint32), P(out, C.c_float), C.byref(p))
+        tr, out = out, tr
+        assert bits_equal(a, sim.agents), f"agents differ at step {step}"
+        assert bits_equal(tr, sim.trail), f"trail differs at step {step}"
