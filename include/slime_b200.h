@@ -89,6 +89,7 @@ typedef struct sm_timing {       /* CUDA-event totals since sm_reset_timing() */
     double exchange_ms;          /* halo exchange + migration (multi-GPU) */
     uint64_t agent_launches, trail_launches, sort_launches, exchange_launches;
     uint64_t steps;
+    uint64_t kernel_launches;    /* every kernel the engine launched (counted even with timing off) */
 } sm_timing;
 
 typedef struct sm_trail_stats {  /* computed on the device over the owned strip */

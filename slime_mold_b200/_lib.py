@@ -40,7 +40,7 @@ class SmTiming(C.Structure):
     _fields_ = [
         ("agents_ms", C.c_double), ("trail_ms", C.c_double), ("sort_ms", C.c_double), ("exchange_ms", C.c_double),
         ("agent_launches", C.c_uint64), ("trail_launches", C.c_uint64), ("sort_launches", C.c_uint64),
-        ("exchange_launches", C.c_uint64), ("steps", C.c_uint64),
+        ("exchange_launches", C.c_uint64), ("steps", C.c_uint64), ("kernel_launches", C.c_uint64),
     ]
 
 

@@ -207,6 +207,7 @@ int sm_engine::sort_agents()
     smk::k_tile_scatter<<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, tile_hist,
                                                                       agents[1 - acur], ids[1 - acur], tiles);
     SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 5;
     acur = 1 - acur;
     identity_order = false;
     SM_TRY(toc());
@@ -220,6 +221,7 @@ int sm_engine::launch_agents()
     smk::k_agents<<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, trail_ptr(cur),
                                                                 counts_ptr(ccur), agent_consts());
     SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 1;
     SM_TRY(toc());
     return SM_OK;
 }
@@ -248,6 +250,7 @@ int sm_engine::launch_trail(bool has_counts)
         dim3 grid(bx, (unsigned)((rows + rpc - 1) / rpc));
         if (has_counts) smk::k_trail_rows<true, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
         else smk::k_trail_rows<false, 4><<<grid, bs, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc);
+        timing.kernel_launches += 1;
     } else {
         g.rows_per_chunk = 1;
         for (uint32_t y0 = 0; y0 < rows; y0 += 32768) {
@@ -255,6 +258,7 @@ int sm_engine::launch_trail(bool has_counts)
             dim3 grid(blocks_for(W, 256), ny);
             if (has_counts) smk::k_trail_generic<true><<<grid, 256, 0, stream>>>(tin, cin, czero, tout, g, tc, (int64_t)y0);
             else smk::k_trail_generic<false><<<grid, 256, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc, (int64_t)y0);
+            timing.kernel_launches += 1;
         }
     }
     SM_CUDA(cudaGetLastError());
@@ -294,11 +298,13 @@ int sm_engine::launch_gauss(bool has_counts, const smk::TrailGeom& g, const smd:
         dim3 grid(blocks_for(W, bs), ny);
         if (has_counts) smk::k_gauss_h<true><<<grid, bs, smem, stream>>>(tin, cin, czero, gauss_dec, gauss_hb, g, tc, gc, (int64_t)y0);
         else smk::k_gauss_h<false><<<grid, bs, smem, stream>>>(tin, nullptr, nullptr, gauss_dec, gauss_hb, g, tc, gc, (int64_t)y0);
+        timing.kernel_launches += 1;
     }
     for (uint32_t y0 = 0; y0 < rows; y0 += 32768) {
         uint32_t ny = std::min<uint32_t>(32768, rows - y0);
         dim3 grid(blocks_for(W, bs), ny);
         smk::k_gauss_v<<<grid, bs, 0, stream>>>(gauss_dec, gauss_hb, tout, czero, has_counts ? 1 : 0, g, tc, gc, (int64_t)y0);
+        timing.kernel_launches += 1;
     }
     return SM_OK;
 }

@@ -1,0 +1,239 @@
+"""Parity tests proper: the CUDA path (through the C ABI / CudaBackend) against the CPU
+oracle on identical seeded inputs -- bit-exact on agents (x, y, angle, speed) and on
+the trail.  -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+import slime_mold_b200 as sm
+from conftest import bits_equal, mismatch_report
+from presets_util import PRESET_NAMES, preset_uniform, random_trail, to_oracle_params
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def settings_for(name):
+    return sm.init_preset_manager().get_preset(name).settings
+
+
+def run_pair(oracle, name, W, H, N, steps, seed=3, trail=None, check_every=None, **backend_kw):
+    s = settings_for(name)
+    u = preset_uniform(name, W, H)
+    p = to_oracle_params(oracle, u)
+    ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, seed)
+    sim = oracle.Sim(p, ag, trail=trail)
+    be = sm.CudaBackend.new(W, H, s, agent_count=N, **backend_kw)
+    be.write_agents(ag)
+    if trail is not None:
+        be.write_trail(trail)
+    done = 0
+    for chunk in (check_every or [steps]):
+        sim.step(chunk)
+        be.step(chunk)
+        done += chunk
+        a = be.read_agents()
+        t = be.read_trail()
+        assert bits_equal(a, sim.agents), f"{name} step {done}: " + mismatch_report(a, sim.agents, "agents")
+        assert bits_equal(t, sim.trail), f"{name} step {done}: " + mismatch_report(t, sim.trail, "trail")
+    be.close()
+
+
+@pytest.mark.parametrize("name", PRESET_NAMES)
+def test_preset_one_and_many_steps(oracle, engine_lib, name):
+    # 320x256 map, 40k agents: fast kernel (W % 4 == 0), sort every 16 steps (default)
+    run_pair(oracle, name, 320, 256, 40000, 60, check_every=[1, 1, 18, 40])
+
+
+@pytest.mark.parametrize("name", ["Default", "Snake", "Curls"])
+def test_large_sensor_on_bigger_map(oracle, engine_lib, name):
+    # sd = 225 (Snake) needs a map where the sensors actually land inside
+    run_pair(oracle, name, 1024, 768, 200000, 20, trail=random_trail(1024, 768, seed=5), check_every=[1, 19])
+
+
+@pytest.mark.parametrize("shape", [(37, 23), (5, 3), (8, 1), (4, 4), (12, 7), (1, 1), (2, 2), (1000, 3)])
+def test_ragged_and_tiny_maps(oracle, engine_lib, shape):
+    W, H = shape
+    run_pair(oracle, "Default", W, H, 500, 8, trail=random_trail(W, H, seed=1, density=0.6), check_every=[1, 7])
+
+
+def test_single_agent_and_sort_modes(oracle, engine_lib):
+    run_pair(oracle, "Waves", 64, 64, 1, 10)
+    run_pair(oracle, "Waves", 256, 128, 30000, 20, flags=sm.SM_FLAG_NO_SORT)
+    run_pair(oracle, "Waves", 256, 128, 30000, 20, sort_interval=1)
+    run_pair(oracle, "Waves", 256, 128, 30000, 20, sort_interval=3)
+
+
+def test_device_init_matches_oracle(oracle, engine_lib):
+    W, H, N = 640, 480, 100000
+    s = settings_for("Threads")
+    be = sm.CudaBackend.new(W, H, s, agent_count=N)
+    be.init_agents(seed=77)
+    a = be.read_agents()
+    ref = oracle.init_agents(N, W, H, s.agent_speed_min, s.agent_speed_max, 77)
+    assert bits_equal(a, ref), mismatch_report(a, ref, "init")
+    be.step(5)
+    p = to_oracle_params(oracle, preset_uniform("Threads", W, H))
+    sim = oracle.Sim(p, ref)
+    sim.step(5)
+    assert bits_equal(be.read_agents(), sim.agents) and bits_equal(be.read_trail(), sim.trail)
+    # reassign_agent_speeds (main.rs:101-145), seeded, on the device, after the agents were cell-sorted
+    be.reassign_agent_speeds(seed=5)
+    exp = sim.agents.copy()
+    oracle.reassign_speeds(exp, s.agent_speed_min, s.agent_speed_max, 5)
+    assert bits_equal(be.read_agents(), exp)
+    be.close()
+
+
+def test_partial_upload_download_and_trail_rectangles(oracle, engine_lib):
+    W, H, N = 128, 96, 5000
+    be = sm.CudaBackend.new(W, H, agent_count=N)
+    ag = oracle.init_agents(N, W, H, 30, 50, 1)
+    be.write_agents(ag)
+    be.step(3)                                   # forces a sort: storage order != index order
+    base = be.read_agents()
+    patch = oracle.init_agents(700, W, H, 30, 50, 9)
+    be.write_agents(patch, first=1200)
+    got = be.read_agents()
+    exp = base.copy(); exp[1200:1900] = patch
+    assert bits_equal(got, exp)
+    assert bits_equal(be.read_agents(first=1000, n=500), exp[1000:1500])
+    # trail rectangles
+    full = be.read_trail()
+    rect = np.random.default_rng(0).random((10, 20), dtype=np.float32)
+    be.write_trail(rect, x0=30, y0=40)
+    exp_t = full.copy(); exp_t[40:50, 30:50] = rect
+    assert bits_equal(be.read_trail(), exp_t)
+    assert bits_equal(be.read_trail(x0=25, y0=38, w=40, h=20), exp_t[38:58, 25:65])
+    be.clear_trail()
+    assert not be.read_trail().any()
+    with pytest.raises(sm.SlimeError):
+        be.read_trail(x0=100, y0=0, w=100, h=1)
+    with pytest.raises(sm.SlimeError):
+        be.write_agents(patch, first=N - 10)
+    be.close()
+
+
+def test_agent_count_change_and_resize(oracle, engine_lib):
+    W, H = 200, 120
+    s = settings_for("Default")
+    be = sm.CudaBackend.new(W, H, s, agent_count=1000)
+    be.init_agents(1)
+    be.step(2)
+    be.set_agent_count(7000, seed=4)              # N key: everything re-randomised (main.rs:697-713)
+    assert be.agent_count == 7000
+    ref = oracle.init_agents(7000, W, H, s.agent_speed_min, s.agent_speed_max, 4)
+    assert bits_equal(be.read_agents(), ref)
+    be.step(4)
+    before = be.read_agents()
+    be.resize(320, 240)                           # main.rs:954-1015
+    exp = before.copy(); oracle.rescale_agents(exp, W, H, 320, 240)
+    assert bits_equal(be.read_agents(), exp)
+    assert be.read_trail().shape == (240, 320) and not be.read_trail().any()
+    p = to_oracle_params(oracle, preset_uniform("Default", 320, 240))
+    sim = oracle.Sim(p, exp)
+    sim.step(6); be.step(6)
+    assert bits_equal(be.read_agents(), sim.agents) and bits_equal(be.read_trail(), sim.trail)
+    be.close()
+
+
+def test_parameter_update_mid_run(oracle, engine_lib):
+    # update_settings (main.rs:83-99) between frames; preset switch does not touch the agents (:794-833)
+    W, H, N = 256, 256, 30000
+    be = sm.CudaBackend.new(W, H, settings_for("Default"), agent_count=N)
+    ag = oracle.init_agents(N, W, H, 30, 50, 2)
+    be.write_agents(ag)
+    sim = oracle.Sim(to_oracle_params(oracle, preset_uniform("Default", W, H)), ag)
+    sim.step(5); be.step(5)
+    for name in ("Curls", "Mesh", "Sponge"):
+        be.update_settings(settings_for(name))
+        sim.p = to_oracle_params(oracle, preset_uniform(name, W, H))
+        sim.step(5); be.step(5)
+        assert bits_equal(be.read_agents(), sim.agents), name
+        assert bits_equal(be.read_trail(), sim.trail), name
+    be.close()
+
+
+@pytest.mark.parametrize("dep", [0.05, 0.3, 2.5])
+def test_fractional_and_large_deposit(oracle, engine_lib, dep):
+    W, H, N = 128, 128, 60000            # ~3.7 agents per cell: multi-deposit cells are common
+    s = settings_for("Default").clone(pheromone_deposition_amount=dep, pheromone_decay_factor=30.0)
+    u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
+    ag = oracle.init_agents(N, W, H, 30, 50, 8)
+    sim = oracle.Sim(to_oracle_params(oracle, u), ag)
+    be = sm.CudaBackend.new(W, H, s, agent_count=N)
+    be.write_agents(ag)
+    sim.step(12); be.step(12)
+    assert bits_equal(be.read_agents(), sim.agents) and bits_equal(be.read_trail(), sim.trail)
+    be.close()
+
+
+@pytest.mark.parametrize("shape", [(4096, 64), (1920, 1080), (333, 77), (8, 8)])
+def test_diffuse_only(oracle, engine_lib, shape):
+    W, H = shape
+    u = preset_uniform("Default", W, H)
+    p = to_oracle_params(oracle, u)
+    field = np.random.default_rng(W).random((H, W), dtype=np.float32)
+    be = sm.CudaBackend.new(W, H, agent_count=1)
+    be.write_trail(field)
+    be.diffuse_only(3)
+    ref = field
+    for _ in range(3):
+        ref = oracle.trail_pass(ref, p, counts=None)
+    got = be.read_trail()
+    assert bits_equal(got, ref), mismatch_report(got, ref, "diffuse_only")
+    st = be.trail_statistics()
+    assert abs(st.sum - ref.sum(dtype=np.float64)) < 1e-6 * ref.size
+    assert st.max == ref.max() and st.nonzero == np.count_nonzero(ref)
+    be.close()
+
+
+@pytest.mark.parametrize("R,sigma", [(1, 0.5), (2, 1.0), (4, 2.0), (8, 4.0)])
+def test_gaussian_extension(oracle, engine_lib, R, sigma):
+    # EXTENSION, no reference semantics: compared with the oracle's definition only
+    W, H = 200, 150
+    s = settings_for("Default").clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=0.6)
+    u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
+    p = to_oracle_params(oracle, u)
+    field = np.random.default_rng(R).random((H, W), dtype=np.float32)
+    be = sm.CudaBackend.new(W, H, s, agent_count=1, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+    be.write_trail(field)
+    be.diffuse_only(2)
+    ref = field
+    for _ in range(2):
+        ref = oracle.trail_pass(ref, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
+    got = be.read_trail()
+    assert bits_equal(got, ref), mismatch_report(got, ref, "gauss")
+    be.close()
+
+
+@pytest.mark.parametrize("name", PRESET_NAMES)
+def test_golden_vectors(engine_lib, name):
+    g = np.load(os.path.join(GOLD, "golden_" + name.lower().replace(" ", "_") + ".npz"))
+    H, W = g["trail1"].shape
+    be = sm.CudaBackend.new(W, H, settings_for(name), agent_count=g["agents0"].shape[0])
+    assert bytes(be.read_uniform()) == g["params"].tobytes()
+    be.write_agents(g["agents0"])
+    be.step(1)
+    assert bits_equal(be.read_agents(), g["agents1"]) and bits_equal(be.read_trail(), g["trail1"])
+    be.step(24)
+    assert bits_equal(be.read_agents(), g["agents25"]) and bits_equal(be.read_trail(), g["trail25"])
+    be.clear_trail(); be.write_trail(g["field"]); be.diffuse_only(1)
+    assert bits_equal(be.read_trail(), g["diffused"])
+    be.close()
+
+
+def test_error_behaviour(engine_lib):
+    with pytest.raises(sm.SlimeError):
+        sm.CudaBackend.new(0, 10, agent_count=1)
+    be = sm.CudaBackend.new(32, 32, agent_count=10)
+    with pytest.raises(sm.SlimeError):
+        be.step(1)                                # agents never initialised
+    bad = sm.SimSizeUniform.new(64, 32, 10.0, sm.Settings.default())
+    with pytest.raises(sm.SlimeError):
+        be.write_uniform(bad)                     # size mismatch must be an error, not a silent resize
+    with pytest.raises(sm.SlimeError):
+        be.comm_init(b"\0" * 128)
+    be.close()
