@@ -21,7 +21,19 @@ struct AgentConsts {
     // strip of the trail this kernel may read (multi-GPU): global rows
     // [row0 - halo, row0 + rows + halo) live at trail + (row - row_base) * W
     int64_t row_base;
+    int32_t rows_local;        // rows this rank owns (== H on a single GPU)
+    int32_t ghost;             // ghost rows kept above and below the strip (0 on a single GPU)
 };
+
+// Local row (relative to the strip's first owned row) of global row `gy`, folded across the
+// toroidal seam so that rows just above strip 0 / just below the last strip land in the ghosts.
+SM_HD int64_t local_row(int64_t gy, const AgentConsts& c)
+{
+    int64_t lr = gy - c.row_base;
+    if (lr >= (int64_t)c.rows_local + c.ghost) lr -= c.H;
+    else if (lr < -(int64_t)c.ghost) lr += c.H;
+    return lr;
+}
 
 constexpr float kTau = 6.28318530718f;             // compute.wgsl:4
 constexpr float kTwoPi = 2.0f * 3.14159265359f;    // compute.wgsl:121

@@ -69,6 +69,8 @@ smd::AgentConsts sm_engine::agent_consts() const
     c.sensor_distance = params.agent_sensor_distance;
     c.jitter = params.agent_jitter;
     c.row_base = (int64_t)row0;
+    c.rows_local = (int32_t)rows;
+    c.ghost = (int32_t)ghost;
     return c;
 }
 
@@ -200,7 +202,7 @@ int sm_engine::sort_agents()
     if (n_local == 0) return SM_OK;
     SM_TRY(tic(2));
     SM_CUDA(cudaMemsetAsync(tile_hist, 0, n_tiles * sizeof(uint32_t), stream));
-    smk::k_tile_hist<<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], n_local, tile_hist, tiles);
+    smk::k_tile_hist<<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, tile_hist, tiles);
     smk::k_scan_block<<<n_scan_blocks, smk::kScanBlock, 0, stream>>>(tile_hist, tile_hist, tile_sums, (uint32_t)n_tiles);
     smk::k_scan_sums<<<1, 1024, 0, stream>>>(tile_sums, n_scan_blocks);
     smk::k_scan_add<<<n_scan_blocks, smk::kScanBlock, 0, stream>>>(tile_hist, tile_sums, (uint32_t)n_tiles);
@@ -210,6 +212,7 @@ int sm_engine::sort_agents()
     timing.kernel_launches += 5;
     acur = 1 - acur;
     identity_order = false;
+    if (world > 1) n_local = n_live;      // the scatter dropped the dead (migrated-away) slots
     SM_TRY(toc());
     return SM_OK;
 }
@@ -218,8 +221,17 @@ int sm_engine::launch_agents()
 {
     if (n_local == 0) return SM_OK;
     SM_TRY(tic(0));
-    smk::k_agents<<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, trail_ptr(cur),
-                                                                counts_ptr(ccur), agent_consts());
+    smk::LeaverBufs lv{};
+    if (world > 1) {
+        for (int d = 0; d < 2; ++d) { lv.send_a[d] = mig[d].send_a; lv.send_id[d] = mig[d].send_id; }
+        lv.counters = mig_counters;
+        lv.cap = (uint32_t)mig[0].cap;
+        smk::k_agents<true><<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, trail_ptr(cur),
+                                                                          counts_ptr(ccur), agent_consts(), lv);
+    } else {
+        smk::k_agents<false><<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, trail_ptr(cur),
+                                                                           counts_ptr(ccur), agent_consts(), lv);
+    }
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
     SM_TRY(toc());
@@ -386,6 +398,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     e->n_global = cfg->agent_count;
     e->sort_interval = cfg->sort_interval ? cfg->sort_interval : (uint32_t)env_int("SM_SORT_INTERVAL", 16);
     if (cfg->flags & SM_FLAG_NO_SORT) e->sort_interval = 0;
+    if (e->world > 1 && e->sort_interval == 0) e->sort_interval = 16;   // strips need the sort to compact migrated-away slots
     e->force_generic = env_int("SM_FORCE_GENERIC_TRAIL", 0) != 0;
     e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
 
@@ -465,7 +478,7 @@ int sm_get_params(sm_engine* e, sm_params* p)
 }
 
 uint64_t sm_agent_count(sm_engine* e) { return e ? e->n_global : 0; }
-uint64_t sm_local_agent_count(sm_engine* e) { return e ? e->n_local : 0; }
+uint64_t sm_local_agent_count(sm_engine* e) { return e ? (e->world > 1 ? e->n_live : e->n_local) : 0; }
 
 static inline uint32_t owner_row(float y, uint32_t H)
 {
@@ -516,6 +529,7 @@ int sm_upload_agents(sm_engine* e, const float* xyas, uint64_t first, uint64_t n
     SM_CUDA(cudaMemcpy(e->agents[e->acur], keep.data(), m * sizeof(float4), cudaMemcpyHostToDevice));
     SM_CUDA(cudaMemcpy(e->ids[e->acur], keep_ids.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
     e->n_local = m;
+    e->n_live = m;
     e->agents_valid = true;
     e->identity_order = false;
     e->steps_since_sort = e->sort_interval;

@@ -62,22 +62,51 @@ k_rescale_agents(float4* __restrict__ agents, uint64_t n, float fx, float fy)
     agents[i] = a;
 }
 
+constexpr uint32_t kDeadAgent = 0xFFFFFFFFu;   // multi-GPU: slot whose agent migrated away (dropped by the next sort)
+
+// Migration staging filled by k_agents<true>: agents whose new row belongs to a ring neighbour.
+struct LeaverBufs {
+    float4* send_a[2];                 // 0: towards rank-1 (up), 1: towards rank+1 (down)
+    uint32_t* send_id[2];
+    unsigned long long* counters;      // [0] leave_up, [1] leave_down, [4] overflow flag
+    uint32_t cap;
+};
+
 // One agent per thread.  `trail` and `counts` point at owned row 0 of this rank's
 // strip (global row c.row_base); ghost rows sit at negative / >= rows offsets.
+template <bool MULTI>
 static __global__ void __launch_bounds__(256)
-k_agents(float4* __restrict__ agents, const uint32_t* __restrict__ ids, uint64_t n,
-         const float* __restrict__ trail, uint32_t* __restrict__ counts, const AgentConsts c)
+k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
+         const float* __restrict__ trail, uint32_t* __restrict__ counts, const AgentConsts c,
+         const LeaverBufs lv)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint32_t id = ids[i];
+    if (MULTI && id == kDeadAgent) return;
     float4 a = agents[i];
-    int32_t idx = (int32_t)ids[i];
     int32_t cx, cy;
-    smd::agent_update(a.x, a.y, a.z, a.w, idx, trail, c, LdgF32(), cx, cy);
+    smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, trail, c, LdgF32(), cx, cy);
     agents[i] = a;
     if (cx >= 0) {
         // deposit: integer count, order-free (phase_split form of compute.wgsl:140)
-        atomicAdd(counts + ((int64_t)cy - c.row_base) * (int64_t)c.W + cx, 1u);
+        atomicAdd(counts + smd::local_row(cy, c) * (int64_t)c.W + cx, 1u);
+    }
+    if (MULTI) {
+        // owner row of the new position (x == W / y == H rounding corner and NaN clamp like the host)
+        int64_t oy = !(a.y >= 0.0f) ? 0 : (a.y >= c.Hf ? (int64_t)c.H - 1 : (int64_t)(int32_t)a.y);
+        int64_t lr = smd::local_row(oy, c);
+        if (lr < 0 || lr >= (int64_t)c.rows_local) {
+            const int dir = lr < 0 ? 0 : 1;
+            unsigned long long slot = atomicAdd(lv.counters + dir, 1ull);
+            if (slot < lv.cap) {
+                lv.send_a[dir][slot] = a;
+                lv.send_id[dir][slot] = id;
+                ids[i] = kDeadAgent;
+            } else {
+                atomicExch(lv.counters + 4, 1ull);   // staging overflow: reported by the host
+            }
+        }
     }
 }
 
@@ -305,10 +334,12 @@ __device__ __forceinline__ uint32_t tile_key(float x, float y, const TileGeom& t
 }
 
 static __global__ void __launch_bounds__(256)
-k_tile_hist(const float4* __restrict__ agents, uint64_t n, uint32_t* __restrict__ hist, const TileGeom t)
+k_tile_hist(const float4* __restrict__ agents, const uint32_t* __restrict__ ids, uint64_t n,
+            uint32_t* __restrict__ hist, const TileGeom t)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (ids[i] == kDeadAgent) return;
     float4 a = agents[i];
     atomicAdd(hist + tile_key(a.x, a.y, t), 1u);
 }
@@ -409,10 +440,12 @@ k_tile_scatter(const float4* __restrict__ agents, const uint32_t* __restrict__ i
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint32_t id = ids[i];
+    if (id == kDeadAgent) return;
     float4 a = agents[i];
     uint32_t pos = atomicAdd(cursor + tile_key(a.x, a.y, t), 1u);
     agents_out[pos] = a;
-    ids_out[pos] = ids[i];
+    ids_out[pos] = id;
 }
 
 // ---------------------------------------------------------------------------

@@ -31,6 +31,8 @@ static smd::AgentConsts make_consts(const hc_params* p)
     c.sensor_angle = p->agent_sensor_angle; c.sensor_distance = p->agent_sensor_distance;
     c.jitter = p->agent_jitter;
     c.row_base = 0;
+    c.rows_local = (int32_t)c.H;
+    c.ghost = 0;
     return c;
 }
 

@@ -1,0 +1,88 @@
+"""Multi-GPU strips on real devices (needs >= 2 B200s: run with `gpurun --gpus 2`): one process per
+GPU, NCCL halo exchange + deposit-count exchange + agent migration, compared bit for bit with the
+single-domain oracle.  -m gpu; skipped when fewer than 2 devices are visible."""
+import os
+import sys
+import time
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal, mismatch_report
+from presets_util import preset_uniform, random_trail, to_oracle_params
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASES = {
+    # name: (preset, W, H, N, steps, device_init)
+    "waves_upload": ("Waves", 256, 512, 100_000, 40, False),
+    "default_devinit": ("Default", 512, 768, 300_000, 35, True),
+    "curls_upload": ("Curls", 128, 384, 60_000, 50, False),
+}
+
+
+def _worker(rank, world, case, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch  # noqa: F401  (first, so the process ends up with torch's libnccl)
+    import slime_mold_b200 as sm
+    from oracle import slime_oracle as so
+    preset, W, H, N, steps, device_init = CASES[case]
+    s = sm.init_preset_manager().get_preset(preset).settings
+    be = sm.CudaBackend.new(W, H, s, agent_count=N, device=rank, rank=rank, world_size=world)
+    idf = os.path.join(out_dir, "nccl_id.bin")
+    if rank == 0:
+        uid = be.comm_unique_id()
+        with open(idf + ".tmp", "wb") as f:
+            f.write(uid)
+        os.rename(idf + ".tmp", idf)
+    else:
+        t0 = time.time()
+        while not os.path.exists(idf):
+            time.sleep(0.05)
+            assert time.time() - t0 < 120
+        uid = open(idf, "rb").read()
+    be.comm_init(uid)
+    if device_init:
+        be.init_agents(seed=11)
+    else:
+        be.write_agents(so.init_agents(N, W, H, s.agent_speed_min, s.agent_speed_max, 11))
+        be.write_trail(random_trail(W, H, seed=4))
+    be.step(steps)
+    a = be.read_agents()
+    t = be.read_trail()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), agents=a, trail=t, owned=be.last_owned, local=be.local_agent_count)
+    be.close()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world):
+    import slime_mold_b200 as sm
+    if sm.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    preset, W, H, N, steps, device_init = CASES[case]
+    if H // world < 64:
+        pytest.skip("strips too thin for this case")
+    mp.spawn(_worker, args=(world, case, str(tmp_path)), nprocs=world, join=True)
+    u = preset_uniform(preset, W, H)
+    ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 11)
+    sim = oracle.Sim(to_oracle_params(oracle, u), ag, trail=None if device_init else random_trail(W, H, seed=4))
+    sim.step(steps)
+    a = np.full((N, 4), np.nan, np.float32)
+    t = np.full((H, W), np.nan, np.float32)
+    owned = 0
+    for r in range(world):
+        d = np.load(tmp_path / f"rank{r}.npz")
+        m = ~np.isnan(d["agents"][:, 0])
+        assert not (m & ~np.isnan(a[:, 0])).any(), "an agent is owned by two strips"
+        a[m] = d["agents"][m]
+        tm = ~np.isnan(d["trail"])
+        t[tm] = d["trail"][tm]
+        owned += int(d["owned"])
+        assert int(d["owned"]) == int(d["local"])
+    assert owned == N
+    assert bits_equal(a, sim.agents), mismatch_report(a, sim.agents, "agents")
+    assert bits_equal(t, sim.trail), mismatch_report(t, sim.trail, "trail")
