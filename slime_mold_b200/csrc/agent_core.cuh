@@ -41,16 +41,17 @@ constexpr float kRcpTwoPi = 0.15915494f;
 constexpr float kTimeStep = 0.016f;                // compute.wgsl:55
 
 // sample_trail_map, compute.wgsl:7-29.  LD(ptr) loads one f32 of the trail.
-template <class LD>
+// IdxT = int32_t when the strip (with ghosts) has fewer than 2^31 cells, else int64_t.
+template <class IdxT, class LD>
 SM_HD float sample_trail(const float* __restrict__ trail, const AgentConsts& c, float px, float py, LD ld)
 {
     float fx = ::floorf(px), fy = ::floorf(py);
     // x0 < 0 || x1 >= W || y0 < 0 || y1 >= H -> 0 (sensing is NOT toroidal); NaN -> outside
     if (!(fx >= 0.0f && fx <= c.xmax && fy >= 0.0f && fy <= c.ymax)) return 0.0f;
-    int64_t x0 = (int64_t)(int32_t)fx;
-    int64_t y0 = (int64_t)(int32_t)fy;
+    IdxT x0 = (IdxT)(int32_t)fx;
+    IdxT y0 = (IdxT)(int32_t)fy;
     float dx = sub(px, fx), dy = sub(py, fy);
-    const float* r0 = trail + (y0 - c.row_base) * (int64_t)c.W + x0;
+    const float* r0 = trail + ((y0 - (IdxT)c.row_base) * (IdxT)c.W + x0);
     const float* r1 = r0 + c.W;
     float v00 = ld(r0), v10 = ld(r0 + 1), v01 = ld(r1), v11 = ld(r1 + 1);
     float omdx = sub(1.0f, dx);
@@ -61,7 +62,7 @@ SM_HD float sample_trail(const float* __restrict__ trail, const AgentConsts& c, 
 
 // Returns the deposit cell as (cx, cy) with cx < 0 when the deposit is skipped
 // (compute.wgsl:138: x == W can occur by rounding).
-template <class LD>
+template <class IdxT, class LD>
 SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t agent_index,
                         const float* __restrict__ trail, const AgentConsts& c, LD ld,
                         int32_t& cx, int32_t& cy)
@@ -69,13 +70,22 @@ SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t 
     speed = clampf(speed, c.speed_min, c.speed_max);                       // :72
 
     float sL, cL, sR, cR, sC, cC;
-    sincos(sub(angle, c.sensor_angle), sL, cL);                            // :75
-    sincos(add(angle, c.sensor_angle), sR, cR);                            // :76
-    sincos(angle, sC, cC);                                                 // :77
+    const float aL = sub(angle, c.sensor_angle);                           // :75
+    const float aR = add(angle, c.sensor_angle);                           // :76
+    if (::fabsf(angle) <= 4096.0f && ::fabsf(c.sensor_angle) <= 4096.0f) {
+        // |angle +- sa| <= 8192: the spec's fast path, evaluated without the per-call range test
+        sincos_small(aL, sL, cL);
+        sincos_small(aR, sR, cR);
+        sincos_small(angle, sC, cC);                                       // :77
+    } else {
+        sincos(aL, sL, cL);
+        sincos(aR, sR, cR);
+        sincos(angle, sC, cC);
+    }
     const float sd = c.sensor_distance;
-    float vL = sample_trail(trail, c, add(x, mul(sd, cL)), add(y, mul(sd, sL)), ld);   // :79-82,93
-    float vR = sample_trail(trail, c, add(x, mul(sd, cR)), add(y, mul(sd, sR)), ld);   // :83-86,94
-    float vC = sample_trail(trail, c, add(x, mul(sd, cC)), add(y, mul(sd, sC)), ld);   // :87-90,95
+    float vL = sample_trail<IdxT>(trail, c, add(x, mul(sd, cL)), add(y, mul(sd, sL)), ld);   // :79-82,93
+    float vR = sample_trail<IdxT>(trail, c, add(x, mul(sd, cR)), add(y, mul(sd, sR)), ld);   // :83-86,94
+    float vC = sample_trail<IdxT>(trail, c, add(x, mul(sd, cC)), add(y, mul(sd, sC)), ld);   // :87-90,95
 
     if (vC > vL && vC > vR) {                                              // :98
     } else if (vL > vR) {                                                  // :100-104
@@ -86,15 +96,21 @@ SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t 
         angle = add(angle, mul(::fminf(c.turn_speed, ::fabsf(diff)), signf(diff)));
     }
 
-    float rnd = hash01(agent_index, x, y);                                 // :117 (pre-move x, y)
-    angle = add(angle, mul(sub(mul(rnd, 2.0f), 1.0f), c.jitter));          // :118
+    // :115-118  angle += (hash*2 - 1) * jitter.  With jitter == +-0 the addend is +-0 (or NaN when x / y
+    // are not finite), which changes `angle` only if angle is a zero: in every other case the hash cannot
+    // influence the result and is skipped.  Bit-exact, not an approximation.
+    const bool hash_is_dead = (c.jitter == 0.0f) && (angle != 0.0f) && (::fabsf(x) <= 1.0e30f) && (::fabsf(y) <= 1.0e30f);
+    if (!hash_is_dead) {
+        float rnd = hash01(agent_index, x, y);                             // :117 (pre-move x, y)
+        angle = add(angle, mul(sub(mul(rnd, 2.0f), 1.0f), c.jitter));      // :118
+    }
 
     angle = fmod_exact(angle, kTwoPi, kRcpTwoPi);                          // :121
     if (angle < 0.0f) angle = add(angle, kTwoPi);                          // :122
 
     float move = mul(speed, kTimeStep);                                    // :125
     float sM, cM;
-    sincos(angle, sM, cM);
+    sincos_small(angle, sM, cM);                                           // angle in [0, 2pi] or NaN here
     x = add(x, mul(move, cM));                                             // :126
     y = add(y, mul(move, sM));                                             // :127
 

@@ -116,10 +116,8 @@ SM_HD void reduce_pio2(float x, float& r, uint32_t& q)
     }
 }
 
-SM_HD void sincos(float x, float& sn, float& cs)
+SM_HD void sincos_poly(float r, uint32_t q, float& sn, float& cs)
 {
-    float r; uint32_t q;
-    reduce_pio2(x, r, q);
     float s2 = mul(r, r);
     float p = fma(-1.9515295891e-4f, s2, 8.3321608736e-3f);
     p = fma(p, s2, -1.6666654611e-1f);
@@ -134,6 +132,27 @@ SM_HD void sincos(float x, float& sn, float& cs)
     // sign flips as XOR on the sign bit (q&2 -> sin, (q+1)&2 -> cos)
     sn = u2f(f2u(so) ^ ((q & 2u) << 30));
     cs = u2f(f2u(co) ^ (((q + 1u) & 2u) << 30));
+}
+
+SM_HD void sincos(float x, float& sn, float& cs)
+{
+    float r; uint32_t q;
+    reduce_pio2(x, r, q);
+    sincos_poly(r, q, sn, cs);
+}
+
+// Branch-free form for callers that have already established |x| <= 8192 (or x is NaN, for which
+// both paths of the spec return NaN): identical results to sincos(), no range test.
+SM_HD void sincos_small(float x, float& sn, float& cs)
+{
+    const float magic = 12582912.0f;
+    float t = fma(x, 0x1.45f306p-1f, magic);
+    uint32_t q = f2u(t) & 3u;
+    float nk = -sub(t, magic);
+    float r = fma(nk, 0x1.921fb6p+0f, x);
+    r = fma(nk, -0x1.777a5cp-25f, r);
+    r = fma(nk, -0x1.ee59dap-50f, r);
+    sincos_poly(r, q, sn, cs);
 }
 
 // ---- exact truncated remainder (WGSL float %, == IEEE fmodf) ----------------
@@ -165,7 +184,7 @@ SM_HD float div9(float s)
     float q = mul(s, c);
     float r = fma(-q, 9.0f, s);
     float q2 = fma(r, c, q);
-    return (::fabsf(s) <= 3.402823466e38f) ? q2 : s / 9.0f;   // inf/NaN: true division
+    return (::fabsf(s) <= 3.402823466e38f) ? q2 : s;   // inf / 9 = inf, NaN stays NaN
 }
 
 // ---- WGSL builtins ----------------------------------------------------------

@@ -222,15 +222,22 @@ int sm_engine::launch_agents()
     if (n_local == 0) return SM_OK;
     SM_TRY(tic(0));
     smk::LeaverBufs lv{};
+    const bool idx32 = (uint64_t)(rows + 2 * (uint64_t)ghost) * W < (1ull << 31);
+    const unsigned nb = blocks_for(n_local, 256);
+    float4* a = agents[acur];
+    uint32_t* id = ids[acur];
+    const float* t = trail_ptr(cur);
+    uint32_t* cn = counts_ptr(ccur);
+    const smd::AgentConsts ac = agent_consts();
     if (world > 1) {
         for (int d = 0; d < 2; ++d) { lv.send_a[d] = mig[d].send_a; lv.send_id[d] = mig[d].send_id; }
         lv.counters = mig_counters;
         lv.cap = (uint32_t)mig[0].cap;
-        smk::k_agents<true><<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, trail_ptr(cur),
-                                                                          counts_ptr(ccur), agent_consts(), lv);
+        if (idx32) smk::k_agents<true, int32_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
+        else smk::k_agents<true, int64_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
     } else {
-        smk::k_agents<false><<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, trail_ptr(cur),
-                                                                           counts_ptr(ccur), agent_consts(), lv);
+        if (idx32) smk::k_agents<false, int32_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
+        else smk::k_agents<false, int64_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
     }
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
@@ -250,7 +257,7 @@ int sm_engine::launch_trail(bool has_counts)
     SM_TRY(tic(1));
     if (cfg.flags & SM_FLAG_GAUSSIAN_BLUR) {
         SM_TRY(launch_gauss(has_counts, g, tc));
-    } else if (W % 4 == 0 && W >= 8 && !force_generic) {
+    } else if (W % 4 == 0 && W >= 8 && (W / 4) % 32 != 1 && !force_generic) {
         const unsigned bs = 128;
         const unsigned bx = blocks_for(W / 4, bs);
         // aim for >= 8 resident CTAs per SM; 2/rows_per_chunk of the reads are halo re-reads

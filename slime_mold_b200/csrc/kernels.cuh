@@ -74,7 +74,7 @@ struct LeaverBufs {
 
 // One agent per thread.  `trail` and `counts` point at owned row 0 of this rank's
 // strip (global row c.row_base); ghost rows sit at negative / >= rows offsets.
-template <bool MULTI>
+template <bool MULTI, class IdxT>
 static __global__ void __launch_bounds__(256)
 k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
          const float* __restrict__ trail, uint32_t* __restrict__ counts, const AgentConsts c,
@@ -86,11 +86,11 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     if (MULTI && id == kDeadAgent) return;
     float4 a = agents[i];
     int32_t cx, cy;
-    smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, trail, c, LdgF32(), cx, cy);
+    smd::agent_update<IdxT>(a.x, a.y, a.z, a.w, (int32_t)id, trail, c, LdgF32(), cx, cy);
     agents[i] = a;
     if (cx >= 0) {
         // deposit: integer count, order-free (phase_split form of compute.wgsl:140)
-        atomicAdd(counts + smd::local_row(cy, c) * (int64_t)c.W + cx, 1u);
+        atomicAdd(counts + ((IdxT)smd::local_row(cy, c) * (IdxT)c.W + (IdxT)cx), 1u);
     }
     if (MULTI) {
         // owner row of the new position (x == W / y == H rounding corner and NaN clamp like the host)
@@ -133,14 +133,17 @@ template <bool HAS_COUNTS>
 struct RawRow {
     float4 t;
     uint4 k;
-    float tl, tr;
-    uint32_t kl, kr;
+    float te;      // edge cell (left for lane 0, right for the last lane of a row segment)
+    uint32_t ke;
 };
 
 // Each thread owns 4 consecutive columns and walks down `rows_per_chunk` rows with a
 // 3-row register window of decayed values; the horizontal neighbours come from the
 // adjacent lanes by shuffle (warp-edge lanes fetch one extra cell).  Loads for
 // UNROLL rows are issued before any of them is consumed.
+//
+// Requirements (checked by the host): W % 4 == 0 and (W / 4) % 32 != 1, so that a lane is never
+// both the left edge (lane 0) and the right edge (last column group) of its warp.
 template <bool HAS_COUNTS, int UNROLL>
 static __global__ void __launch_bounds__(128)
 k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
@@ -153,30 +156,35 @@ k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
     const uint32_t lane = threadIdx.x & 31u;
     const bool left_edge = active && (lane == 0u);
     const bool right_edge = active && (lane == 31u || x0 + 4u >= g.W);
-    const uint32_t xl = (x0 == 0u) ? g.W - 1u : x0 - 1u;
-    const uint32_t xr = (x0 + 4u >= g.W) ? 0u : x0 + 4u;
+    const bool edge = left_edge || right_edge;
+    // column of the one extra cell an edge lane fetches
+    const uint32_t xe = left_edge ? ((x0 == 0u) ? g.W - 1u : x0 - 1u) : ((x0 + 4u >= g.W) ? 0u : x0 + 4u);
 
-    const int64_t y_begin = (int64_t)blockIdx.y * g.rows_per_chunk;
-    int64_t y_end = y_begin + g.rows_per_chunk;
-    if (y_end > (int64_t)g.rows) y_end = g.rows;
+    const int y_begin = (int)(blockIdx.y * g.rows_per_chunk);
+    const int y_end = min(y_begin + (int)g.rows_per_chunk, (int)g.rows);
+    const size_t W = g.W;
+    // halo rows: only these two can wrap (single GPU) -- rows inside the chunk never do
+    const int y_top = (g.wrap_y && y_begin == 0) ? (int)g.rows - 1 : y_begin - 1;
+    const int y_bot = (g.wrap_y && y_end == (int)g.rows) ? 0 : y_end;
 
-    auto issue = [&](int64_t y, RawRow<HAS_COUNTS>& r) {
-        const int64_t off = row_index(y, g) * (int64_t)g.W;
+    const float* tp = tin + x0;
+    const float* te = tin + xe;
+    const uint32_t* cp = HAS_COUNTS ? cin + x0 : nullptr;
+    const uint32_t* ce = HAS_COUNTS ? cin + xe : nullptr;
+
+    auto issue = [&](int y, RawRow<HAS_COUNTS>& r) {
+        const ptrdiff_t off = (ptrdiff_t)y * (ptrdiff_t)W;
         r.t = make_float4(0.f, 0.f, 0.f, 0.f);
         r.k = make_uint4(0u, 0u, 0u, 0u);
-        r.tl = r.tr = 0.f;
-        r.kl = r.kr = 0u;
+        r.te = 0.f;
+        r.ke = 0u;
         if (active) {
-            r.t = __ldg(reinterpret_cast<const float4*>(tin + off + x0));
-            if (HAS_COUNTS) r.k = __ldg(reinterpret_cast<const uint4*>(cin + off + x0));
+            r.t = __ldg(reinterpret_cast<const float4*>(tp + off));
+            if (HAS_COUNTS) r.k = __ldg(reinterpret_cast<const uint4*>(cp + off));
         }
-        if (left_edge) {
-            r.tl = __ldg(tin + off + xl);
-            if (HAS_COUNTS) r.kl = __ldg(cin + off + xl);
-        }
-        if (right_edge) {
-            r.tr = __ldg(tin + off + xr);
-            if (HAS_COUNTS) r.kr = __ldg(cin + off + xr);
+        if (edge) {
+            r.te = __ldg(te + off);
+            if (HAS_COUNTS) r.ke = __ldg(ce + off);
         }
     };
     auto cell = [&](float t, uint32_t k) {
@@ -189,27 +197,27 @@ k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
         d[2] = cell(r.t.y, r.k.y);
         d[3] = cell(r.t.z, r.k.z);
         d[4] = cell(r.t.w, r.k.w);
-        float from_left = __shfl_up_sync(0xffffffffu, d[4], 1);
-        float from_right = __shfl_down_sync(0xffffffffu, d[1], 1);
-        d[0] = left_edge ? cell(r.tl, r.kl) : from_left;
-        d[5] = right_edge ? cell(r.tr, r.kr) : from_right;
+        const float de = cell(r.te, r.ke);
+        const float from_left = __shfl_up_sync(0xffffffffu, d[4], 1);
+        const float from_right = __shfl_down_sync(0xffffffffu, d[1], 1);
+        d[0] = left_edge ? de : from_left;
+        d[5] = right_edge ? de : from_right;
     };
 
     float prev[6], cur[6], next[6];
     {
         RawRow<HAS_COUNTS> r0, r1;
-        issue(y_begin - 1, r0);
+        issue(y_top, r0);
         issue(y_begin, r1);
         finish(r0, prev);
         finish(r1, cur);
     }
-    for (int64_t y = y_begin; y < y_end; y += UNROLL) {
+    for (int y = y_begin; y < y_end; y += UNROLL) {
         RawRow<HAS_COUNTS> raw[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            int64_t yy = y + u + 1;
-            if (yy > y_end) yy = y_end;          // past the chunk: harmless re-load of the halo row
-            issue(yy, raw[u]);
+            const int yy = y + u + 1;
+            issue(yy >= y_end ? y_bot : yy, raw[u]);     // past the chunk: harmless re-load of the halo row
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -220,7 +228,7 @@ k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
                 o.y = smd::box9_mix(prev[1], prev[2], prev[3], cur[1], cur[2], cur[3], next[1], next[2], next[3], tc);
                 o.z = smd::box9_mix(prev[2], prev[3], prev[4], cur[2], cur[3], cur[4], next[2], next[3], next[4], tc);
                 o.w = smd::box9_mix(prev[3], prev[4], prev[5], cur[3], cur[4], cur[5], next[3], next[4], next[5], tc);
-                const int64_t off = (y + u) * (int64_t)g.W + x0;
+                const size_t off = (size_t)(y + u) * W + x0;
                 *reinterpret_cast<float4*>(tout + off) = o;
                 if (HAS_COUNTS) *reinterpret_cast<uint4*>(czero + off) = make_uint4(0u, 0u, 0u, 0u);
             }
@@ -333,15 +341,32 @@ __device__ __forceinline__ uint32_t tile_key(float x, float y, const TileGeom& t
     return ((uint32_t)cy >> t.shift_y) * t.tiles_x + ((uint32_t)cx >> t.shift_x);
 }
 
+// Lanes of a warp that target the same tile are combined into one atomic (the agents are nearly
+// sorted already, so a warp usually holds one or two distinct keys).  Returns this lane's slot
+// offset within the group and the group size; the leader lane is the lowest lane of the group.
+__device__ __forceinline__ void warp_group(uint32_t key, uint32_t& rank_in_group, uint32_t& group_size, bool& leader,
+                                           uint32_t& group_mask)
+{
+    group_mask = __match_any_sync(0xffffffffu, key);
+    const uint32_t lane = threadIdx.x & 31u;
+    rank_in_group = __popc(group_mask & ((1u << lane) - 1u));
+    group_size = __popc(group_mask);
+    leader = rank_in_group == 0u;
+}
+
 static __global__ void __launch_bounds__(256)
 k_tile_hist(const float4* __restrict__ agents, const uint32_t* __restrict__ ids, uint64_t n,
             uint32_t* __restrict__ hist, const TileGeom t)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (ids[i] == kDeadAgent) return;
-    float4 a = agents[i];
-    atomicAdd(hist + tile_key(a.x, a.y, t), 1u);
+    uint32_t key = 0xFFFFFFFFu;                                  // invalid / dead lanes group together
+    if (i < n && ids[i] != kDeadAgent) {
+        float4 a = agents[i];
+        key = tile_key(a.x, a.y, t);
+    }
+    uint32_t r, sz, gm; bool leader;
+    warp_group(key, r, sz, leader, gm);
+    if (leader && key != 0xFFFFFFFFu) atomicAdd(hist + key, sz);
 }
 
 // exclusive scan of `n` u32 in three phases (block sums -> scan of sums -> add).
@@ -439,13 +464,25 @@ k_tile_scatter(const float4* __restrict__ agents, const uint32_t* __restrict__ i
                const TileGeom t)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t id = ids[i];
-    if (id == kDeadAgent) return;
-    float4 a = agents[i];
-    uint32_t pos = atomicAdd(cursor + tile_key(a.x, a.y, t), 1u);
-    agents_out[pos] = a;
-    ids_out[pos] = id;
+    uint32_t key = 0xFFFFFFFFu;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t id = kDeadAgent;
+    if (i < n) {
+        id = ids[i];
+        if (id != kDeadAgent) {
+            a = agents[i];
+            key = tile_key(a.x, a.y, t);
+        }
+    }
+    uint32_t r, sz, gm; bool leader;
+    warp_group(key, r, sz, leader, gm);
+    uint32_t base = 0;
+    if (leader && key != 0xFFFFFFFFu) base = atomicAdd(cursor + key, sz);
+    base = __shfl_sync(gm, base, __ffs(gm) - 1);
+    if (key != 0xFFFFFFFFu) {
+        agents_out[base + r] = a;
+        ids_out[base + r] = id;
+    }
 }
 
 // ---------------------------------------------------------------------------

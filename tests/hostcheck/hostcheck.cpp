@@ -66,7 +66,7 @@ void hc_agents_phase_split(float* agents, const uint32_t* ids, uint64_t n, const
     for (uint64_t i = 0; i < n; ++i) {
         int32_t cx, cy;
         int32_t idx = ids ? (int32_t)ids[i] : (int32_t)i;
-        smd::agent_update(agents[4 * i], agents[4 * i + 1], agents[4 * i + 2], agents[4 * i + 3], idx, trail, c, HostLd(), cx, cy);
+        smd::agent_update<int64_t>(agents[4 * i], agents[4 * i + 1], agents[4 * i + 2], agents[4 * i + 3], idx, trail, c, HostLd(), cx, cy);
         if (cx >= 0) counts[(size_t)cy * p->width + cx] += 1u;
     }
 }

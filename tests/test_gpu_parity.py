@@ -8,7 +8,7 @@ import pytest
 
 import slime_mold_b200 as sm
 from conftest import bits_equal, mismatch_report
-from presets_util import PRESET_NAMES, preset_uniform, random_trail, to_oracle_params
+from presets_util import PRESET_NAMES, edge_agents, preset_uniform, random_trail, to_oracle_params
 
 pytestmark = pytest.mark.gpu
 
@@ -236,4 +236,24 @@ def test_error_behaviour(engine_lib):
         be.write_uniform(bad)                     # size mismatch must be an error, not a silent resize
     with pytest.raises(sm.SlimeError):
         be.comm_init(b"\0" * 128)
+    be.close()
+
+
+@pytest.mark.parametrize("name", ["Default", "Waves", "Mesh"])
+def test_edge_agents(oracle, engine_lib, name):
+    """Rare paths on the device: +-0 headings with jitter 0 (dead-hash shortcut), huge headings (f64
+    reduction, library fmod), positions outside the map / on the seams, non-finite state."""
+    W, H = 160, 96
+    ag = edge_agents(W, H)
+    trail = random_trail(W, H, seed=6, density=0.7)
+    u = preset_uniform(name, W, H)
+    sim = oracle.Sim(to_oracle_params(oracle, u), ag, trail=trail)
+    be = sm.CudaBackend.new(W, H, settings_for(name), agent_count=len(ag), flags=sm.SM_FLAG_NO_SORT)
+    be.write_agents(ag)
+    be.write_trail(trail)
+    for step in range(3):
+        sim.step(1); be.step(1)
+        a = be.read_agents()
+        assert bits_equal(a, sim.agents), (step, mismatch_report(a, sim.agents, "agents"))
+        assert bits_equal(be.read_trail(), sim.trail), step
     be.close()

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import bits_equal
-from presets_util import PRESET_NAMES, preset_uniform, to_oracle_params
+from presets_util import PRESET_NAMES, edge_agents, preset_uniform, random_trail, to_oracle_params
 
 
 def P(a, t):
@@ -89,3 +89,20 @@ def test_step_loop_bits(oracle, hostcheck, name):
         tr, out = out, tr
         assert bits_equal(a, sim.agents), f"agents differ at step {step}"
         assert bits_equal(tr, sim.trail), f"trail differs at step {step}"
+
+
+@pytest.mark.parametrize("name", ["Default", "Waves", "Mesh"])
+def test_edge_agents_bits(oracle, hostcheck, name):
+    """Rare paths: +-0 headings with jitter 0 (the dead-hash shortcut must not change a bit), huge
+    headings (f64 reduction, library fmod), out-of-map and non-finite state."""
+    W, H = 160, 96
+    u = preset_uniform(name, W, H)
+    p = to_oracle_params(oracle, u)
+    ag = edge_agents(W, H)
+    trail = random_trail(W, H, seed=6, density=0.7)
+    a0 = ag.copy(); c0 = np.zeros((H, W), np.uint32)
+    oracle.agents_phase_split(a0, trail, c0, p)
+    a1 = ag.copy(); c1 = np.zeros((H, W), np.uint32)
+    hostcheck.hc_agents_phase_split(P(a1, C.c_float), None, C.c_uint64(len(ag)), P(trail, C.c_float), P(c1, C.c_uint32), C.byref(p))
+    assert bits_equal(a0, a1), [(i, ag[i], a0[i], a1[i]) for i in range(len(ag)) if not bits_equal(a0[i], a1[i])][:4]
+    assert np.array_equal(c0, c1)

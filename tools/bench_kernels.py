@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""Kernel-level sweeps on one GPU (not the headline bench): diffusion GB/s by map size and chunking,
+agent-kernel time by sort tile shape / sort interval.  Writes JSON lines to gpurun_out/kernel_sweep.jsonl.
+
+    python tools/bench_kernels.py [diffusion] [agents] [presets]
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402,F401
+import slime_mold_b200 as sm  # noqa: E402
+
+OUT = os.path.join(ROOT, "gpurun_out", "kernel_sweep.jsonl")
+PEAK = 6553.9
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def emit(d):
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    with open(OUT, "a") as f:
+        f.write(json.dumps(d) + "\n")
+    print(json.dumps(d), flush=True)
+
+
+def event_time(be, fn):
+    stream = torch.cuda.ExternalStream(be.stream_handle)
+    be.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    fn()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def diffusion_sweep():
+    for S in (4096, 8192, 16384, 32768):
+        for rpc in (0, 16, 32, 64, 128):
+            os.environ["SM_TRAIL_ROWS_PER_CHUNK"] = str(rpc)
+            be = sm.CudaBackend.new(S, S, agent_count=1)
+            be.write_trail(np.random.default_rng(0).random((256, S), dtype=np.float32), y0=0)
+            passes = max(10, min(200, int(2e10 / (S * S * 8))))
+            be.diffuse_only(5)
+            ms = event_time(be, lambda: be.diffuse_only(passes))
+            gbs = 8.0 * S * S * passes / (ms * 1e-3) / 1e9
+            emit({"sweep": "diffusion", "size": S, "rows_per_chunk": rpc, "passes": passes, "ms_per_pass": ms / passes,
+                  "gbs": gbs, "frac_of_measured_peak": gbs / PEAK, "frac_of_8TBs": gbs / 8000.0})
+            be.close()
+    os.environ.pop("SM_TRAIL_ROWS_PER_CHUNK", None)
+
+
+def agents_sweep():
+    N, W, H = 16_777_216, 4096, 4096
+    for (sx, sy) in ((4, 4), (5, 3), (5, 5), (6, 4), (3, 3), (6, 6)):
+        for interval in (8, 16, 32):
+            os.environ["SM_TILE_SHIFT_X"], os.environ["SM_TILE_SHIFT_Y"] = str(sx), str(sy)
+            be = sm.CudaBackend.new(W, H, agent_count=N, sort_interval=interval)
+            be.init_agents(1)
+            be.step(200)
+            steps = 96
+            ms = event_time(be, lambda: be.step(steps))
+            be.set_timing_enabled(True); be.reset_timing()
+            be.step(steps)
+            t = be.timing()
+            emit({"sweep": "agents", "tile": [1 << sx, 1 << sy], "sort_interval": interval, "ms_per_step": ms / steps,
+                  "agent_steps_per_s": N * steps / (ms * 1e-3), "agents_ms": t.agents_ms / t.agent_launches,
+                  "trail_ms": t.trail_ms / t.trail_launches, "sort_ms_each": t.sort_ms / max(t.sort_launches, 1),
+                  "sort_ms_per_step": t.sort_ms / steps})
+            be.close()
+    os.environ.pop("SM_TILE_SHIFT_X", None); os.environ.pop("SM_TILE_SHIFT_Y", None)
+    # no sort at all (random order forever)
+    be = sm.CudaBackend.new(W, H, agent_count=N, flags=sm.SM_FLAG_NO_SORT)
+    be.init_agents(1); be.step(200)
+    ms = event_time(be, lambda: be.step(48))
+    emit({"sweep": "agents", "tile": None, "sort_interval": 0, "ms_per_step": ms / 48, "agent_steps_per_s": N * 48 / (ms * 1e-3)})
+    be.close()
+
+
+def presets_sweep():
+    N, W, H = 16_777_216, 4096, 4096
+    pm = sm.init_preset_manager()
+    for name in pm.get_preset_names():
+        be = sm.CudaBackend.new(W, H, pm.get_preset(name).settings, agent_count=N)
+        be.init_agents(1)
+        ms0 = event_time(be, lambda: be.step(50))             # uniform-random initial state
+        be.step(450)
+        ms1 = event_time(be, lambda: be.step(100))            # steady state (>= 500 steps in)
+        st = be.trail_statistics()
+        emit({"sweep": "presets", "preset": name, "initial_agent_steps_per_s": N * 50 / (ms0 * 1e-3),
+              "steady_agent_steps_per_s": N * 100 / (ms1 * 1e-3), "steady_ms_per_step": ms1 / 100,
+              "trail_mean": st.sum / (W * H), "occupied_frac": st.nonzero / (W * H)})
+        be.close()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["diffusion", "agents", "presets"]
+    t0 = time.time()
+    if "diffusion" in which:
+        diffusion_sweep()
+    if "agents" in which:
+        agents_sweep()
+    if "presets" in which:
+        presets_sweep()
+    print("sweeps done in", round(time.time() - t0, 1), "s")
