@@ -179,8 +179,8 @@ int sm_engine::setup_tiles()
 {
     if (tile_hist) { cudaFree(tile_hist); tile_hist = nullptr; }
     if (tile_sums) { cudaFree(tile_sums); tile_sums = nullptr; }
-    tiles.shift_x = (uint32_t)env_int("SM_TILE_SHIFT_X", 4);
-    tiles.shift_y = (uint32_t)env_int("SM_TILE_SHIFT_Y", 4);
+    tiles.shift_x = (uint32_t)env_int("SM_TILE_SHIFT_X", 3);
+    tiles.shift_y = (uint32_t)env_int("SM_TILE_SHIFT_Y", 3);
     tiles.W = W;
     tiles.rows = rows;
     tiles.row_base = (int64_t)row0;
@@ -260,10 +260,10 @@ int sm_engine::launch_trail(bool has_counts)
     } else if (W % 4 == 0 && W >= 8 && (W / 4) % 32 != 1 && !force_generic) {
         const unsigned bs = 128;
         const unsigned bx = blocks_for(W / 4, bs);
-        // aim for >= 8 resident CTAs per SM; 2/rows_per_chunk of the reads are halo re-reads
-        uint64_t want_blocks = (uint64_t)num_sms * 16;
-        uint64_t rpc = ((uint64_t)rows * bx + want_blocks - 1) / want_blocks;
-        rpc = std::min<uint64_t>(std::max<uint64_t>(rpc, 8), 64);
+        // 16 rows per chunk measured best from 4096^2 to 32768^2 (profiles/README.md): 2/16 of the reads are
+        // halo re-reads that hit L2; small maps take shorter chunks to keep >= 4 CTAs per SM
+        uint64_t rpc = 16;
+        while (rpc > 4 && (uint64_t)bx * ((rows + rpc - 1) / rpc) < (uint64_t)num_sms * 4) rpc /= 2;
         if (rpc_override > 0) rpc = rpc_override;
         g.rows_per_chunk = (uint32_t)rpc;
         dim3 grid(bx, (unsigned)((rows + rpc - 1) / rpc));
