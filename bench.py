@@ -277,6 +277,7 @@ def run_ours(args):
         "agents": {"ms": agent_ms, "alg_bytes": agent_bytes, "gbs": agent_bytes / (agent_ms * 1e-3) / 1e9 if agent_ms else None},
         "trail": {"ms": trail_ms, "alg_bytes": trail_bytes, "gbs": trail_bytes / (trail_ms * 1e-3) / 1e9 if trail_ms else None},
         "sort_ms_per_step": sort_ms_per_step,
+        "exchange_ms_per_step": t.exchange_ms / max(t.steps, 1),
     }
     dom = "agents" if agent_ms >= trail_ms else "trail"
     traffic = None

@@ -29,9 +29,13 @@ struct AgentConsts {
 // toroidal seam so that rows just above strip 0 / just below the last strip land in the ghosts.
 SM_HD int64_t local_row(int64_t gy, const AgentConsts& c)
 {
+    // fold to the representative nearest to the strip: rows just past the seam become small negative /
+    // just-above-`rows` numbers whatever the ghost depth is (with two strips the ghosts can cover the
+    // whole other strip, so the ghost depth itself cannot be the folding threshold)
+    const int64_t spare = (int64_t)c.H - c.rows_local;          // rows this rank does not own
     int64_t lr = gy - c.row_base;
-    if (lr >= (int64_t)c.rows_local + c.ghost) lr -= c.H;
-    else if (lr < -(int64_t)c.ghost) lr += c.H;
+    if (lr >= (int64_t)c.rows_local + (spare + 1) / 2) lr -= c.H;
+    else if (lr < -(spare / 2)) lr += c.H;
     return lr;
 }
 

@@ -135,7 +135,7 @@ int sm_engine::resolve_timing()
 // ---------------------------------------------------------------------------
 int sm_engine::alloc_trail()
 {
-    const size_t cells = (size_t)(rows + 2 * (size_t)ghost) * W;
+    const size_t cells = field_cells();
     for (int i = 0; i < 2; ++i) {
         SM_CUDA(cudaMalloc(&trail_base[i], cells * sizeof(float)));
         SM_CUDA(cudaMemsetAsync(trail_base[i], 0, cells * sizeof(float), stream));
@@ -199,6 +199,7 @@ int sm_engine::setup_tiles()
 // ---------------------------------------------------------------------------
 int sm_engine::sort_agents()
 {
+    if (world > 1) SM_TRY(refresh_counters());
     if (n_local == 0) return SM_OK;
     SM_TRY(tic(2));
     SM_CUDA(cudaMemsetAsync(tile_hist, 0, n_tiles * sizeof(uint32_t), stream));
@@ -212,13 +213,17 @@ int sm_engine::sort_agents()
     timing.kernel_launches += 5;
     acur = 1 - acur;
     identity_order = false;
-    if (world > 1) n_local = n_live;      // the scatter dropped the dead (migrated-away) slots
+    if (world > 1) {                      // the scatter dropped the dead (migrated-away) slots
+        n_local = n_live;
+        SM_TRY(push_counters());
+    }
     SM_TRY(toc());
     return SM_OK;
 }
 
 int sm_engine::launch_agents()
 {
+    if (world > 1) n_local = n_upper;            // grid bound; the kernel reads the exact count on the device
     if (n_local == 0) return SM_OK;
     SM_TRY(tic(0));
     smk::LeaverBufs lv{};
@@ -230,9 +235,14 @@ int sm_engine::launch_agents()
     uint32_t* cn = counts_ptr(ccur);
     const smd::AgentConsts ac = agent_consts();
     if (world > 1) {
-        for (int d = 0; d < 2; ++d) { lv.send_a[d] = mig[d].send_a; lv.send_id[d] = mig[d].send_id; }
-        lv.counters = mig_counters;
-        lv.cap = (uint32_t)mig[0].cap;
+        for (int d = 0; d < 2; ++d) {
+            lv.send_count[d] = reinterpret_cast<unsigned long long*>(mig[d].send);
+            lv.send_a[d] = reinterpret_cast<float4*>(mig[d].send + 16);
+            lv.send_id[d] = reinterpret_cast<uint32_t*>(mig[d].send + 16 + mig_cap * sizeof(float4));
+        }
+        lv.overflow = dev_counters + 2;
+        lv.n_ptr = dev_counters;
+        lv.cap = (uint32_t)mig_cap;
         if (idx32) smk::k_agents<true, int32_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
         else smk::k_agents<true, int64_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
     } else {
@@ -401,6 +411,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         uint32_t want = cfg->reserved ? cfg->reserved : 232u;   // >= ceil(225)+2 (Snake/Mesh presets) + slack
         uint32_t min_rows = e->H / e->world;                    // thinnest strip
         e->ghost = std::min(want, min_rows);
+        e->pad_rows = 16;
     }
     e->n_global = cfg->agent_count;
     e->sort_interval = cfg->sort_interval ? cfg->sort_interval : (uint32_t)env_int("SM_SORT_INTERVAL", 16);
@@ -485,7 +496,12 @@ int sm_get_params(sm_engine* e, sm_params* p)
 }
 
 uint64_t sm_agent_count(sm_engine* e) { return e ? e->n_global : 0; }
-uint64_t sm_local_agent_count(sm_engine* e) { return e ? (e->world > 1 ? e->n_live : e->n_local) : 0; }
+uint64_t sm_local_agent_count(sm_engine* e)
+{
+    if (!e) return 0;
+    if (e->world > 1) { if (e->refresh_counters() != SM_OK) return 0; return e->n_live; }
+    return e->n_local;
+}
 
 static inline uint32_t owner_row(float y, uint32_t H)
 {
@@ -537,6 +553,7 @@ int sm_upload_agents(sm_engine* e, const float* xyas, uint64_t first, uint64_t n
     SM_CUDA(cudaMemcpy(e->ids[e->acur], keep_ids.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
     e->n_local = m;
     e->n_live = m;
+    if (e->comm_ready) SM_TRY(e->push_counters());
     e->agents_valid = true;
     e->identity_order = false;
     e->steps_since_sort = e->sort_interval;
@@ -556,7 +573,7 @@ int sm_download_agents(sm_engine* e, float* xyas, uint64_t first, uint64_t n, ui
         if (n_owned) *n_owned = n;
         return SM_OK;
     }
-    SM_CUDA(cudaStreamSynchronize(e->stream));
+    SM_TRY(e->refresh_counters());
     std::vector<float> a((size_t)e->n_local * 4);
     std::vector<uint32_t> id((size_t)e->n_local);
     SM_CUDA(cudaMemcpy(a.data(), e->agents[e->acur], e->n_local * sizeof(float4), cudaMemcpyDeviceToHost));
@@ -612,6 +629,7 @@ int sm_reassign_speeds(sm_engine* e, uint64_t seed)
 {
     SM_ENTER(e);
     if (!e->agents_valid) return sm_fail(SM_ERR_STATE, "agents were never initialised or uploaded");
+    if (e->world > 1) SM_TRY(e->refresh_counters());
     if (e->n_local)
         smk::k_reassign_speeds<<<blocks_for(e->n_local, 256), 256, 0, e->stream>>>(
             e->agents[e->acur], e->ids[e->acur], e->n_local, seed, e->params.agent_speed_min, e->params.agent_speed_max);
@@ -622,8 +640,9 @@ int sm_reassign_speeds(sm_engine* e, uint64_t seed)
 int sm_clear_trail(sm_engine* e)
 {
     SM_ENTER(e);
-    const size_t cells = (size_t)(e->rows + 2 * (size_t)e->ghost) * e->W;
+    const size_t cells = e->field_cells();
     SM_CUDA(cudaMemsetAsync(e->trail_base[e->cur], 0, cells * sizeof(float), e->stream));
+    e->ghost_stale = true;
     return SM_OK;
 }
 
@@ -725,10 +744,7 @@ int sm_step(sm_engine* e, uint32_t n_steps)
         SM_TRY(e->launch_agents());                      // src/main.rs:1164-1181
         if (e->world > 1) SM_TRY(e->exchange_counts());
         SM_TRY(e->launch_trail(true));                   // src/main.rs:1184-1199 + 1220-1235
-        if (e->world > 1) {
-            SM_TRY(e->exchange_trail_ghosts());
-            SM_TRY(e->migrate_agents());
-        }
+        if (e->world > 1) SM_TRY(e->migrate_agents());   // trail ghosts + leavers, one NCCL group
         e->steps_since_sort++;
         e->timing.steps++;
     }

@@ -12,11 +12,10 @@ int sm_fail(int code, const char* fmt, ...);
 
 struct EvPair { cudaEvent_t a, b; int kind; };
 
-// Per-direction migration staging (multi-GPU): agents leaving towards a ring neighbour.
+// Per-direction migration message (multi-GPU): [u64 count][u64 pad][float4 a[cap]][u32 id[cap]]
 struct MigrateBuf {
-    float4* send_a = nullptr;
-    uint32_t* send_id = nullptr;
-    uint64_t cap = 0;
+    uint8_t* send = nullptr;   // filled by k_agents<true>, sent to the ring neighbour after the trail pass
+    uint8_t* recv = nullptr;   // the neighbour's message
 };
 
 struct sm_engine {
@@ -39,8 +38,9 @@ struct sm_engine {
     bool ghost_stale = true;          // ghost rows of trail[cur] need a (re-)exchange
     float* gauss_dec = nullptr;       // extension scratch
     float* gauss_hb = nullptr;
-    float* trail_ptr(int i) const { return trail_base[i] + (size_t)ghost * W; }        // owned row 0
-    uint32_t* counts_ptr(int i) const { return counts_base[i] + (size_t)ghost * W; }
+    float* trail_ptr(int i) const { return trail_base[i] + (size_t)(ghost + pad_rows) * W; }        // owned row 0
+    uint32_t* counts_ptr(int i) const { return counts_base[i] + (size_t)(ghost + pad_rows) * W; }
+    size_t field_cells() const { return (size_t)(rows + 2 * (size_t)(ghost + pad_rows)) * W; }
 
     // agents: float4 state + u32 persistent index, double buffered for the cell sort
     float4* agents[2] = {nullptr, nullptr};
@@ -78,8 +78,13 @@ struct sm_engine {
     uint32_t* counts_xchg = nullptr;  // recv staging for the deposit-count exchange
     uint64_t counts_xchg_rows = 0;
     MigrateBuf mig[2];                // 0: towards rank-1 (up), 1: towards rank+1 (down)
-    unsigned long long* mig_counters = nullptr;   // device: [leave_up, leave_down, arrive_from_down, arrive_from_up]
-    unsigned long long* mig_counters_host = nullptr;  // pinned mirror
+    uint64_t mig_cap = 0;             // agents per message
+    size_t mig_bytes = 0;             // bytes per message
+    // device counters: [0] slots in use (n_local), [1] live agents, [2] overflow flag
+    unsigned long long* dev_counters = nullptr;
+    unsigned long long* host_counters = nullptr;      // pinned mirror
+    uint64_t n_upper = 0;             // host-side upper bound of slots in use between sorts
+    uint32_t pad_rows = 0;            // physical padding rows beyond the ghosts (multi-GPU memory-safety slack)
 
     smd::AgentConsts agent_consts() const;
     smd::TrailConsts trail_consts() const;
@@ -106,5 +111,7 @@ struct sm_engine {
     int exchange_counts();
     int exchange_trail_ghosts();
     int migrate_agents();
+    int refresh_counters();           // multi-GPU: sync and read the device counters into n_local / n_live
+    int push_counters();              // multi-GPU: write n_local / n_live to the device counters
     void comm_destroy();
 };

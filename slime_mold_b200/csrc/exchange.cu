@@ -8,11 +8,13 @@
 //   k_agents<true>     senses from trail rows own +- g (ghost rows), counts deposits into own +- m,
 //                      stages agents whose new row belongs to a neighbour (leavers)
 //   exchange_counts()  to each neighbour: the m ghost count rows on its side + my own boundary row
-//                      (contiguous (m+1) x W u32), and my leaver count; one host sync to learn the
-//                      arrival counts
+//                      (contiguous (m+1) x W u32)
 //   k_trail_rows       merge -> decay -> 3x3 mean on the owned rows (ghost row +-1 now complete)
 //   exchange_trail_ghosts() + migrate_agents(): my new top / bottom g trail rows -> the neighbours'
-//                      ghost rows, leavers -> the tail of the neighbour's agent arrays
+//                      ghost rows; the two fixed-size leaver messages -> the neighbours, whose
+//                      k_append_arrivals adds them behind a device-side cursor.  No host round trip per
+//                      step: slot counts live on the device and are read back only when the agents are
+//                      sorted (every 16 steps), downloaded or counted.
 //
 // g = ceil(sensor_distance) + 3,  m = ceil(speed_max * 0.016) + 1.
 // The toroidal seam (strip 0 <-> strip G-1) carries diffusion and motion; sensing is not
@@ -110,6 +112,41 @@ k_counts_add(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint6
     if (i < n) dst[i] += src[i];
 }
 
+// Appends the agents of the two received messages behind the device-side cursor counters[0].
+static __global__ void __launch_bounds__(256)
+k_append_arrivals(const uint8_t* __restrict__ msg_from_down, const uint8_t* __restrict__ msg_from_up, uint32_t cap,
+                  float4* __restrict__ agents, uint32_t* __restrict__ ids, unsigned long long* __restrict__ counters,
+                  uint64_t cap_local)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 2u * cap) return;
+    const uint32_t which = j / cap, k = j % cap;
+    const unsigned long long c0 = min(*reinterpret_cast<const unsigned long long*>(msg_from_down), (unsigned long long)cap);
+    const unsigned long long c1 = min(*reinterpret_cast<const unsigned long long*>(msg_from_up), (unsigned long long)cap);
+    const uint8_t* msg = which ? msg_from_up : msg_from_down;
+    if (k >= (which ? c1 : c0)) return;
+    const unsigned long long pos = counters[0] + (which ? c0 : 0ull) + k;
+    if (pos >= cap_local) { atomicExch(counters + 2, 2ull); return; }
+    agents[pos] = reinterpret_cast<const float4*>(msg + 16)[k];
+    ids[pos] = reinterpret_cast<const uint32_t*>(msg + 16 + (size_t)cap * sizeof(float4))[k];
+}
+
+// One thread: advance the cursors, retire this step's outgoing message headers.
+static __global__ void k_bump_counters(unsigned long long* counters, const uint8_t* msg_from_down, const uint8_t* msg_from_up,
+                                       unsigned long long* send_up, unsigned long long* send_down, uint32_t cap,
+                                       uint64_t cap_local)
+{
+    const unsigned long long c0 = min(*reinterpret_cast<const unsigned long long*>(msg_from_down), (unsigned long long)cap);
+    const unsigned long long c1 = min(*reinterpret_cast<const unsigned long long*>(msg_from_up), (unsigned long long)cap);
+    const unsigned long long left = min(*send_up, (unsigned long long)cap) + min(*send_down, (unsigned long long)cap);
+    unsigned long long arrived = c0 + c1;
+    if (counters[0] + arrived > cap_local) arrived = cap_local - counters[0];
+    counters[0] += arrived;
+    counters[1] = counters[1] + arrived - left;
+    *send_up = 0ull;
+    *send_down = 0ull;
+}
+
 // Seeded start-up fill restricted to one strip: every rank walks all agent indices and keeps
 // the agents whose row it owns (same counter-based generator as k_init_agents).
 static __global__ void __launch_bounds__(256)
@@ -170,22 +207,29 @@ extern "C" int sm_comm_init(sm_engine* e, const uint8_t id[SM_COMM_ID_BYTES])
     SM_NCCL(ncclCommInitRank(&comm, e->world, u, e->rank));
     e->comm = comm;
 
-    // staging: received count rows (2 x (ghost + 1) rows), leaver buffers, counters
+    // staging: received count rows (2 x (ghost + 1) rows), migration messages, device counters
     e->counts_xchg_rows = (uint64_t)e->ghost + 1;
     SM_CUDA(cudaMalloc(&e->counts_xchg, 2 * e->counts_xchg_rows * e->W * sizeof(uint32_t)));
-    // leavers per step ~ (agents per row) * m rows; generous: 1/8 of the strip's capacity, at least 64k
-    uint64_t cap = std::max<uint64_t>(e->cap_local / 8, 65536);
-    cap = std::min<uint64_t>(cap, 0x7fffffffull);
+    // Leavers per step and direction ~ density * W * |v_y| * dt (a few thousand at W = 32768); the whole
+    // fixed-size message is sent every step, so keep it small: 64 Ki agents (1.3 MB, ~2 us on NVLink),
+    // SM_MIGRATE_CAP overrides.  Overflow is detected on the device and reported at the next sync point.
+    uint64_t cap = 65536;
+    if (const char* v = getenv("SM_MIGRATE_CAP")) cap = std::max<uint64_t>(1024, strtoull(v, nullptr, 10));
+    cap = (cap + 3) & ~3ull;
+    e->mig_cap = cap;
+    e->mig_bytes = 16 + cap * (sizeof(float4) + sizeof(uint32_t));
     for (int d = 0; d < 2; ++d) {
-        e->mig[d].cap = cap;
-        SM_CUDA(cudaMalloc(&e->mig[d].send_a, cap * sizeof(float4)));
-        SM_CUDA(cudaMalloc(&e->mig[d].send_id, cap * sizeof(uint32_t)));
+        SM_CUDA(cudaMalloc(&e->mig[d].send, e->mig_bytes));
+        SM_CUDA(cudaMalloc(&e->mig[d].recv, e->mig_bytes));
+        SM_CUDA(cudaMemset(e->mig[d].send, 0, 16));
+        SM_CUDA(cudaMemset(e->mig[d].recv, 0, 16));
     }
-    SM_CUDA(cudaMalloc(&e->mig_counters, 8 * sizeof(unsigned long long)));
-    SM_CUDA(cudaMemset(e->mig_counters, 0, 8 * sizeof(unsigned long long)));
-    SM_CUDA(cudaMallocHost(&e->mig_counters_host, 8 * sizeof(unsigned long long)));
+    SM_CUDA(cudaMalloc(&e->dev_counters, 8 * sizeof(unsigned long long)));
+    SM_CUDA(cudaMemset(e->dev_counters, 0, 8 * sizeof(unsigned long long)));
+    SM_CUDA(cudaMallocHost(&e->host_counters, 8 * sizeof(unsigned long long)));
     e->comm_ready = true;
     e->ghost_stale = true;
+    SM_TRY(e->push_counters());          // agents may have been uploaded before the communicator existed
     return SM_OK;
 }
 
@@ -194,12 +238,12 @@ void sm_engine::comm_destroy()
     if (comm && g_nccl.ok) { ncclCommDestroy((ncclComm_t)comm); comm = nullptr; }
     if (counts_xchg) { cudaFree(counts_xchg); counts_xchg = nullptr; }
     for (int d = 0; d < 2; ++d) {
-        if (mig[d].send_a) cudaFree(mig[d].send_a);
-        if (mig[d].send_id) cudaFree(mig[d].send_id);
+        if (mig[d].send) cudaFree(mig[d].send);
+        if (mig[d].recv) cudaFree(mig[d].recv);
         mig[d] = MigrateBuf{};
     }
-    if (mig_counters) { cudaFree(mig_counters); mig_counters = nullptr; }
-    if (mig_counters_host) { cudaFreeHost(mig_counters_host); mig_counters_host = nullptr; }
+    if (dev_counters) { cudaFree(dev_counters); dev_counters = nullptr; }
+    if (host_counters) { cudaFreeHost(host_counters); host_counters = nullptr; }
     comm_ready = false;
 }
 
@@ -221,6 +265,7 @@ int sm_engine::init_agents_strip(uint64_t seed)
         return sm_fail(SM_ERR_OOM, "strip %d would own %llu agents, capacity %llu", rank, got, (unsigned long long)cap_local);
     n_local = n_live = got;
     identity_order = false;
+    SM_TRY(push_counters());
     return SM_OK;
 }
 
@@ -239,12 +284,8 @@ int sm_engine::exchange_counts()
     SM_NCCL(ncclGroupStart());
     SM_NCCL(ncclSend(cnt - (int64_t)m * W, msg, ncclUint32, up, c, stream));                 // rows [-m, 0]
     SM_NCCL(ncclSend(cnt + (int64_t)(rows - 1) * W, msg, ncclUint32, down, c, stream));      // rows [rows-1, rows+m)
-    SM_NCCL(ncclSend(mig_counters + 0, 1, ncclUint64, up, c, stream));
-    SM_NCCL(ncclSend(mig_counters + 1, 1, ncclUint64, down, c, stream));
     SM_NCCL(ncclRecv(from_down, msg, ncclUint32, down, c, stream));
     SM_NCCL(ncclRecv(from_up, msg, ncclUint32, up, c, stream));
-    SM_NCCL(ncclRecv(mig_counters + 2, 1, ncclUint64, down, c, stream));                     // arrivals from down
-    SM_NCCL(ncclRecv(mig_counters + 3, 1, ncclUint64, up, c, stream));                       // arrivals from up
     SM_NCCL(ncclGroupEnd());
     // from_up lands on my rows [-1, m): its own last row completes my ghost row -1, its ghost rows my first m rows
     smk::k_counts_add<<<blocks_for(msg, 256), 256, 0, stream>>>(cnt - (int64_t)W, from_up, msg);
@@ -252,12 +293,11 @@ int sm_engine::exchange_counts()
     smk::k_counts_add<<<blocks_for(msg, 256), 256, 0, stream>>>(cnt + (int64_t)(rows - m) * W, from_down, msg);
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 2;
-    SM_CUDA(cudaMemcpyAsync(mig_counters_host, mig_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     SM_TRY(toc());
     return SM_OK;
 }
 
-// New trail rows -> neighbours' ghost rows.
+// New trail rows -> neighbours' ghost rows (also used alone after uploads / clears).
 int sm_engine::exchange_trail_ghosts()
 {
     uint32_t g = 0, m = 0;
@@ -278,8 +318,9 @@ int sm_engine::exchange_trail_ghosts()
     return SM_OK;
 }
 
-// Leavers -> neighbours; arrivals appended to the live arrays.  Also retires the ghost count rows
-// this step used (the trail kernel only zeroes the owned rows of the *other* count buffer).
+// After the trail pass: new trail rows -> neighbours' ghost rows and the two leaver messages -> the
+// neighbours, in ONE NCCL group; arrivals are appended on the device.  Also retires the ghost count
+// rows this step used (the trail kernel only zeroes the owned rows of the *other* count buffer).
 int sm_engine::migrate_agents()
 {
     uint32_t g = 0, m = 0;
@@ -289,41 +330,56 @@ int sm_engine::migrate_agents()
     SM_CUDA(cudaMemsetAsync(used - (int64_t)m * W, 0, (size_t)m * W * sizeof(uint32_t), stream));
     SM_CUDA(cudaMemsetAsync(used + (int64_t)rows * W, 0, (size_t)m * W * sizeof(uint32_t), stream));
 
-    SM_CUDA(cudaStreamSynchronize(stream));            // the one host round trip per step: leaver / arrival counts
-    const unsigned long long leave_up = mig_counters_host[0], leave_down = mig_counters_host[1];
-    const unsigned long long arr_down = mig_counters_host[2], arr_up = mig_counters_host[3];
-    if (mig_counters_host[4])
-        return sm_fail(SM_ERR_OOM, "migration staging overflow on rank %d (%llu up, %llu down, capacity %llu)", rank,
-                       leave_up, leave_down, (unsigned long long)mig[0].cap);
-    if (n_local + arr_down + arr_up > cap_local)
-        return sm_fail(SM_ERR_OOM, "rank %d agent capacity exceeded: %llu + %llu arrivals > %llu", rank,
-                       (unsigned long long)n_local, arr_down + arr_up, (unsigned long long)cap_local);
     SM_TRY(tic(3));
     ncclComm_t c = (ncclComm_t)comm;
     const int up = (rank - 1 + world) % world, down = (rank + 1) % world;
-    float4* a = agents[acur];
-    uint32_t* id = ids[acur];
+    float* t = trail_ptr(cur);
+    const size_t tmsg = (size_t)g * W;
     SM_NCCL(ncclGroupStart());
-    if (leave_up) {
-        SM_NCCL(ncclSend(mig[0].send_a, leave_up * 4, ncclFloat, up, c, stream));
-        SM_NCCL(ncclSend(mig[0].send_id, leave_up, ncclUint32, up, c, stream));
-    }
-    if (leave_down) {
-        SM_NCCL(ncclSend(mig[1].send_a, leave_down * 4, ncclFloat, down, c, stream));
-        SM_NCCL(ncclSend(mig[1].send_id, leave_down, ncclUint32, down, c, stream));
-    }
-    if (arr_down) {
-        SM_NCCL(ncclRecv(a + n_local, arr_down * 4, ncclFloat, down, c, stream));
-        SM_NCCL(ncclRecv(id + n_local, arr_down, ncclUint32, down, c, stream));
-    }
-    if (arr_up) {
-        SM_NCCL(ncclRecv(a + n_local + arr_down, arr_up * 4, ncclFloat, up, c, stream));
-        SM_NCCL(ncclRecv(id + n_local + arr_down, arr_up, ncclUint32, up, c, stream));
-    }
+    SM_NCCL(ncclSend(t, tmsg, ncclFloat, up, c, stream));
+    SM_NCCL(ncclSend(t + (int64_t)(rows - g) * W, tmsg, ncclFloat, down, c, stream));
+    SM_NCCL(ncclSend(mig[0].send, mig_bytes, ncclUint8, up, c, stream));
+    SM_NCCL(ncclSend(mig[1].send, mig_bytes, ncclUint8, down, c, stream));
+    SM_NCCL(ncclRecv(t + (int64_t)rows * W, tmsg, ncclFloat, down, c, stream));
+    SM_NCCL(ncclRecv(t - (int64_t)g * W, tmsg, ncclFloat, up, c, stream));
+    SM_NCCL(ncclRecv(mig[1].recv, mig_bytes, ncclUint8, down, c, stream));                   // what `down` sent up
+    SM_NCCL(ncclRecv(mig[0].recv, mig_bytes, ncclUint8, up, c, stream));                     // what `up` sent down
     SM_NCCL(ncclGroupEnd());
-    SM_CUDA(cudaMemsetAsync(mig_counters, 0, 8 * sizeof(unsigned long long), stream));
+    ghost_stale = false;
+    smk::k_append_arrivals<<<blocks_for(2 * mig_cap, 256), 256, 0, stream>>>(mig[1].recv, mig[0].recv, (uint32_t)mig_cap,
+                                                                            agents[acur], ids[acur], dev_counters, cap_local);
+    smk::k_bump_counters<<<1, 1, 0, stream>>>(dev_counters, mig[1].recv, mig[0].recv,
+                                              reinterpret_cast<unsigned long long*>(mig[0].send),
+                                              reinterpret_cast<unsigned long long*>(mig[1].send), (uint32_t)mig_cap, cap_local);
+    SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 2;
     SM_TRY(toc());
-    n_local += arr_down + arr_up;
-    n_live = n_live - leave_up - leave_down + arr_down + arr_up;
+    n_upper = std::min<uint64_t>(cap_local, n_upper + 2 * mig_cap);
+    return SM_OK;
+}
+
+int sm_engine::refresh_counters()
+{
+    if (!dev_counters) { SM_CUDA(cudaStreamSynchronize(stream)); return SM_OK; }
+    SM_CUDA(cudaMemcpyAsync(host_counters, dev_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    SM_CUDA(cudaStreamSynchronize(stream));
+    if (host_counters[2])
+        return sm_fail(SM_ERR_OOM, "rank %d: %s overflow (raise SM_MIGRATE_CAP or the agent capacity)", rank,
+                       host_counters[2] == 1 ? "migration message" : "agent array");
+    n_local = host_counters[0];
+    n_live = host_counters[1];
+    n_upper = n_local;
+    return SM_OK;
+}
+
+int sm_engine::push_counters()
+{
+    n_upper = n_local;
+    if (!dev_counters) return SM_OK;
+    host_counters[0] = n_local;
+    host_counters[1] = n_live;
+    host_counters[2] = 0;
+    SM_CUDA(cudaMemcpyAsync(dev_counters, host_counters, 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    SM_CUDA(cudaStreamSynchronize(stream));
     return SM_OK;
 }

@@ -64,11 +64,16 @@ k_rescale_agents(float4* __restrict__ agents, uint64_t n, float fx, float fy)
 
 constexpr uint32_t kDeadAgent = 0xFFFFFFFFu;   // multi-GPU: slot whose agent migrated away (dropped by the next sort)
 
-// Migration staging filled by k_agents<true>: agents whose new row belongs to a ring neighbour.
+// Migration staging filled by k_agents<true>: agents whose new row belongs to a ring neighbour are
+// written straight into the fixed-size message that exchange.cu sends after the trail pass
+// (layout: [u64 count][u64 pad][float4 a[cap]][u32 id[cap]]).  All counters live on the device, so a
+// step needs no host round trip.
 struct LeaverBufs {
-    float4* send_a[2];                 // 0: towards rank-1 (up), 1: towards rank+1 (down)
+    float4* send_a[2];                   // 0: towards rank-1 (up), 1: towards rank+1 (down)
     uint32_t* send_id[2];
-    unsigned long long* counters;      // [0] leave_up, [1] leave_down, [4] overflow flag
+    unsigned long long* send_count[2];   // message headers
+    unsigned long long* overflow;        // sticky error flag, checked by the host at the next sync point
+    const unsigned long long* n_ptr;     // device-side number of agent slots in use
     uint32_t cap;
 };
 
@@ -81,6 +86,7 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
          const LeaverBufs lv)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (MULTI) n = *lv.n_ptr;            // the host only knows an upper bound between sorts
     if (i >= n) return;
     const uint32_t id = ids[i];
     if (MULTI && id == kDeadAgent) return;
@@ -90,7 +96,9 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     agents[i] = a;
     if (cx >= 0) {
         // deposit: integer count, order-free (phase_split form of compute.wgsl:140)
-        atomicAdd(counts + ((IdxT)smd::local_row(cy, c) * (IdxT)c.W + (IdxT)cx), 1u);
+        const int64_t lrd = smd::local_row(cy, c);
+        if (!MULTI || (lrd >= -(int64_t)c.ghost && lrd < (int64_t)c.rows_local + c.ghost))
+            atomicAdd(counts + ((IdxT)lrd * (IdxT)c.W + (IdxT)cx), 1u);
     }
     if (MULTI) {
         // owner row of the new position (x == W / y == H rounding corner and NaN clamp like the host)
@@ -98,13 +106,13 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
         int64_t lr = smd::local_row(oy, c);
         if (lr < 0 || lr >= (int64_t)c.rows_local) {
             const int dir = lr < 0 ? 0 : 1;
-            unsigned long long slot = atomicAdd(lv.counters + dir, 1ull);
+            unsigned long long slot = atomicAdd(lv.send_count[dir], 1ull);
             if (slot < lv.cap) {
                 lv.send_a[dir][slot] = a;
                 lv.send_id[dir][slot] = id;
                 ids[i] = kDeadAgent;
             } else {
-                atomicExch(lv.counters + 4, 1ull);   // staging overflow: reported by the host
+                atomicExch(lv.overflow, 1ull);       // staging overflow: reported by the host
             }
         }
     }
