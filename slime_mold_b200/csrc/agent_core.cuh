@@ -44,32 +44,44 @@ constexpr float kTwoPi = 2.0f * 3.14159265359f;    // compute.wgsl:121
 constexpr float kRcpTwoPi = 0.15915494f;
 constexpr float kTimeStep = 0.016f;                // compute.wgsl:55
 
-// sample_trail_map, compute.wgsl:7-29.  LD(ptr) loads one f32 of the trail.
-// IdxT = int32_t when the strip (with ghosts) has fewer than 2^31 cells, else int64_t.
-template <class IdxT, class LD>
-SM_HD float sample_trail(const float* __restrict__ trail, const AgentConsts& c, float px, float py, LD ld)
+// sample_trail_map, compute.wgsl:7-29.  FETCH(x0, y0, v00, v10, v01, v11) returns the 2x2 footprint
+// whose top-left cell is global (x0, y0): four scalar loads from the row-major field (host / LDG
+// path) or one texture gather from the block-linear copy (device TEX path) -- raw f32 either way.
+template <class FETCH>
+SM_HD float sample_trail(const AgentConsts& c, float px, float py, FETCH fetch)
 {
     float fx = ::floorf(px), fy = ::floorf(py);
     // x0 < 0 || x1 >= W || y0 < 0 || y1 >= H -> 0 (sensing is NOT toroidal); NaN -> outside
     if (!(fx >= 0.0f && fx <= c.xmax && fy >= 0.0f && fy <= c.ymax)) return 0.0f;
-    IdxT x0 = (IdxT)(int32_t)fx;
-    IdxT y0 = (IdxT)(int32_t)fy;
     float dx = sub(px, fx), dy = sub(py, fy);
-    const float* r0 = trail + ((y0 - (IdxT)c.row_base) * (IdxT)c.W + x0);
-    const float* r1 = r0 + c.W;
-    float v00 = ld(r0), v10 = ld(r0 + 1), v01 = ld(r1), v11 = ld(r1 + 1);
+    float v00, v10, v01, v11;
+    fetch((int32_t)fx, (int32_t)fy, v00, v10, v01, v11);
     float omdx = sub(1.0f, dx);
     float v0 = mixf_pre(v00, v10, dx, omdx);
     float v1 = mixf_pre(v01, v11, dx, omdx);
     return mixf(v0, v1, dy);
 }
 
+// Footprint fetch from the row-major field.  IdxT = int32_t when the strip (with ghosts) has fewer
+// than 2^31 cells, else int64_t.  LD(ptr) loads one f32.
+template <class IdxT, class LD>
+struct FetchLinear {
+    const float* trail;      // owned row 0 of this rank's strip
+    IdxT W, row_base;
+    LD ld;
+    SM_HD void operator()(int32_t x0, int32_t y0, float& v00, float& v10, float& v01, float& v11) const
+    {
+        const float* r0 = trail + (((IdxT)y0 - row_base) * W + (IdxT)x0);
+        const float* r1 = r0 + W;
+        v00 = ld(r0); v10 = ld(r0 + 1); v01 = ld(r1); v11 = ld(r1 + 1);
+    }
+};
+
 // Returns the deposit cell as (cx, cy) with cx < 0 when the deposit is skipped
 // (compute.wgsl:138: x == W can occur by rounding).
-template <class IdxT, class LD>
+template <class FETCH>
 SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t agent_index,
-                        const float* __restrict__ trail, const AgentConsts& c, LD ld,
-                        int32_t& cx, int32_t& cy)
+                        const AgentConsts& c, FETCH fetch, int32_t& cx, int32_t& cy)
 {
     speed = clampf(speed, c.speed_min, c.speed_max);                       // :72
 
@@ -87,9 +99,9 @@ SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t 
         sincos(angle, sC, cC);
     }
     const float sd = c.sensor_distance;
-    float vL = sample_trail<IdxT>(trail, c, add(x, mul(sd, cL)), add(y, mul(sd, sL)), ld);   // :79-82,93
-    float vR = sample_trail<IdxT>(trail, c, add(x, mul(sd, cR)), add(y, mul(sd, sR)), ld);   // :83-86,94
-    float vC = sample_trail<IdxT>(trail, c, add(x, mul(sd, cC)), add(y, mul(sd, sC)), ld);   // :87-90,95
+    float vL = sample_trail(c, add(x, mul(sd, cL)), add(y, mul(sd, sL)), fetch);   // :79-82,93
+    float vR = sample_trail(c, add(x, mul(sd, cR)), add(y, mul(sd, sR)), fetch);   // :83-86,94
+    float vC = sample_trail(c, add(x, mul(sd, cC)), add(y, mul(sd, sC)), fetch);   // :87-90,95
 
     if (vC > vL && vC > vR) {                                              // :98
     } else if (vL > vR) {                                                  // :100-104

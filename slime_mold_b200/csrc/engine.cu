@@ -143,10 +143,12 @@ int sm_engine::alloc_trail()
         SM_CUDA(cudaMemsetAsync(counts_base[i], 0, cells * sizeof(uint32_t), stream));
     }
     cur = 0; ccur = 0;
+    if (use_tex) SM_TRY(setup_tex());
     return SM_OK;
 }
 void sm_engine::free_trail()
 {
+    free_tex();
     for (int i = 0; i < 2; ++i) {
         if (trail_base[i]) cudaFree(trail_base[i]);
         if (counts_base[i]) cudaFree(counts_base[i]);
@@ -175,6 +177,78 @@ void sm_engine::free_agents()
         agents[i] = nullptr; ids[i] = nullptr;
     }
 }
+// ---- texture-gather sampler: block-linear copy of the trail -------------------------------------
+static int make_tex(cudaArray_t arr, cudaTextureObject_t* tex)
+{
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    SM_CUDA(cudaCreateTextureObject(tex, &rd, &td, nullptr));
+    return SM_OK;
+}
+
+// Does tex2Dgather return the footprint in the component order FetchTex assumes?
+static int gather_probe_ok(bool* ok)
+{
+    *ok = false;
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+    float* out = nullptr;
+    float host[16], got[4] = {0, 0, 0, 0};
+    for (int y = 0; y < 4; ++y)
+        for (int x = 0; x < 4; ++x) host[y * 4 + x] = 10.0f * y + x;
+    cudaError_t err = cudaMallocArray(&arr, &fd, 4, 4, cudaArrayTextureGather);
+    if (err == cudaSuccess) err = cudaMemcpy2DToArray(arr, 0, 0, host, 16, 16, 4, cudaMemcpyHostToDevice);
+    int rc = SM_OK;
+    if (err == cudaSuccess) rc = make_tex(arr, &tex);
+    if (err == cudaSuccess && rc == SM_OK) err = cudaMalloc(&out, 16);
+    if (err == cudaSuccess && rc == SM_OK) {
+        smk::k_gather_probe<<<1, 1>>>(tex, out);
+        err = cudaMemcpy(got, out, 16, cudaMemcpyDeviceToHost);
+    }
+    if (tex) cudaDestroyTextureObject(tex);
+    if (arr) cudaFreeArray(arr);
+    if (out) cudaFree(out);
+    if (err != cudaSuccess) { cudaGetLastError(); return SM_OK; }      // probe unavailable -> LDG sampler
+    *ok = (got[0] == 11.0f && got[1] == 12.0f && got[2] == 21.0f && got[3] == 22.0f);
+    return rc;
+}
+
+int sm_engine::setup_tex()
+{
+    free_tex();
+    const size_t htot = rows + 2 * (size_t)(ghost + pad_rows);
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+    SM_CUDA(cudaMallocArray(&trail_arr, &fd, W, htot, cudaArraySurfaceLoadStore | cudaArrayTextureGather));
+    SM_TRY(make_tex(trail_arr, &trail_tex));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = trail_arr;
+    SM_CUDA(cudaCreateSurfaceObject(&trail_surf, &rd));
+    arr_stale = true;
+    return SM_OK;
+}
+void sm_engine::free_tex()
+{
+    if (trail_tex) { cudaDestroyTextureObject(trail_tex); trail_tex = 0; }
+    if (trail_surf) { cudaDestroySurfaceObject(trail_surf); trail_surf = 0; }
+    if (trail_arr) { cudaFreeArray(trail_arr); trail_arr = nullptr; }
+}
+int sm_engine::refresh_tex(int64_t local_row_begin, int64_t n_rows)
+{
+    if (!use_tex || n_rows <= 0) return SM_OK;
+    const int64_t arr_row = local_row_begin + (int64_t)(ghost + pad_rows);
+    SM_CUDA(cudaMemcpy2DToArrayAsync(trail_arr, 0, (size_t)arr_row, trail_ptr(cur) + local_row_begin * (int64_t)W,
+                                     (size_t)W * 4, (size_t)W * 4, (size_t)n_rows, cudaMemcpyDeviceToDevice, stream));
+    return SM_OK;
+}
+
 int sm_engine::setup_tiles()
 {
     if (tile_hist) { cudaFree(tile_hist); tile_hist = nullptr; }
@@ -227,11 +301,10 @@ int sm_engine::launch_agents()
     if (n_local == 0) return SM_OK;
     SM_TRY(tic(0));
     smk::LeaverBufs lv{};
-    const bool idx32 = (uint64_t)(rows + 2 * (uint64_t)ghost) * W < (1ull << 31);
+    const bool idx32 = (uint64_t)field_cells() < (1ull << 31);
     const unsigned nb = blocks_for(n_local, 256);
     float4* a = agents[acur];
     uint32_t* id = ids[acur];
-    const float* t = trail_ptr(cur);
     uint32_t* cn = counts_ptr(ccur);
     const smd::AgentConsts ac = agent_consts();
     if (world > 1) {
@@ -243,11 +316,28 @@ int sm_engine::launch_agents()
         lv.overflow = dev_counters + 2;
         lv.n_ptr = dev_counters;
         lv.cap = (uint32_t)mig_cap;
-        if (idx32) smk::k_agents<true, int32_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
-        else smk::k_agents<true, int64_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
+    }
+    if (use_tex) {
+        if (arr_stale) {                                  // the array lost track of trail[cur]: one full copy
+            SM_TRY(refresh_tex(-(int64_t)(ghost + pad_rows), (int64_t)rows + 2 * (int64_t)(ghost + pad_rows)));
+            arr_stale = false;
+        }
+        const smk::FetchTex f{trail_tex, (int32_t)(ghost + pad_rows) - (int32_t)row0};
+        if (world > 1) {
+            if (idx32) smk::k_agents<true, int32_t, smk::FetchTex><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
+            else smk::k_agents<true, int64_t, smk::FetchTex><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
+        } else {
+            if (idx32) smk::k_agents<false, int32_t, smk::FetchTex><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
+            else smk::k_agents<false, int64_t, smk::FetchTex><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
+        }
+    } else if (idx32) {
+        const smd::FetchLinear<int32_t, smk::LdgF32> f{trail_ptr(cur), (int32_t)W, (int32_t)row0, smk::LdgF32()};
+        if (world > 1) smk::k_agents<true, int32_t, decltype(f)><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
+        else smk::k_agents<false, int32_t, decltype(f)><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
     } else {
-        if (idx32) smk::k_agents<false, int32_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
-        else smk::k_agents<false, int64_t><<<nb, 256, 0, stream>>>(a, id, n_local, t, cn, ac, lv);
+        const smd::FetchLinear<int64_t, smk::LdgF32> f{trail_ptr(cur), (int64_t)W, (int64_t)row0, smk::LdgF32()};
+        if (world > 1) smk::k_agents<true, int64_t, decltype(f)><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
+        else smk::k_agents<false, int64_t, decltype(f)><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
     }
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
@@ -260,6 +350,11 @@ int sm_engine::launch_trail(bool has_counts)
     const smd::TrailConsts tc = trail_consts();
     smk::TrailGeom g{};
     g.W = W; g.rows = rows; g.wrap_y = (world == 1) ? 1 : 0;
+    // the full step keeps the sampler's block-linear copy in step; other passes just mark it stale
+    const bool write_surf = use_tex && has_counts && !(cfg.flags & SM_FLAG_GAUSSIAN_BLUR);
+    g.surf = write_surf ? trail_surf : 0;
+    g.surf_row0 = (int)(ghost + pad_rows);
+    if (!write_surf) arr_stale = true;
     const float* tin = trail_ptr(cur);
     float* tout = trail_ptr(1 - cur);
     const uint32_t* cin = counts_ptr(ccur);
@@ -417,6 +512,13 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     e->sort_interval = cfg->sort_interval ? cfg->sort_interval : (uint32_t)env_int("SM_SORT_INTERVAL", 16);
     if (cfg->flags & SM_FLAG_NO_SORT) e->sort_interval = 0;
     if (e->world > 1 && e->sort_interval == 0) e->sort_interval = 16;   // strips need the sort to compact migrated-away slots
+    {
+        const char* smp = getenv("SM_SAMPLER");
+        bool want_tex = !(smp && std::string(smp) == "ldg");
+        bool probe = false;
+        if (want_tex) { int prc = gather_probe_ok(&probe); if (prc != SM_OK) { delete e; return prc; } }
+        e->use_tex = want_tex && probe;
+    }
     e->force_generic = env_int("SM_FORCE_GENERIC_TRAIL", 0) != 0;
     e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
 
@@ -643,6 +745,7 @@ int sm_clear_trail(sm_engine* e)
     const size_t cells = e->field_cells();
     SM_CUDA(cudaMemsetAsync(e->trail_base[e->cur], 0, cells * sizeof(float), e->stream));
     e->ghost_stale = true;
+    e->arr_stale = true;
     return SM_OK;
 }
 
@@ -669,6 +772,7 @@ int sm_upload_trail(sm_engine* e, const float* src, uint32_t x0, uint32_t y0, ui
         SM_CUDA(cudaStreamSynchronize(e->stream));
     }
     e->ghost_stale = true;
+    e->arr_stale = true;
     return SM_OK;
 }
 

@@ -36,6 +36,12 @@ struct sm_engine {
     uint32_t* counts_base[2] = {nullptr, nullptr};
     int cur = 0, ccur = 0;
     bool ghost_stale = true;          // ghost rows of trail[cur] need a (re-)exchange
+    // block-linear copy of trail[cur] for the texture-gather sampler of the agent kernel
+    cudaArray_t trail_arr = nullptr;
+    cudaTextureObject_t trail_tex = 0;
+    cudaSurfaceObject_t trail_surf = 0;
+    bool use_tex = false;             // SM_SAMPLER=tex (default) and the gather probe passed
+    bool arr_stale = true;            // the array does not mirror trail[cur] (upload / clear / diffuse-only ...)
     float* gauss_dec = nullptr;       // extension scratch
     float* gauss_hb = nullptr;
     float* trail_ptr(int i) const { return trail_base[i] + (size_t)(ghost + pad_rows) * W; }        // owned row 0
@@ -98,6 +104,9 @@ struct sm_engine {
     int alloc_agents(uint64_t capacity);
     void free_agents();
     int setup_tiles();
+    int setup_tex();
+    void free_tex();
+    int refresh_tex(int64_t local_row_begin, int64_t n_rows);   // linear trail[cur] rows -> array
 
     int sort_agents();
     int launch_agents();

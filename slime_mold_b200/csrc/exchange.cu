@@ -315,6 +315,10 @@ int sm_engine::exchange_trail_ghosts()
     SM_NCCL(ncclGroupEnd());
     SM_TRY(toc());
     ghost_stale = false;
+    if (!arr_stale) {
+        SM_TRY(refresh_tex(-(int64_t)g, g));
+        SM_TRY(refresh_tex((int64_t)rows, g));
+    }
     return SM_OK;
 }
 
@@ -346,6 +350,10 @@ int sm_engine::migrate_agents()
     SM_NCCL(ncclRecv(mig[0].recv, mig_bytes, ncclUint8, up, c, stream));                     // what `up` sent down
     SM_NCCL(ncclGroupEnd());
     ghost_stale = false;
+    if (!arr_stale) {                                   // the TEX sampler's copy needs the new ghost rows too
+        SM_TRY(refresh_tex(-(int64_t)g, g));
+        SM_TRY(refresh_tex((int64_t)rows, g));
+    }
     smk::k_append_arrivals<<<blocks_for(2 * mig_cap, 256), 256, 0, stream>>>(mig[1].recv, mig[0].recv, (uint32_t)mig_cap,
                                                                             agents[acur], ids[acur], dev_counters, cap_local);
     smk::k_bump_counters<<<1, 1, 0, stream>>>(dev_counters, mig[1].recv, mig[0].recv,

@@ -25,6 +25,30 @@ struct LdgF32 {
     __device__ __forceinline__ float operator()(const float* p) const { return __ldg(p); }
 };
 
+// 2x2 footprint by ONE texture gather from the block-linear copy of the trail (cudaArray with
+// cudaArrayTextureGather; point sampling, unnormalised coordinates -> raw f32 texels, no filtering
+// arithmetic).  At (x0 + 1, y0 + 1) -- the common corner of the four texels -- the footprint is
+// {x0, x0+1} x {y0, y0+1}; components come back as (x0,y0+1), (x0+1,y0+1), (x0+1,y0), (x0,y0)
+// (verified at sm_create by k_gather_probe: the engine refuses the TEX path otherwise).
+struct FetchTex {
+    cudaTextureObject_t tex;
+    int32_t row_off;         // array row of global row 0:  ghost + pad - row_base
+    __device__ __forceinline__ void operator()(int32_t x0, int32_t y0, float& v00, float& v10, float& v01, float& v11) const
+    {
+        float4 g = tex2Dgather<float4>(tex, (float)(x0 + 1), (float)(y0 + row_off + 1), 0);
+        v01 = g.x; v11 = g.y; v10 = g.z; v00 = g.w;
+    }
+};
+
+// out[0..3] = gather at the corner of texels (1,1),(2,1),(1,2),(2,2) of a probe array holding T[y][x] = 10*y + x
+static __global__ void k_gather_probe(cudaTextureObject_t tex, float* out)
+{
+    FetchTex f{tex, 0};
+    float v00, v10, v01, v11;
+    f(1, 1, v00, v10, v01, v11);
+    out[0] = v00; out[1] = v10; out[2] = v01; out[3] = v11;
+}
+
 // ---------------------------------------------------------------------------
 // agents
 // ---------------------------------------------------------------------------
@@ -79,10 +103,10 @@ struct LeaverBufs {
 
 // One agent per thread.  `trail` and `counts` point at owned row 0 of this rank's
 // strip (global row c.row_base); ghost rows sit at negative / >= rows offsets.
-template <bool MULTI, class IdxT>
+template <bool MULTI, class IdxT, class FETCH>
 static __global__ void __launch_bounds__(256)
 k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
-         const float* __restrict__ trail, uint32_t* __restrict__ counts, const AgentConsts c,
+         const FETCH fetch, uint32_t* __restrict__ counts, const AgentConsts c,
          const LeaverBufs lv)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,7 +116,7 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     if (MULTI && id == kDeadAgent) return;
     float4 a = agents[i];
     int32_t cx, cy;
-    smd::agent_update<IdxT>(a.x, a.y, a.z, a.w, (int32_t)id, trail, c, LdgF32(), cx, cy);
+    smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, c, fetch, cx, cy);
     agents[i] = a;
     if (cx >= 0) {
         // deposit: integer count, order-free (phase_split form of compute.wgsl:140)
@@ -105,11 +129,15 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
         int64_t oy = !(a.y >= 0.0f) ? 0 : (a.y >= c.Hf ? (int64_t)c.H - 1 : (int64_t)(int32_t)a.y);
         int64_t lr = smd::local_row(oy, c);
         if (lr < 0 || lr >= (int64_t)c.rows_local) {
-            const int dir = lr < 0 ? 0 : 1;
-            unsigned long long slot = atomicAdd(lv.send_count[dir], 1ull);
+            // (no dynamic indexing of the parameter arrays: that would force a per-thread local copy)
+            const bool up = lr < 0;
+            unsigned long long* cnt = up ? lv.send_count[0] : lv.send_count[1];
+            float4* sa = up ? lv.send_a[0] : lv.send_a[1];
+            uint32_t* si = up ? lv.send_id[0] : lv.send_id[1];
+            unsigned long long slot = atomicAdd(cnt, 1ull);
             if (slot < lv.cap) {
-                lv.send_a[dir][slot] = a;
-                lv.send_id[dir][slot] = id;
+                sa[slot] = a;
+                si[slot] = id;
                 ids[i] = kDeadAgent;
             } else {
                 atomicExch(lv.overflow, 1ull);       // staging overflow: reported by the host
@@ -126,6 +154,8 @@ struct TrailGeom {
     uint32_t rows;       // owned rows
     uint32_t rows_per_chunk;
     int wrap_y;          // 1: rows wrap toroidally inside the buffer (single GPU); 0: ghost rows
+    cudaSurfaceObject_t surf;   // block-linear copy of the output for the TEX sampler (0 = none)
+    int surf_row0;              // array row of owned row 0
 };
 
 __device__ __forceinline__ int64_t row_index(int64_t y, const TrailGeom& g)
@@ -238,6 +268,8 @@ k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
                 o.w = smd::box9_mix(prev[3], prev[4], prev[5], cur[3], cur[4], cur[5], next[3], next[4], next[5], tc);
                 const size_t off = (size_t)(y + u) * W + x0;
                 *reinterpret_cast<float4*>(tout + off) = o;
+                // keep the block-linear copy the agent kernel gathers from in step (4 B/cell extra)
+                if (g.surf) surf2Dwrite(o, g.surf, (int)(x0 * 4u), y + u + g.surf_row0);
                 if (HAS_COUNTS) *reinterpret_cast<uint4*>(czero + off) = make_uint4(0u, 0u, 0u, 0u);
             }
 #pragma unroll
@@ -270,7 +302,9 @@ k_trail_generic(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
         }
     }
     const int64_t off = y * (int64_t)g.W + x;
-    tout[off] = smd::box9_mix(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], tc);
+    const float o = smd::box9_mix(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], tc);
+    tout[off] = o;
+    if (g.surf) surf2Dwrite(o, g.surf, (int)(x * 4), (int)y + g.surf_row0);
     if (HAS_COUNTS) czero[off] = 0u;
 }
 

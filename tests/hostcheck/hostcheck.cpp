@@ -66,7 +66,8 @@ void hc_agents_phase_split(float* agents, const uint32_t* ids, uint64_t n, const
     for (uint64_t i = 0; i < n; ++i) {
         int32_t cx, cy;
         int32_t idx = ids ? (int32_t)ids[i] : (int32_t)i;
-        smd::agent_update<int64_t>(agents[4 * i], agents[4 * i + 1], agents[4 * i + 2], agents[4 * i + 3], idx, trail, c, HostLd(), cx, cy);
+        smd::FetchLinear<int64_t, HostLd> fetch{trail, (int64_t)c.W, (int64_t)c.row_base, HostLd()};
+        smd::agent_update(agents[4 * i], agents[4 * i + 1], agents[4 * i + 2], agents[4 * i + 3], idx, c, fetch, cx, cy);
         if (cx >= 0) counts[(size_t)cy * p->width + cx] += 1u;
     }
 }
