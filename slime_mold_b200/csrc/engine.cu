@@ -141,8 +141,12 @@ int sm_engine::alloc_trail()
         SM_CUDA(cudaMemsetAsync(trail_base[i], 0, cells * sizeof(float), stream));
         SM_CUDA(cudaMalloc(&counts_base[i], cells * sizeof(uint32_t)));
         SM_CUDA(cudaMemsetAsync(counts_base[i], 0, cells * sizeof(uint32_t), stream));
+        SM_CUDA(cudaMalloc(&flags_base[i], cells));
+        SM_CUDA(cudaMemsetAsync(flags_base[i], 0, cells, stream));
     }
     cur = 0; ccur = 0;
+    trail_nonneg = true;
+    deposit_mode = 0;
     if (use_tex) SM_TRY(setup_tex());
     return SM_OK;
 }
@@ -152,7 +156,8 @@ void sm_engine::free_trail()
     for (int i = 0; i < 2; ++i) {
         if (trail_base[i]) cudaFree(trail_base[i]);
         if (counts_base[i]) cudaFree(counts_base[i]);
-        trail_base[i] = nullptr; counts_base[i] = nullptr;
+        if (flags_base[i]) cudaFree(flags_base[i]);
+        trail_base[i] = nullptr; counts_base[i] = nullptr; flags_base[i] = nullptr;
     }
     if (gauss_dec) cudaFree(gauss_dec);
     if (gauss_hb) cudaFree(gauss_hb);
@@ -269,6 +274,30 @@ int sm_engine::setup_tiles()
 }
 
 // ---------------------------------------------------------------------------
+// deposit representation
+// ---------------------------------------------------------------------------
+bool sm_engine::flag_mode() const
+{
+    if (no_flags || (cfg.flags & SM_FLAG_GAUSSIAN_BLUR)) return false;
+    return trail_nonneg && params.pheromone_deposition_amount >= 1.0f;
+}
+
+// Both representations are all-zero while idle.  The buffer the last agents pass wrote is only
+// zeroed by the NEXT trail pass of the same mode, so a mode change has to retire it explicitly.
+int sm_engine::switch_deposit_mode(int mode)
+{
+    if (deposit_mode != 0 && deposit_mode != mode) {
+        const size_t cells = field_cells();
+        for (int i = 0; i < 2; ++i) {
+            if (deposit_mode == 1) SM_CUDA(cudaMemsetAsync(counts_base[i], 0, cells * sizeof(uint32_t), stream));
+            else SM_CUDA(cudaMemsetAsync(flags_base[i], 0, cells, stream));
+        }
+    }
+    deposit_mode = mode;
+    return SM_OK;
+}
+
+// ---------------------------------------------------------------------------
 // kernels: launch helpers
 // ---------------------------------------------------------------------------
 int sm_engine::sort_agents()
@@ -302,12 +331,15 @@ int sm_engine::launch_agents()
     SM_TRY(tic(0));
     smk::LeaverBufs lv{};
     const bool idx32 = (uint64_t)field_cells() < (1ull << 31);
+    const bool flags = flag_mode();
+    SM_TRY(switch_deposit_mode(flags ? 2 : 1));
     const unsigned nb = blocks_for(n_local, 256);
     float4* a = agents[acur];
     uint32_t* id = ids[acur];
-    uint32_t* cn = counts_ptr(ccur);
+    void* dep = flags ? (void*)flags_ptr(ccur) : (void*)counts_ptr(ccur);
     const smd::AgentConsts ac = agent_consts();
-    if (world > 1) {
+    const bool multi = world > 1;
+    if (multi) {
         for (int d = 0; d < 2; ++d) {
             lv.send_count[d] = reinterpret_cast<unsigned long long*>(mig[d].send);
             lv.send_a[d] = reinterpret_cast<float4*>(mig[d].send + 16);
@@ -317,27 +349,29 @@ int sm_engine::launch_agents()
         lv.n_ptr = dev_counters;
         lv.cap = (uint32_t)mig_cap;
     }
+    auto launch = [&](auto fetch, auto idx_tag) {
+        using F = decltype(fetch);
+        using I = decltype(idx_tag);
+        if (multi) {
+            if (flags) smk::k_agents<true, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+            else smk::k_agents<true, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+        } else {
+            if (flags) smk::k_agents<false, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+            else smk::k_agents<false, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+        }
+    };
     if (use_tex) {
         if (arr_stale) {                                  // the array lost track of trail[cur]: one full copy
             SM_TRY(refresh_tex(-(int64_t)(ghost + pad_rows), (int64_t)rows + 2 * (int64_t)(ghost + pad_rows)));
             arr_stale = false;
         }
         const smk::FetchTex f{trail_tex, (int32_t)(ghost + pad_rows) - (int32_t)row0};
-        if (world > 1) {
-            if (idx32) smk::k_agents<true, int32_t, smk::FetchTex><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
-            else smk::k_agents<true, int64_t, smk::FetchTex><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
-        } else {
-            if (idx32) smk::k_agents<false, int32_t, smk::FetchTex><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
-            else smk::k_agents<false, int64_t, smk::FetchTex><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
-        }
+        if (idx32) launch(f, int32_t{});
+        else launch(f, int64_t{});
     } else if (idx32) {
-        const smd::FetchLinear<int32_t, smk::LdgF32> f{trail_ptr(cur), (int32_t)W, (int32_t)row0, smk::LdgF32()};
-        if (world > 1) smk::k_agents<true, int32_t, decltype(f)><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
-        else smk::k_agents<false, int32_t, decltype(f)><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
+        launch(smd::FetchLinear<int32_t, smk::LdgF32>{trail_ptr(cur), (int32_t)W, (int32_t)row0, smk::LdgF32()}, int32_t{});
     } else {
-        const smd::FetchLinear<int64_t, smk::LdgF32> f{trail_ptr(cur), (int64_t)W, (int64_t)row0, smk::LdgF32()};
-        if (world > 1) smk::k_agents<true, int64_t, decltype(f)><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
-        else smk::k_agents<false, int64_t, decltype(f)><<<nb, 256, 0, stream>>>(a, id, n_local, f, cn, ac, lv);
+        launch(smd::FetchLinear<int64_t, smk::LdgF32>{trail_ptr(cur), (int64_t)W, (int64_t)row0, smk::LdgF32()}, int64_t{});
     }
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
@@ -357,8 +391,10 @@ int sm_engine::launch_trail(bool has_counts)
     if (!write_surf) arr_stale = true;
     const float* tin = trail_ptr(cur);
     float* tout = trail_ptr(1 - cur);
-    const uint32_t* cin = counts_ptr(ccur);
-    uint32_t* czero = counts_ptr(1 - ccur);
+    // deposit representation the agents pass of this step used (none for diffusion-only)
+    const int cm = !has_counts ? smk::CM_NONE : (deposit_mode == 2 ? smk::CM_FLAGS : smk::CM_COUNTS);
+    const void* cin = cm == smk::CM_FLAGS ? (const void*)flags_ptr(ccur) : (const void*)counts_ptr(ccur);
+    void* czero = cm == smk::CM_FLAGS ? (void*)flags_ptr(1 - ccur) : (void*)counts_ptr(1 - ccur);
     SM_TRY(tic(1));
     if (cfg.flags & SM_FLAG_GAUSSIAN_BLUR) {
         SM_TRY(launch_gauss(has_counts, g, tc));
@@ -372,16 +408,18 @@ int sm_engine::launch_trail(bool has_counts)
         if (rpc_override > 0) rpc = rpc_override;
         g.rows_per_chunk = (uint32_t)rpc;
         dim3 grid(bx, (unsigned)((rows + rpc - 1) / rpc));
-        if (has_counts) smk::k_trail_rows<true, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
-        else smk::k_trail_rows<false, 4><<<grid, bs, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc);
+        if (cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
+        else if (cm == smk::CM_FLAGS) smk::k_trail_rows<smk::CM_FLAGS, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
+        else smk::k_trail_rows<smk::CM_NONE, 4><<<grid, bs, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc);
         timing.kernel_launches += 1;
     } else {
         g.rows_per_chunk = 1;
         for (uint32_t y0 = 0; y0 < rows; y0 += 32768) {
             uint32_t ny = std::min<uint32_t>(32768, rows - y0);
             dim3 grid(blocks_for(W, 256), ny);
-            if (has_counts) smk::k_trail_generic<true><<<grid, 256, 0, stream>>>(tin, cin, czero, tout, g, tc, (int64_t)y0);
-            else smk::k_trail_generic<false><<<grid, 256, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc, (int64_t)y0);
+            if (cm == smk::CM_COUNTS) smk::k_trail_generic<smk::CM_COUNTS><<<grid, 256, 0, stream>>>(tin, cin, czero, tout, g, tc, (int64_t)y0);
+            else if (cm == smk::CM_FLAGS) smk::k_trail_generic<smk::CM_FLAGS><<<grid, 256, 0, stream>>>(tin, cin, czero, tout, g, tc, (int64_t)y0);
+            else smk::k_trail_generic<smk::CM_NONE><<<grid, 256, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc, (int64_t)y0);
             timing.kernel_launches += 1;
         }
     }
@@ -389,6 +427,7 @@ int sm_engine::launch_trail(bool has_counts)
     SM_TRY(toc());
     cur = 1 - cur;
     if (has_counts) ccur = 1 - ccur;
+    trail_nonneg = true;          // decay clamps at 0 (NaN included), the mix of non-negatives is non-negative
     return SM_OK;
 }
 
@@ -520,6 +559,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         e->use_tex = want_tex && probe;
     }
     e->force_generic = env_int("SM_FORCE_GENERIC_TRAIL", 0) != 0;
+    e->no_flags = env_int("SM_NO_DEPOSIT_FLAGS", 0) != 0;
     e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
 
     // defaults = Settings::default(), /root/reference/src/settings.rs:8-27
@@ -746,6 +786,7 @@ int sm_clear_trail(sm_engine* e)
     SM_CUDA(cudaMemsetAsync(e->trail_base[e->cur], 0, cells * sizeof(float), e->stream));
     e->ghost_stale = true;
     e->arr_stale = true;
+    e->trail_nonneg = true;
     return SM_OK;
 }
 
@@ -766,6 +807,15 @@ int sm_upload_trail(sm_engine* e, const float* src, uint32_t x0, uint32_t y0, ui
     uint32_t ya = 0, yb = 0;
     SM_TRY(clip_rows(e, x0, y0, w, h, pitch, &ya, &yb));
     if (ya < yb && w) {
+        if (e->trail_nonneg) {
+            bool ok = true;
+            for (uint32_t y = ya; y < yb && ok; ++y) {
+                const float* rowp = src + (size_t)(y - y0) * pitch;
+                for (uint32_t x = 0; x < w; ++x)
+                    if (!(rowp[x] >= 0.0f)) { ok = false; break; }    // negative or NaN: counts mode until the next pass
+            }
+            e->trail_nonneg = ok;
+        }
         float* dst = e->trail_ptr(e->cur) + (size_t)(ya - e->row0) * e->W + x0;
         SM_CUDA(cudaMemcpy2DAsync(dst, (size_t)e->W * 4, src + (size_t)(ya - y0) * pitch, pitch * 4, (size_t)w * 4,
                                   yb - ya, cudaMemcpyHostToDevice, e->stream));

@@ -35,6 +35,14 @@ struct sm_engine {
     float* trail_base[2] = {nullptr, nullptr};
     uint32_t* counts_base[2] = {nullptr, nullptr};
     int cur = 0, ccur = 0;
+    // u8 deposit flags (same geometry, two alternating buffers): used instead of the counts whenever
+    // dep >= 1 and the field is known to be non-negative (then any deposit saturates the cell to 1.0)
+    uint8_t* flags_base[2] = {nullptr, nullptr};
+    bool trail_nonneg = true;         // every cell of trail[cur] is >= 0 and not NaN
+    int deposit_mode = 0;             // mode of the most recent agents pass: 1 counts, 2 flags
+    uint8_t* flags_ptr(int i) const { return flags_base[i] + (size_t)(ghost + pad_rows) * W; }
+    bool flag_mode() const;
+    int switch_deposit_mode(int mode);
     bool ghost_stale = true;          // ghost rows of trail[cur] need a (re-)exchange
     // block-linear copy of trail[cur] for the texture-gather sampler of the agent kernel
     cudaArray_t trail_arr = nullptr;
@@ -67,6 +75,7 @@ struct sm_engine {
 
     // tuning overrides (environment, read at sm_create)
     bool force_generic = false;
+    bool no_flags = false;            // SM_NO_DEPOSIT_FLAGS=1: always count deposits (A/B switch)
     int rpc_override = 0;
 
     // statistics scratch

@@ -112,6 +112,14 @@ k_counts_add(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint6
     if (i < n) dst[i] += src[i];
 }
 
+// dst[i] |= src[i] over a contiguous range of deposit flags
+static __global__ void __launch_bounds__(256)
+k_flags_or(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] |= src[i];
+}
+
 // Appends the agents of the two received messages behind the device-side cursor counters[0].
 static __global__ void __launch_bounds__(256)
 k_append_arrivals(const uint8_t* __restrict__ msg_from_down, const uint8_t* __restrict__ msg_from_up, uint32_t cap,
@@ -277,20 +285,35 @@ int sm_engine::exchange_counts()
     SM_TRY(tic(3));
     ncclComm_t c = (ncclComm_t)comm;
     const int up = (rank - 1 + world) % world, down = (rank + 1) % world;
-    uint32_t* cnt = counts_ptr(ccur);
-    const size_t msg = (size_t)(m + 1) * W;                       // u32 elements per direction
-    uint32_t* from_down = counts_xchg;                            // [down's top ghost m rows | down's own first row]
-    uint32_t* from_up = counts_xchg + counts_xchg_rows * W;       // [up's own last row | up's bottom ghost m rows]
-    SM_NCCL(ncclGroupStart());
-    SM_NCCL(ncclSend(cnt - (int64_t)m * W, msg, ncclUint32, up, c, stream));                 // rows [-m, 0]
-    SM_NCCL(ncclSend(cnt + (int64_t)(rows - 1) * W, msg, ncclUint32, down, c, stream));      // rows [rows-1, rows+m)
-    SM_NCCL(ncclRecv(from_down, msg, ncclUint32, down, c, stream));
-    SM_NCCL(ncclRecv(from_up, msg, ncclUint32, up, c, stream));
-    SM_NCCL(ncclGroupEnd());
-    // from_up lands on my rows [-1, m): its own last row completes my ghost row -1, its ghost rows my first m rows
-    smk::k_counts_add<<<blocks_for(msg, 256), 256, 0, stream>>>(cnt - (int64_t)W, from_up, msg);
-    // from_down lands on my rows [rows-m, rows]: its ghost rows my last m rows, its own first row my ghost row `rows`
-    smk::k_counts_add<<<blocks_for(msg, 256), 256, 0, stream>>>(cnt + (int64_t)(rows - m) * W, from_down, msg);
+    const size_t msg = (size_t)(m + 1) * W;                       // elements per direction
+    if (deposit_mode == 2) {
+        // u8 flags: same rows, one byte per cell, combined with OR
+        uint8_t* f = flags_ptr(ccur);
+        uint8_t* from_down = reinterpret_cast<uint8_t*>(counts_xchg);
+        uint8_t* from_up = from_down + counts_xchg_rows * W;
+        SM_NCCL(ncclGroupStart());
+        SM_NCCL(ncclSend(f - (int64_t)m * W, msg, ncclUint8, up, c, stream));                  // rows [-m, 0]
+        SM_NCCL(ncclSend(f + (int64_t)(rows - 1) * W, msg, ncclUint8, down, c, stream));       // rows [rows-1, rows+m)
+        SM_NCCL(ncclRecv(from_down, msg, ncclUint8, down, c, stream));
+        SM_NCCL(ncclRecv(from_up, msg, ncclUint8, up, c, stream));
+        SM_NCCL(ncclGroupEnd());
+        smk::k_flags_or<<<blocks_for(msg, 256), 256, 0, stream>>>(f - (int64_t)W, from_up, msg);
+        smk::k_flags_or<<<blocks_for(msg, 256), 256, 0, stream>>>(f + (int64_t)(rows - m) * W, from_down, msg);
+    } else {
+        uint32_t* cnt = counts_ptr(ccur);
+        uint32_t* from_down = counts_xchg;                            // [down's top ghost m rows | down's own first row]
+        uint32_t* from_up = counts_xchg + counts_xchg_rows * W;       // [up's own last row | up's bottom ghost m rows]
+        SM_NCCL(ncclGroupStart());
+        SM_NCCL(ncclSend(cnt - (int64_t)m * W, msg, ncclUint32, up, c, stream));                 // rows [-m, 0]
+        SM_NCCL(ncclSend(cnt + (int64_t)(rows - 1) * W, msg, ncclUint32, down, c, stream));      // rows [rows-1, rows+m)
+        SM_NCCL(ncclRecv(from_down, msg, ncclUint32, down, c, stream));
+        SM_NCCL(ncclRecv(from_up, msg, ncclUint32, up, c, stream));
+        SM_NCCL(ncclGroupEnd());
+        // from_up lands on my rows [-1, m): its own last row completes my ghost row -1, its ghost rows my first m rows
+        smk::k_counts_add<<<blocks_for(msg, 256), 256, 0, stream>>>(cnt - (int64_t)W, from_up, msg);
+        // from_down lands on my rows [rows-m, rows]: its ghost rows my last m rows, its own first row my ghost row `rows`
+        smk::k_counts_add<<<blocks_for(msg, 256), 256, 0, stream>>>(cnt + (int64_t)(rows - m) * W, from_down, msg);
+    }
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 2;
     SM_TRY(toc());
@@ -330,9 +353,15 @@ int sm_engine::migrate_agents()
     uint32_t g = 0, m = 0;
     SM_TRY(halo_depths(this, &g, &m));
     // counts buffer the agent kernel of THIS step wrote is 1 - ccur now (launch_trail flipped it)
-    uint32_t* used = counts_ptr(1 - ccur);
-    SM_CUDA(cudaMemsetAsync(used - (int64_t)m * W, 0, (size_t)m * W * sizeof(uint32_t), stream));
-    SM_CUDA(cudaMemsetAsync(used + (int64_t)rows * W, 0, (size_t)m * W * sizeof(uint32_t), stream));
+    if (deposit_mode == 2) {
+        uint8_t* used = flags_ptr(1 - ccur);
+        SM_CUDA(cudaMemsetAsync(used - (int64_t)m * W, 0, (size_t)m * W, stream));
+        SM_CUDA(cudaMemsetAsync(used + (int64_t)rows * W, 0, (size_t)m * W, stream));
+    } else {
+        uint32_t* used = counts_ptr(1 - ccur);
+        SM_CUDA(cudaMemsetAsync(used - (int64_t)m * W, 0, (size_t)m * W * sizeof(uint32_t), stream));
+        SM_CUDA(cudaMemsetAsync(used + (int64_t)rows * W, 0, (size_t)m * W * sizeof(uint32_t), stream));
+    }
 
     SM_TRY(tic(3));
     ncclComm_t c = (ncclComm_t)comm;

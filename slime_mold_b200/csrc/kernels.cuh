@@ -103,10 +103,13 @@ struct LeaverBufs {
 
 // One agent per thread.  `trail` and `counts` point at owned row 0 of this rank's
 // strip (global row c.row_base); ghost rows sit at negative / >= rows offsets.
-template <bool MULTI, class IdxT, class FETCH>
+// FLAGS: deposits are u8 "somebody deposited here" marks written with plain stores instead of u32
+// counts bumped with RED atomics -- exact whenever dep >= 1 and the field is non-negative, because
+// clamp(t + k*dep, 0, 1) == 1 for every k >= 1 (all shipped presets: dep = 1.0).
+template <bool MULTI, class IdxT, class FETCH, bool FLAGS>
 static __global__ void __launch_bounds__(256)
 k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
-         const FETCH fetch, uint32_t* __restrict__ counts, const AgentConsts c,
+         const FETCH fetch, void* __restrict__ deposits, const AgentConsts c,
          const LeaverBufs lv)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,8 +124,11 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     if (cx >= 0) {
         // deposit: integer count, order-free (phase_split form of compute.wgsl:140)
         const int64_t lrd = smd::local_row(cy, c);
-        if (!MULTI || (lrd >= -(int64_t)c.ghost && lrd < (int64_t)c.rows_local + c.ghost))
-            atomicAdd(counts + ((IdxT)lrd * (IdxT)c.W + (IdxT)cx), 1u);
+        if (!MULTI || (lrd >= -(int64_t)c.ghost && lrd < (int64_t)c.rows_local + c.ghost)) {
+            const IdxT off = (IdxT)lrd * (IdxT)c.W + (IdxT)cx;
+            if (FLAGS) static_cast<uint8_t*>(deposits)[off] = 1;
+            else atomicAdd(static_cast<uint32_t*>(deposits) + off, 1u);
+        }
     }
     if (MULTI) {
         // owner row of the new position (x == W / y == H rounding corner and NaN clamp like the host)
@@ -167,13 +173,23 @@ __device__ __forceinline__ int64_t row_index(int64_t y, const TrailGeom& g)
     return y;
 }
 
-template <bool HAS_COUNTS>
+// Deposit representation seen by the trail pass: none (diffusion only), u32 counts, u8 flags.
+enum { CM_NONE = 0, CM_COUNTS = 1, CM_FLAGS = 2 };
+
 struct RawRow {
     float4 t;
-    uint4 k;
+    uint4 k;       // CM_COUNTS: four counts; CM_FLAGS: .x holds the four flag bytes
     float te;      // edge cell (left for lane 0, right for the last lane of a row segment)
     uint32_t ke;
 };
+
+template <int CM>
+__device__ __forceinline__ float trail_cell(float t, uint32_t k, const TrailConsts& tc)
+{
+    if (CM == CM_COUNTS) t = smd::merge_deposit(t, k, tc.dep);
+    if (CM == CM_FLAGS) t = k ? 1.0f : t;          // clamp(t + k*dep, 0, 1) with dep >= 1, t >= 0
+    return smd::decay_cell(t, tc.decay_sub);
+}
 
 // Each thread owns 4 consecutive columns and walks down `rows_per_chunk` rows with a
 // 3-row register window of decayed values; the horizontal neighbours come from the
@@ -182,10 +198,10 @@ struct RawRow {
 //
 // Requirements (checked by the host): W % 4 == 0 and (W / 4) % 32 != 1, so that a lane is never
 // both the left edge (lane 0) and the right edge (last column group) of its warp.
-template <bool HAS_COUNTS, int UNROLL>
+template <int CM, int UNROLL>
 static __global__ void __launch_bounds__(128)
-k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
-             uint32_t* __restrict__ czero, float* __restrict__ tout,
+k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
+             void* __restrict__ czero_v, float* __restrict__ tout,
              const TrailGeom g, const TrailConsts tc)
 {
     const uint32_t grp = blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,10 +223,10 @@ k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
 
     const float* tp = tin + x0;
     const float* te = tin + xe;
-    const uint32_t* cp = HAS_COUNTS ? cin + x0 : nullptr;
-    const uint32_t* ce = HAS_COUNTS ? cin + xe : nullptr;
+    const uint32_t* cin = static_cast<const uint32_t*>(cin_v);
+    const uint8_t* fin = static_cast<const uint8_t*>(cin_v);
 
-    auto issue = [&](int y, RawRow<HAS_COUNTS>& r) {
+    auto issue = [&](int y, RawRow& r) {
         const ptrdiff_t off = (ptrdiff_t)y * (ptrdiff_t)W;
         r.t = make_float4(0.f, 0.f, 0.f, 0.f);
         r.k = make_uint4(0u, 0u, 0u, 0u);
@@ -218,24 +234,29 @@ k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
         r.ke = 0u;
         if (active) {
             r.t = __ldg(reinterpret_cast<const float4*>(tp + off));
-            if (HAS_COUNTS) r.k = __ldg(reinterpret_cast<const uint4*>(cp + off));
+            if (CM == CM_COUNTS) r.k = __ldg(reinterpret_cast<const uint4*>(cin + off + x0));
+            if (CM == CM_FLAGS) r.k.x = __ldg(reinterpret_cast<const uint32_t*>(fin + off + x0));
         }
         if (edge) {
             r.te = __ldg(te + off);
-            if (HAS_COUNTS) r.ke = __ldg(ce + off);
+            if (CM == CM_COUNTS) r.ke = __ldg(cin + off + xe);
+            if (CM == CM_FLAGS) r.ke = __ldg(fin + off + xe);
         }
     };
-    auto cell = [&](float t, uint32_t k) {
-        if (HAS_COUNTS) t = smd::merge_deposit(t, k, tc.dep);
-        return smd::decay_cell(t, tc.decay_sub);
-    };
     // d[0] = column x0-1, d[1..4] = own columns, d[5] = column x0+4 (all decayed)
-    auto finish = [&](const RawRow<HAS_COUNTS>& r, float (&d)[6]) {
-        d[1] = cell(r.t.x, r.k.x);
-        d[2] = cell(r.t.y, r.k.y);
-        d[3] = cell(r.t.z, r.k.z);
-        d[4] = cell(r.t.w, r.k.w);
-        const float de = cell(r.te, r.ke);
+    auto finish = [&](const RawRow& r, float (&d)[6]) {
+        if (CM == CM_FLAGS) {
+            d[1] = trail_cell<CM>(r.t.x, r.k.x & 0xffu, tc);
+            d[2] = trail_cell<CM>(r.t.y, r.k.x & 0xff00u, tc);
+            d[3] = trail_cell<CM>(r.t.z, r.k.x & 0xff0000u, tc);
+            d[4] = trail_cell<CM>(r.t.w, r.k.x & 0xff000000u, tc);
+        } else {
+            d[1] = trail_cell<CM>(r.t.x, r.k.x, tc);
+            d[2] = trail_cell<CM>(r.t.y, r.k.y, tc);
+            d[3] = trail_cell<CM>(r.t.z, r.k.z, tc);
+            d[4] = trail_cell<CM>(r.t.w, r.k.w, tc);
+        }
+        const float de = trail_cell<CM>(r.te, r.ke, tc);
         const float from_left = __shfl_up_sync(0xffffffffu, d[4], 1);
         const float from_right = __shfl_down_sync(0xffffffffu, d[1], 1);
         d[0] = left_edge ? de : from_left;
@@ -244,14 +265,14 @@ k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
 
     float prev[6], cur[6], next[6];
     {
-        RawRow<HAS_COUNTS> r0, r1;
+        RawRow r0, r1;
         issue(y_top, r0);
         issue(y_begin, r1);
         finish(r0, prev);
         finish(r1, cur);
     }
     for (int y = y_begin; y < y_end; y += UNROLL) {
-        RawRow<HAS_COUNTS> raw[UNROLL];
+        RawRow raw[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int yy = y + u + 1;
@@ -270,7 +291,8 @@ k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
                 *reinterpret_cast<float4*>(tout + off) = o;
                 // keep the block-linear copy the agent kernel gathers from in step (4 B/cell extra)
                 if (g.surf) surf2Dwrite(o, g.surf, (int)(x0 * 4u), y + u + g.surf_row0);
-                if (HAS_COUNTS) *reinterpret_cast<uint4*>(czero + off) = make_uint4(0u, 0u, 0u, 0u);
+                if (CM == CM_COUNTS) *reinterpret_cast<uint4*>(static_cast<uint32_t*>(czero_v) + off) = make_uint4(0u, 0u, 0u, 0u);
+                if (CM == CM_FLAGS) *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(czero_v) + off) = 0u;
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) { prev[j] = cur[j]; cur[j] = next[j]; }
@@ -279,10 +301,10 @@ k_trail_rows(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
 }
 
 // Any W, H >= 1 (ragged sizes, W % 4 != 0): one cell per thread, nine direct loads.
-template <bool HAS_COUNTS>
+template <int CM>
 static __global__ void __launch_bounds__(256)
-k_trail_generic(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
-                uint32_t* __restrict__ czero, float* __restrict__ tout,
+k_trail_generic(const float* __restrict__ tin, const void* __restrict__ cin_v,
+                void* __restrict__ czero_v, float* __restrict__ tout,
                 const TrailGeom g, const TrailConsts tc, int64_t y_first)
 {
     const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,16 +318,18 @@ k_trail_generic(const float* __restrict__ tin, const uint32_t* __restrict__ cin,
         for (int dx = -1; dx <= 1; ++dx) {
             int64_t nx = (x + dx + g.W) % (int64_t)g.W;
             int64_t off = ry * (int64_t)g.W + nx;
-            float t = __ldg(tin + off);
-            if (HAS_COUNTS) t = smd::merge_deposit(t, __ldg(cin + off), tc.dep);
-            v[j++] = smd::decay_cell(t, tc.decay_sub);
+            uint32_t k = 0u;
+            if (CM == CM_COUNTS) k = __ldg(static_cast<const uint32_t*>(cin_v) + off);
+            if (CM == CM_FLAGS) k = __ldg(static_cast<const uint8_t*>(cin_v) + off);
+            v[j++] = trail_cell<CM>(__ldg(tin + off), k, tc);
         }
     }
     const int64_t off = y * (int64_t)g.W + x;
     const float o = smd::box9_mix(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], tc);
     tout[off] = o;
     if (g.surf) surf2Dwrite(o, g.surf, (int)(x * 4), (int)y + g.surf_row0);
-    if (HAS_COUNTS) czero[off] = 0u;
+    if (CM == CM_COUNTS) static_cast<uint32_t*>(czero_v)[off] = 0u;
+    if (CM == CM_FLAGS) static_cast<uint8_t*>(czero_v)[off] = 0;
 }
 
 // ---------------------------------------------------------------------------

@@ -257,3 +257,29 @@ def test_edge_agents(oracle, engine_lib, name):
         assert bits_equal(a, sim.agents), (step, mismatch_report(a, sim.agents, "agents"))
         assert bits_equal(be.read_trail(), sim.trail), step
     be.close()
+
+
+def test_deposit_mode_switching_and_negative_trail(oracle, engine_lib):
+    """The engine marks deposits with u8 flags when dep >= 1 and the field is non-negative, and counts
+    them otherwise; switching back and forth mid-run (dep 1.0 -> 0.3 -> 2.0 -> 0.05) and starting from a
+    field with negative / NaN cells must not change a bit."""
+    W, H, N = 192, 160, 50000
+    s = settings_for("Default")
+    ag = oracle.init_agents(N, W, H, s.agent_speed_min, s.agent_speed_max, 21)
+    trail = random_trail(W, H, seed=9, density=0.8)
+    trail[5:20, 7:90] = -0.25          # negative cells: clamp(t + dep, 0, 1) != 1 for dep = 1 only if t < 0 ...
+    trail[40, 40] = np.nan
+    trail[41, 41] = -3.0               # ... e.g. -3 + 1 -> clamp -> 0
+    be = sm.CudaBackend.new(W, H, s, agent_count=N)
+    be.write_agents(ag)
+    be.write_trail(trail)
+    sim = oracle.Sim(to_oracle_params(oracle, preset_uniform("Default", W, H)), ag, trail=trail)
+    for dep in (1.0, 1.0, 0.3, 0.3, 2.0, 1.0, 0.05, 1.0, 1.0):
+        ss = s.clone(pheromone_deposition_amount=dep)
+        be.update_settings(ss)
+        sim.p = to_oracle_params(oracle, sm.SimSizeUniform.new(W, H, ss.pheromone_decay_factor, ss))
+        sim.step(3); be.step(3)
+        a, t = be.read_agents(), be.read_trail()
+        assert bits_equal(a, sim.agents), (dep, mismatch_report(a, sim.agents, "agents"))
+        assert bits_equal(t, sim.trail), (dep, mismatch_report(t, sim.trail, "trail"))
+    be.close()
