@@ -12,7 +12,7 @@ import os
 from .settings import SimSizeUniform
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslime_b200.so")
+LIB_PATH = os.environ.get("SM_LIB_PATH") or os.path.join(_HERE, "libslime_b200.so")   # SM_LIB_PATH: A/B builds only
 
 SM_FLAG_GAUSSIAN_BLUR = 1 << 0
 SM_FLAG_NO_SORT = 1 << 1

@@ -148,11 +148,29 @@ int sm_engine::alloc_trail()
     trail_nonneg = true;
     deposit_mode = 0;
     if (use_tex) SM_TRY(setup_tex());
+    if (use_texlin) {
+        for (int i = 0; i < 2; ++i) {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypePitch2D;
+            rd.res.pitch2D.devPtr = trail_base[i];
+            rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+            rd.res.pitch2D.width = W;
+            rd.res.pitch2D.height = rows + 2 * (size_t)(ghost + pad_rows);
+            rd.res.pitch2D.pitchInBytes = (size_t)W * 4;
+            cudaTextureDesc td{};
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            SM_CUDA(cudaCreateTextureObject(&lin_tex[i], &rd, &td, nullptr));
+        }
+    }
     return SM_OK;
 }
 void sm_engine::free_trail()
 {
     free_tex();
+    for (int i = 0; i < 2; ++i) if (lin_tex[i]) { cudaDestroyTextureObject(lin_tex[i]); lin_tex[i] = 0; }
     for (int i = 0; i < 2; ++i) {
         if (trail_base[i]) cudaFree(trail_base[i]);
         if (counts_base[i]) cudaFree(counts_base[i]);
@@ -368,6 +386,10 @@ int sm_engine::launch_agents()
         const smk::FetchTex f{trail_tex, (int32_t)(ghost + pad_rows) - (int32_t)row0};
         if (idx32) launch(f, int32_t{});
         else launch(f, int64_t{});
+    } else if (use_texlin) {
+        const smk::FetchTexLinear f{lin_tex[cur], (int32_t)(ghost + pad_rows) - (int32_t)row0};
+        if (idx32) launch(f, int32_t{});
+        else launch(f, int64_t{});
     } else if (idx32) {
         launch(smd::FetchLinear<int32_t, smk::LdgF32>{trail_ptr(cur), (int32_t)W, (int32_t)row0, smk::LdgF32()}, int32_t{});
     } else {
@@ -408,9 +430,15 @@ int sm_engine::launch_trail(bool has_counts)
         if (rpc_override > 0) rpc = rpc_override;
         g.rows_per_chunk = (uint32_t)rpc;
         dim3 grid(bx, (unsigned)((rows + rpc - 1) / rpc));
-        if (cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
-        else if (cm == smk::CM_FLAGS) smk::k_trail_rows<smk::CM_FLAGS, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
-        else smk::k_trail_rows<smk::CM_NONE, 4><<<grid, bs, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc);
+        if (cm == smk::CM_NONE) {
+            smk::k_trail_rows<smk::CM_NONE, false, 4><<<grid, bs, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc);
+        } else if (g.surf) {
+            if (cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, true, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
+            else smk::k_trail_rows<smk::CM_FLAGS, true, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
+        } else {
+            if (cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, false, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
+            else smk::k_trail_rows<smk::CM_FLAGS, false, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
+        }
         timing.kernel_launches += 1;
     } else {
         g.rows_per_chunk = 1;
@@ -557,6 +585,9 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         bool probe = false;
         if (want_tex) { int prc = gather_probe_ok(&probe); if (prc != SM_OK) { delete e; return prc; } }
         e->use_tex = want_tex && probe;
+        // experiment: pitch-linear point-sampled textures (needs a 32-byte row pitch)
+        e->use_texlin = smp && std::string(smp) == "texlin" && (cfg->width % 8 == 0);
+        if (e->use_texlin) e->use_tex = false;
     }
     e->force_generic = env_int("SM_FORCE_GENERIC_TRAIL", 0) != 0;
     e->no_flags = env_int("SM_NO_DEPOSIT_FLAGS", 0) != 0;

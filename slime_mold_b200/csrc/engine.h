@@ -49,6 +49,8 @@ struct sm_engine {
     cudaTextureObject_t trail_tex = 0;
     cudaSurfaceObject_t trail_surf = 0;
     bool use_tex = false;             // SM_SAMPLER=tex (default) and the gather probe passed
+    bool use_texlin = false;          // SM_SAMPLER=texlin: point-sampled pitch-linear textures over trail[0/1]
+    cudaTextureObject_t lin_tex[2] = {0, 0};
     bool arr_stale = true;            // the array does not mirror trail[cur] (upload / clear / diffuse-only ...)
     float* gauss_dec = nullptr;       // extension scratch
     float* gauss_hb = nullptr;

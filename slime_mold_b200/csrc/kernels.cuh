@@ -40,6 +40,21 @@ struct FetchTex {
     }
 };
 
+// 2x2 footprint by four point-sampled texture fetches from a pitch-linear texture bound directly to
+// the row-major field (no block-linear copy to maintain).  Texel (i, j) is fetched at (i + 0.5, j + 0.5).
+struct FetchTexLinear {
+    cudaTextureObject_t tex;
+    int32_t row_off;         // buffer row of global row 0:  ghost + pad - row_base
+    __device__ __forceinline__ void operator()(int32_t x0, int32_t y0, float& v00, float& v10, float& v01, float& v11) const
+    {
+        const float fx = (float)x0 + 0.5f, fy = (float)(y0 + row_off) + 0.5f;
+        v00 = tex2D<float>(tex, fx, fy);
+        v10 = tex2D<float>(tex, fx + 1.0f, fy);
+        v01 = tex2D<float>(tex, fx, fy + 1.0f);
+        v11 = tex2D<float>(tex, fx + 1.0f, fy + 1.0f);
+    }
+};
+
 // out[0..3] = gather at the corner of texels (1,1),(2,1),(1,2),(2,2) of a probe array holding T[y][x] = 10*y + x
 static __global__ void k_gather_probe(cudaTextureObject_t tex, float* out)
 {
@@ -198,7 +213,7 @@ __device__ __forceinline__ float trail_cell(float t, uint32_t k, const TrailCons
 //
 // Requirements (checked by the host): W % 4 == 0 and (W / 4) % 32 != 1, so that a lane is never
 // both the left edge (lane 0) and the right edge (last column group) of its warp.
-template <int CM, int UNROLL>
+template <int CM, bool SURF, int UNROLL>
 static __global__ void __launch_bounds__(128)
 k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
              void* __restrict__ czero_v, float* __restrict__ tout,
@@ -229,9 +244,11 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
     auto issue = [&](int y, RawRow& r) {
         const ptrdiff_t off = (ptrdiff_t)y * (ptrdiff_t)W;
         r.t = make_float4(0.f, 0.f, 0.f, 0.f);
-        r.k = make_uint4(0u, 0u, 0u, 0u);
         r.te = 0.f;
-        r.ke = 0u;
+        if (CM != CM_NONE) {
+            r.k = make_uint4(0u, 0u, 0u, 0u);
+            r.ke = 0u;
+        }
         if (active) {
             r.t = __ldg(reinterpret_cast<const float4*>(tp + off));
             if (CM == CM_COUNTS) r.k = __ldg(reinterpret_cast<const uint4*>(cin + off + x0));
@@ -290,7 +307,7 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
                 const size_t off = (size_t)(y + u) * W + x0;
                 *reinterpret_cast<float4*>(tout + off) = o;
                 // keep the block-linear copy the agent kernel gathers from in step (4 B/cell extra)
-                if (g.surf) surf2Dwrite(o, g.surf, (int)(x0 * 4u), y + u + g.surf_row0);
+                if (SURF) surf2Dwrite(o, g.surf, (int)(x0 * 4u), y + u + g.surf_row0);
                 if (CM == CM_COUNTS) *reinterpret_cast<uint4*>(static_cast<uint32_t*>(czero_v) + off) = make_uint4(0u, 0u, 0u, 0u);
                 if (CM == CM_FLAGS) *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(czero_v) + off) = 0u;
             }
