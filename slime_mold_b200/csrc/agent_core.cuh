@@ -23,19 +23,19 @@ struct AgentConsts {
     int64_t row_base;
     int32_t rows_local;        // rows this rank owns (== H on a single GPU)
     int32_t ghost;             // ghost rows kept above and below the strip (0 on a single GPU)
+    int32_t fold_hi, fold_lo;  // seam folding thresholds of local_row()
 };
 
 // Local row (relative to the strip's first owned row) of global row `gy`, folded across the
 // toroidal seam so that rows just above strip 0 / just below the last strip land in the ghosts.
-SM_HD int64_t local_row(int64_t gy, const AgentConsts& c)
+// Fold to the representative nearest to the strip: with two strips the ghosts can cover the whole
+// other strip, so the ghost depth itself cannot be the folding threshold.  fold_hi / fold_lo are
+// rows_local + ceil(spare / 2) and -floor(spare / 2) with spare = H - rows_local (host-computed).
+SM_HD int32_t local_row(int32_t gy, const AgentConsts& c)
 {
-    // fold to the representative nearest to the strip: rows just past the seam become small negative /
-    // just-above-`rows` numbers whatever the ghost depth is (with two strips the ghosts can cover the
-    // whole other strip, so the ghost depth itself cannot be the folding threshold)
-    const int64_t spare = (int64_t)c.H - c.rows_local;          // rows this rank does not own
-    int64_t lr = gy - c.row_base;
-    if (lr >= (int64_t)c.rows_local + (spare + 1) / 2) lr -= c.H;
-    else if (lr < -(spare / 2)) lr += c.H;
+    int32_t lr = gy - (int32_t)c.row_base;
+    if (lr >= c.fold_hi) lr -= (int32_t)c.H;
+    else if (lr < c.fold_lo) lr += (int32_t)c.H;
     return lr;
 }
 
@@ -44,8 +44,8 @@ constexpr float kTwoPi = 2.0f * 3.14159265359f;    // compute.wgsl:121
 constexpr float kRcpTwoPi = 0.15915494f;
 constexpr float kTimeStep = 0.016f;                // compute.wgsl:55
 
-// sample_trail_map, compute.wgsl:7-29.  FETCH(x0, y0, v00, v10, v01, v11) returns the 2x2 footprint
-// whose top-left cell is global (x0, y0): four scalar loads from the row-major field (host / LDG
+// sample_trail_map, compute.wgsl:7-29.  FETCH(fx, fy, v00, v10, v01, v11) returns the 2x2 footprint
+// whose top-left cell is global (fx, fy) (integral floats): four scalar loads from the row-major field (host / LDG
 // path) or one texture gather from the block-linear copy (device TEX path) -- raw f32 either way.
 template <class FETCH>
 SM_HD float sample_trail(const AgentConsts& c, float px, float py, FETCH fetch)
@@ -55,7 +55,7 @@ SM_HD float sample_trail(const AgentConsts& c, float px, float py, FETCH fetch)
     if (!(fx >= 0.0f && fx <= c.xmax && fy >= 0.0f && fy <= c.ymax)) return 0.0f;
     float dx = sub(px, fx), dy = sub(py, fy);
     float v00, v10, v01, v11;
-    fetch((int32_t)fx, (int32_t)fy, v00, v10, v01, v11);
+    fetch(fx, fy, v00, v10, v01, v11);        // fx, fy: integral, inside [0, W-2] x [0, H-2]
     float omdx = sub(1.0f, dx);
     float v0 = mixf_pre(v00, v10, dx, omdx);
     float v1 = mixf_pre(v01, v11, dx, omdx);
@@ -69,9 +69,10 @@ struct FetchLinear {
     const float* trail;      // owned row 0 of this rank's strip
     IdxT W, row_base;
     LD ld;
-    SM_HD void operator()(int32_t x0, int32_t y0, float& v00, float& v10, float& v01, float& v11) const
+    SM_HD void operator()(float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
     {
-        const float* r0 = trail + (((IdxT)y0 - row_base) * W + (IdxT)x0);
+        const IdxT x0 = (IdxT)(int32_t)fx, y0 = (IdxT)(int32_t)fy;
+        const float* r0 = trail + ((y0 - row_base) * W + x0);
         const float* r1 = r0 + W;
         v00 = ld(r0); v10 = ld(r0 + 1); v01 = ld(r1); v11 = ld(r1 + 1);
     }

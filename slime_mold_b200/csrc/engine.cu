@@ -71,6 +71,9 @@ smd::AgentConsts sm_engine::agent_consts() const
     c.row_base = (int64_t)row0;
     c.rows_local = (int32_t)rows;
     c.ghost = (int32_t)ghost;
+    const int32_t spare = (int32_t)H - (int32_t)rows;
+    c.fold_hi = (int32_t)rows + (spare + 1) / 2;
+    c.fold_lo = -(spare / 2);
     return c;
 }
 
@@ -383,11 +386,11 @@ int sm_engine::launch_agents()
             SM_TRY(refresh_tex(-(int64_t)(ghost + pad_rows), (int64_t)rows + 2 * (int64_t)(ghost + pad_rows)));
             arr_stale = false;
         }
-        const smk::FetchTex f{trail_tex, (int32_t)(ghost + pad_rows) - (int32_t)row0};
+        const smk::FetchTex f{trail_tex, (float)((int32_t)(ghost + pad_rows) - (int32_t)row0 + 1)};
         if (idx32) launch(f, int32_t{});
         else launch(f, int64_t{});
     } else if (use_texlin) {
-        const smk::FetchTexLinear f{lin_tex[cur], (int32_t)(ghost + pad_rows) - (int32_t)row0};
+        const smk::FetchTexLinear f{lin_tex[cur], (float)((int32_t)(ghost + pad_rows) - (int32_t)row0)};
         if (idx32) launch(f, int32_t{});
         else launch(f, int64_t{});
     } else if (idx32) {

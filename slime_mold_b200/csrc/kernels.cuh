@@ -32,10 +32,11 @@ struct LdgF32 {
 // (verified at sm_create by k_gather_probe: the engine refuses the TEX path otherwise).
 struct FetchTex {
     cudaTextureObject_t tex;
-    int32_t row_off;         // array row of global row 0:  ghost + pad - row_base
-    __device__ __forceinline__ void operator()(int32_t x0, int32_t y0, float& v00, float& v10, float& v01, float& v11) const
+    float row_off1;          // (array row of global row 0) + 1 = ghost + pad - row_base + 1, exact in f32
+    __device__ __forceinline__ void operator()(float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
     {
-        float4 g = tex2Dgather<float4>(tex, (float)(x0 + 1), (float)(y0 + row_off + 1), 0);
+        // coordinates stay in float: fx, fy are integral and < 2^17, so the sums are exact
+        float4 g = tex2Dgather<float4>(tex, fx + 1.0f, fy + row_off1, 0);
         v01 = g.x; v11 = g.y; v10 = g.z; v00 = g.w;
     }
 };
@@ -44,10 +45,10 @@ struct FetchTex {
 // the row-major field (no block-linear copy to maintain).  Texel (i, j) is fetched at (i + 0.5, j + 0.5).
 struct FetchTexLinear {
     cudaTextureObject_t tex;
-    int32_t row_off;         // buffer row of global row 0:  ghost + pad - row_base
-    __device__ __forceinline__ void operator()(int32_t x0, int32_t y0, float& v00, float& v10, float& v01, float& v11) const
+    float row_off;           // buffer row of global row 0:  ghost + pad - row_base
+    __device__ __forceinline__ void operator()(float x0, float y0, float& v00, float& v10, float& v01, float& v11) const
     {
-        const float fx = (float)x0 + 0.5f, fy = (float)(y0 + row_off) + 0.5f;
+        const float fx = x0 + 0.5f, fy = (y0 + row_off) + 0.5f;
         v00 = tex2D<float>(tex, fx, fy);
         v10 = tex2D<float>(tex, fx + 1.0f, fy);
         v01 = tex2D<float>(tex, fx, fy + 1.0f);
@@ -58,9 +59,9 @@ struct FetchTexLinear {
 // out[0..3] = gather at the corner of texels (1,1),(2,1),(1,2),(2,2) of a probe array holding T[y][x] = 10*y + x
 static __global__ void k_gather_probe(cudaTextureObject_t tex, float* out)
 {
-    FetchTex f{tex, 0};
+    FetchTex f{tex, 1.0f};
     float v00, v10, v01, v11;
-    f(1, 1, v00, v10, v01, v11);
+    f(1.0f, 1.0f, v00, v10, v01, v11);
     out[0] = v00; out[1] = v10; out[2] = v01; out[3] = v11;
 }
 
@@ -137,9 +138,9 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, c, fetch, cx, cy);
     agents[i] = a;
     if (cx >= 0) {
-        // deposit: integer count, order-free (phase_split form of compute.wgsl:140)
-        const int64_t lrd = smd::local_row(cy, c);
-        if (!MULTI || (lrd >= -(int64_t)c.ghost && lrd < (int64_t)c.rows_local + c.ghost)) {
+        // deposit: order-free (phase_split form of compute.wgsl:140)
+        const int32_t lrd = MULTI ? smd::local_row(cy, c) : cy - (int32_t)c.row_base;
+        if (!MULTI || (lrd >= -c.ghost && lrd < c.rows_local + c.ghost)) {
             const IdxT off = (IdxT)lrd * (IdxT)c.W + (IdxT)cx;
             if (FLAGS) static_cast<uint8_t*>(deposits)[off] = 1;
             else atomicAdd(static_cast<uint32_t*>(deposits) + off, 1u);
@@ -147,9 +148,9 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     }
     if (MULTI) {
         // owner row of the new position (x == W / y == H rounding corner and NaN clamp like the host)
-        int64_t oy = !(a.y >= 0.0f) ? 0 : (a.y >= c.Hf ? (int64_t)c.H - 1 : (int64_t)(int32_t)a.y);
-        int64_t lr = smd::local_row(oy, c);
-        if (lr < 0 || lr >= (int64_t)c.rows_local) {
+        const int32_t oy = !(a.y >= 0.0f) ? 0 : (a.y >= c.Hf ? (int32_t)c.H - 1 : (int32_t)a.y);
+        const int32_t lr = smd::local_row(oy, c);
+        if (lr < 0 || lr >= c.rows_local) {
             // (no dynamic indexing of the parameter arrays: that would force a per-thread local copy)
             const bool up = lr < 0;
             unsigned long long* cnt = up ? lv.send_count[0] : lv.send_count[1];

@@ -33,6 +33,8 @@ static smd::AgentConsts make_consts(const hc_params* p)
     c.row_base = 0;
     c.rows_local = (int32_t)c.H;
     c.ghost = 0;
+    c.fold_hi = (int32_t)c.H;
+    c.fold_lo = 0;
     return c;
 }
 
