@@ -184,6 +184,7 @@ def workload_config(args, N):
                     f"BASELINE configs[1]: {args.agents} agents on a {args.width}x{args.height} trail map, preset {args.preset}",
         "agents": args.agents * N, "width": args.width, "height": args.height * N, "preset": args.preset,
         "parallelism": f"strips{N}" if N > 1 else "single",
+        "exchange": (os.environ.get("SM_EXCHANGE") or "p2p") if N > 1 else None,
         "spinup_steps": args.spinup, "seed": args.seed,
         "l2": "agent state (335 MB/GPU) exceeds L2; no flush between steps (state is streamed every step)",
     }

@@ -151,29 +151,11 @@ int sm_engine::alloc_trail()
     trail_nonneg = true;
     deposit_mode = 0;
     if (use_tex) SM_TRY(setup_tex());
-    if (use_texlin) {
-        for (int i = 0; i < 2; ++i) {
-            cudaResourceDesc rd{};
-            rd.resType = cudaResourceTypePitch2D;
-            rd.res.pitch2D.devPtr = trail_base[i];
-            rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
-            rd.res.pitch2D.width = W;
-            rd.res.pitch2D.height = rows + 2 * (size_t)(ghost + pad_rows);
-            rd.res.pitch2D.pitchInBytes = (size_t)W * 4;
-            cudaTextureDesc td{};
-            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModePoint;
-            td.readMode = cudaReadModeElementType;
-            td.normalizedCoords = 0;
-            SM_CUDA(cudaCreateTextureObject(&lin_tex[i], &rd, &td, nullptr));
-        }
-    }
     return SM_OK;
 }
 void sm_engine::free_trail()
 {
     free_tex();
-    for (int i = 0; i < 2; ++i) if (lin_tex[i]) { cudaDestroyTextureObject(lin_tex[i]); lin_tex[i] = 0; }
     for (int i = 0; i < 2; ++i) {
         if (trail_base[i]) cudaFree(trail_base[i]);
         if (counts_base[i]) cudaFree(counts_base[i]);
@@ -313,6 +295,9 @@ int sm_engine::switch_deposit_mode(int mode)
             if (deposit_mode == 1) SM_CUDA(cudaMemsetAsync(counts_base[i], 0, cells * sizeof(uint32_t), stream));
             else SM_CUDA(cudaMemsetAsync(flags_base[i], 0, cells, stream));
         }
+        // the neighbours write into these fields during their agent pass: nobody may start it before
+        // every rank has finished wiping (all ranks switch at the same step)
+        if (world > 1 && p2p) SM_TRY(p2p_barrier());
     }
     deposit_mode = mode;
     return SM_OK;
@@ -339,6 +324,7 @@ int sm_engine::sort_agents()
     identity_order = false;
     if (world > 1) {                      // the scatter dropped the dead (migrated-away) slots
         n_local = n_live;
+        SM_TRY(mark_tail_dead());
         SM_TRY(push_counters());
     }
     SM_TRY(toc());
@@ -360,25 +346,42 @@ int sm_engine::launch_agents()
     void* dep = flags ? (void*)flags_ptr(ccur) : (void*)counts_ptr(ccur);
     const smd::AgentConsts ac = agent_consts();
     const bool multi = world > 1;
-    if (multi) {
+    if (multi && p2p) {
+        // leavers and out-of-strip deposits go straight into the neighbours' HBM (CUDA IPC mappings)
+        for (int d = 0; d < 2; ++d) {
+            // I am the DOWN neighbour of `up` (d == 0) and the UP neighbour of `down` (d == 1)
+            uint8_t* arr = peer[d].window + (d == 0 ? window_arrival_off[1] : window_arrival_off[0]);
+            lv.send_count[d] = reinterpret_cast<unsigned long long*>(arr);
+            lv.send_a[d] = reinterpret_cast<float4*>(arr + 16);
+            lv.send_id[d] = reinterpret_cast<uint32_t*>(arr + 16 + mig_cap * sizeof(float4));
+            const size_t row0_off = (size_t)(ghost + pad_rows) * W;
+            lv.peer_dep[d] = flags ? (void*)(peer[d].flags8[ccur] + row0_off) : (void*)(peer[d].counts[ccur] + row0_off);
+        }
+        lv.rows_up = (int32_t)peer[0].rows;
+        lv.overflow = dev_counters + 2;
+        lv.left_count = dev_counters + 3;
+        lv.cap = (uint32_t)mig_cap;
+    } else if (multi) {
         for (int d = 0; d < 2; ++d) {
             lv.send_count[d] = reinterpret_cast<unsigned long long*>(mig[d].send);
             lv.send_a[d] = reinterpret_cast<float4*>(mig[d].send + 16);
             lv.send_id[d] = reinterpret_cast<uint32_t*>(mig[d].send + 16 + mig_cap * sizeof(float4));
         }
         lv.overflow = dev_counters + 2;
-        lv.n_ptr = dev_counters;
         lv.cap = (uint32_t)mig_cap;
     }
     auto launch = [&](auto fetch, auto idx_tag) {
         using F = decltype(fetch);
         using I = decltype(idx_tag);
-        if (multi) {
-            if (flags) smk::k_agents<true, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
-            else smk::k_agents<true, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+        if (multi && p2p) {
+            if (flags) smk::k_agents<smk::XM_P2P, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+            else smk::k_agents<smk::XM_P2P, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+        } else if (multi) {
+            if (flags) smk::k_agents<smk::XM_NCCL, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+            else smk::k_agents<smk::XM_NCCL, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
         } else {
-            if (flags) smk::k_agents<false, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
-            else smk::k_agents<false, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+            if (flags) smk::k_agents<smk::XM_SINGLE, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+            else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
         }
     };
     if (use_tex) {
@@ -387,10 +390,6 @@ int sm_engine::launch_agents()
             arr_stale = false;
         }
         const smk::FetchTex f{trail_tex, (float)((int32_t)(ghost + pad_rows) - (int32_t)row0 + 1)};
-        if (idx32) launch(f, int32_t{});
-        else launch(f, int64_t{});
-    } else if (use_texlin) {
-        const smk::FetchTexLinear f{lin_tex[cur], (float)((int32_t)(ghost + pad_rows) - (int32_t)row0)};
         if (idx32) launch(f, int32_t{});
         else launch(f, int64_t{});
     } else if (idx32) {
@@ -588,9 +587,6 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         bool probe = false;
         if (want_tex) { int prc = gather_probe_ok(&probe); if (prc != SM_OK) { delete e; return prc; } }
         e->use_tex = want_tex && probe;
-        // experiment: pitch-linear point-sampled textures (needs a 32-byte row pitch)
-        e->use_texlin = smp && std::string(smp) == "texlin" && (cfg->width % 8 == 0);
-        if (e->use_texlin) e->use_tex = false;
     }
     e->force_generic = env_int("SM_FORCE_GENERIC_TRAIL", 0) != 0;
     e->no_flags = env_int("SM_NO_DEPOSIT_FLAGS", 0) != 0;
@@ -729,7 +725,7 @@ int sm_upload_agents(sm_engine* e, const float* xyas, uint64_t first, uint64_t n
     SM_CUDA(cudaMemcpy(e->ids[e->acur], keep_ids.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
     e->n_local = m;
     e->n_live = m;
-    if (e->comm_ready) SM_TRY(e->push_counters());
+    if (e->comm_ready) { SM_TRY(e->mark_tail_dead()); SM_TRY(e->push_counters()); }
     e->agents_valid = true;
     e->identity_order = false;
     e->steps_since_sort = e->sort_interval;
@@ -850,6 +846,7 @@ int sm_upload_trail(sm_engine* e, const float* src, uint32_t x0, uint32_t y0, ui
             }
             e->trail_nonneg = ok;
         }
+        if (e->world > 1) e->trail_nonneg = false;   // the decision must be the same on every rank
         float* dst = e->trail_ptr(e->cur) + (size_t)(ya - e->row0) * e->W + x0;
         SM_CUDA(cudaMemcpy2DAsync(dst, (size_t)e->W * 4, src + (size_t)(ya - y0) * pitch, pitch * 4, (size_t)w * 4,
                                   yb - ya, cudaMemcpyHostToDevice, e->stream));
@@ -930,9 +927,9 @@ int sm_step(sm_engine* e, uint32_t n_steps)
             e->steps_since_sort = 0;
         }
         SM_TRY(e->launch_agents());                      // src/main.rs:1164-1181
-        if (e->world > 1) SM_TRY(e->exchange_counts());
+        if (e->world > 1) SM_TRY(e->p2p ? e->p2p_after_agents() : e->exchange_counts());
         SM_TRY(e->launch_trail(true));                   // src/main.rs:1184-1199 + 1220-1235
-        if (e->world > 1) SM_TRY(e->migrate_agents());   // trail ghosts + leavers, one NCCL group
+        if (e->world > 1) SM_TRY(e->p2p ? e->p2p_after_trail() : e->migrate_agents());
         e->steps_since_sort++;
         e->timing.steps++;
     }

@@ -49,8 +49,6 @@ struct sm_engine {
     cudaTextureObject_t trail_tex = 0;
     cudaSurfaceObject_t trail_surf = 0;
     bool use_tex = false;             // SM_SAMPLER=tex (default) and the gather probe passed
-    bool use_texlin = false;          // SM_SAMPLER=texlin: point-sampled pitch-linear textures over trail[0/1]
-    cudaTextureObject_t lin_tex[2] = {0, 0};
     bool arr_stale = true;            // the array does not mirror trail[cur] (upload / clear / diffuse-only ...)
     float* gauss_dec = nullptr;       // extension scratch
     float* gauss_hb = nullptr;
@@ -103,6 +101,25 @@ struct sm_engine {
     uint64_t n_upper = 0;             // host-side upper bound of slots in use between sorts
     uint32_t pad_rows = 0;            // physical padding rows beyond the ghosts (multi-GPU memory-safety slack)
 
+    // XM_P2P: CUDA IPC views of the two ring neighbours' buffers (peer[0] = up, peer[1] = down)
+    struct PeerView {
+        uint32_t* counts[2] = {nullptr, nullptr};   // their counts_base[0/1]
+        uint8_t* flags8[2] = {nullptr, nullptr};    // their flags_base[0/1]
+        float* trail[2] = {nullptr, nullptr};       // their trail_base[0/1]
+        uint8_t* window = nullptr;                  // their barrier flags + arrival buffers
+        uint32_t rows = 0;                          // rows they own
+    };
+    bool p2p = false;
+    PeerView peer[2];
+    std::vector<void*> ipc_opened;    // every pointer obtained from cudaIpcOpenMemHandle
+    uint8_t* window = nullptr;        // [64 B barrier flags][arrivals from up][arrivals from down]
+    size_t window_arrival_off[2] = {0, 0};          // offset of the arrival buffer filled by up / by down
+    uint32_t barrier_seq = 0;
+    int setup_p2p();
+    int p2p_barrier();
+    int p2p_after_agents();           // barrier 1 + pull of the neighbours' boundary deposit rows
+    int p2p_after_trail();            // push trail ghost rows, append arrivals, barrier 2
+
     smd::AgentConsts agent_consts() const;
     smd::TrailConsts trail_consts() const;
 
@@ -133,5 +150,6 @@ struct sm_engine {
     int migrate_agents();
     int refresh_counters();           // multi-GPU: sync and read the device counters into n_local / n_live
     int push_counters();              // multi-GPU: write n_local / n_live to the device counters
+    int mark_tail_dead();             // multi-GPU: ids[n_local .. bound) = kDeadAgent (slots the grid may cover before the next sort)
     void comm_destroy();
 };

@@ -155,6 +155,89 @@ static __global__ void k_bump_counters(unsigned long long* counters, const uint8
     *send_down = 0ull;
 }
 
+// ---- XM_P2P: flag barrier between ring neighbours --------------------------------------------
+// Window layout (one per rank, IPC-mapped by both neighbours):
+//   [0]  u32 seq written by my UP neighbour      [4]  u32 seq written by my DOWN neighbour
+//   [64 ...] arrival buffer filled by up, then arrival buffer filled by down
+// A barrier = "tell both neighbours I reached sequence number s, wait until both told me the same".
+// Everything this rank wrote into a neighbour's memory earlier in the stream is fenced before the flag.
+// The wait gives up after ~20 s and raises the sticky error flag instead of hanging the GPU.
+__device__ __forceinline__ void ring_barrier(volatile uint32_t* mine, volatile uint32_t* up_slot, volatile uint32_t* down_slot,
+                                             uint32_t seq, unsigned long long* err)
+{
+    __threadfence_system();
+    *up_slot = seq;        // I am the DOWN neighbour of `up`: its slot [4]
+    *down_slot = seq;      // I am the UP neighbour of `down`: its slot [0]
+    __threadfence_system();
+    const long long t0 = clock64();
+    while ((int32_t)(mine[0] - seq) < 0 || (int32_t)(mine[1] - seq) < 0) {
+        __nanosleep(200);
+        if (clock64() - t0 > 40000000000ll) { atomicExch(err, 3ull); break; }   // ~20 s: the neighbour is gone
+    }
+    __threadfence_system();
+}
+
+// Barrier 1 (all neighbours finished their agent pass: their deposits and leavers have landed here),
+// then pull the one deposit row of each neighbour that the 3x3 blur of my boundary rows needs.
+template <class T>
+static __global__ void __launch_bounds__(1024)
+k_barrier_pull(uint32_t* window, uint32_t* up_window, uint32_t* down_window, uint32_t seq, unsigned long long* err,
+               T* my_row_above, const T* up_last_row, T* my_row_below, const T* down_first_row, uint32_t W)
+{
+    if (threadIdx.x == 0)
+        ring_barrier(window, up_window + 1, down_window + 0, seq, err);
+    __syncthreads();
+    for (uint32_t x = threadIdx.x; x < W; x += blockDim.x) {
+        my_row_above[x] = up_last_row[x];
+        my_row_below[x] = down_first_row[x];
+    }
+}
+
+static __global__ void k_barrier_only(uint32_t* window, uint32_t* up_window, uint32_t* down_window, uint32_t seq,
+                                      unsigned long long* err)
+{
+    ring_barrier(window, up_window + 1, down_window + 0, seq, err);
+}
+
+// Push my new top / bottom g trail rows into the neighbours' ghost rows (float4 stores over NVLink).
+static __global__ void __launch_bounds__(256)
+k_push_rows(const float4* __restrict__ my_top, float4* __restrict__ up_bottom_ghost,
+            const float4* __restrict__ my_bottom, float4* __restrict__ down_top_ghost, uint64_t n4)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        up_bottom_ghost[i] = my_top[i];
+        down_top_ghost[i] = my_bottom[i];
+    }
+}
+static __global__ void __launch_bounds__(256)
+k_push_rows_scalar(const float* __restrict__ my_top, float* __restrict__ up_bottom_ghost,
+                   const float* __restrict__ my_bottom, float* __restrict__ down_top_ghost, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        up_bottom_ghost[i] = my_top[i];
+        down_top_ghost[i] = my_bottom[i];
+    }
+}
+
+// Barrier 2: bookkeeping of this step's migration (one thread), then the barrier that lets every
+// rank start its next agent pass (ghost rows pushed, arrival buffers drained and reset).
+static __global__ void k_bump_barrier(unsigned long long* counters, uint8_t* arr_from_down, uint8_t* arr_from_up, uint32_t cap,
+                                      uint64_t cap_local, uint32_t* window, uint32_t* up_window, uint32_t* down_window,
+                                      uint32_t seq)
+{
+    unsigned long long* c0p = reinterpret_cast<unsigned long long*>(arr_from_down);
+    unsigned long long* c1p = reinterpret_cast<unsigned long long*>(arr_from_up);
+    const unsigned long long c0 = min(*c0p, (unsigned long long)cap), c1 = min(*c1p, (unsigned long long)cap);
+    unsigned long long arrived = c0 + c1;
+    if (counters[0] + arrived > cap_local) arrived = cap_local - counters[0];
+    counters[0] += arrived;
+    counters[1] = counters[1] + arrived - counters[3];
+    counters[3] = 0ull;
+    *c0p = 0ull;
+    *c1p = 0ull;
+    ring_barrier(window, up_window + 1, down_window + 0, seq, counters + 2);
+}
+
 // Seeded start-up fill restricted to one strip: every rank walks all agent indices and keeps
 // the agents whose row it owns (same counter-based generator as k_init_agents).
 static __global__ void __launch_bounds__(256)
@@ -235,8 +318,10 @@ extern "C" int sm_comm_init(sm_engine* e, const uint8_t id[SM_COMM_ID_BYTES])
     SM_CUDA(cudaMalloc(&e->dev_counters, 8 * sizeof(unsigned long long)));
     SM_CUDA(cudaMemset(e->dev_counters, 0, 8 * sizeof(unsigned long long)));
     SM_CUDA(cudaMallocHost(&e->host_counters, 8 * sizeof(unsigned long long)));
+    SM_TRY(e->setup_p2p());
     e->comm_ready = true;
     e->ghost_stale = true;
+    SM_TRY(e->mark_tail_dead());
     SM_TRY(e->push_counters());          // agents may have been uploaded before the communicator existed
     return SM_OK;
 }
@@ -250,6 +335,10 @@ void sm_engine::comm_destroy()
         if (mig[d].recv) cudaFree(mig[d].recv);
         mig[d] = MigrateBuf{};
     }
+    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+    ipc_opened.clear();
+    if (window) { cudaFree(window); window = nullptr; }
+    p2p = false;
     if (dev_counters) { cudaFree(dev_counters); dev_counters = nullptr; }
     if (host_counters) { cudaFreeHost(host_counters); host_counters = nullptr; }
     comm_ready = false;
@@ -273,6 +362,7 @@ int sm_engine::init_agents_strip(uint64_t seed)
         return sm_fail(SM_ERR_OOM, "strip %d would own %llu agents, capacity %llu", rank, got, (unsigned long long)cap_local);
     n_local = n_live = got;
     identity_order = false;
+    SM_TRY(mark_tail_dead());
     SM_TRY(push_counters());
     return SM_OK;
 }
@@ -395,11 +485,25 @@ int sm_engine::migrate_agents()
     return SM_OK;
 }
 
+// Between two sorts the agent kernel's grid covers n_upper >= (slots in use) slots; the ones that are
+// not in use must read as dead.  Arrivals overwrite them from the front (k_append_arrivals).
+int sm_engine::mark_tail_dead()
+{
+    if (world == 1) return SM_OK;
+    const uint64_t steps = (uint64_t)std::max<uint32_t>(sort_interval, 1) + 1;
+    const uint64_t end = std::min<uint64_t>(cap_local, n_local + steps * 2 * std::max<uint64_t>(mig_cap, 65536));
+    if (end > n_local)
+        SM_CUDA(cudaMemsetAsync(ids[acur] + n_local, 0xFF, (end - n_local) * sizeof(uint32_t), stream));
+    return SM_OK;
+}
+
 int sm_engine::refresh_counters()
 {
     if (!dev_counters) { SM_CUDA(cudaStreamSynchronize(stream)); return SM_OK; }
     SM_CUDA(cudaMemcpyAsync(host_counters, dev_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     SM_CUDA(cudaStreamSynchronize(stream));
+    if (host_counters[2] == 3)
+        return sm_fail(SM_ERR_STATE, "rank %d: a ring neighbour did not reach the step barrier within 20 s", rank);
     if (host_counters[2])
         return sm_fail(SM_ERR_OOM, "rank %d: %s overflow (raise SM_MIGRATE_CAP or the agent capacity)", rank,
                        host_counters[2] == 1 ? "migration message" : "agent array");
@@ -418,5 +522,192 @@ int sm_engine::push_counters()
     host_counters[2] = 0;
     SM_CUDA(cudaMemcpyAsync(dev_counters, host_counters, 3 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
     SM_CUDA(cudaStreamSynchronize(stream));
+    return SM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// XM_P2P: direct peer writes over NVLink (CUDA IPC) instead of NCCL messages
+// ---------------------------------------------------------------------------
+namespace {
+struct IpcBundle { cudaIpcMemHandle_t h[7]; uint32_t rows; uint32_t pad[15]; };   // counts0/1, flags0/1, trail0/1, window
+}
+
+// Exchanges IPC handles of the deposit fields, trail fields and the window with both ring neighbours
+// (over the NCCL communicator that already exists) and maps them.  Any failure leaves the engine on
+// the NCCL path (p2p = false) -- both are device paths; SM_EXCHANGE=nccl forces it.
+int sm_engine::setup_p2p()
+{
+    p2p = false;
+    const char* mode = getenv("SM_EXCHANGE");
+    const bool want = !(mode && std::string(mode) == "nccl");
+    // the decision must be collective: every rank exchanges a bundle even if it will not use it
+    const size_t arr_bytes = (mig_bytes + 63) & ~(size_t)63;
+    window_arrival_off[0] = 64;
+    window_arrival_off[1] = 64 + arr_bytes;
+    const size_t wbytes = 64 + 2 * arr_bytes;
+    SM_CUDA(cudaMalloc(&window, wbytes));
+    SM_CUDA(cudaMemset(window, 0, wbytes));
+
+    IpcBundle mine{};
+    bool ok = want;
+    void* ptrs[7] = {counts_base[0], counts_base[1], flags_base[0], flags_base[1], trail_base[0], trail_base[1], window};
+    for (int i = 0; i < 7 && ok; ++i)
+        if (cudaIpcGetMemHandle(&mine.h[i], ptrs[i]) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    mine.rows = ok ? rows : 0u;        // rows == 0 announces "no P2P on this rank"
+
+    IpcBundle* dev = nullptr;          // [0] mine, [1] from up, [2] from down
+    SM_CUDA(cudaMalloc(&dev, 3 * sizeof(IpcBundle)));
+    SM_CUDA(cudaMemcpy(dev, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    ncclComm_t c = (ncclComm_t)comm;
+    const int up = (rank - 1 + world) % world, down = (rank + 1) % world;
+    SM_NCCL(ncclGroupStart());
+    SM_NCCL(ncclSend(dev, sizeof(IpcBundle), ncclUint8, up, c, stream));
+    SM_NCCL(ncclSend(dev, sizeof(IpcBundle), ncclUint8, down, c, stream));
+    SM_NCCL(ncclRecv(dev + 2, sizeof(IpcBundle), ncclUint8, down, c, stream));
+    SM_NCCL(ncclRecv(dev + 1, sizeof(IpcBundle), ncclUint8, up, c, stream));
+    SM_NCCL(ncclGroupEnd());
+    SM_CUDA(cudaStreamSynchronize(stream));
+    IpcBundle got[2];
+    SM_CUDA(cudaMemcpy(got, dev + 1, 2 * sizeof(IpcBundle), cudaMemcpyDeviceToHost));
+    cudaFree(dev);
+    if (!ok || got[0].rows == 0 || got[1].rows == 0) return SM_OK;      // somebody cannot: stay on NCCL
+
+    auto open_all = [&](const IpcBundle& b, PeerView& v) -> bool {
+        void* p[7];
+        for (int i = 0; i < 7; ++i) {
+            if (cudaIpcOpenMemHandle(&p[i], b.h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            ipc_opened.push_back(p[i]);
+        }
+        v.counts[0] = (uint32_t*)p[0]; v.counts[1] = (uint32_t*)p[1];
+        v.flags8[0] = (uint8_t*)p[2]; v.flags8[1] = (uint8_t*)p[3];
+        v.trail[0] = (float*)p[4]; v.trail[1] = (float*)p[5];
+        v.window = (uint8_t*)p[6];
+        v.rows = b.rows;
+        return true;
+    };
+    bool mapped = open_all(got[0], peer[0]);
+    if (mapped) {
+        if (up == down) peer[1] = peer[0];            // two strips: both neighbours are the same process
+        else mapped = open_all(got[1], peer[1]);
+    }
+    // agree on the outcome (a rank that failed to map must not leave the others spinning on flags)
+    unsigned int* flag = nullptr;
+    SM_CUDA(cudaMalloc(&flag, 3 * sizeof(unsigned int)));
+    unsigned int mineok = mapped ? 1u : 0u;
+    SM_CUDA(cudaMemcpy(flag, &mineok, sizeof mineok, cudaMemcpyHostToDevice));
+    SM_NCCL(ncclGroupStart());
+    SM_NCCL(ncclSend(flag, 1, ncclUint32, up, c, stream));
+    SM_NCCL(ncclSend(flag, 1, ncclUint32, down, c, stream));
+    SM_NCCL(ncclRecv(flag + 2, 1, ncclUint32, down, c, stream));
+    SM_NCCL(ncclRecv(flag + 1, 1, ncclUint32, up, c, stream));
+    SM_NCCL(ncclGroupEnd());
+    SM_CUDA(cudaStreamSynchronize(stream));
+    unsigned int oks[3];
+    SM_CUDA(cudaMemcpy(oks, flag, sizeof oks, cudaMemcpyDeviceToHost));
+    cudaFree(flag);
+    // neighbours-only agreement is enough: a rank uses P2P with its two neighbours, and each of them
+    // sees this rank's flag.  For the whole ring to take one path we need a global AND, reached here by
+    // world/2 + 1 relay rounds of the same neighbour exchange.
+    unsigned int all = oks[0] & oks[1] & oks[2];
+    for (int round = 0; round < world / 2 + 1; ++round) {
+        unsigned int* f2 = nullptr;
+        SM_CUDA(cudaMalloc(&f2, 3 * sizeof(unsigned int)));
+        SM_CUDA(cudaMemcpy(f2, &all, sizeof all, cudaMemcpyHostToDevice));
+        SM_NCCL(ncclGroupStart());
+        SM_NCCL(ncclSend(f2, 1, ncclUint32, up, c, stream));
+        SM_NCCL(ncclSend(f2, 1, ncclUint32, down, c, stream));
+        SM_NCCL(ncclRecv(f2 + 2, 1, ncclUint32, down, c, stream));
+        SM_NCCL(ncclRecv(f2 + 1, 1, ncclUint32, up, c, stream));
+        SM_NCCL(ncclGroupEnd());
+        SM_CUDA(cudaStreamSynchronize(stream));
+        unsigned int r[3];
+        SM_CUDA(cudaMemcpy(r, f2, sizeof r, cudaMemcpyDeviceToHost));
+        cudaFree(f2);
+        all = r[0] & r[1] & r[2];
+    }
+    p2p = all != 0;
+    barrier_seq = 0;
+    return SM_OK;
+}
+
+// A bare barrier: used when a rank-local memset must be ordered against the neighbours' next writes.
+int sm_engine::p2p_barrier()
+{
+    ++barrier_seq;
+    smk::k_barrier_only<<<1, 1, 0, stream>>>(reinterpret_cast<uint32_t*>(window), reinterpret_cast<uint32_t*>(peer[0].window),
+                                             reinterpret_cast<uint32_t*>(peer[1].window), barrier_seq, dev_counters + 2);
+    SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 1;
+    return SM_OK;
+}
+
+int sm_engine::p2p_after_agents()
+{
+    uint32_t g = 0, m = 0;
+    SM_TRY(halo_depths(this, &g, &m));
+    SM_TRY(tic(3));
+    ++barrier_seq;
+    uint32_t* w = reinterpret_cast<uint32_t*>(window);
+    uint32_t* wu = reinterpret_cast<uint32_t*>(peer[0].window);
+    uint32_t* wd = reinterpret_cast<uint32_t*>(peer[1].window);
+    const size_t row0_off = (size_t)(ghost + pad_rows) * W;
+    if (deposit_mode == 2) {
+        uint8_t* f = flags_ptr(ccur);
+        const uint8_t* up_last = peer[0].flags8[ccur] + row0_off + (size_t)(peer[0].rows - 1) * W;
+        const uint8_t* down_first = peer[1].flags8[ccur] + row0_off;
+        smk::k_barrier_pull<uint8_t><<<1, 1024, 0, stream>>>(w, wu, wd, barrier_seq, dev_counters + 2, f - (int64_t)W, up_last,
+                                                            f + (int64_t)rows * W, down_first, W);
+    } else {
+        uint32_t* cn = counts_ptr(ccur);
+        const uint32_t* up_last = peer[0].counts[ccur] + row0_off + (size_t)(peer[0].rows - 1) * W;
+        const uint32_t* down_first = peer[1].counts[ccur] + row0_off;
+        smk::k_barrier_pull<uint32_t><<<1, 1024, 0, stream>>>(w, wu, wd, barrier_seq, dev_counters + 2, cn - (int64_t)W, up_last,
+                                                             cn + (int64_t)rows * W, down_first, W);
+    }
+    SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 1;
+    SM_TRY(toc());
+    return SM_OK;
+}
+
+int sm_engine::p2p_after_trail()
+{
+    uint32_t g = 0, m = 0;
+    SM_TRY(halo_depths(this, &g, &m));
+    SM_TRY(tic(3));
+    // my new rows -> the neighbours' ghost rows of THEIR trail[cur] (all ranks flip `cur` in lock step)
+    const size_t row0_off = (size_t)(ghost + pad_rows) * W;
+    const float* t = trail_ptr(cur);
+    float* up_ghost = peer[0].trail[cur] + row0_off + (size_t)peer[0].rows * W;      // up's bottom ghost rows [rows_up, rows_up + g)
+    float* down_ghost = peer[1].trail[cur] + row0_off - (size_t)g * W;               // down's top ghost rows [-g, 0)
+    const uint64_t n = (uint64_t)g * W;
+    const unsigned nb = (unsigned)std::min<uint64_t>((n / 4 + 255) / 256 + 1, (uint64_t)num_sms);
+    if (W % 4 == 0)
+        smk::k_push_rows<<<nb, 256, 0, stream>>>(reinterpret_cast<const float4*>(t), reinterpret_cast<float4*>(up_ghost),
+                                                reinterpret_cast<const float4*>(t + (size_t)(rows - g) * W),
+                                                reinterpret_cast<float4*>(down_ghost), n / 4);
+    else
+        smk::k_push_rows_scalar<<<nb, 256, 0, stream>>>(t, up_ghost, t + (size_t)(rows - g) * W, down_ghost, n);
+    // arrivals (written by the neighbours during their agent pass, complete since barrier 1)
+    uint8_t* from_up = window + window_arrival_off[0];
+    uint8_t* from_down = window + window_arrival_off[1];
+    smk::k_append_arrivals<<<blocks_for(2 * mig_cap, 256), 256, 0, stream>>>(from_down, from_up, (uint32_t)mig_cap, agents[acur],
+                                                                            ids[acur], dev_counters, cap_local);
+    ++barrier_seq;
+    smk::k_bump_barrier<<<1, 1, 0, stream>>>(dev_counters, from_down, from_up, (uint32_t)mig_cap, cap_local,
+                                             reinterpret_cast<uint32_t*>(window), reinterpret_cast<uint32_t*>(peer[0].window),
+                                             reinterpret_cast<uint32_t*>(peer[1].window), barrier_seq);
+    SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 3;
+    ghost_stale = false;
+    if (!arr_stale) {                                   // the TEX sampler's copy needs the new ghost rows too
+        SM_TRY(refresh_tex(-(int64_t)g, g));
+        SM_TRY(refresh_tex((int64_t)rows, g));
+    }
+    SM_TRY(toc());
+    n_upper = std::min<uint64_t>(cap_local, n_upper + 2 * mig_cap);
     return SM_OK;
 }

@@ -41,21 +41,6 @@ struct FetchTex {
     }
 };
 
-// 2x2 footprint by four point-sampled texture fetches from a pitch-linear texture bound directly to
-// the row-major field (no block-linear copy to maintain).  Texel (i, j) is fetched at (i + 0.5, j + 0.5).
-struct FetchTexLinear {
-    cudaTextureObject_t tex;
-    float row_off;           // buffer row of global row 0:  ghost + pad - row_base
-    __device__ __forceinline__ void operator()(float x0, float y0, float& v00, float& v10, float& v01, float& v11) const
-    {
-        const float fx = x0 + 0.5f, fy = (y0 + row_off) + 0.5f;
-        v00 = tex2D<float>(tex, fx, fy);
-        v10 = tex2D<float>(tex, fx + 1.0f, fy);
-        v01 = tex2D<float>(tex, fx, fy + 1.0f);
-        v11 = tex2D<float>(tex, fx + 1.0f, fy + 1.0f);
-    }
-};
-
 // out[0..3] = gather at the corner of texels (1,1),(2,1),(1,2),(2,2) of a probe array holding T[y][x] = 10*y + x
 static __global__ void k_gather_probe(cudaTextureObject_t tex, float* out)
 {
@@ -104,32 +89,45 @@ k_rescale_agents(float4* __restrict__ agents, uint64_t n, float fx, float fy)
 
 constexpr uint32_t kDeadAgent = 0xFFFFFFFFu;   // multi-GPU: slot whose agent migrated away (dropped by the next sort)
 
-// Migration staging filled by k_agents<true>: agents whose new row belongs to a ring neighbour are
-// written straight into the fixed-size message that exchange.cu sends after the trail pass
-// (layout: [u64 count][u64 pad][float4 a[cap]][u32 id[cap]]).  All counters live on the device, so a
-// step needs no host round trip.
+// How the agent kernel takes part in the multi-GPU exchange.
+//   XM_SINGLE : one GPU, nothing to exchange
+//   XM_NCCL   : deposits that land in a neighbour's rows go to the local ghost rows, leavers to local
+//               fixed-size messages; exchange.cu ships both with NCCL send/recv
+//   XM_P2P    : the kernel writes straight into the neighbour's HBM over NVLink (CUDA IPC peer
+//               mappings): deposits into the neighbour's deposit field, leavers into the neighbour's
+//               arrival buffer -- no staging, no collective; exchange.cu only runs two flag barriers
+enum { XM_SINGLE = 0, XM_NCCL = 1, XM_P2P = 2 };
+
+// Leaver records: [u64 count][u64 pad][float4 a[cap]][u32 id[cap]] -- a local message (XM_NCCL) or the
+// neighbour's arrival buffer (XM_P2P).  All counters live on the device: a step needs no host round trip.
 struct LeaverBufs {
     float4* send_a[2];                   // 0: towards rank-1 (up), 1: towards rank+1 (down)
     uint32_t* send_id[2];
-    unsigned long long* send_count[2];   // message headers
+    unsigned long long* send_count[2];   // record counters (message headers)
     unsigned long long* overflow;        // sticky error flag, checked by the host at the next sync point
-    const unsigned long long* n_ptr;     // device-side number of agent slots in use
+    unsigned long long* left_count;      // XM_P2P: how many agents left this rank during the step
     uint32_t cap;
+    // XM_P2P: deposit fields of the two ring neighbours (pointer to THEIR owned row 0) and the row
+    // count of the upper neighbour (a deposit on my row -k lands on its row rows_up - k)
+    void* peer_dep[2];
+    int32_t rows_up;
 };
 
-// One agent per thread.  `trail` and `counts` point at owned row 0 of this rank's
-// strip (global row c.row_base); ghost rows sit at negative / >= rows offsets.
+// One agent per thread.  `deposits` points at owned row 0 of this rank's strip (global row
+// c.row_base); ghost rows sit at negative / >= rows offsets.
 // FLAGS: deposits are u8 "somebody deposited here" marks written with plain stores instead of u32
 // counts bumped with RED atomics -- exact whenever dep >= 1 and the field is non-negative, because
 // clamp(t + k*dep, 0, 1) == 1 for every k >= 1 (all shipped presets: dep = 1.0).
-template <bool MULTI, class IdxT, class FETCH, bool FLAGS>
+template <int XM, class IdxT, class FETCH, bool FLAGS>
 static __global__ void __launch_bounds__(256)
 k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
          const FETCH fetch, void* __restrict__ deposits, const AgentConsts c,
          const LeaverBufs lv)
 {
+    constexpr bool MULTI = XM != XM_SINGLE;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (MULTI) n = *lv.n_ptr;            // the host only knows an upper bound between sorts
+    // MULTI: n is the host's upper bound of the slots in use; every slot past the live ones holds
+    // kDeadAgent (kept so by the sort and by k_append_arrivals), so no device-side count is needed here
     if (i >= n) return;
     const uint32_t id = ids[i];
     if (MULTI && id == kDeadAgent) return;
@@ -139,11 +137,20 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     agents[i] = a;
     if (cx >= 0) {
         // deposit: order-free (phase_split form of compute.wgsl:140)
-        const int32_t lrd = MULTI ? smd::local_row(cy, c) : cy - (int32_t)c.row_base;
-        if (!MULTI || (lrd >= -c.ghost && lrd < c.rows_local + c.ghost)) {
+        int32_t lrd = MULTI ? smd::local_row(cy, c) : cy - (int32_t)c.row_base;
+        void* base = deposits;
+        bool ok = true;
+        if (XM == XM_NCCL) ok = lrd >= -c.ghost && lrd < c.rows_local + c.ghost;
+        if (XM == XM_P2P) {
+            // rows above / below the strip belong to a neighbour: write into ITS field over NVLink
+            if (lrd < 0) { base = lv.peer_dep[0]; lrd += lv.rows_up; ok = lrd >= 0; }
+            else if (lrd >= c.rows_local) { base = lv.peer_dep[1]; lrd -= c.rows_local; ok = lrd < c.ghost; }
+        }
+        if (ok) {
             const IdxT off = (IdxT)lrd * (IdxT)c.W + (IdxT)cx;
-            if (FLAGS) static_cast<uint8_t*>(deposits)[off] = 1;
-            else atomicAdd(static_cast<uint32_t*>(deposits) + off, 1u);
+            if (FLAGS) static_cast<uint8_t*>(base)[off] = 1;
+            else if (XM == XM_P2P) atomicAdd_system(static_cast<uint32_t*>(base) + off, 1u);
+            else atomicAdd(static_cast<uint32_t*>(base) + off, 1u);
         }
     }
     if (MULTI) {
@@ -156,11 +163,12 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
             unsigned long long* cnt = up ? lv.send_count[0] : lv.send_count[1];
             float4* sa = up ? lv.send_a[0] : lv.send_a[1];
             uint32_t* si = up ? lv.send_id[0] : lv.send_id[1];
-            unsigned long long slot = atomicAdd(cnt, 1ull);
+            unsigned long long slot = (XM == XM_P2P) ? atomicAdd_system(cnt, 1ull) : atomicAdd(cnt, 1ull);
             if (slot < lv.cap) {
                 sa[slot] = a;
                 si[slot] = id;
                 ids[i] = kDeadAgent;
+                if (XM == XM_P2P) atomicAdd(lv.left_count, 1ull);
             } else {
                 atomicExch(lv.overflow, 1ull);       // staging overflow: reported by the host
             }

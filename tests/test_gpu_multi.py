@@ -22,10 +22,12 @@ CASES = {
     # ghost depth == strip height (the ghosts cover the whole neighbour): seam folding must not depend on it
     "thin_strips": ("Default", 256, 128, 30_000, 40, False),
     "firecracker_devinit": ("Firecracker Trees", 1024, 1024, 1_000_000, 33, True),
+    "mode_switch": ("Default", 256, 512, 150_000, 40, False),
 }
 
 
-def _worker(rank, world, case, out_dir):
+def _worker(rank, world, case, out_dir, exchange):
+    os.environ["SM_EXCHANGE"] = exchange
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch  # noqa: F401  (first, so the process ends up with torch's libnccl)
@@ -52,16 +54,23 @@ def _worker(rank, world, case, out_dir):
     else:
         be.write_agents(so.init_agents(N, W, H, s.agent_speed_min, s.agent_speed_max, 11))
         be.write_trail(random_trail(W, H, seed=4))
-    be.step(steps)
+    if case == "mode_switch":
+        # deposit representation changes mid-run (flags <-> counts) on every rank at the same step
+        for dep in (1.0, 0.3, 2.0, 0.05, 1.0):
+            be.update_settings(s.clone(pheromone_deposition_amount=dep))
+            be.step(steps // 5)
+    else:
+        be.step(steps)
     a = be.read_agents()
     t = be.read_trail()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), agents=a, trail=t, owned=be.last_owned, local=be.local_agent_count)
     be.close()
 
 
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world):
+def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, exchange):
     import slime_mold_b200 as sm
     if sm.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -69,11 +78,21 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world):
     preset, W, H, N, steps, device_init = CASES[case]
     if H // world < 32:
         pytest.skip("strips too thin for this case")
-    mp.spawn(_worker, args=(world, case, str(tmp_path)), nprocs=world, join=True)
+    if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips"):
+        pytest.skip("NCCL path: three representative cases")
+    mp.spawn(_worker, args=(world, case, str(tmp_path), exchange), nprocs=world, join=True)
     u = preset_uniform(preset, W, H)
     ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 11)
     sim = oracle.Sim(to_oracle_params(oracle, u), ag, trail=None if device_init else random_trail(W, H, seed=4))
-    sim.step(steps)
+    if case == "mode_switch":
+        import slime_mold_b200 as sm2
+        s0 = sm2.init_preset_manager().get_preset(preset).settings
+        for dep in (1.0, 0.3, 2.0, 0.05, 1.0):
+            ss = s0.clone(pheromone_deposition_amount=dep)
+            sim.p = to_oracle_params(oracle, sm2.SimSizeUniform.new(W, H, ss.pheromone_decay_factor, ss))
+            sim.step(steps // 5)
+    else:
+        sim.step(steps)
     a = np.full((N, 4), np.nan, np.float32)
     t = np.full((H, W), np.nan, np.float32)
     owned = 0
