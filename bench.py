@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--independent", action="store_true", help="diagnostic: N ranks, each an independent single-GPU engine")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = min(steps, 100))")
     return ap.parse_args()
 
@@ -213,8 +214,12 @@ def run_ours(args):
 
     width, height, agents = args.width, args.height * N, args.agents * N
     settings = sm.init_preset_manager().get_preset(args.preset).settings
-    be = sm.CudaBackend.new(width, height, settings, agent_count=agents, device=local_rank, rank=rank, world_size=N)
-    if N > 1:
+    if args.independent:
+        width, height, agents = args.width, args.height, args.agents
+        be = sm.CudaBackend.new(width, height, settings, agent_count=agents, device=local_rank)
+    else:
+        be = sm.CudaBackend.new(width, height, settings, agent_count=agents, device=local_rank, rank=rank, world_size=N)
+    if N > 1 and not args.independent:
         ids = [be.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         be.comm_init(ids[0])

@@ -257,6 +257,18 @@ int sm_engine::refresh_tex(int64_t local_row_begin, int64_t n_rows)
     return SM_OK;
 }
 
+int sm_engine::refresh_tex_ghosts(uint32_t g)
+{
+    if (!use_tex || arr_stale || g == 0) return SM_OK;
+    const int32_t off = (int32_t)(ghost + pad_rows);
+    const uint64_t total = 2ull * g * W;
+    const unsigned nb = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms * 4);
+    smk::k_rows_to_surface<<<nb, 256, 0, stream>>>(trail_base[cur], trail_surf, W, off - (int32_t)g, off + (int32_t)rows, (int32_t)g);
+    SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 1;
+    return SM_OK;
+}
+
 int sm_engine::setup_tiles()
 {
     if (tile_hist) { cudaFree(tile_hist); tile_hist = nullptr; }
@@ -615,6 +627,9 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         return fail(sm_fail(SM_ERR_OOM, "cudaMalloc(stats) failed"));
     e->n_local = 0;
     e->agents_valid = false;
+    if (e->world > 1 && env_int("SM_FAKE_MULTI", 0)) {
+        if ((rc = e->fake_comm_init()) != SM_OK) return fail(rc);
+    }
     if (cudaStreamSynchronize(e->stream) != cudaSuccess)
         return fail(sm_fail(SM_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out = e;

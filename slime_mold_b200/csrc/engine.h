@@ -110,6 +110,8 @@ struct sm_engine {
         uint32_t rows = 0;                          // rows they own
     };
     bool p2p = false;
+    bool fake_multi = false;          // SM_FAKE_MULTI=1 (profiling only): strip geometry and kernels of a 2-rank run without any exchange
+    int fake_comm_init();
     PeerView peer[2];
     std::vector<void*> ipc_opened;    // every pointer obtained from cudaIpcOpenMemHandle
     uint8_t* window = nullptr;        // [64 B barrier flags][arrivals from up][arrivals from down]
@@ -135,6 +137,7 @@ struct sm_engine {
     int setup_tex();
     void free_tex();
     int refresh_tex(int64_t local_row_begin, int64_t n_rows);   // linear trail[cur] rows -> array
+    int refresh_tex_ghosts(uint32_t g);                         // both ghost bands, by a kernel
 
     int sort_agents();
     int launch_agents();

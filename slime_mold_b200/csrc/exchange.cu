@@ -326,6 +326,29 @@ extern "C" int sm_comm_init(sm_engine* e, const uint8_t id[SM_COMM_ID_BYTES])
     return SM_OK;
 }
 
+// PROFILING ONLY (SM_FAKE_MULTI=1): lets one process run the multi-GPU kernels (strip geometry, leaver
+// staging, ghost rows) under ncu without a peer.  Nothing is exchanged, so results are meaningless.
+int sm_engine::fake_comm_init()
+{
+    counts_xchg_rows = (uint64_t)ghost + 1;
+    SM_CUDA(cudaMalloc(&counts_xchg, 2 * counts_xchg_rows * W * sizeof(uint32_t)));
+    mig_cap = 65536;
+    mig_bytes = 16 + mig_cap * (sizeof(float4) + sizeof(uint32_t));
+    for (int d = 0; d < 2; ++d) {
+        SM_CUDA(cudaMalloc(&mig[d].send, mig_bytes));
+        SM_CUDA(cudaMalloc(&mig[d].recv, mig_bytes));
+        SM_CUDA(cudaMemset(mig[d].send, 0, 16));
+        SM_CUDA(cudaMemset(mig[d].recv, 0, 16));
+    }
+    SM_CUDA(cudaMalloc(&dev_counters, 8 * sizeof(unsigned long long)));
+    SM_CUDA(cudaMemset(dev_counters, 0, 8 * sizeof(unsigned long long)));
+    SM_CUDA(cudaMallocHost(&host_counters, 8 * sizeof(unsigned long long)));
+    fake_multi = true;
+    comm_ready = true;
+    p2p = false;
+    return SM_OK;
+}
+
 void sm_engine::comm_destroy()
 {
     if (comm && g_nccl.ok) { ncclCommDestroy((ncclComm_t)comm); comm = nullptr; }
@@ -370,6 +393,7 @@ int sm_engine::init_agents_strip(uint64_t seed)
 // Deposit counts (+ leaver counts).  Leaves counts[ccur] complete on rows [-1, rows].
 int sm_engine::exchange_counts()
 {
+    if (fake_multi) return SM_OK;
     uint32_t g = 0, m = 0;
     SM_TRY(halo_depths(this, &g, &m));
     SM_TRY(tic(3));
@@ -413,6 +437,7 @@ int sm_engine::exchange_counts()
 // New trail rows -> neighbours' ghost rows (also used alone after uploads / clears).
 int sm_engine::exchange_trail_ghosts()
 {
+    if (fake_multi) { ghost_stale = false; return SM_OK; }
     uint32_t g = 0, m = 0;
     SM_TRY(halo_depths(this, &g, &m));
     SM_TRY(tic(3));
@@ -428,10 +453,7 @@ int sm_engine::exchange_trail_ghosts()
     SM_NCCL(ncclGroupEnd());
     SM_TRY(toc());
     ghost_stale = false;
-    if (!arr_stale) {
-        SM_TRY(refresh_tex(-(int64_t)g, g));
-        SM_TRY(refresh_tex((int64_t)rows, g));
-    }
+    SM_TRY(refresh_tex_ghosts(g));
     return SM_OK;
 }
 
@@ -440,6 +462,10 @@ int sm_engine::exchange_trail_ghosts()
 // rows this step used (the trail kernel only zeroes the owned rows of the *other* count buffer).
 int sm_engine::migrate_agents()
 {
+    if (fake_multi) {
+        for (int d = 0; d < 2; ++d) SM_CUDA(cudaMemsetAsync(mig[d].send, 0, 16, stream));
+        return SM_OK;
+    }
     uint32_t g = 0, m = 0;
     SM_TRY(halo_depths(this, &g, &m));
     // counts buffer the agent kernel of THIS step wrote is 1 - ccur now (launch_trail flipped it)
@@ -469,10 +495,7 @@ int sm_engine::migrate_agents()
     SM_NCCL(ncclRecv(mig[0].recv, mig_bytes, ncclUint8, up, c, stream));                     // what `up` sent down
     SM_NCCL(ncclGroupEnd());
     ghost_stale = false;
-    if (!arr_stale) {                                   // the TEX sampler's copy needs the new ghost rows too
-        SM_TRY(refresh_tex(-(int64_t)g, g));
-        SM_TRY(refresh_tex((int64_t)rows, g));
-    }
+    SM_TRY(refresh_tex_ghosts(g));                      // the TEX sampler's copy needs the new ghost rows too
     smk::k_append_arrivals<<<blocks_for(2 * mig_cap, 256), 256, 0, stream>>>(mig[1].recv, mig[0].recv, (uint32_t)mig_cap,
                                                                             agents[acur], ids[acur], dev_counters, cap_local);
     smk::k_bump_counters<<<1, 1, 0, stream>>>(dev_counters, mig[1].recv, mig[0].recv,
@@ -703,10 +726,7 @@ int sm_engine::p2p_after_trail()
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 3;
     ghost_stale = false;
-    if (!arr_stale) {                                   // the TEX sampler's copy needs the new ghost rows too
-        SM_TRY(refresh_tex(-(int64_t)g, g));
-        SM_TRY(refresh_tex((int64_t)rows, g));
-    }
+    SM_TRY(refresh_tex_ghosts(g));                      // the TEX sampler's copy needs the new ghost rows too
     SM_TRY(toc());
     n_upper = std::min<uint64_t>(cap_local, n_upper + 2 * mig_cap);
     return SM_OK;

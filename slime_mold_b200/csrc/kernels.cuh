@@ -41,6 +41,21 @@ struct FetchTex {
     }
 };
 
+// Row-major trail rows -> the block-linear copy the TEX sampler reads (ghost rows after an exchange).
+// A kernel instead of cudaMemcpy2DToArray: it stays on the compute engine (no copy-engine hand-off
+// inside the step loop).  Two row ranges per launch: [r0a, r0a + n) and [r0b, r0b + n) (buffer rows).
+static __global__ void __launch_bounds__(256)
+k_rows_to_surface(const float* __restrict__ base, cudaSurfaceObject_t surf, uint32_t W, int32_t r0a, int32_t r0b, int32_t n)
+{
+    const uint64_t total = 2ull * (uint64_t)n * W;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = (uint32_t)(i % W);
+        const uint64_t r = i / W;
+        const int32_t row = r < (uint64_t)n ? r0a + (int32_t)r : r0b + (int32_t)(r - n);
+        surf2Dwrite(base[(size_t)row * W + x], surf, (int)(x * 4u), row);
+    }
+}
+
 // out[0..3] = gather at the corner of texels (1,1),(2,1),(1,2),(2,2) of a probe array holding T[y][x] = 10*y + x
 static __global__ void k_gather_probe(cudaTextureObject_t tex, float* out)
 {
@@ -130,14 +145,23 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     // kDeadAgent (kept so by the sort and by k_append_arrivals), so no device-side count is needed here
     if (i >= n) return;
     const uint32_t id = ids[i];
-    if (MULTI && id == kDeadAgent) return;
-    float4 a = agents[i];
+    float4 a;
+    if (MULTI) {
+        // issue the state load together with the id load instead of behind the dead-slot test (the
+        // compiler sinks a plain load below the early exit, which serialises two DRAM latencies)
+        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(agents + i));
+        if (id == kDeadAgent) return;
+    } else {
+        a = agents[i];
+    }
     int32_t cx, cy;
     smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, c, fetch, cx, cy);
     agents[i] = a;
+    int32_t lr = 0;                       // local row of the agent's new cell (MULTI: also decides migration)
     if (cx >= 0) {
         // deposit: order-free (phase_split form of compute.wgsl:140)
-        int32_t lrd = MULTI ? smd::local_row(cy, c) : cy - (int32_t)c.row_base;
+        lr = MULTI ? smd::local_row(cy, c) : cy - (int32_t)c.row_base;
+        int32_t lrd = lr;
         void* base = deposits;
         bool ok = true;
         if (XM == XM_NCCL) ok = lrd >= -c.ghost && lrd < c.rows_local + c.ghost;
@@ -154,9 +178,11 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
         }
     }
     if (MULTI) {
-        // owner row of the new position (x == W / y == H rounding corner and NaN clamp like the host)
-        const int32_t oy = !(a.y >= 0.0f) ? 0 : (a.y >= c.Hf ? (int32_t)c.H - 1 : (int32_t)a.y);
-        const int32_t lr = smd::local_row(oy, c);
+        if (cx < 0) {
+            // no deposit cell (x == W / y == H rounding corner, non-finite state): owner row clamped like the host
+            const int32_t oy = !(a.y >= 0.0f) ? 0 : (a.y >= c.Hf ? (int32_t)c.H - 1 : (int32_t)a.y);
+            lr = smd::local_row(oy, c);
+        }
         if (lr < 0 || lr >= c.rows_local) {
             // (no dynamic indexing of the parameter arrays: that would force a per-thread local copy)
             const bool up = lr < 0;
