@@ -893,7 +893,7 @@ int sm_trail_statistics(sm_engine* e, sm_trail_stats* out)
     if (!out) return sm_fail(SM_ERR_BAD_ARG, "null output");
     SM_CUDA(cudaMemsetAsync(e->stats_dev, 0, sizeof(smk::StatsAcc), e->stream));
     const uint64_t cells = (uint64_t)e->rows * e->W;
-    unsigned nb = (unsigned)std::min<uint64_t>((cells + 255) / 256, (uint64_t)e->num_sms * 8);
+    unsigned nb = (unsigned)std::min<uint64_t>((cells / 16 + 255) / 256 + 1, (uint64_t)e->num_sms * 16);
     smk::k_trail_stats<<<nb, 256, 0, e->stream>>>(e->trail_ptr(e->cur), cells, (smk::StatsAcc*)e->stats_dev);
     SM_CUDA(cudaGetLastError());
     smk::StatsAcc h{};
