@@ -437,9 +437,9 @@ int sm_engine::launch_trail(bool has_counts)
     } else if (W % 4 == 0 && W >= 8 && (W / 4) % 32 != 1 && !force_generic) {
         const unsigned bs = 128;
         const unsigned bx = blocks_for(W / 4, bs);
-        // 16 rows per chunk measured best from 4096^2 to 32768^2 (profiles/README.md): 2/16 of the reads are
-        // halo re-reads that hit L2; small maps take shorter chunks to keep >= 4 CTAs per SM
-        uint64_t rpc = 16;
+        // 8-16 rows per chunk measured best from 4096^2 to 32768^2 (profiles/README.md): the 2/rpc halo
+        // re-reads hit L2; small maps take shorter chunks to keep >= 4 CTAs per SM
+        uint64_t rpc = 8;
         while (rpc > 4 && (uint64_t)bx * ((rows + rpc - 1) / rpc) < (uint64_t)num_sms * 4) rpc /= 2;
         if (rpc_override > 0) rpc = rpc_override;
         g.rows_per_chunk = (uint32_t)rpc;
