@@ -160,33 +160,42 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     int32_t cx, cy;
     smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, c, fetch, cx, cy);
     agents[i] = a;
-    int32_t lr = 0;                       // local row of the agent's new cell (MULTI: also decides migration)
-    if (cx >= 0) {
+    // Fast path (every agent on one GPU, all but the strip-boundary agents otherwise): the new cell is
+    // on a row this rank owns -> local deposit, no migration.  One subtract + one unsigned compare.
+    int32_t lr = cy - (int32_t)c.row_base;
+    const bool interior = cx >= 0 && (!MULTI || (uint32_t)lr < (uint32_t)c.rows_local);
+    if (interior) {
         // deposit: order-free (phase_split form of compute.wgsl:140)
-        lr = MULTI ? smd::local_row(cy, c) : cy - (int32_t)c.row_base;
-        int32_t lrd = lr;
-        void* base = deposits;
-        bool ok = true;
-        if (XM == XM_NCCL) ok = lrd >= -c.ghost && lrd < c.rows_local + c.ghost;
-        if (XM == XM_P2P) {
-            // rows above / below the strip belong to a neighbour: write into ITS field over NVLink
-            if (lrd < 0) { base = lv.peer_dep[0]; lrd += lv.rows_up; ok = lrd >= 0; }
-            else if (lrd >= c.rows_local) { base = lv.peer_dep[1]; lrd -= c.rows_local; ok = lrd < c.ghost; }
-        }
-        if (ok) {
-            const IdxT off = (IdxT)lrd * (IdxT)c.W + (IdxT)cx;
-            if (FLAGS) static_cast<uint8_t*>(base)[off] = 1;
-            else if (XM == XM_P2P) atomicAdd_system(static_cast<uint32_t*>(base) + off, 1u);
-            else atomicAdd(static_cast<uint32_t*>(base) + off, 1u);
-        }
+        const IdxT off = (IdxT)lr * (IdxT)c.W + (IdxT)cx;
+        if (FLAGS) static_cast<uint8_t*>(deposits)[off] = 1;
+        else atomicAdd(static_cast<uint32_t*>(deposits) + off, 1u);
     }
-    if (MULTI) {
-        if (cx < 0) {
+    if (MULTI && !interior) {
+        // Slow path: the cell belongs to a ring neighbour (or there is no deposit cell at all).
+        if (cx >= 0) {
+            lr = smd::local_row(cy, c);                       // folded across the toroidal seam
+            int32_t lrd = lr;
+            void* base = deposits;
+            bool ok = true;
+            if (XM == XM_NCCL) ok = lrd >= -c.ghost && lrd < c.rows_local + c.ghost;
+            if (XM == XM_P2P) {
+                // write into the neighbour's field over NVLink
+                if (lrd < 0) { base = lv.peer_dep[0]; lrd += lv.rows_up; ok = lrd >= 0; }
+                else { base = lv.peer_dep[1]; lrd -= c.rows_local; ok = lrd < c.ghost; }
+            }
+            if (ok) {
+                const IdxT off = (IdxT)lrd * (IdxT)c.W + (IdxT)cx;
+                if (FLAGS) static_cast<uint8_t*>(base)[off] = 1;
+                else if (XM == XM_P2P) atomicAdd_system(static_cast<uint32_t*>(base) + off, 1u);
+                else atomicAdd(static_cast<uint32_t*>(base) + off, 1u);
+            }
+        } else {
             // no deposit cell (x == W / y == H rounding corner, non-finite state): owner row clamped like the host
             const int32_t oy = !(a.y >= 0.0f) ? 0 : (a.y >= c.Hf ? (int32_t)c.H - 1 : (int32_t)a.y);
             lr = smd::local_row(oy, c);
         }
         if (lr < 0 || lr >= c.rows_local) {
+            // migration: hand the agent to the neighbour that owns its row
             // (no dynamic indexing of the parameter arrays: that would force a per-thread local copy)
             const bool up = lr < 0;
             unsigned long long* cnt = up ? lv.send_count[0] : lv.send_count[1];
