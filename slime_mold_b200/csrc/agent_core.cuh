@@ -18,6 +18,7 @@ struct AgentConsts {
     float turn_speed;
     float sensor_angle, sensor_distance;
     float jitter;
+    float neg_zero;            // -0.0f, opaque to the compiler (see mul2_nofuse)
     // strip of the trail this kernel may read (multi-GPU): global rows
     // [row0 - halo, row0 + rows + halo) live at trail + (row - row_base) * W
     int64_t row_base;
@@ -44,22 +45,39 @@ constexpr float kTwoPi = 2.0f * 3.14159265359f;    // compute.wgsl:121
 constexpr float kRcpTwoPi = 0.15915494f;
 constexpr float kTimeStep = 0.016f;                // compute.wgsl:55
 
-// sample_trail_map, compute.wgsl:7-29.  FETCH(fx, fy, v00, v10, v01, v11) returns the 2x2 footprint
+// sample_trail_map, compute.wgsl:7-29.  FETCH(inside, fx, fy, v00, v10, v01, v11) returns the 2x2 footprint
 // whose top-left cell is global (fx, fy) (integral floats): four scalar loads from the row-major field (host / LDG
-// path) or one texture gather from the block-linear copy (device TEX path) -- raw f32 either way.
+// path) or one texture gather from the block-linear copy (device TEX path) -- raw f32 either way.  `inside`
+// is the reference's bounds test; an implementation may fetch regardless (the texture path does: clamped
+// addressing makes any coordinate harmless and an unconditional TLD4 needs no predicate bookkeeping) or
+// skip the loads (the row-major path must) -- the footprint is only consumed when `inside` holds.
+//
+// The sample is split in two so that the per-sensor position arithmetic (px - floor, 1 - d) of the left
+// and right sensors can run as packed pairs: bilinear_at() takes the integral corner and the fractions.
+SM_HD bool tap_inside(const AgentConsts& c, float fx, float fy)
+{
+    // x0 < 0 || x1 >= W || y0 < 0 || y1 >= H -> 0 (sensing is NOT toroidal); NaN -> outside
+    return fx >= 0.0f && fx <= c.xmax && fy >= 0.0f && fy <= c.ymax;
+}
+
+template <class FETCH>
+SM_HD float bilinear_at(const AgentConsts& c, float fx, float fy, float dx, float omdx, float dy, float omdy, FETCH fetch)
+{
+    const bool inside = tap_inside(c, fx, fy);
+    float v00, v10, v01, v11;
+    fetch(inside, fx, fy, v00, v10, v01, v11);   // fx, fy: integral; inside [0, W-2] x [0, H-2] when `inside`
+    float v0 = mixf_pre(v00, v10, dx, omdx);                               // :26
+    float v1 = mixf_pre(v01, v11, dx, omdx);                               // :27
+    float v = mixf_pre(v0, v1, dy, omdy);                                  // :28
+    return inside ? v : 0.0f;                                              // :14-16
+}
+
 template <class FETCH>
 SM_HD float sample_trail(const AgentConsts& c, float px, float py, FETCH fetch)
 {
     float fx = ::floorf(px), fy = ::floorf(py);
-    // x0 < 0 || x1 >= W || y0 < 0 || y1 >= H -> 0 (sensing is NOT toroidal); NaN -> outside
-    if (!(fx >= 0.0f && fx <= c.xmax && fy >= 0.0f && fy <= c.ymax)) return 0.0f;
     float dx = sub(px, fx), dy = sub(py, fy);
-    float v00, v10, v01, v11;
-    fetch(fx, fy, v00, v10, v01, v11);        // fx, fy: integral, inside [0, W-2] x [0, H-2]
-    float omdx = sub(1.0f, dx);
-    float v0 = mixf_pre(v00, v10, dx, omdx);
-    float v1 = mixf_pre(v01, v11, dx, omdx);
-    return mixf(v0, v1, dy);
+    return bilinear_at(c, fx, fy, dx, sub(1.0f, dx), dy, sub(1.0f, dy), fetch);
 }
 
 // Footprint fetch from the row-major field.  IdxT = int32_t when the strip (with ghosts) has fewer
@@ -69,48 +87,73 @@ struct FetchLinear {
     const float* trail;      // owned row 0 of this rank's strip
     IdxT W, row_base;
     LD ld;
-    SM_HD void operator()(float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
+    SM_HD void operator()(bool inside, float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
     {
-        const IdxT x0 = (IdxT)(int32_t)fx, y0 = (IdxT)(int32_t)fy;
-        const float* r0 = trail + ((y0 - row_base) * W + x0);
-        const float* r1 = r0 + W;
-        v00 = ld(r0); v10 = ld(r0 + 1); v01 = ld(r1); v11 = ld(r1 + 1);
+        v00 = v10 = v01 = v11 = 0.0f;
+        if (inside) {
+            const IdxT x0 = (IdxT)(int32_t)fx, y0 = (IdxT)(int32_t)fy;
+            const float* r0 = trail + ((y0 - row_base) * W + x0);
+            const float* r1 = r0 + W;
+            v00 = ld(r0); v10 = ld(r0 + 1); v01 = ld(r1); v11 = ld(r1 + 1);
+        }
     }
 };
 
+// x % m with the reference's follow-up `if (x < 0) x += m` (compute.wgsl:130-133)
+SM_HD float wrap_coord(float v, float m, float rcp_m)
+{
+    v = fmod_exact(v, m, rcp_m);
+    if (v < 0.0f) v = add(v, m);
+    return v;
+}
+
 // Returns the deposit cell as (cx, cy) with cx < 0 when the deposit is skipped
 // (compute.wgsl:138: x == W can occur by rounding).
+//
+// Statement order and every rounding follow compute.wgsl:65-144; what is specific to this engine is
+// only how the independent operations are grouped for issue: the left / right sensor headings,
+// positions and fractions run as packed pairs (sincos_small2, add2 / mul2), steering is one
+// branch-free expression, and the toroidal wrap is skipped when the moved position is already in
+// range (x % W == x for 0 <= x < W, -0 included).
 template <class FETCH>
 SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t agent_index,
                         const AgentConsts& c, FETCH fetch, int32_t& cx, int32_t& cy)
 {
     speed = clampf(speed, c.speed_min, c.speed_max);                       // :72
 
-    float sL, cL, sR, cR, sC, cC;
-    const float aL = sub(angle, c.sensor_angle);                           // :75
-    const float aR = add(angle, c.sensor_angle);                           // :76
+    f2 sLR, cLR;           // lo = left sensor, hi = right sensor
+    float sC, cC;
+    const f2 aLR = mk2(sub(angle, c.sensor_angle), add(angle, c.sensor_angle));   // :75-76
     if (::fabsf(angle) <= 4096.0f && ::fabsf(c.sensor_angle) <= 4096.0f) {
         // |angle +- sa| <= 8192: the spec's fast path, evaluated without the per-call range test
-        sincos_small(aL, sL, cL);
-        sincos_small(aR, sR, cR);
+        sincos_small2(aLR, sLR, cLR);
         sincos_small(angle, sC, cC);                                       // :77
     } else {
-        sincos(aL, sL, cL);
-        sincos(aR, sR, cR);
+        sincos(aLR.lo, sLR.lo, cLR.lo);
+        sincos(aLR.hi, sLR.hi, cLR.hi);
         sincos(angle, sC, cC);
     }
     const float sd = c.sensor_distance;
-    float vL = sample_trail(c, add(x, mul(sd, cL)), add(y, mul(sd, sL)), fetch);   // :79-82,93
-    float vR = sample_trail(c, add(x, mul(sd, cR)), add(y, mul(sd, sR)), fetch);   // :83-86,94
-    float vC = sample_trail(c, add(x, mul(sd, cC)), add(y, mul(sd, sC)), fetch);   // :87-90,95
+    const f2 sd2 = splat2(sd), one2 = splat2(1.0f);
+    const f2 pxLR = add2(splat2(x), mul2_nofuse(sd2, cLR, c.neg_zero));                       // :79-86
+    const f2 pyLR = add2(splat2(y), mul2_nofuse(sd2, sLR, c.neg_zero));
+    const f2 fxLR = mk2(::floorf(pxLR.lo), ::floorf(pxLR.hi));             // :8-9
+    const f2 fyLR = mk2(::floorf(pyLR.lo), ::floorf(pyLR.hi));
+    const f2 dxLR = sub2(pxLR, fxLR), dyLR = sub2(pyLR, fyLR);             // :18-19
+    const f2 mxLR = sub2(one2, dxLR), myLR = sub2(one2, dyLR);             // the (1 - t) of mix()
+    float vL = bilinear_at(c, fxLR.lo, fyLR.lo, dxLR.lo, mxLR.lo, dyLR.lo, myLR.lo, fetch);   // :93
+    float vR = bilinear_at(c, fxLR.hi, fyLR.hi, dxLR.hi, mxLR.hi, dyLR.hi, myLR.hi, fetch);   // :94
+    float vC = sample_trail(c, add(x, mul(sd, cC)), add(y, mul(sd, sC)), fetch);              // :87-90,95
 
-    if (vC > vL && vC > vR) {                                              // :98
-    } else if (vL > vR) {                                                  // :100-104
-        float diff = sub(sub(angle, kTau), angle);
-        angle = add(angle, mul(::fminf(c.turn_speed, ::fabsf(diff)), signf(diff)));
-    } else if (vR > vL) {                                                  // :105-109
-        float diff = sub(add(angle, kTau), angle);
-        angle = add(angle, mul(::fminf(c.turn_speed, ::fabsf(diff)), signf(diff)));
+    // :98-112  keep | turn left (towards angle - TAU) | turn right (towards angle + TAU) | keep (vL == vR).
+    // angle - TAU == angle + (-TAU) bit for bit, so both turns are one expression in the signed TAU.
+    {
+        const bool keep = vC > vL && vC > vR;
+        const bool left = vL > vR, right = vR > vL;
+        const float tau = left ? -kTau : kTau;
+        const float diff = sub(add(angle, tau), angle);                    // :101,106
+        const float turned = add(angle, mul(::fminf(c.turn_speed, ::fabsf(diff)), signf(diff)));   // :104,109
+        angle = (!keep && (left || right)) ? turned : angle;
     }
 
     // :115-118  angle += (hash*2 - 1) * jitter.  With jitter == +-0 the addend is +-0 (or NaN when x / y
@@ -128,15 +171,19 @@ SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t 
     float move = mul(speed, kTimeStep);                                    // :125
     float sM, cM;
     sincos_small(angle, sM, cM);                                           // angle in [0, 2pi] or NaN here
-    x = add(x, mul(move, cM));                                             // :126
-    y = add(y, mul(move, sM));                                             // :127
+    const f2 moved = add2(mk2(x, y), mul2_nofuse(splat2(move), mk2(cM, sM), c.neg_zero));     // :126-127
+    x = moved.lo;
+    y = moved.hi;
 
-    x = fmod_exact(x, c.Wf, c.rcpW);                                       // :130
-    if (x < 0.0f) x = add(x, c.Wf);                                        // :131
-    y = fmod_exact(y, c.Hf, c.rcpH);                                       // :132
-    if (y < 0.0f) y = add(y, c.Hf);                                        // :133
-
-    if (x >= 0.0f && x < c.Wf && y >= 0.0f && y < c.Hf) {                  // :136-138
+    // :130-133 wrap, :136-138 deposit bounds -- the same four comparisons decide both: a position already
+    // inside [0, W) x [0, H) is left untouched by `%` and by the negative fix-up
+    bool inside = x >= 0.0f && x < c.Wf && y >= 0.0f && y < c.Hf;
+    if (!inside) {
+        x = wrap_coord(x, c.Wf, c.rcpW);                                   // :130-131
+        y = wrap_coord(y, c.Hf, c.rcpH);                                   // :132-133
+        inside = x >= 0.0f && x < c.Wf && y >= 0.0f && y < c.Hf;           // :136-138
+    }
+    if (inside) {
         cx = (int32_t)x; cy = (int32_t)y;
     } else {
         cx = -1; cy = -1;

@@ -76,6 +76,62 @@ SM_HD float u2f(uint32_t u)
 #endif
 }
 
+// ---- packed pairs: two independent f32 lanes per instruction ------------------
+// sm_100a has FADD2 / FMUL2 / FFMA2 (PTX add/mul/fma.rn.f32x2): one issue slot, two IEEE binary32
+// results, each lane rounded exactly like the scalar instruction (measured on B200,
+// tools/microbench/ffma2.cu: 126.6 lane-ops/clk/SM packed vs 98.4 scalar, and the packed form leaves
+// the issue slot of the second lane free for other pipes).  The agent kernel is issue-bound, so every
+// pair of identical scalar operations on independent values is written as one packed operation.
+// Lane semantics are identical to add()/mul()/fma() above -- the host form below IS those functions.
+struct alignas(8) f2 { float lo, hi; };
+SM_HD f2 mk2(float lo, float hi) { f2 v; v.lo = lo; v.hi = hi; return v; }
+SM_HD f2 splat2(float s) { return mk2(s, s); }
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long pk2(f2 v)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.lo), "f"(v.hi));
+    return r;
+}
+__device__ __forceinline__ f2 upk2(unsigned long long r)
+{
+    f2 v;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.lo), "=f"(v.hi) : "l"(r));
+    return v;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+    return upk2(d);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+    return upk2(d);
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+    return upk2(d);
+}
+#else
+SM_HD f2 add2(f2 a, f2 b) { return mk2(add(a.lo, b.lo), add(a.hi, b.hi)); }
+SM_HD f2 mul2(f2 a, f2 b) { return mk2(mul(a.lo, b.lo), mul(a.hi, b.hi)); }
+SM_HD f2 fma2(f2 a, f2 b, f2 c) { return mk2(fma(a.lo, b.lo, c.lo), fma(a.hi, b.hi, c.hi)); }
+#endif
+// Product that must stay a product.  ptxas 12.9 contracts mul.rn.f32x2 followed by add.rn.f32x2 into
+// one FFMA2 -- a single rounding -- even under --fmad=false (it honours the flag and the .rn modifiers
+// only for the scalar forms).  Wherever a packed product feeds a packed sum the product is therefore
+// written as an FFMA2 whose addend is a -0.0 the compiler cannot see (`neg_zero` comes from the kernel's
+// parameter block): a*b + (-0.0) rounds once, to RN(a*b), sign of zero included, and an FMA cannot be
+// contracted with the following add.  The bit-parity tests against the oracle guard this.
+SM_HD f2 mul2_nofuse(f2 a, f2 b, float neg_zero) { return fma2(a, b, splat2(neg_zero)); }
+SM_HD f2 neg2(f2 a) { return mk2(-a.lo, -a.hi); }
+SM_HD f2 sub2(f2 a, f2 b) { return add2(a, neg2(b)); }      // a - b == a + (-b) bit for bit
+
 // ---- SPEC-SINCOS -------------------------------------------------------------
 // x = k*(pi/2) + r by the round-to-integer magic constant; q = k mod 4 read from
 // the low mantissa bits.  Fast path: three f32 FMAs against a 3-way split of pi/2
@@ -116,6 +172,16 @@ SM_HD void reduce_pio2(float x, float& r, uint32_t& q)
     }
 }
 
+// sin / cos of k*(pi/2) + r from sin(r), cos(r): q = k (only its two low bits are used).
+SM_HD void quadrant_fix(float sinr, float cosr, uint32_t q, float& sn, float& cs)
+{
+    float so = (q & 1u) ? cosr : sinr;
+    float co = (q & 1u) ? sinr : cosr;
+    // sign flips as XOR on the sign bit (q&2 -> sin, (q+1)&2 -> cos); shifting by 30 drops the bits above
+    sn = u2f(f2u(so) ^ (((q << 30)) & 0x80000000u));
+    cs = u2f(f2u(co) ^ (((q << 30) + 0x40000000u) & 0x80000000u));
+}
+
 SM_HD void sincos_poly(float r, uint32_t q, float& sn, float& cs)
 {
     float s2 = mul(r, r);
@@ -127,11 +193,7 @@ SM_HD void sincos_poly(float r, uint32_t q, float& sn, float& cs)
     c = fma(c, s2, 4.166664568298827e-2f);
     c = fma(c, s2, -0.5f);
     float cosr = fma(c, s2, 1.0f);
-    float so = (q & 1u) ? cosr : sinr;
-    float co = (q & 1u) ? sinr : cosr;
-    // sign flips as XOR on the sign bit (q&2 -> sin, (q+1)&2 -> cos)
-    sn = u2f(f2u(so) ^ ((q & 2u) << 30));
-    cs = u2f(f2u(co) ^ (((q + 1u) & 2u) << 30));
+    quadrant_fix(sinr, cosr, q, sn, cs);
 }
 
 SM_HD void sincos(float x, float& sn, float& cs)
@@ -153,6 +215,30 @@ SM_HD void sincos_small(float x, float& sn, float& cs)
     r = fma(nk, -0x1.777a5cp-25f, r);
     r = fma(nk, -0x1.ee59dap-50f, r);
     sincos_poly(r, q, sn, cs);
+}
+
+// Two angles at once (the left / right sensor headings): the same statement sequence as
+// sincos_small() on each lane, so the results are bit-identical to two scalar calls.
+SM_HD void sincos_small2(f2 x, f2& sn, f2& cs)
+{
+    const f2 magic = splat2(12582912.0f);
+    f2 t = fma2(x, splat2(0x1.45f306p-1f), magic);
+    const uint32_t tl = f2u(t.lo), th = f2u(t.hi);
+    f2 nk = neg2(add2(t, splat2(-12582912.0f)));              // -(t - magic), the sign of a zero matters (x = -0)
+    f2 r = fma2(nk, splat2(0x1.921fb6p+0f), x);
+    r = fma2(nk, splat2(-0x1.777a5cp-25f), r);
+    r = fma2(nk, splat2(-0x1.ee59dap-50f), r);
+    f2 s2 = mul2(r, r);
+    f2 p = fma2(splat2(-1.9515295891e-4f), s2, splat2(8.3321608736e-3f));
+    p = fma2(p, s2, splat2(-1.6666654611e-1f));
+    p = mul2(p, s2);
+    f2 sinr = fma2(p, r, r);
+    f2 c = fma2(splat2(2.443315711809948e-5f), s2, splat2(-1.388731625493765e-3f));
+    c = fma2(c, s2, splat2(4.166664568298827e-2f));
+    c = fma2(c, s2, splat2(-0.5f));
+    f2 cosr = fma2(c, s2, splat2(1.0f));
+    quadrant_fix(sinr.lo, cosr.lo, tl, sn.lo, cs.lo);
+    quadrant_fix(sinr.hi, cosr.hi, th, sn.hi, cs.hi);
 }
 
 // ---- exact truncated remainder (WGSL float %, == IEEE fmodf) ----------------

@@ -62,6 +62,7 @@ smd::AgentConsts sm_engine::agent_consts() const
     c.W = W; c.H = H;
     c.Wf = (float)W; c.Hf = (float)H;
     c.rcpW = 1.0f / c.Wf; c.rcpH = 1.0f / c.Hf;
+    c.neg_zero = -0.0f;
     c.xmax = (float)W - 2.0f; c.ymax = (float)H - 2.0f;
     c.speed_min = params.agent_speed_min; c.speed_max = params.agent_speed_max;
     c.turn_speed = params.agent_turn_speed;

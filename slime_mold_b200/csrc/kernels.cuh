@@ -33,9 +33,11 @@ struct LdgF32 {
 struct FetchTex {
     cudaTextureObject_t tex;
     float row_off1;          // (array row of global row 0) + 1 = ghost + pad - row_base + 1, exact in f32
-    __device__ __forceinline__ void operator()(float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
+    __device__ __forceinline__ void operator()(bool /*inside*/, float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
     {
-        // coordinates stay in float: fx, fy are integral and < 2^17, so the sums are exact
+        // fetched whether or not the tap is inside the map (clamped addressing; the caller discards the
+        // footprint of an outside tap).  Coordinates stay in float: for an inside tap fx, fy are integral
+        // and < 2^17, so the sums are exact
         float4 g = tex2Dgather<float4>(tex, fx + 1.0f, fy + row_off1, 0);
         v01 = g.x; v11 = g.y; v10 = g.z; v00 = g.w;
     }
@@ -61,7 +63,7 @@ static __global__ void k_gather_probe(cudaTextureObject_t tex, float* out)
 {
     FetchTex f{tex, 1.0f};
     float v00, v10, v01, v11;
-    f(1.0f, 1.0f, v00, v10, v01, v11);
+    f(true, 1.0f, 1.0f, v00, v10, v01, v11);
     out[0] = v00; out[1] = v10; out[2] = v01; out[3] = v11;
 }
 

@@ -25,6 +25,7 @@ static smd::AgentConsts make_consts(const hc_params* p)
     c.W = p->width; c.H = p->height;
     c.Wf = (float)c.W; c.Hf = (float)c.H;
     c.rcpW = 1.0f / c.Wf; c.rcpH = 1.0f / c.Hf;
+    c.neg_zero = -0.0f;
     c.xmax = c.Wf - 2.0f; c.ymax = c.Hf - 2.0f;
     c.speed_min = p->agent_speed_min; c.speed_max = p->agent_speed_max;
     c.turn_speed = p->agent_turn_speed;
