@@ -45,39 +45,69 @@ constexpr float kTwoPi = 2.0f * 3.14159265359f;    // compute.wgsl:121
 constexpr float kRcpTwoPi = 0.15915494f;
 constexpr float kTimeStep = 0.016f;                // compute.wgsl:55
 
-// sample_trail_map, compute.wgsl:7-29.  FETCH(inside, fx, fy, v00, v10, v01, v11) returns the 2x2 footprint
+// sample_trail_map, compute.wgsl:7-29.  FETCH(consts, fx, fy, v00, v10, v01, v11) returns the 2x2 footprint
 // whose top-left cell is global (fx, fy) (integral floats): four scalar loads from the row-major field (host / LDG
-// path) or one texture gather from the block-linear copy (device TEX path) -- raw f32 either way.  `inside`
-// is the reference's bounds test; an implementation may fetch regardless (the texture path does: clamped
-// addressing makes any coordinate harmless and an unconditional TLD4 needs no predicate bookkeeping) or
-// skip the loads (the row-major path must) -- the footprint is only consumed when `inside` holds.
+// path) or one texture gather from the block-linear copy (device TEX path) -- raw f32 either way.  An
+// implementation may fetch whether or not the tap passes the reference's bounds test (the texture path
+// does: clamped addressing makes any coordinate harmless and an unconditional TLD4 needs no predicate
+// bookkeeping) or test and skip the loads (the row-major path must) -- the footprint of an outside tap
+// is discarded by zero_unless_inside().
 //
 // The sample is split in two so that the per-sensor position arithmetic (px - floor, 1 - d) of the left
-// and right sensors can run as packed pairs: bilinear_at() takes the integral corner and the fractions.
+// and right sensors can run as packed pairs, and so that all three footprints can be in flight at once:
+// fetch_footprint() issues the loads, bilinear() takes the footprint and the fractions.
 SM_HD bool tap_inside(const AgentConsts& c, float fx, float fy)
 {
     // x0 < 0 || x1 >= W || y0 < 0 || y1 >= H -> 0 (sensing is NOT toroidal); NaN -> outside
     return fx >= 0.0f && fx <= c.xmax && fy >= 0.0f && fy <= c.ymax;
 }
 
-template <class FETCH>
-SM_HD float bilinear_at(const AgentConsts& c, float fx, float fy, float dx, float omdx, float dy, float omdy, FETCH fetch)
+// inside ? v : 0 -- on the device as ONE predicate chain (4 FSETP + 1 FSEL).  Left to the compiler the
+// conjunction becomes four nested selects (8 instructions per sensor); the kernel is issue-bound.
+SM_HD float zero_unless_inside(const AgentConsts& c, float fx, float fy, float v)
 {
-    const bool inside = tap_inside(c, fx, fy);
-    float v00, v10, v01, v11;
-    fetch(inside, fx, fy, v00, v10, v01, v11);   // fx, fy: integral; inside [0, W-2] x [0, H-2] when `inside`
-    float v0 = mixf_pre(v00, v10, dx, omdx);                               // :26
-    float v1 = mixf_pre(v01, v11, dx, omdx);                               // :27
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ge.f32 p, %1, 0f00000000;\n\t"
+        "setp.le.and.f32 p, %1, %2, p;\n\t"
+        "setp.ge.and.f32 p, %3, 0f00000000, p;\n\t"
+        "setp.le.and.f32 p, %3, %4, p;\n\t"
+        "selp.f32 %0, %5, 0f00000000, p;\n\t}"
+        : "=f"(r) : "f"(fx), "f"(c.xmax), "f"(fy), "f"(c.ymax), "f"(v));
+    return r;
+#else
+    return tap_inside(c, fx, fy) ? v : 0.0f;
+#endif
+}
+
+// A 2x2 footprint, corner (fx, fy): v[] = {v00, v10, v01, v11}
+struct Footprint { float fx, fy, v00, v10, v01, v11; };
+
+template <class FETCH>
+SM_HD Footprint fetch_footprint(const AgentConsts& c, float fx, float fy, FETCH fetch)
+{
+    Footprint f;
+    f.fx = fx; f.fy = fy;
+    fetch(c, fx, fy, f.v00, f.v10, f.v01, f.v11);   // fx, fy: integral; inside [0, W-2] x [0, H-2] when the tap is inside
+    return f;
+}
+
+SM_HD float bilinear(const AgentConsts& c, const Footprint& f, float dx, float omdx, float dy, float omdy)
+{
+    float v0 = mixf_pre(f.v00, f.v10, dx, omdx);                           // :26
+    float v1 = mixf_pre(f.v01, f.v11, dx, omdx);                           // :27
     float v = mixf_pre(v0, v1, dy, omdy);                                  // :28
-    return inside ? v : 0.0f;                                              // :14-16
+    return zero_unless_inside(c, f.fx, f.fy, v);                           // :14-16
 }
 
 template <class FETCH>
 SM_HD float sample_trail(const AgentConsts& c, float px, float py, FETCH fetch)
 {
     float fx = ::floorf(px), fy = ::floorf(py);
+    const Footprint f = fetch_footprint(c, fx, fy, fetch);
     float dx = sub(px, fx), dy = sub(py, fy);
-    return bilinear_at(c, fx, fy, dx, sub(1.0f, dx), dy, sub(1.0f, dy), fetch);
+    return bilinear(c, f, dx, sub(1.0f, dx), dy, sub(1.0f, dy));
 }
 
 // Footprint fetch from the row-major field.  IdxT = int32_t when the strip (with ghosts) has fewer
@@ -87,10 +117,10 @@ struct FetchLinear {
     const float* trail;      // owned row 0 of this rank's strip
     IdxT W, row_base;
     LD ld;
-    SM_HD void operator()(bool inside, float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
+    SM_HD void operator()(const AgentConsts& c, float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
     {
         v00 = v10 = v01 = v11 = 0.0f;
-        if (inside) {
+        if (tap_inside(c, fx, fy)) {
             const IdxT x0 = (IdxT)(int32_t)fx, y0 = (IdxT)(int32_t)fy;
             const float* r0 = trail + ((y0 - row_base) * W + x0);
             const float* r1 = r0 + W;
@@ -115,16 +145,21 @@ SM_HD float wrap_coord(float v, float m, float rcp_m)
 // positions and fractions run as packed pairs (sincos_small2, add2 / mul2), steering is one
 // branch-free expression, and the toroidal wrap is skipped when the moved position is already in
 // range (x % W == x for 0 <= x < W, -0 included).
-template <class FETCH>
-SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t agent_index,
-                        const AgentConsts& c, FETCH fetch, int32_t& cx, int32_t& cy)
+//
+// TAME = |angle| <= 4096 and |sensor_angle| <= 4096 (every agent after its first step: headings are wrapped
+// into [0, 2pi]).  It licenses two shortcuts that are identities on that range: the spec's small-argument
+// sincos without its range test, and sign(diff) == sign(tau) in the turn (diff = (angle +- TAU) - angle is
+// within 2^-11 of +-TAU).  The generic instantiation keeps the literal statements.
+template <bool TAME, class FETCH>
+SM_HD void agent_update_impl(float& x, float& y, float& angle, float& speed, int32_t agent_index,
+                             const AgentConsts& c, FETCH fetch, int32_t& cx, int32_t& cy)
 {
     speed = clampf(speed, c.speed_min, c.speed_max);                       // :72
 
     f2 sLR, cLR;           // lo = left sensor, hi = right sensor
     float sC, cC;
     const f2 aLR = mk2(sub(angle, c.sensor_angle), add(angle, c.sensor_angle));   // :75-76
-    if (::fabsf(angle) <= 4096.0f && ::fabsf(c.sensor_angle) <= 4096.0f) {
+    if (TAME) {
         // |angle +- sa| <= 8192: the spec's fast path, evaluated without the per-call range test
         sincos_small2(aLR, sLR, cLR);
         sincos_small(angle, sC, cC);                                       // :77
@@ -139,11 +174,18 @@ SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t 
     const f2 pyLR = add2(splat2(y), mul2_nofuse(sd2, sLR, c.neg_zero));
     const f2 fxLR = mk2(::floorf(pxLR.lo), ::floorf(pxLR.hi));             // :8-9
     const f2 fyLR = mk2(::floorf(pyLR.lo), ::floorf(pyLR.hi));
+    const float pxC = add(x, mul(sd, cC)), pyC = add(y, mul(sd, sC));      // :87-90
+    const float fxC = ::floorf(pxC), fyC = ::floorf(pyC);
+    // all three footprints are requested before any of them is consumed: one exposed memory latency, not three
+    const Footprint qL = fetch_footprint(c, fxLR.lo, fyLR.lo, fetch);      // :93
+    const Footprint qR = fetch_footprint(c, fxLR.hi, fyLR.hi, fetch);      // :94
+    const Footprint qC = fetch_footprint(c, fxC, fyC, fetch);              // :95
     const f2 dxLR = sub2(pxLR, fxLR), dyLR = sub2(pyLR, fyLR);             // :18-19
     const f2 mxLR = sub2(one2, dxLR), myLR = sub2(one2, dyLR);             // the (1 - t) of mix()
-    float vL = bilinear_at(c, fxLR.lo, fyLR.lo, dxLR.lo, mxLR.lo, dyLR.lo, myLR.lo, fetch);   // :93
-    float vR = bilinear_at(c, fxLR.hi, fyLR.hi, dxLR.hi, mxLR.hi, dyLR.hi, myLR.hi, fetch);   // :94
-    float vC = sample_trail(c, add(x, mul(sd, cC)), add(y, mul(sd, sC)), fetch);              // :87-90,95
+    const float dxC = sub(pxC, fxC), dyC = sub(pyC, fyC);
+    float vL = bilinear(c, qL, dxLR.lo, mxLR.lo, dyLR.lo, myLR.lo);
+    float vR = bilinear(c, qR, dxLR.hi, mxLR.hi, dyLR.hi, myLR.hi);
+    float vC = bilinear(c, qC, dxC, sub(1.0f, dxC), dyC, sub(1.0f, dyC));
 
     // :98-112  keep | turn left (towards angle - TAU) | turn right (towards angle + TAU) | keep (vL == vR).
     // angle - TAU == angle + (-TAU) bit for bit, so both turns are one expression in the signed TAU.
@@ -152,7 +194,10 @@ SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t 
         const bool left = vL > vR, right = vR > vL;
         const float tau = left ? -kTau : kTau;
         const float diff = sub(add(angle, tau), angle);                    // :101,106
-        const float turned = add(angle, mul(::fminf(c.turn_speed, ::fabsf(diff)), signf(diff)));   // :104,109
+        const float reach = ::fminf(c.turn_speed, ::fabsf(diff));
+        // TAME: sign(diff) is -1 for a left turn, +1 for a right turn, and reach * (+-1) == +-reach exactly
+        const float turn = TAME ? (left ? -reach : reach) : mul(reach, signf(diff));
+        const float turned = add(angle, turn);                             // :104,109
         angle = (!keep && (left || right)) ? turned : angle;
     }
 
@@ -188,6 +233,16 @@ SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t 
     } else {
         cx = -1; cy = -1;
     }
+}
+
+template <class FETCH>
+SM_HD void agent_update(float& x, float& y, float& angle, float& speed, int32_t agent_index,
+                        const AgentConsts& c, FETCH fetch, int32_t& cx, int32_t& cy)
+{
+    if (::fabsf(angle) <= 4096.0f && ::fabsf(c.sensor_angle) <= 4096.0f)
+        agent_update_impl<true>(x, y, angle, speed, agent_index, c, fetch, cx, cy);
+    else
+        agent_update_impl<false>(x, y, angle, speed, agent_index, c, fetch, cx, cy);
 }
 
 // seeded start-up fill, /root/reference/src/main.rs:269-282

@@ -353,7 +353,7 @@ int sm_engine::launch_agents()
     const bool idx32 = (uint64_t)field_cells() < (1ull << 31);
     const bool flags = flag_mode();
     SM_TRY(switch_deposit_mode(flags ? 2 : 1));
-    const unsigned nb = blocks_for(n_local, 256);
+    const unsigned nb = blocks_for(n_local, smk::kAgentsPerBlock);     // a CTA steps kAgentsPerBlock consecutive slots
     float4* a = agents[acur];
     uint32_t* id = ids[acur];
     void* dep = flags ? (void*)flags_ptr(ccur) : (void*)counts_ptr(ccur);

@@ -33,7 +33,7 @@ struct LdgF32 {
 struct FetchTex {
     cudaTextureObject_t tex;
     float row_off1;          // (array row of global row 0) + 1 = ghost + pad - row_base + 1, exact in f32
-    __device__ __forceinline__ void operator()(bool /*inside*/, float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
+    __device__ __forceinline__ void operator()(const AgentConsts&, float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
     {
         // fetched whether or not the tap is inside the map (clamped addressing; the caller discards the
         // footprint of an outside tap).  Coordinates stay in float: for an inside tap fx, fy are integral
@@ -63,7 +63,7 @@ static __global__ void k_gather_probe(cudaTextureObject_t tex, float* out)
 {
     FetchTex f{tex, 1.0f};
     float v00, v10, v01, v11;
-    f(true, 1.0f, 1.0f, v00, v10, v01, v11);
+    f(AgentConsts{}, 1.0f, 1.0f, v00, v10, v01, v11);
     out[0] = v00; out[1] = v10; out[2] = v01; out[3] = v11;
 }
 
@@ -130,35 +130,18 @@ struct LeaverBufs {
     int32_t rows_up;
 };
 
-// One agent per thread.  `deposits` points at owned row 0 of this rank's strip (global row
+// One agent: compute.wgsl:57-145 on slot i, then the deposit (and, on strips, the hand-over of an agent whose
+// new row belongs to a neighbour).  `deposits` points at owned row 0 of this rank's strip (global row
 // c.row_base); ghost rows sit at negative / >= rows offsets.
 // FLAGS: deposits are u8 "somebody deposited here" marks written with plain stores instead of u32
 // counts bumped with RED atomics -- exact whenever dep >= 1 and the field is non-negative, because
 // clamp(t + k*dep, 0, 1) == 1 for every k >= 1 (all shipped presets: dep = 1.0).
-#ifndef SM_AGENTS_MIN_BLOCKS
-#define SM_AGENTS_MIN_BLOCKS 8        // 8 x 256 threads = full occupancy (<= 32 registers): measured 6% faster than ptxas's own 36-register choice
-#endif
 template <int XM, class IdxT, class FETCH, bool FLAGS>
-static __global__ void __launch_bounds__(256, SM_AGENTS_MIN_BLOCKS)
-k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
-         const FETCH fetch, void* __restrict__ deposits, const AgentConsts c,
-         const LeaverBufs lv)
+__device__ __forceinline__ void step_agent_slot(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
+                                                float4 a, uint32_t id, const FETCH& fetch, void* __restrict__ deposits,
+                                                const AgentConsts& c, const LeaverBufs& lv)
 {
     constexpr bool MULTI = XM != XM_SINGLE;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // MULTI: n is the host's upper bound of the slots in use; every slot past the live ones holds
-    // kDeadAgent (kept so by the sort and by k_append_arrivals), so no device-side count is needed here
-    if (i >= n) return;
-    const uint32_t id = ids[i];
-    float4 a;
-    if (MULTI) {
-        // issue the state load together with the id load instead of behind the dead-slot test (the
-        // compiler sinks a plain load below the early exit, which serialises two DRAM latencies)
-        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(agents + i));
-        if (id == kDeadAgent) return;
-    } else {
-        a = agents[i];
-    }
     int32_t cx, cy;
     smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, c, fetch, cx, cy);
     agents[i] = a;
@@ -213,6 +196,56 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
                 atomicExch(lv.overflow, 1ull);       // staging overflow: reported by the host
             }
         }
+    }
+}
+
+#ifndef SM_AGENTS_MIN_BLOCKS
+#define SM_AGENTS_MIN_BLOCKS 5        // 5 x 256 threads: 48 registers -- room for three texture gathers + the next agent's state in flight
+                                      // (measured on config 2, us per launch: 8 CTAs/32 regs 178, 6/40 171, 5/48 164, 4/52 179)
+#endif
+#ifndef SM_AGENTS_PER_THREAD
+#define SM_AGENTS_PER_THREAD 4        // agents one thread steps in sequence (a CTA owns 256 * this many consecutive slots); 1: 181 us, 2: 175, 4: 164, 8: 164
+#endif
+constexpr int kAgentsPerThread = SM_AGENTS_PER_THREAD;
+constexpr uint32_t kAgentsPerBlock = 256u * kAgentsPerThread;
+
+__device__ __forceinline__ void load_agent_slot(const float4* agents, const uint32_t* ids, uint64_t i, float4& a, uint32_t& id)
+{
+    // asm volatile: the loads stay where they are written (ahead of the previous agent's arithmetic) --
+    // left to the compiler a plain load is sunk to its first use, which exposes the full DRAM latency
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(agents + i));
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(id) : "l"(ids + i));
+}
+
+template <int XM, class IdxT, class FETCH, bool FLAGS>
+static __global__ void __launch_bounds__(256, SM_AGENTS_MIN_BLOCKS)
+k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
+         const FETCH fetch, void* __restrict__ deposits, const AgentConsts c,
+         const LeaverBufs lv)
+{
+    constexpr bool MULTI = XM != XM_SINGLE;
+    // A CTA steps kAgentsPerBlock consecutive slots, thread t taking slots t, t + 256, ... (coalesced).
+    // The state of the next slot is requested before the current one is stepped, so only the first
+    // load of a thread waits for DRAM; consecutive slots are neighbours in the cell-sorted order, so
+    // their footprints also reuse this SM's L1.
+    // MULTI: n is the host's upper bound of the slots in use; every slot past the live ones holds
+    // kDeadAgent (kept so by the sort and by k_append_arrivals), so no device-side count is needed here
+    uint64_t i = (uint64_t)blockIdx.x * kAgentsPerBlock + threadIdx.x;
+    if (i >= n) return;
+    float4 a_next;
+    uint32_t id_next;
+    load_agent_slot(agents, ids, i, a_next, id_next);
+#pragma unroll 1
+    for (int j = 0; j < kAgentsPerThread; ++j) {
+        float4 a = a_next;
+        const uint32_t id = id_next;
+        const uint64_t i_next = i + 256u;
+        const bool more = (j + 1 < kAgentsPerThread) && i_next < n;
+        if (more) load_agent_slot(agents, ids, i_next, a_next, id_next);
+        if (!MULTI || id != kDeadAgent)
+            step_agent_slot<XM, IdxT, FETCH, FLAGS>(agents, ids, i, a, id, fetch, deposits, c, lv);
+        if (!more) break;
+        i = i_next;
     }
 }
 
