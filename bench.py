@@ -274,6 +274,9 @@ def run_ours(args):
     agent_ms = t.agents_ms / max(t.agent_launches, 1)
     trail_ms = t.trail_ms / max(t.trail_launches, 1)
     sort_ms_per_step = t.sort_ms / max(t.steps, 1)
+    if os.environ.get("SM_SIDE_TIMING"):      # diagnostics: per-rank kernel split (only rank 0's goes into the JSON line)
+        print(f"[rank {rank}] agents {agent_ms * 1e3:.1f} us  trail {trail_ms * 1e3:.1f} us  sort/step {sort_ms_per_step * 1e3:.1f} us  "
+              f"exchange/step {t.exchange_ms / max(t.steps, 1) * 1e3:.1f} us  local agents {local_agents}", file=sys.stderr, flush=True)
     peak, peak_src = hbm_peak()
     # algorithmic bytes: agents 32 B/agent-step + trail sensing read 4 + deposit write 4 B/cell;
     # fused decay+diffuse 8 B/cell-pass

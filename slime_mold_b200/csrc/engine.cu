@@ -93,8 +93,9 @@ smd::TrailConsts sm_engine::trail_consts() const
 // ---------------------------------------------------------------------------
 // timing helpers
 // ---------------------------------------------------------------------------
-int sm_engine::tic(int kind)
+int sm_engine::tic(int kind, cudaStream_t st)
 {
+    if (!st) st = stream;
     if (!timing_enabled) return SM_OK;
     if (ev_used == ev_pool.size()) {
         if (ev_pool.size() >= 4096) SM_TRY(resolve_timing());
@@ -106,13 +107,14 @@ int sm_engine::tic(int kind)
         }
     }
     ev_pool[ev_used].kind = kind;
-    SM_CUDA(cudaEventRecord(ev_pool[ev_used].a, stream));
+    SM_CUDA(cudaEventRecord(ev_pool[ev_used].a, st));
     return SM_OK;
 }
-int sm_engine::toc()
+int sm_engine::toc(cudaStream_t st)
 {
     if (!timing_enabled) return SM_OK;
-    SM_CUDA(cudaEventRecord(ev_pool[ev_used].b, stream));
+    if (!st) st = stream;
+    SM_CUDA(cudaEventRecord(ev_pool[ev_used].b, st));
     ev_used++;
     return SM_OK;
 }
@@ -127,7 +129,10 @@ int sm_engine::resolve_timing()
         case 0: timing.agents_ms += ms; timing.agent_launches++; break;
         case 1: timing.trail_ms += ms; timing.trail_launches++; break;
         case 2: timing.sort_ms += ms; timing.sort_launches++; break;
-        default: timing.exchange_ms += ms; timing.exchange_launches++; break;
+        case 3: timing.exchange_ms += ms; timing.exchange_launches++; break;
+        default:                                     // >= 10: side-stream pieces of the overlapped exchange (diagnostics only)
+            if (ev_pool[i].kind - 10 < 8) { side_dbg_ms[ev_pool[i].kind - 10] += ms; side_dbg_n[ev_pool[i].kind - 10]++; }
+            break;
         }
     }
     ev_used = 0;
@@ -416,61 +421,91 @@ int sm_engine::launch_agents()
     return SM_OK;
 }
 
-int sm_engine::launch_trail(bool has_counts)
+// What one trail pass reads and writes (fixed for the pass; the launch may be split into row bands).
+int sm_engine::trail_plan(bool has_counts, TrailPass& p)
 {
-    const smd::TrailConsts tc = trail_consts();
-    smk::TrailGeom g{};
-    g.W = W; g.rows = rows; g.wrap_y = (world == 1) ? 1 : 0;
+    p.tc = trail_consts();
+    p.g = smk::TrailGeom{};
+    p.g.W = W; p.g.rows = rows; p.g.wrap_y = (world == 1) ? 1 : 0;
+    p.g.y_first = 0; p.g.y_last = rows; p.g.chunks1 = 0xFFFFFFFFu; p.g.y_first2 = p.g.y_last2 = 0;
     // the full step keeps the sampler's block-linear copy in step; other passes just mark it stale
     const bool write_surf = use_tex && has_counts && !(cfg.flags & SM_FLAG_GAUSSIAN_BLUR);
-    g.surf = write_surf ? trail_surf : 0;
-    g.surf_row0 = (int)(ghost + pad_rows);
+    p.g.surf = write_surf ? trail_surf : 0;
+    p.g.surf_row0 = (int)(ghost + pad_rows);
     if (!write_surf) arr_stale = true;
-    const float* tin = trail_ptr(cur);
-    float* tout = trail_ptr(1 - cur);
+    p.tin = trail_ptr(cur);
+    p.tout = trail_ptr(1 - cur);
     // deposit representation the agents pass of this step used (none for diffusion-only)
-    const int cm = !has_counts ? smk::CM_NONE : (deposit_mode == 2 ? smk::CM_FLAGS : smk::CM_COUNTS);
-    const void* cin = cm == smk::CM_FLAGS ? (const void*)flags_ptr(ccur) : (const void*)counts_ptr(ccur);
-    void* czero = cm == smk::CM_FLAGS ? (void*)flags_ptr(1 - ccur) : (void*)counts_ptr(1 - ccur);
+    p.cm = !has_counts ? smk::CM_NONE : (deposit_mode == 2 ? smk::CM_FLAGS : smk::CM_COUNTS);
+    p.cin = p.cm == smk::CM_FLAGS ? (const void*)flags_ptr(ccur) : (const void*)counts_ptr(ccur);
+    p.czero = p.cm == smk::CM_FLAGS ? (void*)flags_ptr(1 - ccur) : (void*)counts_ptr(1 - ccur);
+    p.fast = !(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && W % 4 == 0 && W >= 8 && (W / 4) % 32 != 1 && !force_generic;
+    // 8-16 rows per chunk measured best from 4096^2 to 32768^2 (profiles/README.md): the 2/rpc halo
+    // re-reads hit L2; small maps take shorter chunks to keep >= 4 CTAs per SM
+    uint64_t rpc = 8;
+    const unsigned bx = blocks_for(W / 4, 128);
+    while (rpc > 4 && (uint64_t)bx * ((rows + rpc - 1) / rpc) < (uint64_t)num_sms * 4) rpc /= 2;
+    if (rpc_override > 0) rpc = rpc_override;
+    p.g.rows_per_chunk = p.fast ? (uint32_t)rpc : 1u;
+    return SM_OK;
+}
+
+// Rows [y_first, y_last) of the pass on stream `st` (fast kernel only).
+int sm_engine::trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t y_last, cudaStream_t st,
+                                 uint32_t y_first2, uint32_t y_last2)
+{
+    if (y_first >= y_last) return SM_OK;
+    smk::TrailGeom g = p.g;
+    const unsigned bs = 128;
+    const uint32_t rpc = g.rows_per_chunk;
+    g.y_first = y_first; g.y_last = y_last;
+    g.chunks1 = (y_last - y_first + rpc - 1) / rpc;
+    g.y_first2 = y_first2; g.y_last2 = y_last2;
+    const uint32_t chunks2 = y_last2 > y_first2 ? (y_last2 - y_first2 + rpc - 1) / rpc : 0u;
+    dim3 grid(blocks_for(W / 4, bs), (unsigned)(g.chunks1 + chunks2));
+    if (p.cm == smk::CM_NONE) {
+        smk::k_trail_rows<smk::CM_NONE, false, 4><<<grid, bs, 0, st>>>(p.tin, nullptr, nullptr, p.tout, g, p.tc);
+    } else if (g.surf) {
+        if (p.cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, true, 4><<<grid, bs, 0, st>>>(p.tin, p.cin, p.czero, p.tout, g, p.tc);
+        else smk::k_trail_rows<smk::CM_FLAGS, true, 4><<<grid, bs, 0, st>>>(p.tin, p.cin, p.czero, p.tout, g, p.tc);
+    } else {
+        if (p.cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, false, 4><<<grid, bs, 0, st>>>(p.tin, p.cin, p.czero, p.tout, g, p.tc);
+        else smk::k_trail_rows<smk::CM_FLAGS, false, 4><<<grid, bs, 0, st>>>(p.tin, p.cin, p.czero, p.tout, g, p.tc);
+    }
+    SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 1;
+    return SM_OK;
+}
+
+void sm_engine::trail_done(bool has_counts)
+{
+    cur = 1 - cur;
+    if (has_counts) ccur = 1 - ccur;
+    trail_nonneg = true;          // decay clamps at 0 (NaN included), the mix of non-negatives is non-negative
+}
+
+int sm_engine::launch_trail(bool has_counts)
+{
+    TrailPass p;
+    SM_TRY(trail_plan(has_counts, p));
     SM_TRY(tic(1));
     if (cfg.flags & SM_FLAG_GAUSSIAN_BLUR) {
-        SM_TRY(launch_gauss(has_counts, g, tc));
-    } else if (W % 4 == 0 && W >= 8 && (W / 4) % 32 != 1 && !force_generic) {
-        const unsigned bs = 128;
-        const unsigned bx = blocks_for(W / 4, bs);
-        // 8-16 rows per chunk measured best from 4096^2 to 32768^2 (profiles/README.md): the 2/rpc halo
-        // re-reads hit L2; small maps take shorter chunks to keep >= 4 CTAs per SM
-        uint64_t rpc = 8;
-        while (rpc > 4 && (uint64_t)bx * ((rows + rpc - 1) / rpc) < (uint64_t)num_sms * 4) rpc /= 2;
-        if (rpc_override > 0) rpc = rpc_override;
-        g.rows_per_chunk = (uint32_t)rpc;
-        dim3 grid(bx, (unsigned)((rows + rpc - 1) / rpc));
-        if (cm == smk::CM_NONE) {
-            smk::k_trail_rows<smk::CM_NONE, false, 4><<<grid, bs, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc);
-        } else if (g.surf) {
-            if (cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, true, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
-            else smk::k_trail_rows<smk::CM_FLAGS, true, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
-        } else {
-            if (cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, false, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
-            else smk::k_trail_rows<smk::CM_FLAGS, false, 4><<<grid, bs, 0, stream>>>(tin, cin, czero, tout, g, tc);
-        }
-        timing.kernel_launches += 1;
+        SM_TRY(launch_gauss(has_counts, p.g, p.tc));
+    } else if (p.fast) {
+        SM_TRY(trail_launch_rows(p, 0, rows, stream));
     } else {
-        g.rows_per_chunk = 1;
         for (uint32_t y0 = 0; y0 < rows; y0 += 32768) {
             uint32_t ny = std::min<uint32_t>(32768, rows - y0);
             dim3 grid(blocks_for(W, 256), ny);
-            if (cm == smk::CM_COUNTS) smk::k_trail_generic<smk::CM_COUNTS><<<grid, 256, 0, stream>>>(tin, cin, czero, tout, g, tc, (int64_t)y0);
-            else if (cm == smk::CM_FLAGS) smk::k_trail_generic<smk::CM_FLAGS><<<grid, 256, 0, stream>>>(tin, cin, czero, tout, g, tc, (int64_t)y0);
-            else smk::k_trail_generic<smk::CM_NONE><<<grid, 256, 0, stream>>>(tin, nullptr, nullptr, tout, g, tc, (int64_t)y0);
+            if (p.cm == smk::CM_COUNTS) smk::k_trail_generic<smk::CM_COUNTS><<<grid, 256, 0, stream>>>(p.tin, p.cin, p.czero, p.tout, p.g, p.tc, (int64_t)y0);
+            else if (p.cm == smk::CM_FLAGS) smk::k_trail_generic<smk::CM_FLAGS><<<grid, 256, 0, stream>>>(p.tin, p.cin, p.czero, p.tout, p.g, p.tc, (int64_t)y0);
+            else smk::k_trail_generic<smk::CM_NONE><<<grid, 256, 0, stream>>>(p.tin, nullptr, nullptr, p.tout, p.g, p.tc, (int64_t)y0);
             timing.kernel_launches += 1;
         }
     }
     SM_CUDA(cudaGetLastError());
     SM_TRY(toc());
-    cur = 1 - cur;
-    if (has_counts) ccur = 1 - ccur;
-    trail_nonneg = true;          // decay clamps at 0 (NaN included), the mix of non-negatives is non-negative
+    trail_done(has_counts);
     return SM_OK;
 }
 
@@ -943,9 +978,13 @@ int sm_step(sm_engine* e, uint32_t n_steps)
             e->steps_since_sort = 0;
         }
         SM_TRY(e->launch_agents());                      // src/main.rs:1164-1181
-        if (e->world > 1) SM_TRY(e->p2p ? e->p2p_after_agents() : e->exchange_counts());
-        SM_TRY(e->launch_trail(true));                   // src/main.rs:1184-1199 + 1220-1235
-        if (e->world > 1) SM_TRY(e->p2p ? e->p2p_after_trail() : e->migrate_agents());
+        if (e->world > 1 && e->p2p && e->overlap_ok()) {
+            SM_TRY(e->p2p_trail_overlapped());           // trail pass with the exchange hidden behind its interior rows
+        } else {
+            if (e->world > 1) SM_TRY(e->p2p ? e->p2p_after_agents() : e->exchange_counts());
+            SM_TRY(e->launch_trail(true));               // src/main.rs:1184-1199 + 1220-1235
+            if (e->world > 1) SM_TRY(e->p2p ? e->p2p_after_trail() : e->migrate_agents());
+        }
         e->steps_since_sort++;
         e->timing.steps++;
     }
@@ -958,8 +997,12 @@ int sm_diffuse_only(sm_engine* e, uint32_t n_passes)
     if (e->world > 1 && !e->comm_ready) return sm_fail(SM_ERR_STATE, "multi-GPU engine: call sm_comm_init first");
     for (uint32_t s = 0; s < n_passes; ++s) {
         if (e->world > 1 && e->ghost_stale) SM_TRY(e->exchange_trail_ghosts());
-        SM_TRY(e->launch_trail(false));
-        if (e->world > 1) SM_TRY(e->exchange_trail_ghosts());
+        if (e->world > 1 && e->p2p && e->overlap_ok()) {
+            SM_TRY(e->p2p_diffuse_overlapped());
+        } else {
+            SM_TRY(e->launch_trail(false));
+            if (e->world > 1) SM_TRY(e->exchange_trail_ghosts());
+        }
     }
     return SM_OK;
 }

@@ -119,14 +119,28 @@ struct sm_engine {
     uint32_t barrier_seq = 0;
     int setup_p2p();
     int p2p_barrier();
-    int p2p_after_agents();           // barrier 1 + pull of the neighbours' boundary deposit rows
-    int p2p_after_trail();            // push trail ghost rows, append arrivals, barrier 2
+    int p2p_after_agents(cudaStream_t st = nullptr, bool timed = true);   // barrier 1 + pull of the neighbours' boundary deposit rows
+    int p2p_after_trail(cudaStream_t st = nullptr, bool timed = true);    // push trail ghost rows, append arrivals, barrier 2
+    // Overlapped form of {p2p_after_agents, trail pass, p2p_after_trail}: the interior rows of the trail
+    // pass need nothing from the neighbours and run on the main stream at once; barrier 1, the two boundary
+    // bands, the ghost-row push, the arrivals and barrier 2 run beside them on `side_stream`.
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap_enabled = true;      // SM_OVERLAP=0 switches back to the serial exchange (A/B)
+    bool overlap_ok();
+    uint32_t overlap_band();          // rows of each boundary band (multiple of the chunk height; 0 = strip too thin)
+    int p2p_trail_overlapped();
+    int p2p_diffuse_overlapped();
+    int p2p_push_ghosts(cudaStream_t st, uint32_t g);
 
     smd::AgentConsts agent_consts() const;
     smd::TrailConsts trail_consts() const;
 
-    int tic(int kind);
-    int toc();
+    int tic(int kind, cudaStream_t st = nullptr);
+    int toc(cudaStream_t st = nullptr);
+    double side_dbg_ms[8] = {0};     // SM_SIDE_TIMING=1: per-piece times of the side stream (printed at comm teardown)
+    uint64_t side_dbg_n[8] = {0};
+    bool side_dbg = false;
     int resolve_timing();
 
     int alloc_trail();
@@ -141,6 +155,17 @@ struct sm_engine {
 
     int sort_agents();
     int launch_agents();
+    struct TrailPass {
+        smk::TrailGeom g;
+        smd::TrailConsts tc;
+        const float* tin; float* tout;
+        int cm; const void* cin; void* czero;
+        bool fast;                    // k_trail_rows applies (else k_trail_generic / the Gaussian extension)
+    };
+    int trail_plan(bool has_counts, TrailPass& p);
+    int trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t y_last, cudaStream_t st,
+                          uint32_t y_first2 = 0, uint32_t y_last2 = 0);   // optional second band in the same launch
+    void trail_done(bool has_counts);
     int launch_trail(bool has_counts);
     int launch_gauss(bool has_counts, const smk::TrailGeom& g, const smd::TrailConsts& tc);
     int restore_identity_order();

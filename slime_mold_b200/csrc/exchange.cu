@@ -162,34 +162,82 @@ static __global__ void k_bump_counters(unsigned long long* counters, const uint8
 // A barrier = "tell both neighbours I reached sequence number s, wait until both told me the same".
 // Everything this rank wrote into a neighbour's memory earlier in the stream is fenced before the flag.
 // The wait gives up after ~20 s and raises the sticky error flag instead of hanging the GPU.
+// Fences: what the neighbours read after the barrier was written by EARLIER kernels of this stream (the agent
+// pass, the ghost-row push), and a kernel boundary already orders those writes before anything this kernel
+// stores.  The barrier itself therefore needs one release fence ahead of the flag stores (for the few words
+// this very thread wrote) and one acquire fence behind the wait.  g_fence_mode (SM_BARRIER_FENCE): 0 = three
+// sequentially-consistent system fences (the first version: each one costs ~10 us while the interior trail
+// pass is streaming beside it), 1 = acq_rel system fences (default), 2 = device-scope fences only (A/B).
+__device__ int g_fence_mode = 1;
+
+__device__ __forceinline__ void barrier_fence()
+{
+    if (g_fence_mode == 0) __threadfence_system();
+    else if (g_fence_mode == 1) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else __threadfence();
+}
+
 __device__ __forceinline__ void ring_barrier(volatile uint32_t* mine, volatile uint32_t* up_slot, volatile uint32_t* down_slot,
                                              uint32_t seq, unsigned long long* err)
 {
-    __threadfence_system();
+    barrier_fence();
     *up_slot = seq;        // I am the DOWN neighbour of `up`: its slot [4]
     *down_slot = seq;      // I am the UP neighbour of `down`: its slot [0]
-    __threadfence_system();
+    if (g_fence_mode == 0) __threadfence_system();
     const long long t0 = clock64();
     while ((int32_t)(mine[0] - seq) < 0 || (int32_t)(mine[1] - seq) < 0) {
-        __nanosleep(200);
+        __nanosleep(100);
         if (clock64() - t0 > 40000000000ll) { atomicExch(err, 3ull); break; }   // ~20 s: the neighbour is gone
     }
-    __threadfence_system();
+    barrier_fence();
+}
+
+// The waiting half of ring_barrier alone (CTAs that did not announce).
+__device__ __forceinline__ void ring_wait(volatile uint32_t* mine, uint32_t seq, unsigned long long* err)
+{
+    const long long t0 = clock64();
+    while ((int32_t)(mine[0] - seq) < 0 || (int32_t)(mine[1] - seq) < 0) {
+        __nanosleep(100);
+        if (clock64() - t0 > 40000000000ll) { atomicExch(err, 3ull); break; }
+    }
+    barrier_fence();
 }
 
 // Barrier 1 (all neighbours finished their agent pass: their deposits and leavers have landed here),
 // then pull the one deposit row of each neighbour that the 3x3 blur of my boundary rows needs.
+// Small CTAs on purpose (128 threads, a few of them): this kernel runs beside the interior trail pass, whose
+// 128-thread CTAs refill every slot an SM frees -- a 1024-thread CTA found no SM with that many free threads
+// until the interior pass had drained (measured: 41 us of queueing per step).  CTA 0 announces this rank;
+// every CTA waits for both neighbours on its own (no CTA depends on another one of this grid).
 template <class T>
-static __global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(128)
 k_barrier_pull(uint32_t* window, uint32_t* up_window, uint32_t* down_window, uint32_t seq, unsigned long long* err,
                T* my_row_above, const T* up_last_row, T* my_row_below, const T* down_first_row, uint32_t W)
 {
-    if (threadIdx.x == 0)
-        ring_barrier(window, up_window + 1, down_window + 0, seq, err);
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) ring_barrier(window, up_window + 1, down_window + 0, seq, err);
+        else ring_wait(window, seq, err);
+    }
     __syncthreads();
-    for (uint32_t x = threadIdx.x; x < W; x += blockDim.x) {
-        my_row_above[x] = up_last_row[x];
-        my_row_below[x] = down_first_row[x];
+    // Remote reads over NVLink cost a round trip each (a few us beside a streaming kernel): the grid is sized so
+    // that a thread has ONE 16-byte read per row in flight, not a loop of dependent narrow ones.
+    const size_t row_bytes = (size_t)W * sizeof(T);
+    const bool wide = (row_bytes % 16 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(my_row_above) | reinterpret_cast<uintptr_t>(up_last_row) |
+                        reinterpret_cast<uintptr_t>(my_row_below) | reinterpret_cast<uintptr_t>(down_first_row)) % 16 == 0);
+    if (wide) {
+        const size_t n16 = row_bytes / 16;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+            const uint4 a = reinterpret_cast<const uint4*>(up_last_row)[i];
+            const uint4 b = reinterpret_cast<const uint4*>(down_first_row)[i];
+            reinterpret_cast<uint4*>(my_row_above)[i] = a;
+            reinterpret_cast<uint4*>(my_row_below)[i] = b;
+        }
+    } else {
+        for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+            my_row_above[x] = up_last_row[x];
+            my_row_below[x] = down_first_row[x];
+        }
     }
 }
 
@@ -361,6 +409,15 @@ void sm_engine::comm_destroy()
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
     ipc_opened.clear();
     if (window) { cudaFree(window); window = nullptr; }
+    if (side_dbg && side_dbg_n[0]) {
+        resolve_timing();
+        fprintf(stderr, "[slime_b200 rank %d] side stream per step: barrier1+pull %.2f us, bands %.2f us, push+arrivals+barrier2 %.2f us (%llu steps)\n",
+                rank, 1e3 * side_dbg_ms[0] / side_dbg_n[0], 1e3 * side_dbg_ms[1] / std::max<uint64_t>(1, side_dbg_n[1]),
+                1e3 * side_dbg_ms[2] / std::max<uint64_t>(1, side_dbg_n[2]), (unsigned long long)side_dbg_n[0]);
+    }
+    if (side_stream) { cudaStreamDestroy(side_stream); side_stream = nullptr; }
+    if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
+    if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
     p2p = false;
     if (dev_counters) { cudaFree(dev_counters); dev_counters = nullptr; }
     if (host_counters) { cudaFreeHost(host_counters); host_counters = nullptr; }
@@ -653,6 +710,21 @@ int sm_engine::setup_p2p()
     }
     p2p = all != 0;
     barrier_seq = 0;
+    if (p2p && !side_stream) {
+        // highest priority: the small exchange kernels must not queue behind the pending CTAs of the
+        // interior trail pass (the block scheduler drains grids of equal priority in launch order)
+        int prio_lo = 0, prio_hi = 0;
+        SM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        SM_CUDA(cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, prio_hi));
+        SM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        SM_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        if (const char* v = getenv("SM_OVERLAP")) overlap_enabled = atoi(v) != 0;
+        if (const char* v = getenv("SM_SIDE_TIMING")) side_dbg = atoi(v) != 0;
+        if (const char* v = getenv("SM_BARRIER_FENCE")) {
+            const int mode = atoi(v);
+            SM_CUDA(cudaMemcpyToSymbol(smk::g_fence_mode, &mode, sizeof mode));
+        }
+    }
     return SM_OK;
 }
 
@@ -667,41 +739,42 @@ int sm_engine::p2p_barrier()
     return SM_OK;
 }
 
-int sm_engine::p2p_after_agents()
+int sm_engine::p2p_after_agents(cudaStream_t st, bool timed)
 {
+    if (!st) st = stream;
     uint32_t g = 0, m = 0;
     SM_TRY(halo_depths(this, &g, &m));
-    SM_TRY(tic(3));
+    if (timed) SM_TRY(tic(3));
     ++barrier_seq;
     uint32_t* w = reinterpret_cast<uint32_t*>(window);
     uint32_t* wu = reinterpret_cast<uint32_t*>(peer[0].window);
     uint32_t* wd = reinterpret_cast<uint32_t*>(peer[1].window);
     const size_t row0_off = (size_t)(ghost + pad_rows) * W;
+    // one 16-byte element per thread and row (flags: W bytes per row, counts: 4 W)
+    const uint64_t pull_elems = ((uint64_t)W * (deposit_mode == 2 ? 1 : 4) + 15) / 16;
+    const unsigned pull_blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(256, (pull_elems + 127) / 128));
     if (deposit_mode == 2) {
         uint8_t* f = flags_ptr(ccur);
         const uint8_t* up_last = peer[0].flags8[ccur] + row0_off + (size_t)(peer[0].rows - 1) * W;
         const uint8_t* down_first = peer[1].flags8[ccur] + row0_off;
-        smk::k_barrier_pull<uint8_t><<<1, 1024, 0, stream>>>(w, wu, wd, barrier_seq, dev_counters + 2, f - (int64_t)W, up_last,
+        smk::k_barrier_pull<uint8_t><<<pull_blocks, 128, 0, st>>>(w, wu, wd, barrier_seq, dev_counters + 2, f - (int64_t)W, up_last,
                                                             f + (int64_t)rows * W, down_first, W);
     } else {
         uint32_t* cn = counts_ptr(ccur);
         const uint32_t* up_last = peer[0].counts[ccur] + row0_off + (size_t)(peer[0].rows - 1) * W;
         const uint32_t* down_first = peer[1].counts[ccur] + row0_off;
-        smk::k_barrier_pull<uint32_t><<<1, 1024, 0, stream>>>(w, wu, wd, barrier_seq, dev_counters + 2, cn - (int64_t)W, up_last,
+        smk::k_barrier_pull<uint32_t><<<pull_blocks, 128, 0, st>>>(w, wu, wd, barrier_seq, dev_counters + 2, cn - (int64_t)W, up_last,
                                                              cn + (int64_t)rows * W, down_first, W);
     }
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
-    SM_TRY(toc());
+    if (timed) SM_TRY(toc());
     return SM_OK;
 }
 
-int sm_engine::p2p_after_trail()
+// my new rows -> the neighbours' ghost rows of THEIR trail[cur] (all ranks flip `cur` in lock step)
+int sm_engine::p2p_push_ghosts(cudaStream_t st, uint32_t g)
 {
-    uint32_t g = 0, m = 0;
-    SM_TRY(halo_depths(this, &g, &m));
-    SM_TRY(tic(3));
-    // my new rows -> the neighbours' ghost rows of THEIR trail[cur] (all ranks flip `cur` in lock step)
     const size_t row0_off = (size_t)(ghost + pad_rows) * W;
     const float* t = trail_ptr(cur);
     float* up_ghost = peer[0].trail[cur] + row0_off + (size_t)peer[0].rows * W;      // up's bottom ghost rows [rows_up, rows_up + g)
@@ -709,25 +782,135 @@ int sm_engine::p2p_after_trail()
     const uint64_t n = (uint64_t)g * W;
     const unsigned nb = (unsigned)std::min<uint64_t>((n / 4 + 255) / 256 + 1, (uint64_t)num_sms);
     if (W % 4 == 0)
-        smk::k_push_rows<<<nb, 256, 0, stream>>>(reinterpret_cast<const float4*>(t), reinterpret_cast<float4*>(up_ghost),
+        smk::k_push_rows<<<nb, 256, 0, st>>>(reinterpret_cast<const float4*>(t), reinterpret_cast<float4*>(up_ghost),
                                                 reinterpret_cast<const float4*>(t + (size_t)(rows - g) * W),
                                                 reinterpret_cast<float4*>(down_ghost), n / 4);
     else
-        smk::k_push_rows_scalar<<<nb, 256, 0, stream>>>(t, up_ghost, t + (size_t)(rows - g) * W, down_ghost, n);
+        smk::k_push_rows_scalar<<<nb, 256, 0, st>>>(t, up_ghost, t + (size_t)(rows - g) * W, down_ghost, n);
+    SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 1;
+    return SM_OK;
+}
+
+int sm_engine::p2p_after_trail(cudaStream_t st, bool timed)
+{
+    const bool own_stream = !st;
+    if (!st) st = stream;
+    uint32_t g = 0, m = 0;
+    SM_TRY(halo_depths(this, &g, &m));
+    if (timed) SM_TRY(tic(3));
+    SM_TRY(p2p_push_ghosts(st, g));
     // arrivals (written by the neighbours during their agent pass, complete since barrier 1)
     uint8_t* from_up = window + window_arrival_off[0];
     uint8_t* from_down = window + window_arrival_off[1];
-    smk::k_append_arrivals<<<blocks_for(2 * mig_cap, 256), 256, 0, stream>>>(from_down, from_up, (uint32_t)mig_cap, agents[acur],
+    smk::k_append_arrivals<<<blocks_for(2 * mig_cap, 256), 256, 0, st>>>(from_down, from_up, (uint32_t)mig_cap, agents[acur],
                                                                             ids[acur], dev_counters, cap_local);
     ++barrier_seq;
-    smk::k_bump_barrier<<<1, 1, 0, stream>>>(dev_counters, from_down, from_up, (uint32_t)mig_cap, cap_local,
+    smk::k_bump_barrier<<<1, 1, 0, st>>>(dev_counters, from_down, from_up, (uint32_t)mig_cap, cap_local,
                                              reinterpret_cast<uint32_t*>(window), reinterpret_cast<uint32_t*>(peer[0].window),
                                              reinterpret_cast<uint32_t*>(peer[1].window), barrier_seq);
     SM_CUDA(cudaGetLastError());
-    timing.kernel_launches += 3;
+    timing.kernel_launches += 2;
     ghost_stale = false;
-    SM_TRY(refresh_tex_ghosts(g));                      // the TEX sampler's copy needs the new ghost rows too
-    SM_TRY(toc());
+    if (own_stream) SM_TRY(refresh_tex_ghosts(g));      // the TEX sampler's copy needs the new ghost rows too (overlapped form: after the join)
+    if (timed) SM_TRY(toc());
     n_upper = std::min<uint64_t>(cap_local, n_upper + 2 * mig_cap);
     return SM_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Overlapped exchange (the default on strips that are tall enough)
+// ---------------------------------------------------------------------------
+// Only the rows within `band` of a strip edge depend on the neighbours during a step: remote deposits
+// land within m rows of the edge, the 3x3 blur of the edge row needs one deposit row of the neighbour,
+// and the g rows next to each edge are what the neighbours need back as ghost rows.  So after the agent
+// pass the main stream runs the trail pass over the interior rows at once, while the side stream runs
+//   barrier 1 + deposit-row pull -> trail pass over the two boundary bands -> ghost-row push over NVLink
+//   -> arrivals -> barrier 2,
+// and the main stream joins it before refreshing the sampler's ghost rows.  Nothing of the exchange but
+// the join and that refresh is left on the critical path.
+uint32_t sm_engine::overlap_band()
+{
+    uint32_t g = 0, m = 0;
+    if (halo_depths(this, &g, &m) != SM_OK) return 0;
+    TrailPass p;
+    if (trail_plan(true, p) != SM_OK || !p.fast) return 0;
+    const uint32_t rpc = p.g.rows_per_chunk;
+    uint32_t band = std::max(g, m + 1);
+    band = (band + rpc - 1) / rpc * rpc;
+    if ((uint64_t)rows < 2ull * band + rpc) return 0;          // no interior worth splitting off
+    return band;
+}
+
+bool sm_engine::overlap_ok()
+{
+    return overlap_enabled && p2p && !fake_multi && world > 1 && side_stream && overlap_band() > 0;
+}
+
+// Diffusion-only pass on strips (sm_diffuse_only): interior rows on the main stream; boundary bands, ghost-row
+// push and ONE barrier beside them.  The barrier of pass p-1 is what makes the neighbours' ghost buffers
+// safe to overwrite in pass p (they finished reading them in their boundary bands of pass p-1).
+int sm_engine::p2p_diffuse_overlapped()
+{
+    const uint32_t band = overlap_band();
+    uint32_t g = 0, m = 0;
+    SM_TRY(halo_depths(this, &g, &m));
+    TrailPass p;
+    SM_TRY(trail_plan(false, p));
+    SM_CUDA(cudaEventRecord(ev_fork, stream));
+    SM_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+    SM_TRY(tic(1));
+    SM_TRY(trail_launch_rows(p, band, rows - band, stream));
+    SM_TRY(toc());
+    SM_TRY(trail_launch_rows(p, 0, band, side_stream, rows - band, rows));
+    trail_done(false);
+    SM_TRY(p2p_push_ghosts(side_stream, g));
+    ++barrier_seq;
+    smk::k_barrier_only<<<1, 1, 0, side_stream>>>(reinterpret_cast<uint32_t*>(window), reinterpret_cast<uint32_t*>(peer[0].window),
+                                                  reinterpret_cast<uint32_t*>(peer[1].window), barrier_seq, dev_counters + 2);
+    SM_CUDA(cudaGetLastError());
+    timing.kernel_launches += 1;
+    SM_CUDA(cudaEventRecord(ev_join, side_stream));
+    SM_TRY(tic(3));
+    SM_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+    SM_TRY(toc());
+    ghost_stale = false;
+    return SM_OK;
+}
+
+int sm_engine::p2p_trail_overlapped()
+{
+    const uint32_t band = overlap_band();
+    uint32_t g = 0, m = 0;
+    SM_TRY(halo_depths(this, &g, &m));
+    TrailPass p;
+    SM_TRY(trail_plan(true, p));
+    // fork: the side stream starts where the agent pass ends
+    SM_CUDA(cudaEventRecord(ev_fork, stream));
+    SM_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+    // side (launched first, so that its one-CTA barrier kernel is resident before the interior pass fills the
+    // machine): barrier 1 -- the neighbours' deposits and leavers have landed -- and the deposit-row pull
+    if (side_dbg) SM_TRY(tic(10, side_stream));
+    SM_TRY(p2p_after_agents(side_stream, false));
+    if (side_dbg) SM_TRY(toc(side_stream));
+    // main: interior rows -- every input is local and final once this rank's agent pass is done
+    SM_TRY(tic(1));
+    SM_TRY(trail_launch_rows(p, band, rows - band, stream));
+    SM_TRY(toc());
+    // side: the two boundary bands in one launch
+    if (side_dbg) SM_TRY(tic(11, side_stream));
+    SM_TRY(trail_launch_rows(p, 0, band, side_stream, rows - band, rows));
+    if (side_dbg) { SM_TRY(toc(side_stream)); SM_TRY(tic(12, side_stream)); }
+    trail_done(true);                                          // host bookkeeping: cur / ccur flip
+    // side: push the new boundary rows, append arrivals, barrier 2
+    SM_TRY(p2p_after_trail(side_stream, false));
+    if (side_dbg) SM_TRY(toc(side_stream));
+    SM_CUDA(cudaEventRecord(ev_join, side_stream));
+    // join; what is timed as "exchange" is the part that is NOT hidden
+    SM_TRY(tic(3));
+    SM_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+    SM_TRY(refresh_tex_ghosts(g));
+    SM_TRY(toc());
+    return SM_OK;
+}
+

@@ -256,6 +256,10 @@ struct TrailGeom {
     uint32_t W;          // row length (cells); fast kernel requires W % 4 == 0
     uint32_t rows;       // owned rows
     uint32_t rows_per_chunk;
+    uint32_t y_first, y_last;   // owned rows [y_first, y_last) this launch covers (the whole strip, or its interior when
+                                // the exchange is overlapped with the interior pass) ...
+    uint32_t chunks1;           // ... in blockIdx.y < chunks1; chunks past that cover a second band [y_first2, y_last2)
+    uint32_t y_first2, y_last2; // (the two boundary bands of a strip in one launch)
     int wrap_y;          // 1: rows wrap toroidally inside the buffer (single GPU); 0: ghost rows
     cudaSurfaceObject_t surf;   // block-linear copy of the output for the TEX sampler (0 = none)
     int surf_row0;              // array row of owned row 0
@@ -311,8 +315,9 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
     // column of the one extra cell an edge lane fetches
     const uint32_t xe = left_edge ? ((x0 == 0u) ? g.W - 1u : x0 - 1u) : ((x0 + 4u >= g.W) ? 0u : x0 + 4u);
 
-    const int y_begin = (int)(blockIdx.y * g.rows_per_chunk);
-    const int y_end = min(y_begin + (int)g.rows_per_chunk, (int)g.rows);
+    const bool band2 = blockIdx.y >= g.chunks1;
+    const int y_begin = band2 ? (int)(g.y_first2 + (blockIdx.y - g.chunks1) * g.rows_per_chunk) : (int)(g.y_first + blockIdx.y * g.rows_per_chunk);
+    const int y_end = min(y_begin + (int)g.rows_per_chunk, (int)(band2 ? g.y_last2 : g.y_last));
     const size_t W = g.W;
     // halo rows: only these two can wrap (single GPU) -- rows inside the chunk never do
     const int y_top = (g.wrap_y && y_begin == 0) ? (int)g.rows - 1 : y_begin - 1;

@@ -23,6 +23,8 @@ CASES = {
     "thin_strips": ("Default", 256, 128, 30_000, 40, False),
     "firecracker_devinit": ("Firecracker Trees", 1024, 1024, 1_000_000, 33, True),
     "mode_switch": ("Default", 256, 512, 150_000, 40, False),
+    # steps, diffusion-only passes (sm_diffuse_only on strips: overlapped ghost push + one barrier per pass), steps
+    "diffuse_mix": ("Sponge", 512, 1024, 200_000, 30, False),
 }
 
 
@@ -59,6 +61,12 @@ def _worker(rank, world, case, out_dir, exchange):
         for dep in (1.0, 0.3, 2.0, 0.05, 1.0):
             be.update_settings(s.clone(pheromone_deposition_amount=dep))
             be.step(steps // 5)
+    elif case == "diffuse_mix":
+        be.step(steps // 3)
+        be.diffuse_only(7)
+        be.step(steps // 3)
+        be.diffuse_only(1)
+        be.step(steps // 3)
     else:
         be.step(steps)
     a = be.read_agents()
@@ -78,7 +86,7 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
     preset, W, H, N, steps, device_init = CASES[case]
     if H // world < 32:
         pytest.skip("strips too thin for this case")
-    if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips"):
+    if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips", "diffuse_mix"):
         pytest.skip("NCCL path: three representative cases")
     mp.spawn(_worker, args=(world, case, str(tmp_path), exchange), nprocs=world, join=True)
     u = preset_uniform(preset, W, H)
@@ -91,6 +99,11 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
             ss = s0.clone(pheromone_deposition_amount=dep)
             sim.p = to_oracle_params(oracle, sm2.SimSizeUniform.new(W, H, ss.pheromone_decay_factor, ss))
             sim.step(steps // 5)
+    elif case == "diffuse_mix":
+        for n_steps, n_passes in ((steps // 3, 7), (steps // 3, 1), (steps // 3, 0)):
+            sim.step(n_steps)
+            for _ in range(n_passes):
+                sim.trail = oracle.trail_pass(sim.trail, sim.p)
     else:
         sim.step(steps)
     a = np.full((N, 4), np.nan, np.float32)
