@@ -161,6 +161,28 @@ int sm_trail_statistics(sm_engine *e, sm_trail_stats *out);
  * trail replaced by a zeroed map of the new size.  Single GPU only. */
 int sm_resize(sm_engine *e, uint32_t width, uint32_t height);
 
+/* ---- display pass -------------------------------------------------
+ * Replaces the `display_pipeline` dispatch of src/main.rs:1202-1217 and its shader
+ * src/display.wgsl:29-86: the trail map is letter-boxed into a tex_width x tex_height
+ * RGBA8 frame through a colour look-up table.
+ * sm_set_lut: 768 bytes laid out as 256 red, 256 green, 256 blue -- a reference .lut file
+ * verbatim (src/lut_manager.rs:162-186), i.e. LutData.red ++ green ++ blue as main.rs:330-334
+ * concatenates them (the reference widens each byte to u32 for its storage buffer).
+ * sm_render_rgba8: `rgba` is a caller-owned host buffer of tex_width * tex_height * 4 bytes,
+ * row-major, R G B A per texel (the rgba8unorm texture of main.rs:296-314).  The frame shows
+ * the trail as it stands after the last completed step (the reference draws between its
+ * decay and diffuse dispatches; this engine fuses those two).  Single GPU. */
+int sm_set_lut(sm_engine *e, const uint8_t *lut768);
+int sm_render_rgba8(sm_engine *e, uint32_t tex_width, uint32_t tex_height, uint8_t *rgba);
+
+/* ---- snapshot / restore (no counterpart in the reference) ------------
+ * Everything a bit-exact continuation needs: parameter block, the owned trail rows and the
+ * owned agents with their persistent indices.  On strips every rank writes / reads its own
+ * file: `path` gets ".rank<r>" appended when world_size > 1.  sm_load_snapshot requires an
+ * engine created with the same map size, agent count and strip layout. */
+int sm_save_snapshot(sm_engine *e, const char *path);
+int sm_load_snapshot(sm_engine *e, const char *path);
+
 /* One frame of src/main.rs:1163-1235 per step: agents -> decay -> diffuse. */
 int sm_step(sm_engine *e, uint32_t n_steps);
 /* decay + diffuse only (BASELINE config 5). */

@@ -416,3 +416,55 @@ void so_field_stats(const float *t, uint64_t cells, double *sum, double *sumsq, 
     }
     *sum = s; *sumsq = s2; *maxv = m; *nonzero = nz;
 }
+
+/* ---------------------------------------------------------------------------
+ * Display / colourise pass -- /root/reference/src/display.wgsl:29-86.
+ * trail (W x H, f32) -> RGBA8 texture (tw x th), letter-boxed, through a 768-entry LUT laid out
+ * as 256 R, 256 G, 256 B (lut_manager.rs:176-178; widened to u32 by main.rs:330-337).
+ * Every f32 operation is the literal one of the shader; the rgba8unorm store is the WGSL
+ * conversion round(clamp(v, 0, 1) * 255).
+ * ------------------------------------------------------------------------- */
+static inline uint8_t so_unorm8(float v)
+{
+    float c = fminf(fmaxf(v, 0.0f), 1.0f);
+    return (uint8_t)lrintf(c * 255.0f);
+}
+
+void so_display(const float *trail, uint32_t W, uint32_t H, const uint8_t *lut768,
+                uint8_t *rgba, uint32_t tw, uint32_t th)
+{
+    const float sim_w = (float)W, sim_h = (float)H;               /* display.wgsl:48-49 */
+    const float tex_w = (float)tw, tex_h = (float)th;             /* :50-51 */
+    const float sim_aspect = sim_w / sim_h;                       /* :54 */
+    const float tex_aspect = tex_w / tex_h;                       /* :55 */
+    float scale, off_x = 0.0f, off_y = 0.0f;                      /* :58-60 */
+    if (tex_aspect > sim_aspect) {                                /* :61-64 fit height */
+        scale = tex_h / sim_h;
+        off_x = (tex_w - sim_w * scale) * 0.5f;
+    } else {                                                      /* :65-69 fit width */
+        scale = tex_w / sim_w;
+        off_y = (tex_h - sim_h * scale) * 0.5f;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t py = 0; py < (int64_t)th; ++py) {
+        for (uint32_t px = 0; px < tw; ++px) {
+            const float fx = ((float)px - off_x) / scale;         /* :72 */
+            const float fy = ((float)py - off_y) / scale;         /* :73 */
+            uint8_t *o = rgba + 4 * ((size_t)py * tw + px);
+            if (fx >= 0.0f && fx < sim_w && fy >= 0.0f && fy < sim_h) {   /* :76 */
+                const int32_t x = (int32_t)fx, y = (int32_t)fy;   /* :77-78 */
+                const int64_t idx = (int64_t)y * (int64_t)W + x;  /* :79 */
+                float t = trail[idx];
+                float inten = fminf(fmaxf(t, 0.0f), 1.0f);        /* :80 (NaN -> 0, the spec's clamp) */
+                inten = fminf(fmaxf(inten, 0.0f), 1.0f);          /* :31 get_lut_color clamps again */
+                const uint32_t li = (uint32_t)(inten * 255.0f);   /* :34 */
+                o[0] = so_unorm8((float)lut768[li] / 255.0f);         /* :37 */
+                o[1] = so_unorm8((float)lut768[li + 256] / 255.0f);   /* :38 */
+                o[2] = so_unorm8((float)lut768[li + 512] / 255.0f);   /* :39 */
+                o[3] = so_unorm8(1.0f);
+            } else {                                              /* :83-85 black bars */
+                o[0] = 0; o[1] = 0; o[2] = 0; o[3] = so_unorm8(1.0f);
+            }
+        }
+    }
+}

@@ -208,6 +208,18 @@ def trail_pass(trail, p: Params, counts=None, gauss_radius=0, gauss_sigma=0.0):
     return out
 
 
+def display(trail, lut768, tex_w, tex_h):
+    """display.wgsl:29-86: trail -> letter-boxed RGBA8 (tex_h, tex_w, 4) through a 768-byte planar LUT."""
+    assert trail.dtype == np.float32 and trail.flags.c_contiguous
+    H, W = trail.shape
+    lut = np.ascontiguousarray(lut768, dtype=np.uint8)
+    assert lut.size == 768
+    out = np.empty((tex_h, tex_w, 4), np.uint8)
+    lib().so_display(_ptr(trail, C.c_float), C.c_uint32(W), C.c_uint32(H), _ptr(lut, C.c_uint8),
+                     _ptr(out, C.c_uint8), C.c_uint32(tex_w), C.c_uint32(tex_h))
+    return out
+
+
 def gauss_weights(R, sigma):
     w = np.empty(2 * R + 1, dtype=np.float32)
     lib().so_gauss_weights(_ptr(w, C.c_float), C.c_int(R), C.c_float(sigma))

@@ -74,6 +74,10 @@ SIGNATURES = {
     "sm_download_trail": (C.c_int, [_E, _P(C.c_float), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t]),
     "sm_trail_statistics": (C.c_int, [_E, _P(SmTrailStats)]),
     "sm_resize": (C.c_int, [_E, C.c_uint32, C.c_uint32]),
+    "sm_set_lut": (C.c_int, [_E, _P(C.c_uint8)]),
+    "sm_render_rgba8": (C.c_int, [_E, C.c_uint32, C.c_uint32, _P(C.c_uint8)]),
+    "sm_save_snapshot": (C.c_int, [_E, C.c_char_p]),
+    "sm_load_snapshot": (C.c_int, [_E, C.c_char_p]),
     "sm_step": (C.c_int, [_E, C.c_uint32]),
     "sm_diffuse_only": (C.c_int, [_E, C.c_uint32]),
     "sm_sync": (C.c_int, [_E]),

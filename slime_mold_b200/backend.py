@@ -11,6 +11,7 @@ happens in libslime_b200.so through the C ABI of include/slime_b200.h.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -165,6 +166,28 @@ class CudaBackend:
 
     def sync(self) -> None:
         check(self._lib.sm_sync(self._h))
+
+    # -- display pass (display.wgsl) and snapshots -----------------------------------
+    def set_lut(self, lut) -> None:
+        """`lut`: a LutData (lut_manager.rs) or 768 bytes laid out red ++ green ++ blue (main.rs:330-334)."""
+        buf = lut.combined() if hasattr(lut, "combined") else np.ascontiguousarray(lut, dtype=np.uint8).reshape(-1)
+        if buf.size != 768:
+            raise ValueError("a LUT is 768 bytes (256 R, 256 G, 256 B)")
+        check(self._lib.sm_set_lut(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def render(self, tex_width: int, tex_height: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """The display dispatch of main.rs:1202-1217: (tex_height, tex_width, 4) uint8 RGBA, letter-boxed."""
+        if out is None:
+            out = np.empty((tex_height, tex_width, 4), np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == (tex_height, tex_width, 4)
+        check(self._lib.sm_render_rgba8(self._h, tex_width, tex_height, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def save_snapshot(self, path: str) -> None:
+        check(self._lib.sm_save_snapshot(self._h, os.fsencode(path)))
+
+    def load_snapshot(self, path: str) -> None:
+        check(self._lib.sm_load_snapshot(self._h, os.fsencode(path)))
 
     # -- instrumentation ---------------------------------------------------------
     def set_timing_enabled(self, enabled: bool) -> None:

@@ -683,6 +683,8 @@ int sm_destroy(sm_engine* e)
     if (e->tile_hist) cudaFree(e->tile_hist);
     if (e->tile_sums) cudaFree(e->tile_sums);
     if (e->stats_dev) cudaFree(e->stats_dev);
+    if (e->lut_dev) cudaFree(e->lut_dev);
+    if (e->frame_dev) cudaFree(e->frame_dev);
     for (auto& p : e->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -938,6 +940,152 @@ int sm_trail_statistics(sm_engine* e, sm_trail_stats* out)
     out->sum = h.sum; out->sum_sq = h.sum_sq; out->nonzero = h.nonzero;
     memcpy(&out->max, &h.max_bits, 4);
     out->_pad = 0;
+    return SM_OK;
+}
+
+// ---- snapshot / restore ---------------------------------------------------------------
+// File: SnapshotHeader, sm_params (56 B), n_agents x u32 persistent index, n_agents x float4, rows x W f32.
+struct SnapshotHeader {
+    char magic[8];                 // "SLIMB200"
+    uint32_t version;              // 1
+    uint32_t width, height;
+    uint32_t world, rank, row0, rows;
+    uint32_t reserved;
+    uint64_t n_global, n_agents;   // agent_count of the engine; agents owned by this rank (stored here)
+    uint64_t steps;                // steps taken since creation (informational)
+};
+
+static std::string snapshot_path(const sm_engine* e, const char* path)
+{
+    std::string p(path);
+    if (e->world > 1) p += ".rank" + std::to_string(e->rank);
+    return p;
+}
+
+int sm_save_snapshot(sm_engine* e, const char* path)
+{
+    SM_ENTER(e);
+    if (!path || !*path) return sm_fail(SM_ERR_BAD_ARG, "null snapshot path");
+    if (!e->agents_valid) return sm_fail(SM_ERR_STATE, "agents were never initialised or uploaded");
+    SM_TRY(e->refresh_counters());                     // syncs; multi-GPU: slots in use / live agents
+    const uint64_t n_slots = e->world == 1 ? e->n_global : e->n_local;
+    std::vector<float> a((size_t)n_slots * 4);
+    std::vector<uint32_t> id((size_t)n_slots);
+    SM_CUDA(cudaMemcpy(a.data(), e->agents[e->acur], n_slots * sizeof(float4), cudaMemcpyDeviceToHost));
+    SM_CUDA(cudaMemcpy(id.data(), e->ids[e->acur], n_slots * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    uint64_t m = 0;                                    // drop the slots of agents that migrated away
+    for (uint64_t i = 0; i < n_slots; ++i)
+        if (id[i] != smk::kDeadAgent) {
+            if (m != i) { id[m] = id[i]; memcpy(&a[4 * m], &a[4 * i], 16); }
+            ++m;
+        }
+    std::vector<float> t((size_t)e->rows * e->W);
+    SM_CUDA(cudaMemcpy(t.data(), e->trail_ptr(e->cur), t.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    SnapshotHeader h{};
+    memcpy(h.magic, "SLIMB200", 8);
+    h.version = 1; h.width = e->W; h.height = e->H;
+    h.world = (uint32_t)e->world; h.rank = (uint32_t)e->rank; h.row0 = e->row0; h.rows = e->rows;
+    h.n_global = e->n_global; h.n_agents = m; h.steps = e->timing.steps;
+    const std::string fn = snapshot_path(e, path);
+    FILE* f = fopen(fn.c_str(), "wb");
+    if (!f) return sm_fail(SM_ERR_BAD_ARG, "cannot open %s for writing", fn.c_str());
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(&e->params, sizeof(sm_params), 1, f) == 1;
+    ok = ok && (m == 0 || (fwrite(id.data(), sizeof(uint32_t), m, f) == m && fwrite(a.data(), 16, m, f) == m));
+    ok = ok && fwrite(t.data(), sizeof(float), t.size(), f) == t.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return sm_fail(SM_ERR_STATE, "short write to %s", fn.c_str());
+    return SM_OK;
+}
+
+int sm_load_snapshot(sm_engine* e, const char* path)
+{
+    SM_ENTER(e);
+    if (!path || !*path) return sm_fail(SM_ERR_BAD_ARG, "null snapshot path");
+    if (e->world > 1 && !e->comm_ready) return sm_fail(SM_ERR_STATE, "multi-GPU engine: call sm_comm_init first");
+    const std::string fn = snapshot_path(e, path);
+    FILE* f = fopen(fn.c_str(), "rb");
+    if (!f) return sm_fail(SM_ERR_BAD_ARG, "cannot open %s", fn.c_str());
+    SnapshotHeader h{};
+    sm_params p{};
+    bool ok = fread(&h, sizeof h, 1, f) == 1 && fread(&p, sizeof p, 1, f) == 1;
+    if (!ok || memcmp(h.magic, "SLIMB200", 8) != 0 || h.version != 1) { fclose(f); return sm_fail(SM_ERR_BAD_ARG, "%s is not a version-1 snapshot", fn.c_str()); }
+    if (h.width != e->W || h.height != e->H || h.n_global != e->n_global || h.world != (uint32_t)e->world ||
+        h.rank != (uint32_t)e->rank || h.row0 != e->row0 || h.rows != e->rows) {
+        fclose(f);
+        return sm_fail(SM_ERR_BAD_ARG, "snapshot %s is for a %ux%u map, %llu agents, rank %u of %u (rows %u+%u); this engine differs",
+                       fn.c_str(), h.width, h.height, (unsigned long long)h.n_global, h.rank, h.world, h.row0, h.rows);
+    }
+    const uint64_t cap = e->world == 1 ? e->n_global : e->cap_local;
+    if (h.n_agents > cap || (e->world == 1 && h.n_agents != e->n_global)) { fclose(f); return sm_fail(SM_ERR_BAD_ARG, "snapshot agent count does not fit this engine"); }
+    std::vector<uint32_t> id((size_t)h.n_agents);
+    std::vector<float> a((size_t)h.n_agents * 4), t((size_t)e->rows * e->W);
+    ok = h.n_agents == 0 || (fread(id.data(), sizeof(uint32_t), h.n_agents, f) == h.n_agents && fread(a.data(), 16, h.n_agents, f) == h.n_agents);
+    ok = ok && fread(t.data(), sizeof(float), t.size(), f) == t.size();
+    fclose(f);
+    if (!ok) return sm_fail(SM_ERR_BAD_ARG, "snapshot %s is truncated", fn.c_str());
+    SM_CUDA(cudaStreamSynchronize(e->stream));
+    SM_TRY(sm_set_params(e, &p));
+    SM_CUDA(cudaMemcpy(e->agents[e->acur], a.data(), h.n_agents * sizeof(float4), cudaMemcpyHostToDevice));
+    SM_CUDA(cudaMemcpy(e->ids[e->acur], id.data(), h.n_agents * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    e->n_local = h.n_agents;
+    e->n_live = h.n_agents;
+    if (e->world > 1 && e->comm_ready) { SM_TRY(e->mark_tail_dead()); SM_TRY(e->push_counters()); }
+    e->agents_valid = true;
+    e->identity_order = false;
+    e->steps_since_sort = e->sort_interval;            // sort before the next step
+    SM_CUDA(cudaMemcpy(e->trail_ptr(e->cur), t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    bool nonneg = e->world == 1;                        // strips: the decision must be the same on every rank
+    for (size_t i = 0; nonneg && i < t.size(); ++i) nonneg = t[i] >= 0.0f;
+    e->trail_nonneg = nonneg;
+    e->ghost_stale = true;
+    e->arr_stale = true;
+    return SM_OK;
+}
+
+// ---- display pass: /root/reference/src/display.wgsl, LUT layout of lut_manager.rs:162-186 -------------
+int sm_set_lut(sm_engine* e, const uint8_t* lut768)
+{
+    SM_ENTER(e);
+    if (!lut768) return sm_fail(SM_ERR_BAD_ARG, "null LUT");
+    if (!e->lut_dev) SM_CUDA(cudaMalloc(&e->lut_dev, 768));
+    SM_CUDA(cudaMemcpyAsync(e->lut_dev, lut768, 768, cudaMemcpyHostToDevice, e->stream));
+    SM_CUDA(cudaStreamSynchronize(e->stream));          // the caller's buffer is only borrowed for the call
+    e->lut_set = true;
+    return SM_OK;
+}
+
+int sm_render_rgba8(sm_engine* e, uint32_t tex_width, uint32_t tex_height, uint8_t* rgba_host)
+{
+    SM_ENTER(e);
+    if (e->world != 1) return sm_fail(SM_ERR_STATE, "sm_render_rgba8 is single-GPU only (download the strips instead)");
+    if (!e->lut_set) return sm_fail(SM_ERR_STATE, "no LUT: call sm_set_lut first");
+    if (!rgba_host) return sm_fail(SM_ERR_BAD_ARG, "null frame buffer");
+    if (tex_width == 0 || tex_height == 0 || tex_width > 65536 || tex_height > 65535) return sm_fail(SM_ERR_BAD_ARG, "bad frame size");
+    const size_t texels = (size_t)tex_width * tex_height;
+    if (texels > e->frame_cap) {
+        if (e->frame_dev) { cudaFree(e->frame_dev); e->frame_dev = nullptr; e->frame_cap = 0; }
+        SM_CUDA(cudaMalloc(&e->frame_dev, texels * 4));
+        e->frame_cap = texels;
+    }
+    smk::DisplayGeom g{};
+    g.W = e->W; g.H = e->H; g.tw = tex_width; g.th = tex_height;
+    {   // display.wgsl:48-69, once per frame instead of once per texel; volatile: no contraction, f32 roundings
+        volatile float sim_w = (float)e->W, sim_h = (float)e->H, tex_w = (float)tex_width, tex_h = (float)tex_height;
+        volatile float sim_aspect = sim_w / sim_h, tex_aspect = tex_w / tex_h;
+        volatile float scale, off_x = 0.0f, off_y = 0.0f, prod, diff;
+        if (tex_aspect > sim_aspect) {
+            scale = tex_h / sim_h; prod = sim_w * scale; diff = tex_w - prod; off_x = diff * 0.5f;
+        } else {
+            scale = tex_w / sim_w; prod = sim_h * scale; diff = tex_h - prod; off_y = diff * 0.5f;
+        }
+        g.sim_w = sim_w; g.sim_h = sim_h; g.scale = scale; g.off_x = off_x; g.off_y = off_y;
+    }
+    dim3 grid(blocks_for((tex_width + 3) / 4, 256), tex_height);
+    smk::k_display<<<grid, 256, 0, e->stream>>>(e->trail_ptr(e->cur), e->lut_dev, e->frame_dev, g);
+    SM_CUDA(cudaGetLastError());
+    e->timing.kernel_launches += 1;
+    SM_CUDA(cudaMemcpyAsync(rgba_host, e->frame_dev, texels * 4, cudaMemcpyDeviceToHost, e->stream));
+    SM_CUDA(cudaStreamSynchronize(e->stream));
     return SM_OK;
 }
 

@@ -81,6 +81,12 @@ struct sm_engine {
     // statistics scratch
     void* stats_dev = nullptr;
 
+    // display pass (display.wgsl): LUT and frame buffer, allocated on first use
+    uint8_t* lut_dev = nullptr;
+    bool lut_set = false;
+    uint32_t* frame_dev = nullptr;
+    size_t frame_cap = 0;           // texels
+
     // timing
     bool timing_enabled = false;
     std::vector<EvPair> ev_pool;

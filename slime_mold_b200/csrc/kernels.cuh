@@ -718,6 +718,58 @@ k_trail_stats(const float* __restrict__ t, uint64_t cells, StatsAcc* __restrict_
 }
 
 // ---------------------------------------------------------------------------
+// display / colourise pass -- /root/reference/src/display.wgsl:29-86
+// trail -> letter-boxed RGBA8 frame through the 768-byte planar LUT (256 R, 256 G, 256 B).
+// One thread per 4 texels of a frame row: 4 trail gathers (a frame row maps to one trail row, so they
+// coalesce whenever the frame is not magnified), 3 LUT bytes each from shared memory, one 16-byte store.
+// 4 B/cell read + 4 B/texel written; HBM-bound.
+// ---------------------------------------------------------------------------
+struct DisplayGeom {
+    uint32_t W, H;            // simulation size (this engine's strip is the whole map: single GPU only)
+    uint32_t tw, th;          // frame size
+    float sim_w, sim_h;       // f32(W), f32(H)                    display.wgsl:48-49
+    float scale, off_x, off_y;   // display.wgsl:58-69, computed once on the host with the same f32 operations
+};
+
+__device__ __forceinline__ uint32_t display_texel(const float* __restrict__ trail, const uint8_t* lut, const DisplayGeom& g,
+                                                  uint32_t px, float fy, bool row_inside)
+{
+    const float fx = __fdiv_rn(smd::sub((float)px, g.off_x), g.scale);               // :72
+    if (!(row_inside && fx >= 0.0f && fx < g.sim_w)) return 0xFF000000u;             // :83-85 black, alpha 1
+    const int32_t x = (int32_t)fx, y = (int32_t)fy;                                  // :77-78
+    const float t = __ldg(trail + (size_t)y * g.W + x);                              // :79
+    const float inten = smd::clampf(smd::clampf(t, 0.0f, 1.0f), 0.0f, 1.0f);         // :80 and :31
+    const uint32_t li = (uint32_t)smd::mul(inten, 255.0f);                           // :34
+    // :37-39 f32(lut)/255 stored as rgba8unorm = round(v * 255) = the LUT byte itself for every byte value
+    // (tests/test_display.py proves it for all 256 through the oracle's literal conversion)
+    return (uint32_t)lut[li] | ((uint32_t)lut[li + 256] << 8) | ((uint32_t)lut[li + 512] << 16) | 0xFF000000u;
+}
+
+static __global__ void __launch_bounds__(256)
+k_display(const float* __restrict__ trail, const uint8_t* __restrict__ lut768, uint32_t* __restrict__ rgba, const DisplayGeom g)
+{
+    __shared__ uint8_t lut[768];
+    for (uint32_t i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = lut768[i];
+    __syncthreads();
+    const uint32_t py = blockIdx.y;
+    const float fy = __fdiv_rn(smd::sub((float)py, g.off_y), g.scale);               // :73
+    const bool row_inside = fy >= 0.0f && fy < g.sim_h;                              // :76
+    const uint32_t px0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (px0 >= g.tw) return;
+    uint32_t* row = rgba + (size_t)py * g.tw;
+    if (px0 + 4u <= g.tw && (g.tw & 3u) == 0u) {
+        uint4 o;
+        o.x = display_texel(trail, lut, g, px0, fy, row_inside);
+        o.y = display_texel(trail, lut, g, px0 + 1u, fy, row_inside);
+        o.z = display_texel(trail, lut, g, px0 + 2u, fy, row_inside);
+        o.w = display_texel(trail, lut, g, px0 + 3u, fy, row_inside);
+        *reinterpret_cast<uint4*>(row + px0) = o;
+    } else {
+        for (uint32_t px = px0; px < g.tw && px < px0 + 4u; ++px) row[px] = display_texel(trail, lut, g, px, fy, row_inside);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // arithmetic-spec probes (sm_test_math)
 // ---------------------------------------------------------------------------
 static __global__ void k_test_math(int what, const float* a, const float* b, const int32_t* iv,

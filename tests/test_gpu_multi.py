@@ -25,6 +25,8 @@ CASES = {
     "mode_switch": ("Default", 256, 512, 150_000, 40, False),
     # steps, diffusion-only passes (sm_diffuse_only on strips: overlapped ghost push + one barrier per pass), steps
     "diffuse_mix": ("Sponge", 512, 1024, 200_000, 30, False),
+    # per-rank snapshot files mid-run, restored into freshly created engines (new communicator), then continued
+    "snapshot_mid": ("Waves", 256, 512, 100_000, 40, False),
 }
 
 
@@ -37,20 +39,23 @@ def _worker(rank, world, case, out_dir, exchange):
     from oracle import slime_oracle as so
     preset, W, H, N, steps, device_init = CASES[case]
     s = sm.init_preset_manager().get_preset(preset).settings
+    def connect(be, tag):
+        idf = os.path.join(out_dir, f"nccl_id_{tag}.bin")
+        if rank == 0:
+            uid = be.comm_unique_id()
+            with open(idf + ".tmp", "wb") as f:
+                f.write(uid)
+            os.rename(idf + ".tmp", idf)
+        else:
+            t0 = time.time()
+            while not os.path.exists(idf):
+                time.sleep(0.05)
+                assert time.time() - t0 < 120
+            uid = open(idf, "rb").read()
+        be.comm_init(uid)
+
     be = sm.CudaBackend.new(W, H, s, agent_count=N, device=rank, rank=rank, world_size=world)
-    idf = os.path.join(out_dir, "nccl_id.bin")
-    if rank == 0:
-        uid = be.comm_unique_id()
-        with open(idf + ".tmp", "wb") as f:
-            f.write(uid)
-        os.rename(idf + ".tmp", idf)
-    else:
-        t0 = time.time()
-        while not os.path.exists(idf):
-            time.sleep(0.05)
-            assert time.time() - t0 < 120
-        uid = open(idf, "rb").read()
-    be.comm_init(uid)
+    connect(be, "a")
     if device_init:
         be.init_agents(seed=11)
     else:
@@ -61,6 +66,15 @@ def _worker(rank, world, case, out_dir, exchange):
         for dep in (1.0, 0.3, 2.0, 0.05, 1.0):
             be.update_settings(s.clone(pheromone_deposition_amount=dep))
             be.step(steps // 5)
+    elif case == "snapshot_mid":
+        be.step(steps // 2)
+        snap = os.path.join(out_dir, "snap.smb")
+        be.save_snapshot(snap)                       # writes snap.smb.rank<r>
+        be.close()
+        be = sm.CudaBackend.new(W, H, sm.Settings.default(), agent_count=N, device=rank, rank=rank, world_size=world)
+        connect(be, "b")
+        be.load_snapshot(snap)
+        be.step(steps - steps // 2)
     elif case == "diffuse_mix":
         be.step(steps // 3)
         be.diffuse_only(7)
