@@ -378,6 +378,7 @@ int sm_engine::launch_agents()
         lv.rows_up = (int32_t)peer[0].rows;
         lv.overflow = dev_counters + 2;
         lv.left_count = dev_counters + 3;
+        lv.slots_in_use = dev_counters;
         lv.cap = (uint32_t)mig_cap;
     } else if (multi) {
         for (int d = 0; d < 2; ++d) {
@@ -386,6 +387,7 @@ int sm_engine::launch_agents()
             lv.send_id[d] = reinterpret_cast<uint32_t*>(mig[d].send + 16 + mig_cap * sizeof(float4));
         }
         lv.overflow = dev_counters + 2;
+        lv.slots_in_use = dev_counters;
         lv.cap = (uint32_t)mig_cap;
     }
     auto launch = [&](auto fetch, auto idx_tag) {

@@ -123,6 +123,7 @@ struct LeaverBufs {
     unsigned long long* send_count[2];   // record counters (message headers)
     unsigned long long* overflow;        // sticky error flag, checked by the host at the next sync point
     unsigned long long* left_count;      // XM_P2P: how many agents left this rank during the step
+    const unsigned long long* slots_in_use;   // device-side count of the slots in use (the grid covers the host's upper bound of it)
     uint32_t cap;
     // XM_P2P: deposit fields of the two ring neighbours (pointer to THEIR owned row 0) and the row
     // count of the upper neighbour (a deposit on my row -k lands on its row rows_up - k)
@@ -231,6 +232,9 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     // MULTI: n is the host's upper bound of the slots in use; every slot past the live ones holds
     // kDeadAgent (kept so by the sort and by k_append_arrivals), so no device-side count is needed here
     uint64_t i = (uint64_t)blockIdx.x * kAgentsPerBlock + threadIdx.x;
+    // MULTI: the host only knows an upper bound of the slots in use between two sorts (it grows by the migration
+    // capacity every step); the exact count lives on the device -- CTAs past it leave without touching HBM
+    if (MULTI) n = min(n, (uint64_t)*lv.slots_in_use);
     if (i >= n) return;
     float4 a_next;
     uint32_t id_next;

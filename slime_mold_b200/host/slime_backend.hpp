@@ -216,6 +216,16 @@ public:
         height_ = h;
     }
     // one frame: agents -> decay -> diffuse (main.rs:1163-1235)
+    // display pass: main.rs:1202-1217 / display.wgsl; `lut768` = LutData.red ++ green ++ blue (main.rs:330-334)
+    void set_lut(const uint8_t* lut768) { check(sm_set_lut(h_, lut768)); }
+    std::vector<uint8_t> render(uint32_t tex_width, uint32_t tex_height)
+    {
+        std::vector<uint8_t> rgba((size_t)tex_width * tex_height * 4);
+        check(sm_render_rgba8(h_, tex_width, tex_height, rgba.data()));
+        return rgba;
+    }
+    void save_snapshot(const std::string& path) { check(sm_save_snapshot(h_, path.c_str())); }
+    void load_snapshot(const std::string& path) { check(sm_load_snapshot(h_, path.c_str())); }
     void step(uint32_t n_steps = 1) { check(sm_step(h_, n_steps)); }
     void diffuse_only(uint32_t n) { check(sm_diffuse_only(h_, n)); }
     void sync() { check(sm_sync(h_)); }
