@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 thread_local std::string g_sm_err;
@@ -154,6 +155,7 @@ int sm_engine::alloc_trail()
         SM_CUDA(cudaMemsetAsync(flags_base[i], 0, cells, stream));
     }
     cur = 0; ccur = 0;
+    stats_fused_valid = false;
     trail_nonneg = true;
     deposit_mode = 0;
     if (use_tex) SM_TRY(setup_tex());
@@ -394,14 +396,14 @@ int sm_engine::launch_agents()
         using F = decltype(fetch);
         using I = decltype(idx_tag);
         if (multi && p2p) {
-            if (flags) smk::k_agents<smk::XM_P2P, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
-            else smk::k_agents<smk::XM_P2P, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+            if (flags) smk::k_agents<smk::XM_P2P, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
+            else smk::k_agents<smk::XM_P2P, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
         } else if (multi) {
-            if (flags) smk::k_agents<smk::XM_NCCL, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
-            else smk::k_agents<smk::XM_NCCL, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+            if (flags) smk::k_agents<smk::XM_NCCL, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
+            else smk::k_agents<smk::XM_NCCL, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
         } else {
-            if (flags) smk::k_agents<smk::XM_SINGLE, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
-            else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv);
+            if (flags) smk::k_agents<smk::XM_SINGLE, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
+            else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
         }
     };
     if (use_tex) {
@@ -442,6 +444,7 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     p.cin = p.cm == smk::CM_FLAGS ? (const void*)flags_ptr(ccur) : (const void*)counts_ptr(ccur);
     p.czero = p.cm == smk::CM_FLAGS ? (void*)flags_ptr(1 - ccur) : (void*)counts_ptr(1 - ccur);
     p.fast = !(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && W % 4 == 0 && W >= 8 && (W / 4) % 32 != 1 && !force_generic;
+    p.stats = has_counts && p.fast && stats_interest > 0;   // fused statistics only while the host keeps asking for them
     // 8-16 rows per chunk measured best from 4096^2 to 32768^2 (profiles/README.md): the 2/rpc halo
     // re-reads hit L2; small maps take shorter chunks to keep >= 4 CTAs per SM
     uint64_t rpc = 8;
@@ -465,14 +468,23 @@ int sm_engine::trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t 
     g.y_first2 = y_first2; g.y_last2 = y_last2;
     const uint32_t chunks2 = y_last2 > y_first2 ? (y_last2 - y_first2 + rpc - 1) / rpc : 0u;
     dim3 grid(blocks_for(W / 4, bs), (unsigned)(g.chunks1 + chunks2));
+    smk::StatsAcc* acc = (smk::StatsAcc*)stats_dev;
+    auto go = [&](auto cm_tag, auto surf_tag, auto stats_tag) {
+        constexpr int CMv = decltype(cm_tag)::value;
+        constexpr bool SURFv = decltype(surf_tag)::value, STATSv = decltype(stats_tag)::value;
+        smk::k_trail_rows<CMv, SURFv, 4, STATSv><<<grid, bs, 0, st>>>(p.tin, CMv == smk::CM_NONE ? nullptr : p.cin,
+                                                                       CMv == smk::CM_NONE ? nullptr : p.czero, p.tout, g, p.tc, acc);
+    };
+    using std::integral_constant;
+    using T = std::true_type; using F = std::false_type;
     if (p.cm == smk::CM_NONE) {
-        smk::k_trail_rows<smk::CM_NONE, false, 4><<<grid, bs, 0, st>>>(p.tin, nullptr, nullptr, p.tout, g, p.tc);
-    } else if (g.surf) {
-        if (p.cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, true, 4><<<grid, bs, 0, st>>>(p.tin, p.cin, p.czero, p.tout, g, p.tc);
-        else smk::k_trail_rows<smk::CM_FLAGS, true, 4><<<grid, bs, 0, st>>>(p.tin, p.cin, p.czero, p.tout, g, p.tc);
+        go(integral_constant<int, smk::CM_NONE>{}, F{}, F{});
+    } else if (p.cm == smk::CM_COUNTS) {
+        if (g.surf) { if (p.stats) go(integral_constant<int, smk::CM_COUNTS>{}, T{}, T{}); else go(integral_constant<int, smk::CM_COUNTS>{}, T{}, F{}); }
+        else        { if (p.stats) go(integral_constant<int, smk::CM_COUNTS>{}, F{}, T{}); else go(integral_constant<int, smk::CM_COUNTS>{}, F{}, F{}); }
     } else {
-        if (p.cm == smk::CM_COUNTS) smk::k_trail_rows<smk::CM_COUNTS, false, 4><<<grid, bs, 0, st>>>(p.tin, p.cin, p.czero, p.tout, g, p.tc);
-        else smk::k_trail_rows<smk::CM_FLAGS, false, 4><<<grid, bs, 0, st>>>(p.tin, p.cin, p.czero, p.tout, g, p.tc);
+        if (g.surf) { if (p.stats) go(integral_constant<int, smk::CM_FLAGS>{}, T{}, T{}); else go(integral_constant<int, smk::CM_FLAGS>{}, T{}, F{}); }
+        else        { if (p.stats) go(integral_constant<int, smk::CM_FLAGS>{}, F{}, T{}); else go(integral_constant<int, smk::CM_FLAGS>{}, F{}, F{}); }
     }
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
@@ -481,6 +493,7 @@ int sm_engine::trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t 
 
 void sm_engine::trail_done(bool has_counts)
 {
+    stats_fused_valid = false;    // the callers that ran a full-step k_trail_rows pass set it again
     cur = 1 - cur;
     if (has_counts) ccur = 1 - ccur;
     trail_nonneg = true;          // decay clamps at 0 (NaN included), the mix of non-negatives is non-negative
@@ -508,6 +521,8 @@ int sm_engine::launch_trail(bool has_counts)
     SM_CUDA(cudaGetLastError());
     SM_TRY(toc());
     trail_done(has_counts);
+    stats_fused_valid = p.stats;
+    if (has_counts && stats_interest) --stats_interest;
     return SM_OK;
 }
 
@@ -872,6 +887,7 @@ int sm_clear_trail(sm_engine* e)
     e->ghost_stale = true;
     e->arr_stale = true;
     e->trail_nonneg = true;
+    e->stats_fused_valid = false;
     return SM_OK;
 }
 
@@ -909,6 +925,7 @@ int sm_upload_trail(sm_engine* e, const float* src, uint32_t x0, uint32_t y0, ui
     }
     e->ghost_stale = true;
     e->arr_stale = true;
+    e->stats_fused_valid = false;
     return SM_OK;
 }
 
@@ -931,11 +948,16 @@ int sm_trail_statistics(sm_engine* e, sm_trail_stats* out)
 {
     SM_ENTER(e);
     if (!out) return sm_fail(SM_ERR_BAD_ARG, "null output");
-    SM_CUDA(cudaMemsetAsync(e->stats_dev, 0, sizeof(smk::StatsAcc), e->stream));
-    const uint64_t cells = (uint64_t)e->rows * e->W;
-    unsigned nb = (unsigned)std::min<uint64_t>((cells / 16 + 255) / 256 + 1, (uint64_t)e->num_sms * 16);
-    smk::k_trail_stats<<<nb, 256, 0, e->stream>>>(e->trail_ptr(e->cur), cells, (smk::StatsAcc*)e->stats_dev);
-    SM_CUDA(cudaGetLastError());
+    e->stats_interest = 64;        // the next full-step passes reduce the statistics on the way (see k_trail_rows)
+    if (!e->stats_fused_valid) {
+        // the field was not produced by a full-step trail pass (upload, clear, diffusion-only, ...): one sweep over it
+        SM_CUDA(cudaMemsetAsync(e->stats_dev, 0, sizeof(smk::StatsAcc), e->stream));
+        const uint64_t cells = (uint64_t)e->rows * e->W;
+        unsigned nb = (unsigned)std::min<uint64_t>((cells / 16 + 255) / 256 + 1, (uint64_t)e->num_sms * 16);
+        smk::k_trail_stats<<<nb, 256, 0, e->stream>>>(e->trail_ptr(e->cur), cells, (smk::StatsAcc*)e->stats_dev);
+        SM_CUDA(cudaGetLastError());
+        e->timing.kernel_launches += 1;
+    }
     smk::StatsAcc h{};
     SM_CUDA(cudaMemcpyAsync(&h, e->stats_dev, sizeof h, cudaMemcpyDeviceToHost, e->stream));
     SM_CUDA(cudaStreamSynchronize(e->stream));
@@ -1041,6 +1063,7 @@ int sm_load_snapshot(sm_engine* e, const char* path)
     e->trail_nonneg = nonneg;
     e->ghost_stale = true;
     e->arr_stale = true;
+    e->stats_fused_valid = false;
     return SM_OK;
 }
 

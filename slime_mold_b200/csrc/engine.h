@@ -78,8 +78,11 @@ struct sm_engine {
     bool no_flags = false;            // SM_NO_DEPOSIT_FLAGS=1: always count deposits (A/B switch)
     int rpc_override = 0;
 
-    // statistics scratch
+    // statistics: accumulator on the device; `stats_fused_valid` = the last thing that changed trail[cur] was a full-step
+    // pass of k_trail_rows, which filled it on the way (else sm_trail_statistics runs k_trail_stats)
     void* stats_dev = nullptr;
+    bool stats_fused_valid = false;
+    uint32_t stats_interest = 0;      // > 0: the host read statistics within the last 64 steps -> passes run the STATS instantiation
 
     // display pass (display.wgsl): LUT and frame buffer, allocated on first use
     uint8_t* lut_dev = nullptr;
@@ -167,6 +170,7 @@ struct sm_engine {
         const float* tin; float* tout;
         int cm; const void* cin; void* czero;
         bool fast;                    // k_trail_rows applies (else k_trail_generic / the Gaussian extension)
+        bool stats;                   // this pass also reduces the field statistics
     };
     int trail_plan(bool has_counts, TrailPass& p);
     int trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t y_last, cudaStream_t st,

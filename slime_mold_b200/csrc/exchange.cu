@@ -902,6 +902,8 @@ int sm_engine::p2p_trail_overlapped()
     SM_TRY(trail_launch_rows(p, 0, band, side_stream, rows - band, rows));
     if (side_dbg) { SM_TRY(toc(side_stream)); SM_TRY(tic(12, side_stream)); }
     trail_done(true);                                          // host bookkeeping: cur / ccur flip
+    stats_fused_valid = p.stats;                               // interior + both bands accumulated this rank's statistics
+    if (stats_interest) --stats_interest;
     // side: push the new boundary rows, append arrivals, barrier 2
     SM_TRY(p2p_after_trail(side_stream, false));
     if (side_dbg) SM_TRY(toc(side_stream));

@@ -104,6 +104,10 @@ k_rescale_agents(float4* __restrict__ agents, uint64_t n, float fx, float fy)
     agents[i] = a;
 }
 
+// field statistics accumulator (sm_trail_statistics): filled by the full-step trail pass as it writes the new
+// field (k_trail_rows<CM != none>), or by k_trail_stats when the field was produced some other way
+struct StatsAcc { double sum, sum_sq; unsigned long long nonzero; unsigned int max_bits; unsigned int pad; };
+
 constexpr uint32_t kDeadAgent = 0xFFFFFFFFu;   // multi-GPU: slot whose agent migrated away (dropped by the next sort)
 
 // How the agent kernel takes part in the multi-GPU exchange.
@@ -222,9 +226,11 @@ template <int XM, class IdxT, class FETCH, bool FLAGS>
 static __global__ void __launch_bounds__(256, SM_AGENTS_MIN_BLOCKS)
 k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
          const FETCH fetch, void* __restrict__ deposits, const AgentConsts c,
-         const LeaverBufs lv)
+         const LeaverBufs lv, StatsAcc* __restrict__ stats_to_zero)
 {
     constexpr bool MULTI = XM != XM_SINGLE;
+    // the trail pass that follows this launch accumulates the field statistics of the step: start it from zero
+    if (blockIdx.x == 0 && threadIdx.x == 0) *stats_to_zero = StatsAcc{0.0, 0.0, 0ull, 0u, 0u};
     // A CTA steps kAgentsPerBlock consecutive slots, thread t taking slots t, t + 256, ... (coalesced).
     // The state of the next slot is requested before the current one is stepped, so only the first
     // load of a thread waits for DRAM; consecutive slots are neighbours in the cell-sorted order, so
@@ -303,12 +309,20 @@ __device__ __forceinline__ float trail_cell(float t, uint32_t k, const TrailCons
 //
 // Requirements (checked by the host): W % 4 == 0 and (W / 4) % 32 != 1, so that a lane is never
 // both the left edge (lane 0) and the right edge (last column group) of its warp.
-template <int CM, bool SURF, int UNROLL>
-static __global__ void __launch_bounds__(128)
+template <int CM, bool SURF, int UNROLL, bool STATS>
+static __global__ void __launch_bounds__(128, 8)
 k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
              void* __restrict__ czero_v, float* __restrict__ tout,
-             const TrailGeom g, const TrailConsts tc)
+             const TrailGeom g, const TrailConsts tc, StatsAcc* __restrict__ stats)
 {
+    // STATS instantiations also reduce the statistics of the field they write -- sum, sum of squares, non-zero
+    // cells, maximum -- so that a host loop that reads the step's result every frame (bench.py's e2e leg,
+    // sm_trail_statistics) does not pay a second sweep over the map (18 us at 4096^2).  The reduction costs this
+    // kernel ~6 us there (its epilogue is amortised over only rows_per_chunk rows), so the engine selects it
+    // only while the host is actually asking for statistics (sm_engine::stats_interest).
+    double st_s = 0.0, st_s2 = 0.0;
+    unsigned int st_nz = 0u;
+    float st_m = 0.0f;
     const uint32_t grp = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t x0 = grp * 4u;
     const bool active = x0 < g.W;
@@ -397,6 +411,18 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
                 o.w = smd::box9_mix(prev[3], prev[4], prev[5], cur[3], cur[4], cur[5], next[3], next[4], next[5], tc);
                 const size_t off = (size_t)(y + u) * W + x0;
                 *reinterpret_cast<float4*>(tout + off) = o;
+                if (STATS) {
+                    // the four cells of a row are combined in f32 (pairwise: <= 3 roundings at magnitude <= 4, i.e. a
+                    // relative error below 2e-7 per quad, random in sign) and only the quad enters the f64 accumulators:
+                    // the FP64 pipe is narrow, 18 FP64 instructions per row cost this kernel 6 us, 4 cost < 1 us
+                    const float q = (o.x + o.y) + (o.z + o.w);
+                    const float q2 = fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+                    st_s += (double)q;
+                    st_s2 += (double)q2;
+                    st_nz += min(__float_as_uint(o.x), 1u) + min(__float_as_uint(o.y), 1u) + min(__float_as_uint(o.z), 1u) +
+                             min(__float_as_uint(o.w), 1u);          // the field is >= +0 here: non-zero <=> any bit set
+                    st_m = fmaxf(fmaxf(st_m, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
+                }
                 // keep the block-linear copy the agent kernel gathers from in step (4 B/cell extra)
                 if (SURF) surf2Dwrite(o, g.surf, (int)(x0 * 4u), y + u + g.surf_row0);
                 if (CM == CM_COUNTS) *reinterpret_cast<uint4*>(static_cast<uint32_t*>(czero_v) + off) = make_uint4(0u, 0u, 0u, 0u);
@@ -404,6 +430,28 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) { prev[j] = cur[j]; cur[j] = next[j]; }
+        }
+    }
+    if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_s += __shfl_down_sync(0xffffffffu, st_s, o);
+            st_s2 += __shfl_down_sync(0xffffffffu, st_s2, o);
+            st_nz += __shfl_down_sync(0xffffffffu, st_nz, o);
+            st_m = fmaxf(st_m, __shfl_down_sync(0xffffffffu, st_m, o));
+        }
+        __shared__ double sh_s[4], sh_s2[4];
+        __shared__ unsigned int sh_nz[4];
+        __shared__ float sh_m[4];
+        const uint32_t warp = threadIdx.x >> 5;
+        if (lane == 0u) { sh_s[warp] = st_s; sh_s2[warp] = st_s2; sh_nz[warp] = st_nz; sh_m[warp] = st_m; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (uint32_t w = 1; w < (blockDim.x >> 5); ++w) { st_s += sh_s[w]; st_s2 += sh_s2[w]; st_nz += sh_nz[w]; st_m = fmaxf(st_m, sh_m[w]); }
+            atomicAdd(&stats->sum, st_s);
+            atomicAdd(&stats->sum_sq, st_s2);
+            atomicAdd(&stats->nonzero, (unsigned long long)st_nz);
+            atomicMax(&stats->max_bits, __float_as_uint(st_m));   // valid ordering: the field is non-negative after decay
         }
     }
 }
@@ -662,8 +710,6 @@ k_tile_scatter(const float4* __restrict__ agents, const uint32_t* __restrict__ i
 // ---------------------------------------------------------------------------
 // field statistics (the per-step "result" a host harness reads back)
 // ---------------------------------------------------------------------------
-struct StatsAcc { double sum, sum_sq; unsigned long long nonzero; unsigned int max_bits; unsigned int pad; };
-
 static __global__ void __launch_bounds__(256)
 k_trail_stats(const float* __restrict__ t, uint64_t cells, StatsAcc* __restrict__ acc)
 {

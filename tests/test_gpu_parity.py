@@ -283,3 +283,40 @@ def test_deposit_mode_switching_and_negative_trail(oracle, engine_lib):
         assert bits_equal(a, sim.agents), (dep, mismatch_report(a, sim.agents, "agents"))
         assert bits_equal(t, sim.trail), (dep, mismatch_report(t, sim.trail, "trail"))
     be.close()
+
+
+@pytest.mark.parametrize("dep", [1.0, 0.3])
+def test_fused_step_statistics(oracle, engine_lib, dep):
+    """sm_trail_statistics after sm_step comes from the trail pass itself (fused reduction; flags and counts
+    deposit modes), after anything else from a sweep of its own: both must describe the field read back."""
+    W, H, N = 512, 384, 150_000
+    s = settings_for("Default").clone(pheromone_deposition_amount=dep)
+    be = sm.CudaBackend.new(W, H, s, agent_count=N, device=0)
+    be.init_agents(seed=3)
+
+    def check():
+        st = be.trail_statistics()
+        t = be.read_trail()
+        t64 = t.astype(np.float64)
+        # fused path: row quads are combined in f32 before they enter the f64 accumulators (relative error < 2e-7 per quad)
+        assert abs(st.sum - t64.sum()) <= 2e-7 * max(t64.sum(), 1.0), (st.sum, t64.sum())
+        assert abs(st.sum_sq - (t64 * t64).sum()) <= 2e-7 * max((t64 * t64).sum(), 1.0)
+        assert st.max == t.max() and st.nonzero == np.count_nonzero(t)
+        return st
+
+    for n in (1, 7, 16, 1):                      # crosses a sort
+        be.step(n)
+        a = check()
+        b = check()                              # reading twice does not disturb the accumulator
+        assert (a.max, a.nonzero) == (b.max, b.nonzero)
+        assert abs(a.sum - b.sum) <= 1e-12 * max(a.sum, 1.0)      # (the separate sweep sums its blocks in atomic order)
+    be.diffuse_only(2)
+    check()                                      # not a full-step pass: separate sweep
+    be.write_trail(random_trail(W, H, seed=8))
+    check()
+    be.step(3)
+    check()
+    be.clear_trail()
+    st = check()
+    assert st.sum == 0.0 and st.nonzero == 0
+    be.close()
