@@ -360,7 +360,8 @@ int sm_engine::launch_agents()
     const bool idx32 = (uint64_t)field_cells() < (1ull << 31);
     const bool flags = flag_mode();
     SM_TRY(switch_deposit_mode(flags ? 2 : 1));
-    const unsigned nb = blocks_for(n_local, smk::kAgentsPerBlock);     // a CTA steps kAgentsPerBlock consecutive slots
+    const int apt = smk::agents_per_thread_for(n_local, num_sms);
+    const unsigned nb = blocks_for(n_local, 256u * (unsigned)apt);        // a CTA steps 256 * apt consecutive slots
     float4* a = agents[acur];
     uint32_t* id = ids[acur];
     void* dep = flags ? (void*)flags_ptr(ccur) : (void*)counts_ptr(ccur);
@@ -396,14 +397,14 @@ int sm_engine::launch_agents()
         using F = decltype(fetch);
         using I = decltype(idx_tag);
         if (multi && p2p) {
-            if (flags) smk::k_agents<smk::XM_P2P, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
-            else smk::k_agents<smk::XM_P2P, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
+            if (flags) smk::k_agents<smk::XM_P2P, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            else smk::k_agents<smk::XM_P2P, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         } else if (multi) {
-            if (flags) smk::k_agents<smk::XM_NCCL, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
-            else smk::k_agents<smk::XM_NCCL, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
+            if (flags) smk::k_agents<smk::XM_NCCL, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            else smk::k_agents<smk::XM_NCCL, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         } else {
-            if (flags) smk::k_agents<smk::XM_SINGLE, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
-            else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev);
+            if (flags) smk::k_agents<smk::XM_SINGLE, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         }
     };
     if (use_tex) {
@@ -676,7 +677,8 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     if (e->world > 1) cap = std::min<uint64_t>(e->n_global, 2 * ((e->n_global + e->world - 1) / e->world) + (1u << 20));
     if ((rc = e->alloc_agents(cap)) != SM_OK) return fail(rc);
     if ((rc = e->setup_tiles()) != SM_OK) return fail(rc);
-    if (cudaMalloc(&e->stats_dev, sizeof(smk::StatsAcc)) != cudaSuccess)
+    if (cudaMalloc(&e->stats_dev, sizeof(smk::StatsAcc)) != cudaSuccess ||
+        cudaMallocHost(&e->stats_host, sizeof(smk::StatsAcc)) != cudaSuccess)       // pinned: the per-frame read-back is a 32-byte DMA
         return fail(sm_fail(SM_ERR_OOM, "cudaMalloc(stats) failed"));
     e->n_local = 0;
     e->agents_valid = false;
@@ -700,6 +702,7 @@ int sm_destroy(sm_engine* e)
     if (e->tile_hist) cudaFree(e->tile_hist);
     if (e->tile_sums) cudaFree(e->tile_sums);
     if (e->stats_dev) cudaFree(e->stats_dev);
+    if (e->stats_host) cudaFreeHost(e->stats_host);
     if (e->lut_dev) cudaFree(e->lut_dev);
     if (e->frame_dev) cudaFree(e->frame_dev);
     for (auto& p : e->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -958,9 +961,9 @@ int sm_trail_statistics(sm_engine* e, sm_trail_stats* out)
         SM_CUDA(cudaGetLastError());
         e->timing.kernel_launches += 1;
     }
-    smk::StatsAcc h{};
-    SM_CUDA(cudaMemcpyAsync(&h, e->stats_dev, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    SM_CUDA(cudaMemcpyAsync(e->stats_host, e->stats_dev, sizeof(smk::StatsAcc), cudaMemcpyDeviceToHost, e->stream));
     SM_CUDA(cudaStreamSynchronize(e->stream));
+    const smk::StatsAcc h = *static_cast<const smk::StatsAcc*>(e->stats_host);
     out->sum = h.sum; out->sum_sq = h.sum_sq; out->nonzero = h.nonzero;
     memcpy(&out->max, &h.max_bits, 4);
     out->_pad = 0;

@@ -81,6 +81,7 @@ struct sm_engine {
     // statistics: accumulator on the device; `stats_fused_valid` = the last thing that changed trail[cur] was a full-step
     // pass of k_trail_rows, which filled it on the way (else sm_trail_statistics runs k_trail_stats)
     void* stats_dev = nullptr;
+    void* stats_host = nullptr;       // pinned mirror
     bool stats_fused_valid = false;
     uint32_t stats_interest = 0;      // > 0: the host read statistics within the last 64 steps -> passes run the STATS instantiation
 

@@ -212,7 +212,14 @@ __device__ __forceinline__ void step_agent_slot(float4* __restrict__ agents, uin
 #define SM_AGENTS_PER_THREAD 4        // agents one thread steps in sequence (a CTA owns 256 * this many consecutive slots); 1: 181 us, 2: 175, 4: 164, 8: 164
 #endif
 constexpr int kAgentsPerThread = SM_AGENTS_PER_THREAD;
-constexpr uint32_t kAgentsPerBlock = 256u * kAgentsPerThread;
+// Small populations take fewer agents per thread (a launch argument) so that the grid still fills the machine:
+// 1 M agents are 977 CTAs at 4 per thread -- 1.3 waves of 148 x 5 -- but 3906 at 1 per thread.
+static inline int agents_per_thread_for(uint64_t n, int num_sms)
+{
+    int apt = kAgentsPerThread;
+    while (apt > 1 && n / (256ull * apt) < 4ull * 5ull * (uint64_t)num_sms) apt >>= 1;
+    return apt;
+}
 
 __device__ __forceinline__ void load_agent_slot(const float4* agents, const uint32_t* ids, uint64_t i, float4& a, uint32_t& id)
 {
@@ -226,18 +233,18 @@ template <int XM, class IdxT, class FETCH, bool FLAGS>
 static __global__ void __launch_bounds__(256, SM_AGENTS_MIN_BLOCKS)
 k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
          const FETCH fetch, void* __restrict__ deposits, const AgentConsts c,
-         const LeaverBufs lv, StatsAcc* __restrict__ stats_to_zero)
+         const LeaverBufs lv, StatsAcc* __restrict__ stats_to_zero, const int agents_per_thread)
 {
     constexpr bool MULTI = XM != XM_SINGLE;
     // the trail pass that follows this launch accumulates the field statistics of the step: start it from zero
     if (blockIdx.x == 0 && threadIdx.x == 0) *stats_to_zero = StatsAcc{0.0, 0.0, 0ull, 0u, 0u};
-    // A CTA steps kAgentsPerBlock consecutive slots, thread t taking slots t, t + 256, ... (coalesced).
+    // A CTA steps 256 * agents_per_thread consecutive slots, thread t taking slots t, t + 256, ... (coalesced).
     // The state of the next slot is requested before the current one is stepped, so only the first
     // load of a thread waits for DRAM; consecutive slots are neighbours in the cell-sorted order, so
     // their footprints also reuse this SM's L1.
     // MULTI: n is the host's upper bound of the slots in use; every slot past the live ones holds
     // kDeadAgent (kept so by the sort and by k_append_arrivals), so no device-side count is needed here
-    uint64_t i = (uint64_t)blockIdx.x * kAgentsPerBlock + threadIdx.x;
+    uint64_t i = (uint64_t)blockIdx.x * (256u * (uint32_t)agents_per_thread) + threadIdx.x;
     // MULTI: the host only knows an upper bound of the slots in use between two sorts (it grows by the migration
     // capacity every step); the exact count lives on the device -- CTAs past it leave without touching HBM
     if (MULTI) n = min(n, (uint64_t)*lv.slots_in_use);
@@ -246,11 +253,11 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     uint32_t id_next;
     load_agent_slot(agents, ids, i, a_next, id_next);
 #pragma unroll 1
-    for (int j = 0; j < kAgentsPerThread; ++j) {
+    for (int j = 0; j < agents_per_thread; ++j) {
         float4 a = a_next;
         const uint32_t id = id_next;
         const uint64_t i_next = i + 256u;
-        const bool more = (j + 1 < kAgentsPerThread) && i_next < n;
+        const bool more = (j + 1 < agents_per_thread) && i_next < n;
         if (more) load_agent_slot(agents, ids, i_next, a_next, id_next);
         if (!MULTI || id != kDeadAgent)
             step_agent_slot<XM, IdxT, FETCH, FLAGS>(agents, ids, i, a, id, fetch, deposits, c, lv);
