@@ -71,7 +71,7 @@ struct sm_engine {
     uint32_t n_scan_blocks = 0;
     uint32_t* tile_hist = nullptr;
     uint32_t* tile_sums = nullptr;
-    uint32_t sort_interval = 16, steps_since_sort = 0;
+    uint32_t sort_interval = 24, steps_since_sort = 0;
 
     // tuning overrides (environment, read at sm_create)
     bool force_generic = false;
