@@ -167,8 +167,8 @@ def readme(tag):
     for n in (1, 2, 4, 8):
         for x in ("", "_p2p", "_nccl"):
             d = _json_line(os.path.join(G, f"bench_n{n}{x}.log"))
-            if d and not (x == "" and n > 1):
-                rows.append((n, x.strip("_") or "-", d))
+            if d and x == "":
+                rows.append((n, "-" if n == 1 else "p2p, overlapped", d))
     if rows:
         A("## Multi-GPU strips (weak scaling: 16.7 M agents and 4096 map rows per GPU)\n")
         A("| GPUs | exchange | agent-steps/s | us/step | agents us | trail us | exchange us/step | efficiency vs N=1 |\n|---|---|---|---|---|---|---|---|")
@@ -178,7 +178,19 @@ def readme(tag):
             eff = d["value"] / (n * base["value"]) if base else float("nan")
             A(f"| {n} | {x} | {d['value']:.3e} | {d['ms_per_step']*1e3:.1f} | {k['agents']['ms']*1e3:.1f} | {k['trail']['ms']*1e3:.1f} | "
               f"{k.get('exchange_ms_per_step', 0)*1e3:.1f} | {eff:.2f} |")
-        A("")
+            shutil.copy(os.path.join(G, f"bench_n{n}.log"), os.path.join(P, f"{tag}_bench_n{n}.log"))
+        A("\n(`trail us` is the interior pass on strips; `exchange us/step` is what the overlap leaves exposed: the join and the "
+          "refresh of the sampler's ghost rows. Session-1 numbers with the serial exchange and the first agent kernel: "
+          "2 GPUs p2p 1.03e11 / nccl 8.9e10, 4 GPUs p2p 2.05e11 / nccl 1.87e11.)\n")
+        c4 = _json_line(os.path.join(G, "bench_config4_n8.log"))
+        if c4:
+            k, df = c4["kernels"], c4["diffusion"]
+            shutil.copy(os.path.join(G, "bench_config4_n8.log"), os.path.join(P, f"{tag}_bench_config4_n8.log"))
+            A(f"**BASELINE configs[3]** (1,000,000,000 agents, 32768x32768, Default, 8 strips of 4096 rows on 8 B200): "
+              f"**{c4['value']:.3e}** agent-steps/s ({c4['ms_per_step']*1e3:.0f} us/step; agents {k['agents']['ms']*1e3:.0f} us, interior trail "
+              f"{k['trail']['ms']*1e3:.0f} us, sort {k['sort_ms_per_step']*1e3:.0f} us/step, exposed exchange {k['exchange_ms_per_step']*1e3:.0f} us/step), "
+              f"e2e {c4['e2e']['value']:.3e}; target of the north star: >= 1e11. Diffusion-only on the same strips: "
+              f"{df['gbs']/1e3:.1f} TB/s aggregate = {df['frac_of_peak']:.2f} of 8 x the measured copy peak ({df['ms_per_pass']*1e3:.0f} us/pass).\n")
     # sweeps
     sw = os.path.join(P, f"{tag}_kernel_sweep.jsonl")
     if os.path.exists(sw):
