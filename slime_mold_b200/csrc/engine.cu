@@ -543,6 +543,37 @@ int sm_engine::launch_gauss(bool has_counts, const smk::TrailGeom& g, const smd:
         }
         for (int d = 0; d <= 2 * R; ++d) gc.w[d] = (float)(tmp[d] / s);
     }
+    const float* tin0 = trail_ptr(cur);
+    float* tout0 = trail_ptr(1 - cur);
+    if (W % 4 == 0 && W >= 160 && rows >= 64 && !gauss_two_pass) {
+        // fused single pass: tiles with halos staged in shared memory (k_gauss_fused)
+        dim3 grid(blocks_for(W, smk::kGaussTX), blocks_for(rows, smk::kGaussTY));
+        auto go = [&](auto r_tag) -> int {
+            constexpr int RR = decltype(r_tag)::value;
+            const size_t smem = smk::gauss_smem_bytes<RR>();
+            if (has_counts) {
+                SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                smk::k_gauss_fused<RR, true><<<grid, 256, smem, stream>>>(tin0, counts_ptr(ccur), counts_ptr(1 - ccur), tout0, g, tc, gc);
+            } else {
+                SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused<RR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                smk::k_gauss_fused<RR, false><<<grid, 256, smem, stream>>>(tin0, nullptr, nullptr, tout0, g, tc, gc);
+            }
+            return SM_OK;
+        };
+        using std::integral_constant;
+        switch (R) {
+        case 1: SM_TRY(go(integral_constant<int, 1>{})); break;
+        case 2: SM_TRY(go(integral_constant<int, 2>{})); break;
+        case 3: SM_TRY(go(integral_constant<int, 3>{})); break;
+        case 4: SM_TRY(go(integral_constant<int, 4>{})); break;
+        case 5: SM_TRY(go(integral_constant<int, 5>{})); break;
+        case 6: SM_TRY(go(integral_constant<int, 6>{})); break;
+        case 7: SM_TRY(go(integral_constant<int, 7>{})); break;
+        default: SM_TRY(go(integral_constant<int, 8>{})); break;
+        }
+        timing.kernel_launches += 1;
+        return SM_OK;
+    }
     const size_t cells = (size_t)rows * W;
     if (!gauss_dec) SM_CUDA(cudaMalloc(&gauss_dec, cells * sizeof(float)));
     if (!gauss_hb) SM_CUDA(cudaMalloc(&gauss_hb, cells * sizeof(float)));
@@ -657,6 +688,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     e->force_generic = env_int("SM_FORCE_GENERIC_TRAIL", 0) != 0;
     e->no_flags = env_int("SM_NO_DEPOSIT_FLAGS", 0) != 0;
     e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
+    e->gauss_two_pass = env_int("SM_GAUSS_TWO_PASS", 0) != 0;
 
     // defaults = Settings::default(), /root/reference/src/settings.rs:8-27
     sm_params p{};

@@ -77,6 +77,7 @@ struct sm_engine {
     bool force_generic = false;
     bool no_flags = false;            // SM_NO_DEPOSIT_FLAGS=1: always count deposits (A/B switch)
     int rpc_override = 0;
+    bool gauss_two_pass = false;      // SM_GAUSS_TWO_PASS=1: the unfused Gaussian passes (A/B; also used for maps below 160 x 64)
 
     // statistics: accumulator on the device; `stats_fused_valid` = the last thing that changed trail[cur] was a full-step
     // pass of k_trail_rows, which filled it on the way (else sm_trail_statistics runs k_trail_stats)

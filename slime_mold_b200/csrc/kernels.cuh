@@ -548,6 +548,125 @@ k_gauss_v(const float* __restrict__ dec, const float* __restrict__ hb, float* __
     if (has_counts) czero[off] = 0u;
 }
 
+// Fused form of the two passes above (the default for maps of at least 160 x 64 cells): one kernel per pass,
+// tiles with halos staged in shared memory, 8 B/cell of HBM traffic plus the halo re-reads instead of 20+.
+//   phase 1  (TY + 2R) x (TX + 2R) cells: merge + decay -> D (shared)
+//   phase 2  horizontal taps for all TY + 2R rows, 4 outputs per thread from a register window -> Hb (shared)
+//   phase 3  vertical taps, one column and 16 rows per thread from a register window; mix with D; coalesced store
+// The per-cell statement sequences (tap order d = -R..R, one FMA per tap starting from 0.0f, the final mix)
+// are those of k_gauss_h / k_gauss_v and of the oracle, so the results are bit-identical to the two-pass form.
+constexpr int kGaussTX = 128, kGaussTY = 32;
+
+template <int R>
+__host__ __device__ constexpr int gauss_ra() { return (R + 3) / 4 * 4; }                        // halo columns staged per side: R rounded up to whole float4s
+template <int R>
+__host__ __device__ constexpr int gauss_dcols() { return kGaussTX + 2 * gauss_ra<R>() + 4; }   // row stride of D (floats), 16-byte multiple, +4 against bank conflicts
+template <int R>
+__host__ __device__ constexpr size_t gauss_smem_bytes()
+{
+    return sizeof(float) * (size_t)(kGaussTY + 2 * R) * (size_t)(gauss_dcols<R>() + kGaussTX);
+}
+
+// Requires W % 4 == 0, W >= 160, rows >= 64 (the host falls back to the two-pass form otherwise).
+template <int R, bool HAS_COUNTS>
+static __global__ void __launch_bounds__(256)
+k_gauss_fused(const float* __restrict__ tin, const uint32_t* __restrict__ cin, uint32_t* __restrict__ czero,
+              float* __restrict__ tout, const TrailGeom g, const TrailConsts tc, const GaussConsts gc)
+{
+    constexpr int TX = kGaussTX, TY = kGaussTY, RW = TY + 2 * R, RA = gauss_ra<R>(), DC = gauss_dcols<R>();
+    constexpr int DC4 = (TX + 2 * RA) / 4;          // float4 columns staged per row
+    extern __shared__ __align__(16) float gsm[];
+    float* D = gsm;                    // [RW][DC]   decayed cells, column c <-> map column x0 - RA + c
+    float* Hb = gsm + RW * DC;         // [RW][TX]   row-blurred cells, row r <-> map row y0 - R + r
+    const int W = (int)g.W, H = (int)g.rows;
+    const int x0 = (int)blockIdx.x * TX, y0 = (int)blockIdx.y * TY;
+
+    // ---- phase 1: every thread requests all its 16-byte pieces of the tile before it touches any of them ----
+    {
+        constexpr int N4 = RW * DC4, PER = (N4 + 255) / 256;
+        float4 t4[PER];
+        uint4 k4[HAS_COUNTS ? PER : 1];
+        int64_t goff[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int e = (int)threadIdx.x + k * 256;
+            goff[k] = -1;
+            if (e < N4) {
+                const int r = e / DC4, c4 = e - r * DC4;
+                int gy = y0 - R + r;
+                if (gy < 0) gy += H; else if (gy >= H) gy -= H;          // toroidal (rows >= TY + 2R: one fold is enough)
+                int gx = x0 - RA + 4 * c4;
+                if (gx < 0) gx += W; else if (gx >= W) gx -= W;          // W % 4 == 0: a float4 never straddles the seam
+                goff[k] = (int64_t)gy * W + gx;
+                t4[k] = __ldg(reinterpret_cast<const float4*>(tin + goff[k]));
+                if (HAS_COUNTS) k4[k] = __ldg(reinterpret_cast<const uint4*>(cin + goff[k]));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int e = (int)threadIdx.x + k * 256;
+            if (e < N4) {
+                const int r = e / DC4, c4 = e - r * DC4;
+                float4 t = t4[k];
+                if (HAS_COUNTS) {
+                    t.x = smd::merge_deposit(t.x, k4[k].x, tc.dep); t.y = smd::merge_deposit(t.y, k4[k].y, tc.dep);
+                    t.z = smd::merge_deposit(t.z, k4[k].z, tc.dep); t.w = smd::merge_deposit(t.w, k4[k].w, tc.dep);
+                    // cells this block owns: retire their counts in the buffer the next step deposits into
+                    const bool own = r >= R && r < R + TY && y0 + (r - R) < H && 4 * c4 >= RA && 4 * c4 < RA + TX && x0 + (4 * c4 - RA) < W;
+                    if (own) *reinterpret_cast<uint4*>(czero + goff[k]) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                t.x = smd::decay_cell(t.x, tc.decay_sub); t.y = smd::decay_cell(t.y, tc.decay_sub);
+                t.z = smd::decay_cell(t.z, tc.decay_sub); t.w = smd::decay_cell(t.w, tc.decay_sub);
+                *reinterpret_cast<float4*>(D + r * DC + 4 * c4) = t;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: Hb[r][xs .. xs+3]; output j taps D columns xs + j + (RA - R) + d, d = 0 .. 2R ----
+    for (int item = threadIdx.x; item < RW * (TX / 4); item += 256) {
+        const int r = item / (TX / 4), xs = (item % (TX / 4)) * 4;
+        constexpr int NV = (4 + RA + R + 3) / 4 * 4, SH = RA - R;
+        float v[NV];
+        const float4* src = reinterpret_cast<const float4*>(D + r * DC + xs);
+#pragma unroll
+        for (int q = 0; q < NV / 4; ++q) {
+            const float4 f = src[q];
+            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+        for (int d = 0; d <= 2 * R; ++d) {
+            const float w = gc.w[d];
+            a0 = smd::fma(w, v[SH + d], a0);
+            a1 = smd::fma(w, v[SH + d + 1], a1);
+            a2 = smd::fma(w, v[SH + d + 2], a2);
+            a3 = smd::fma(w, v[SH + d + 3], a3);
+        }
+        *reinterpret_cast<float4*>(Hb + r * TX + xs) = make_float4(a0, a1, a2, a3);
+    }
+    __syncthreads();
+
+    // ---- phase 3: column x, rows [16*half, 16*half + 16) ----
+    {
+        const int x = threadIdx.x & (TX - 1), half = threadIdx.x / TX;
+        constexpr int ROWS = TY / 2;
+        float v[ROWS + 2 * R];
+#pragma unroll
+        for (int k = 0; k < ROWS + 2 * R; ++k) v[k] = Hb[(half * ROWS + k) * TX + x];
+        const int gx = x0 + x;
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int d = 0; d <= 2 * R; ++d) acc = smd::fma(gc.w[d], v[j + d], acc);
+            const int gy = y0 + half * ROWS + j;
+            if (gx < W && gy < H)
+                tout[(int64_t)gy * W + gx] = smd::mixf_pre(D[(half * ROWS + j + R) * DC + x + RA], acc, tc.rate, tc.one_minus_rate);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // periodic cell sort (counting sort by tile key), carries the persistent index
 // ---------------------------------------------------------------------------

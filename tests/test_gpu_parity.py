@@ -209,6 +209,40 @@ def test_gaussian_extension(oracle, engine_lib, R, sigma):
     be.close()
 
 
+@pytest.mark.parametrize("two_pass", [0, 1])
+@pytest.mark.parametrize("R,sigma,W,H", [(1, 0.7, 160, 64), (2, 1.0, 416, 200), (3, 1.3, 517, 131), (5, 2.5, 1000, 97), (8, 4.0, 640, 333)])
+def test_gaussian_extension_fused_and_two_pass(oracle, engine_lib, monkeypatch, R, sigma, W, H, two_pass):
+    """EXTENSION: the fused shared-memory kernel (ragged tiles, wrap on all four sides) and the two-pass form give the
+    oracle's bits, in diffusion-only passes and in full steps (deposit counts merged by the Gaussian pass)."""
+    monkeypatch.setenv("SM_GAUSS_TWO_PASS", str(two_pass))
+    s = settings_for("Default").clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=0.7, pheromone_deposition_amount=0.4)
+    u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
+    p = to_oracle_params(oracle, u)
+    N = 20_000
+    field = random_trail(W, H, seed=R)
+    ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 4)
+    be = sm.CudaBackend.new(W, H, s, agent_count=N, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+    be.write_trail(field)
+    be.write_agents(ag)
+    be.diffuse_only(2)
+    ref = field
+    for _ in range(2):
+        ref = oracle.trail_pass(ref, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
+    got = be.read_trail()
+    assert bits_equal(got, ref), mismatch_report(got, ref, "gauss diffuse-only")
+    # full steps: agents (phase split) -> counts -> Gaussian pass
+    be.step(3)
+    a = ag.copy()
+    counts = np.zeros((H, W), np.uint32)
+    for _ in range(3):
+        oracle.agents_phase_split(a, ref, counts, p)
+        ref = oracle.trail_pass(ref, p, counts=counts, gauss_radius=R, gauss_sigma=sigma)
+    assert bits_equal(be.read_agents(), a), "agents"
+    got = be.read_trail()
+    assert bits_equal(got, ref), mismatch_report(got, ref, "gauss full step")
+    be.close()
+
+
 @pytest.mark.parametrize("name", PRESET_NAMES)
 def test_golden_vectors(engine_lib, name):
     g = np.load(os.path.join(GOLD, "golden_" + name.lower().replace(" ", "_") + ".npz"))

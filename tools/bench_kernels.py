@@ -100,6 +100,26 @@ def presets_sweep():
         be.close()
 
 
+def gauss_sweep():
+    """EXTENSION (no reference semantics): separable Gaussian, radius 2 / 4 / 8, fused shared-memory kernel vs the
+    two-pass form (BASELINE config 5 names radii 1-8; radius 1 = the reference's box is the parity mode above)."""
+    for S in (8192, 16384):
+        for R in (2, 4, 8):
+            for two_pass in (0, 1):
+                os.environ["SM_GAUSS_TWO_PASS"] = str(two_pass)
+                s = sm.Settings.default().clone(blur_radius=float(R), blur_sigma=R / 2.0)
+                be = sm.CudaBackend.new(S, S, s, agent_count=1, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+                be.write_trail(np.random.default_rng(0).random((256, S), dtype=np.float32), y0=0)
+                passes = max(6, min(60, int(6e9 / (S * S * 8))))
+                be.diffuse_only(3)
+                ms = event_time(be, lambda: be.diffuse_only(passes))
+                gbs = 8.0 * S * S * passes / (ms * 1e-3) / 1e9
+                emit({"sweep": "gauss", "size": S, "radius": R, "kernel": "two_pass" if two_pass else "fused", "passes": passes,
+                      "ms_per_pass": ms / passes, "gbs": gbs, "frac_of_measured_peak": gbs / PEAK, "frac_of_8TBs": gbs / 8000.0})
+                be.close()
+    os.environ.pop("SM_GAUSS_TWO_PASS", None)
+
+
 def diffusion_16k():
     """A handful of diffusion-only passes on a 16384^2 field (1 GiB in, 1 GiB out): the ncu target."""
     S = 16384
@@ -121,4 +141,6 @@ if __name__ == "__main__":
         agents_sweep()
     if "presets" in which:
         presets_sweep()
+    if "gauss" in which:
+        gauss_sweep()
     print("sweeps done in", round(time.time() - t0, 1), "s")

@@ -210,6 +210,17 @@ def readme(tag):
                     A(f"| {r['tile'][0]}x{r['tile'][1]} | {r['sort_interval']} | {r['ms_per_step']*1e3:.1f} | {r['agents_ms']*1e3:.1f} | {r['sort_ms_per_step']*1e3:.1f} |")
                 else:
                     A(f"| never sorted | - | {r['ms_per_step']*1e3:.1f} | | |")
+        if any(r["sweep"] == "gauss" for r in rows):
+            A("\n## EXTENSION: separable Gaussian, radius 2 / 4 / 8 (no reference semantics; BASELINE config 5 names radii 1-8)\n")
+            A("`k_gauss_fused` (one pass, tiles + halos in shared memory) vs the two-pass form it replaced; 8 algorithmic bytes per cell-pass, sigma = R/2.\n")
+            A("| map | radius | kernel | us/pass | GB/s | of measured peak |\n|---|---|---|---|---|---|")
+            last = {}
+            for r in rows:
+                if r["sweep"] == "gauss":
+                    last[(r["size"], r["radius"], r["kernel"])] = r          # the file is appended to: keep the latest run
+            for (size, rad, kern), r in sorted(last.items()):
+                A(f"| {size}^2 | {rad} | {kern} | {r['ms_per_pass']*1e3:.1f} | {r['gbs']:.0f} | {r['frac_of_measured_peak']:.2f} |")
+            A("\nRadius 2 is HBM/L2-bound; radius 4 and 8 are bound by FP32 FMA issue and shared-memory bandwidth ((2R+1) taps x 2.5 per cell).")
         A("\n## All presets at config-2 size (16.7 M agents, 4096^2): uniform-random start vs steady state (>= 500 steps in)\n")
         A("| preset | initial agent-steps/s | steady agent-steps/s | steady us/step | trail mean | occupied cells |\n|---|---|---|---|---|---|")
         for r in rows:
