@@ -179,15 +179,28 @@ def run_reference(args):
 
 
 def workload_config(args, N):
+    total_agents, total_h = args.agents * N, args.height * N
+    if (args.agents, args.width, args.height) == (16777216, 4096, 4096):
+        label = "BASELINE configs[1]" + (" per GPU (weak scaling)" if N > 1 else "")
+    elif (total_agents, args.width, total_h) == (1000000, 1920, 1080):
+        label = "BASELINE configs[0]"
+    elif (total_agents, args.width, total_h) == (100000000, 8192, 8192):
+        label = "BASELINE configs[2]"
+    elif (total_agents, args.width, total_h) == (1000000000, 32768, 32768):
+        label = "BASELINE configs[3]"
+    else:
+        label = "custom size"
     return {
-        "workload": f"BASELINE configs[1] per GPU: {args.agents} agents on a {args.width}x{args.height} trail map, "
+        "workload": f"{label}: {args.agents} agents on a {args.width}x{args.height} trail map per GPU, "
                     f"preset {args.preset}; x{N} strips" if N > 1 else
-                    f"BASELINE configs[1]: {args.agents} agents on a {args.width}x{args.height} trail map, preset {args.preset}",
+                    f"{label}: {args.agents} agents on a {args.width}x{args.height} trail map, preset {args.preset}",
         "agents": args.agents * N, "width": args.width, "height": args.height * N, "preset": args.preset,
         "parallelism": f"strips{N}" if N > 1 else "single",
         "exchange": (os.environ.get("SM_EXCHANGE") or "p2p") if N > 1 else None,
         "spinup_steps": args.spinup, "seed": args.seed,
-        "l2": "agent state (335 MB/GPU) exceeds L2; no flush between steps (state is streamed every step)",
+        "l2": (f"inputs larger than L2: agent state {args.agents * 20 / 1e6:.0f} MB/GPU is streamed every step (no flush between steps)"
+               if args.agents * 20 > 126e6 else
+               f"working set ({args.agents * 20 / 1e6:.0f} MB of agent state per GPU) fits the 126 MB L2: L2-resident, not a DRAM number; no flush"),
     }
 
 
