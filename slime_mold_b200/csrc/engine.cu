@@ -551,7 +551,15 @@ int sm_engine::launch_gauss(bool has_counts, const smk::TrailGeom& g, const smd:
         auto go = [&](auto r_tag) -> int {
             constexpr int RR = decltype(r_tag)::value;
             const size_t smem = smk::gauss_smem_bytes<RR>();
-            if (has_counts) {
+            if (gauss_packed) {
+                if (has_counts) {
+                    SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused_packed<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    smk::k_gauss_fused_packed<RR, true><<<grid, 256, smem, stream>>>(tin0, counts_ptr(ccur), counts_ptr(1 - ccur), tout0, g, tc, gc);
+                } else {
+                    SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused_packed<RR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    smk::k_gauss_fused_packed<RR, false><<<grid, 256, smem, stream>>>(tin0, nullptr, nullptr, tout0, g, tc, gc);
+                }
+            } else if (has_counts) {
                 SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 smk::k_gauss_fused<RR, true><<<grid, 256, smem, stream>>>(tin0, counts_ptr(ccur), counts_ptr(1 - ccur), tout0, g, tc, gc);
             } else {
@@ -689,6 +697,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     e->no_flags = env_int("SM_NO_DEPOSIT_FLAGS", 0) != 0;
     e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
     e->gauss_two_pass = env_int("SM_GAUSS_TWO_PASS", 0) != 0;
+    e->gauss_packed = env_int("SM_GAUSS_PACKED", 0) != 0;   // measured: no faster than the scalar form (the kernel waits on barriers and loads, not on FMA issue)
 
     // defaults = Settings::default(), /root/reference/src/settings.rs:8-27
     sm_params p{};

@@ -77,6 +77,7 @@ struct sm_engine {
     bool force_generic = false;
     bool no_flags = false;            // SM_NO_DEPOSIT_FLAGS=1: always count deposits (A/B switch)
     int rpc_override = 0;
+    bool gauss_packed = false;        // SM_GAUSS_PACKED=1: the FFMA2 form of the fused Gaussian kernel (A/B; measured 3-10 % slower)
     bool gauss_two_pass = false;      // SM_GAUSS_TWO_PASS=1: the unfused Gaussian passes (A/B; also used for maps below 160 x 64)
 
     // statistics: accumulator on the device; `stats_fused_valid` = the last thing that changed trail[cur] was a full-step

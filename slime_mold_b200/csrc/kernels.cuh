@@ -667,6 +667,145 @@ k_gauss_fused(const float* __restrict__ tin, const uint32_t* __restrict__ cin, u
     }
 }
 
+// Packed variant of k_gauss_fused: the tap loops run on FFMA2 (two IEEE binary32 FMAs per issue slot; see the packed
+// pairs of device_math.cuh).  For radius >= 4 the fused kernel is bound by FMA issue and shared-memory reads, not by HBM.
+//   * D is stored row-pair interleaved -- D2[r/2][c] = (D[r][c], D[r+1][c]) -- so one LDS.128 yields two naturally
+//     aligned register pairs and phase 2 computes TWO rows x four columns per thread with every tap an aligned FFMA2;
+//   * phase 3 computes two adjacent columns x eight rows per thread from LDS.64 pairs of Hb.
+// Each lane of a pair is the same FMA sequence as in the scalar kernel: bit-identical results.
+// MEASURED (profiles/README.md): half the tap instructions, yet 3-10 % SLOWER than the scalar kernel at every radius --
+// the fused kernel is bound by its barriers and load latency at 4 CTAs/SM, not by FMA issue.  Kept selectable
+// (SM_GAUSS_PACKED=1) for the record; a pipelined (persistent, double-buffered) tile loop is the next step, not packing.
+template <int R, bool HAS_COUNTS>
+static __global__ void __launch_bounds__(256)
+k_gauss_fused_packed(const float* __restrict__ tin, const uint32_t* __restrict__ cin, uint32_t* __restrict__ czero,
+                     float* __restrict__ tout, const TrailGeom g, const TrailConsts tc, const GaussConsts gc)
+{
+    using smd::f2;
+    constexpr int TX = kGaussTX, TY = kGaussTY, RW = TY + 2 * R, RP = RW / 2, RA = gauss_ra<R>(), DC = gauss_dcols<R>();
+    constexpr int DC4 = (TX + 2 * RA) / 4;
+    static_assert(RW % 2 == 0, "row pairs");
+    extern __shared__ __align__(16) float gsm[];
+    float* D2 = gsm;                   // [RP][DC][2]  (row 2p, row 2p+1) interleaved per column; column c <-> map column x0 - RA + c
+    float* Hb = gsm + RW * DC;         // [RW][TX]
+    const int W = (int)g.W, H = (int)g.rows;
+    const int x0 = (int)blockIdx.x * TX, y0 = (int)blockIdx.y * TY;
+
+    // ---- phase 1: one thread = four columns of a ROW PAIR; all loads requested before any is consumed ----
+    {
+        constexpr int N4 = RP * DC4, PER = (N4 + 255) / 256;
+        float4 ta[PER], tb[PER];
+        uint4 ka[HAS_COUNTS ? PER : 1], kb[HAS_COUNTS ? PER : 1];
+        int64_t oa[PER], ob[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int e = (int)threadIdx.x + k * 256;
+            if (e < N4) {
+                const int rp = e / DC4, c4 = e - rp * DC4;
+                int gya = y0 - R + 2 * rp, gyb = gya + 1;
+                if (gya < 0) gya += H; else if (gya >= H) gya -= H;
+                if (gyb < 0) gyb += H; else if (gyb >= H) gyb -= H;
+                int gx = x0 - RA + 4 * c4;
+                if (gx < 0) gx += W; else if (gx >= W) gx -= W;
+                oa[k] = (int64_t)gya * W + gx;
+                ob[k] = (int64_t)gyb * W + gx;
+                ta[k] = __ldg(reinterpret_cast<const float4*>(tin + oa[k]));
+                tb[k] = __ldg(reinterpret_cast<const float4*>(tin + ob[k]));
+                if (HAS_COUNTS) {
+                    ka[k] = __ldg(reinterpret_cast<const uint4*>(cin + oa[k]));
+                    kb[k] = __ldg(reinterpret_cast<const uint4*>(cin + ob[k]));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int e = (int)threadIdx.x + k * 256;
+            if (e < N4) {
+                const int rp = e / DC4, c4 = e - rp * DC4;
+                float4 a = ta[k], b = tb[k];
+                if (HAS_COUNTS) {
+                    a.x = smd::merge_deposit(a.x, ka[k].x, tc.dep); a.y = smd::merge_deposit(a.y, ka[k].y, tc.dep);
+                    a.z = smd::merge_deposit(a.z, ka[k].z, tc.dep); a.w = smd::merge_deposit(a.w, ka[k].w, tc.dep);
+                    b.x = smd::merge_deposit(b.x, kb[k].x, tc.dep); b.y = smd::merge_deposit(b.y, kb[k].y, tc.dep);
+                    b.z = smd::merge_deposit(b.z, kb[k].z, tc.dep); b.w = smd::merge_deposit(b.w, kb[k].w, tc.dep);
+                    const bool own_col = 4 * c4 >= RA && 4 * c4 < RA + TX && x0 + (4 * c4 - RA) < W;
+                    const int ra = 2 * rp, rb = 2 * rp + 1;
+                    if (own_col && ra >= R && ra < R + TY && y0 + (ra - R) < H) *reinterpret_cast<uint4*>(czero + oa[k]) = make_uint4(0u, 0u, 0u, 0u);
+                    if (own_col && rb >= R && rb < R + TY && y0 + (rb - R) < H) *reinterpret_cast<uint4*>(czero + ob[k]) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                a.x = smd::decay_cell(a.x, tc.decay_sub); a.y = smd::decay_cell(a.y, tc.decay_sub);
+                a.z = smd::decay_cell(a.z, tc.decay_sub); a.w = smd::decay_cell(a.w, tc.decay_sub);
+                b.x = smd::decay_cell(b.x, tc.decay_sub); b.y = smd::decay_cell(b.y, tc.decay_sub);
+                b.z = smd::decay_cell(b.z, tc.decay_sub); b.w = smd::decay_cell(b.w, tc.decay_sub);
+                float4* dst = reinterpret_cast<float4*>(D2 + ((size_t)rp * DC + 4 * c4) * 2);
+                dst[0] = make_float4(a.x, b.x, a.y, b.y);
+                dst[1] = make_float4(a.z, b.z, a.w, b.w);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: rows (2rp, 2rp+1), outputs xs .. xs+3; output j taps columns xs + j + (RA - R) + d ----
+    for (int item = threadIdx.x; item < RP * (TX / 4); item += 256) {
+        const int rp = item / (TX / 4), xs = (item % (TX / 4)) * 4;
+        constexpr int NV = (4 + RA + R + 1) / 2 * 2, SH = RA - R;     // columns in the window (even count: one LDS.128 = 2 columns)
+        f2 v[NV];
+        const float4* src = reinterpret_cast<const float4*>(D2 + ((size_t)rp * DC + xs) * 2);
+#pragma unroll
+        for (int q = 0; q < NV / 2; ++q) {
+            const float4 f = src[q];
+            v[2 * q] = smd::mk2(f.x, f.y);
+            v[2 * q + 1] = smd::mk2(f.z, f.w);
+        }
+        f2 a0 = smd::splat2(0.0f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+        for (int d = 0; d <= 2 * R; ++d) {
+            const f2 w = smd::splat2(gc.w[d]);
+            a0 = smd::fma2(w, v[SH + d], a0);
+            a1 = smd::fma2(w, v[SH + d + 1], a1);
+            a2 = smd::fma2(w, v[SH + d + 2], a2);
+            a3 = smd::fma2(w, v[SH + d + 3], a3);
+        }
+        *reinterpret_cast<float4*>(Hb + (2 * rp) * TX + xs) = make_float4(a0.lo, a1.lo, a2.lo, a3.lo);
+        *reinterpret_cast<float4*>(Hb + (2 * rp + 1) * TX + xs) = make_float4(a0.hi, a1.hi, a2.hi, a3.hi);
+    }
+    __syncthreads();
+
+    // ---- phase 3: columns (2cp, 2cp+1), rows [8*rg, 8*rg + 8) ----
+    {
+        const int cp = threadIdx.x & (TX / 2 - 1), rg = threadIdx.x / (TX / 2);
+        constexpr int ROWS = TY / 4;
+        f2 v[ROWS + 2 * R];
+#pragma unroll
+        for (int k = 0; k < ROWS + 2 * R; ++k) {
+            const float2 f = *reinterpret_cast<const float2*>(Hb + (rg * ROWS + k) * TX + 2 * cp);
+            v[k] = smd::mk2(f.x, f.y);
+        }
+        f2 acc[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) acc[j] = smd::splat2(0.0f);
+#pragma unroll
+        for (int d = 0; d <= 2 * R; ++d) {
+            const f2 w = smd::splat2(gc.w[d]);
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) acc[j] = smd::fma2(w, v[j + d], acc[j]);
+        }
+        const int gx = x0 + 2 * cp;
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            const int row = rg * ROWS + j + R;                                   // row of D
+            const int gy = y0 + rg * ROWS + j;
+            if (gx < W && gy < H) {
+                const float* dc = D2 + ((size_t)(row >> 1) * DC + 2 * cp + RA) * 2 + (row & 1);
+                float2 o;
+                o.x = smd::mixf_pre(dc[0], acc[j].lo, tc.rate, tc.one_minus_rate);
+                o.y = smd::mixf_pre(dc[2], acc[j].hi, tc.rate, tc.one_minus_rate);
+                *reinterpret_cast<float2*>(tout + (int64_t)gy * W + gx) = o;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // periodic cell sort (counting sort by tile key), carries the persistent index
 // ---------------------------------------------------------------------------

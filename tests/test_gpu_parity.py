@@ -209,12 +209,14 @@ def test_gaussian_extension(oracle, engine_lib, R, sigma):
     be.close()
 
 
-@pytest.mark.parametrize("two_pass", [0, 1])
-@pytest.mark.parametrize("R,sigma,W,H", [(1, 0.7, 160, 64), (2, 1.0, 416, 200), (3, 1.3, 517, 131), (5, 2.5, 1000, 97), (8, 4.0, 640, 333)])
-def test_gaussian_extension_fused_and_two_pass(oracle, engine_lib, monkeypatch, R, sigma, W, H, two_pass):
-    """EXTENSION: the fused shared-memory kernel (ragged tiles, wrap on all four sides) and the two-pass form give the
-    oracle's bits, in diffusion-only passes and in full steps (deposit counts merged by the Gaussian pass)."""
-    monkeypatch.setenv("SM_GAUSS_TWO_PASS", str(two_pass))
+@pytest.mark.parametrize("kernel", ["packed", "scalar", "two_pass"])
+@pytest.mark.parametrize("R,sigma,W,H", [(1, 0.7, 160, 64), (2, 1.0, 416, 200), (3, 1.3, 517, 131), (4, 2.0, 256, 96), (5, 2.5, 1000, 97),
+                                         (6, 3.0, 384, 130), (7, 3.5, 772, 65), (8, 4.0, 640, 333)])
+def test_gaussian_extension_fused_and_two_pass(oracle, engine_lib, monkeypatch, R, sigma, W, H, kernel):
+    """EXTENSION: the fused shared-memory kernels (FFMA2-packed and scalar; ragged tiles, wrap on all four sides) and the
+    two-pass form give the oracle's bits, in diffusion-only passes and in full steps (deposit counts merged by the pass)."""
+    monkeypatch.setenv("SM_GAUSS_TWO_PASS", "1" if kernel == "two_pass" else "0")
+    monkeypatch.setenv("SM_GAUSS_PACKED", "1" if kernel == "packed" else "0")
     s = settings_for("Default").clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=0.7, pheromone_deposition_amount=0.4)
     u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
     p = to_oracle_params(oracle, u)

@@ -105,8 +105,10 @@ def gauss_sweep():
     two-pass form (BASELINE config 5 names radii 1-8; radius 1 = the reference's box is the parity mode above)."""
     for S in (8192, 16384):
         for R in (2, 4, 8):
-            for two_pass in (0, 1):
-                os.environ["SM_GAUSS_TWO_PASS"] = str(two_pass)
+            for kern in ("fused_packed", "fused_scalar", "two_pass"):
+                two_pass = kern == "two_pass"
+                os.environ["SM_GAUSS_TWO_PASS"] = "1" if two_pass else "0"
+                os.environ["SM_GAUSS_PACKED"] = "1" if kern == "fused_packed" else "0"
                 s = sm.Settings.default().clone(blur_radius=float(R), blur_sigma=R / 2.0)
                 be = sm.CudaBackend.new(S, S, s, agent_count=1, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
                 be.write_trail(np.random.default_rng(0).random((256, S), dtype=np.float32), y0=0)
@@ -114,10 +116,11 @@ def gauss_sweep():
                 be.diffuse_only(3)
                 ms = event_time(be, lambda: be.diffuse_only(passes))
                 gbs = 8.0 * S * S * passes / (ms * 1e-3) / 1e9
-                emit({"sweep": "gauss", "size": S, "radius": R, "kernel": "two_pass" if two_pass else "fused", "passes": passes,
+                emit({"sweep": "gauss", "size": S, "radius": R, "kernel": kern, "passes": passes,
                       "ms_per_pass": ms / passes, "gbs": gbs, "frac_of_measured_peak": gbs / PEAK, "frac_of_8TBs": gbs / 8000.0})
                 be.close()
     os.environ.pop("SM_GAUSS_TWO_PASS", None)
+    os.environ.pop("SM_GAUSS_PACKED", None)
 
 
 def diffusion_16k():

@@ -220,7 +220,8 @@ def readme(tag):
                     last[(r["size"], r["radius"], r["kernel"])] = r          # the file is appended to: keep the latest run
             for (size, rad, kern), r in sorted(last.items()):
                 A(f"| {size}^2 | {rad} | {kern} | {r['ms_per_pass']*1e3:.1f} | {r['gbs']:.0f} | {r['frac_of_measured_peak']:.2f} |")
-            A("\nRadius 2 is HBM/L2-bound; radius 4 and 8 are bound by FP32 FMA issue and shared-memory bandwidth ((2R+1) taps x 2.5 per cell).")
+            A("\n`fused_scalar` is the default. `fused_packed` halves the tap instructions (FFMA2) and is still slower: the kernel waits on its two "
+              "barriers and on load latency at 4 CTAs/SM, not on FMA issue.")
         A("\n## All presets at config-2 size (16.7 M agents, 4096^2): uniform-random start vs steady state (>= 500 steps in)\n")
         A("| preset | initial agent-steps/s | steady agent-steps/s | steady us/step | trail mean | occupied cells |\n|---|---|---|---|---|---|")
         for r in rows:
