@@ -301,7 +301,8 @@ int sm_engine::setup_tiles()
 // ---------------------------------------------------------------------------
 bool sm_engine::flag_mode() const
 {
-    if (no_flags || (cfg.flags & SM_FLAG_GAUSSIAN_BLUR)) return false;
+    if (no_flags) return false;
+    if ((cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && !gauss_stream_ok()) return false;   // the tile / two-pass Gaussian kernels only merge counts
     return trail_nonneg && params.pheromone_deposition_amount >= 1.0f;
 }
 
@@ -434,7 +435,7 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     p.g.W = W; p.g.rows = rows; p.g.wrap_y = (world == 1) ? 1 : 0;
     p.g.y_first = 0; p.g.y_last = rows; p.g.chunks1 = 0xFFFFFFFFu; p.g.y_first2 = p.g.y_last2 = 0;
     // the full step keeps the sampler's block-linear copy in step; other passes just mark it stale
-    const bool write_surf = use_tex && has_counts && !(cfg.flags & SM_FLAG_GAUSSIAN_BLUR);
+    const bool write_surf = use_tex && has_counts && (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) || gauss_stream_ok());
     p.g.surf = write_surf ? trail_surf : 0;
     p.g.surf_row0 = (int)(ghost + pad_rows);
     if (!write_surf) arr_stale = true;
@@ -506,7 +507,7 @@ int sm_engine::launch_trail(bool has_counts)
     SM_TRY(trail_plan(has_counts, p));
     SM_TRY(tic(1));
     if (cfg.flags & SM_FLAG_GAUSSIAN_BLUR) {
-        SM_TRY(launch_gauss(has_counts, p.g, p.tc));
+        SM_TRY(launch_gauss(has_counts, p));
     } else if (p.fast) {
         SM_TRY(trail_launch_rows(p, 0, rows, stream));
     } else {
@@ -527,8 +528,49 @@ int sm_engine::launch_trail(bool has_counts)
     return SM_OK;
 }
 
-int sm_engine::launch_gauss(bool has_counts, const smk::TrailGeom& g, const smd::TrailConsts& tc)
+// The streaming Gaussian kernel (gauss_stream.cuh) applies: it also merges u8 deposit flags and keeps the sampler's
+// block-linear copy in step, so a Gaussian full step runs the same agent kernel as the box-blur step.
+bool sm_engine::gauss_stream_ok() const
 {
+    return gauss_stream && !gauss_two_pass && world == 1 && W % 4 == 0 && W >= (uint32_t)smk::kGsMinW && rows >= (uint32_t)smk::kGsMinRows;
+}
+
+template <int R, int CM, bool SURF>
+static int launch_gauss_stream(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+{
+    auto kern = smk::k_gauss_stream<R, CM, SURF>;
+    const size_t smem = smk::gs_smem_bytes<R>();
+    SM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, smk::kGsNT, smem));
+    if (per_sm < 1) per_sm = 1;
+    // chunk height: about 256 rows (row halo 2R/chunk), nudged so that the grid is a whole number of waves
+    // of num_sms x resident CTAs
+    smk::GsArgs a = a0;
+    const uint64_t gx = (e->W + smk::kGsTX - 1) / smk::kGsTX;
+    const uint64_t cap = (uint64_t)e->num_sms * per_sm;
+    uint64_t chunk = (uint64_t)e->gauss_chunk;
+    if (chunk == 0) {
+        const double want_chunks = (double)e->rows / 256.0;
+        uint64_t waves = (uint64_t)llround((double)gx * want_chunks / (double)cap);
+        if (waves < 1) waves = 1;
+        uint64_t n_chunks = waves * cap / gx;
+        if (n_chunks < 1) n_chunks = 1;
+        chunk = (e->rows + n_chunks - 1) / n_chunks;
+        if (chunk < 32) chunk = 32;
+    }
+    chunk = (chunk + 7) / 8 * 8;
+    a.chunk_rows = (int)chunk;
+    dim3 grid((unsigned)gx, (unsigned)((e->rows + chunk - 1) / chunk));
+    kern<<<grid, smk::kGsNT, smem, e->stream>>>(a, tc, gc);
+    SM_CUDA(cudaGetLastError());
+    return SM_OK;
+}
+
+int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
+{
+    const smk::TrailGeom& g = p.g;
+    const smd::TrailConsts& tc = p.tc;
     if (world != 1) return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR is single-GPU only");
     int R = (int)lroundf(params.blur_radius);
     if (R < 1 || R > 8) return sm_fail(SM_ERR_BAD_ARG, "gaussian blur radius must round to 1..8 (got %g)", params.blur_radius);
@@ -545,6 +587,35 @@ int sm_engine::launch_gauss(bool has_counts, const smk::TrailGeom& g, const smd:
     }
     const float* tin0 = trail_ptr(cur);
     float* tout0 = trail_ptr(1 - cur);
+    if (gauss_stream_ok()) {
+        // streaming single pass (gauss_stream.cuh): counts or flags merged, sampler copy written in a full step
+        smk::GsArgs a{};
+        a.tin = p.tin; a.cin = p.cm == smk::CM_NONE ? nullptr : p.cin; a.czero = p.cm == smk::CM_NONE ? nullptr : p.czero; a.tout = p.tout;
+        a.W = (int)W; a.H = (int)rows;
+        a.surf = (unsigned long long)g.surf; a.surf_row0 = g.surf_row0;
+        const bool surf = g.surf != 0;
+        auto go = [&](auto r_tag) -> int {
+            constexpr int RR = decltype(r_tag)::value;
+            if (p.cm == smk::CM_NONE) return launch_gauss_stream<RR, smk::GS_NONE, false>(this, a, tc, gc);
+            if (p.cm == smk::CM_COUNTS) return surf ? launch_gauss_stream<RR, smk::GS_COUNTS, true>(this, a, tc, gc)
+                                                    : launch_gauss_stream<RR, smk::GS_COUNTS, false>(this, a, tc, gc);
+            return surf ? launch_gauss_stream<RR, smk::GS_FLAGS, true>(this, a, tc, gc)
+                        : launch_gauss_stream<RR, smk::GS_FLAGS, false>(this, a, tc, gc);
+        };
+        using std::integral_constant;
+        switch (R) {
+        case 1: SM_TRY(go(integral_constant<int, 1>{})); break;
+        case 2: SM_TRY(go(integral_constant<int, 2>{})); break;
+        case 3: SM_TRY(go(integral_constant<int, 3>{})); break;
+        case 4: SM_TRY(go(integral_constant<int, 4>{})); break;
+        case 5: SM_TRY(go(integral_constant<int, 5>{})); break;
+        case 6: SM_TRY(go(integral_constant<int, 6>{})); break;
+        case 7: SM_TRY(go(integral_constant<int, 7>{})); break;
+        default: SM_TRY(go(integral_constant<int, 8>{})); break;
+        }
+        timing.kernel_launches += 1;
+        return SM_OK;
+    }
     if (W % 4 == 0 && W >= 160 && rows >= 64 && !gauss_two_pass) {
         // fused single pass: tiles with halos staged in shared memory (k_gauss_fused)
         dim3 grid(blocks_for(W, smk::kGaussTX), blocks_for(rows, smk::kGaussTY));
@@ -697,6 +768,11 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     e->no_flags = env_int("SM_NO_DEPOSIT_FLAGS", 0) != 0;
     e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
     e->gauss_two_pass = env_int("SM_GAUSS_TWO_PASS", 0) != 0;
+    {
+        const char* gk = getenv("SM_GAUSS_KERNEL");          // "stream" (gauss_stream.cuh) | "tile" (k_gauss_fused)
+        e->gauss_stream = gk ? std::string(gk) == "stream" : false;
+    }
+    e->gauss_chunk = env_int("SM_GAUSS_CHUNK", 0);         // rows per CTA of the streaming kernel (0 = chosen per map)
     e->gauss_packed = env_int("SM_GAUSS_PACKED", 0) != 0;   // measured: no faster than the scalar form (the kernel waits on barriers and loads, not on FMA issue)
 
     // defaults = Settings::default(), /root/reference/src/settings.rs:8-27

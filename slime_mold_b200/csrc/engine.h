@@ -78,6 +78,9 @@ struct sm_engine {
     bool no_flags = false;            // SM_NO_DEPOSIT_FLAGS=1: always count deposits (A/B switch)
     int rpc_override = 0;
     bool gauss_packed = false;        // SM_GAUSS_PACKED=1: the FFMA2 form of the fused Gaussian kernel (A/B; measured 3-10 % slower)
+    bool gauss_stream = false;        // SM_GAUSS_KERNEL=stream: the streaming Gaussian kernel (gauss_stream.cuh) instead of the tile kernel
+    int gauss_chunk = 0;              // SM_GAUSS_CHUNK: rows per CTA of the streaming kernel (0 = chosen per map)
+    bool gauss_stream_ok() const;
     bool gauss_two_pass = false;      // SM_GAUSS_TWO_PASS=1: the unfused Gaussian passes (A/B; also used for maps below 160 x 64)
 
     // statistics: accumulator on the device; `stats_fused_valid` = the last thing that changed trail[cur] was a full-step
@@ -180,7 +183,7 @@ struct sm_engine {
                           uint32_t y_first2 = 0, uint32_t y_last2 = 0);   // optional second band in the same launch
     void trail_done(bool has_counts);
     int launch_trail(bool has_counts);
-    int launch_gauss(bool has_counts, const smk::TrailGeom& g, const smd::TrailConsts& tc);
+    int launch_gauss(bool has_counts, const TrailPass& p);
     int restore_identity_order();
     int fill_identity_ids();
 

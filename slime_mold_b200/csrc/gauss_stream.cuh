@@ -1,0 +1,242 @@
+// gauss_stream.cuh -- EXTENSION (no reference semantics): decay + separable Gaussian, radius 1-8, as ONE
+// streaming pass.  A CTA owns a column strip of TX cells and walks DOWN a chunk of rows in batches of B rows:
+//
+//   stage   the B x (TX + 2RA) cells of the batch -- requested one batch ahead, so their DRAM latency hides behind the
+//           arithmetic of the previous batch -- are merged with the deposits, decayed and parked in a ring of 2B rows (D)
+//   h-blur  row taps for the B new rows, four outputs per item from a register window filled by LDS.128 -> ring Hb
+//   v-blur  the B output rows whose last tap row has just arrived (they lag the newest row by R): four columns x B/4
+//           rows per thread, every Hb row read once per thread and spread over the outputs it feeds; mix with the
+//           decayed centre; one 16-byte store per four cells (plus the sampler's block-linear copy / the retired
+//           deposit marks in a full step)
+//
+// Against the tile kernel it replaces (k_gauss_fused, kernels.cuh): no vertical halo is recomputed (the tile kernel
+// ran the row taps for 32 + 2R rows per 32 output rows), the loads of the next batch overlap the taps of this one,
+// and the rings are 34-68 KB whatever the radius.  HBM traffic: 8 B/cell + 2RA/TX column halo + 2R/chunk row halo.
+//
+// Arithmetic: per output exactly the oracle's statements -- acc = 0.0f; acc = fma(w[d], v[d], acc) for d = -R..R, rows
+// after columns, then mix(decayed centre, acc, rate) -- so the bits equal those of the oracle, the tile kernel and the
+// two-pass form (tests/test_gpu_parity.py, and on the CPU through tests/hostcheck's CTA emulation of THIS source).
+//
+// The body is written against a small context (thread / block index, barrier, global loads, surface store) so that
+// tests/hostcheck can run the very same statements on host threads; the product only ever instantiates DevCtx.
+#pragma once
+#include <cstdint>
+#include "trail_core.cuh"
+
+namespace smk {
+
+#if defined(__CUDACC__)
+#define SM_KD __device__ __forceinline__
+#define SM_HDC __host__ __device__ constexpr
+using F4 = float4;
+using U4 = uint4;
+#else
+#define SM_KD inline
+#define SM_HDC constexpr
+struct alignas(16) F4 { float x, y, z, w; };
+struct alignas(16) U4 { uint32_t x, y, z, w; };
+#endif
+
+struct GaussConsts { int R; float w[17]; };
+
+// deposit representation seen by the pass (same values as CM_* in kernels.cuh)
+enum { GS_NONE = 0, GS_COUNTS = 1, GS_FLAGS = 2 };
+
+constexpr int kGsTX = 256;      // output columns per CTA
+constexpr int kGsNT = 256;      // threads per CTA
+template <int R> SM_HDC int gs_ra() { return (R + 3) / 4 * 4; }                  // halo columns staged per side (whole float4s)
+template <int R> SM_HDC int gs_batch() { return R <= 4 ? 8 : 16; }               // rows per batch; 2R <= B
+template <int R> SM_HDC int gs_dc() { return kGsTX + 2 * gs_ra<R>() + 4; }       // row stride of D (floats): 16-byte multiple, +4 against bank conflicts
+template <int R> SM_HDC size_t gs_smem_bytes() { return sizeof(float) * 2 * gs_batch<R>() * (size_t)(gs_dc<R>() + kGsTX); }
+// smallest map the kernel takes: a float4 never straddles the seam, one fold per coordinate is enough
+constexpr int kGsMinW = kGsTX + 32, kGsMinRows = 64;
+
+struct GsArgs {
+    const float* tin;
+    const void* cin;        // GS_COUNTS: u32 per cell, GS_FLAGS: u8 per cell (deposits of this step)
+    void* czero;            // the other deposit buffer: this pass retires (zeroes) the cells it owns
+    float* tout;
+    int W, H;               // row length, rows of the map (rows wrap toroidally: single GPU)
+    int chunk_rows;         // output rows per CTA (blockIdx.y)
+    unsigned long long surf;   // block-linear copy of the output for the TEX sampler (SURF instantiations)
+    int surf_row0;
+};
+
+template <int R, int CM, bool SURF, class Ctx>
+SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs& a, const smd::TrailConsts& tc, const GaussConsts& gc)
+{
+    constexpr int TX = kGsTX, NT = kGsNT, B = gs_batch<R>(), RA = gs_ra<R>(), DC = gs_dc<R>();
+    constexpr int DC4 = (TX + 2 * RA) / 4;          // float4 columns staged per row
+    constexpr int NR = 2 * B;                       // ring rows (power of two)
+    constexpr int N4 = B * DC4, PER = (N4 + NT - 1) / NT;
+    static_assert(2 * R <= B && (NR & (NR - 1)) == 0, "ring geometry");
+    float* D = gsm;                    // [NR][DC]  decayed cells; column c <-> map column x0 - RA + c; stream row s in slot s & (NR-1)
+    float* Hb = gsm + NR * DC;         // [NR][TX]  row-blurred cells
+    const int tid = cx.tid();
+    const int W = a.W, H = a.H;
+    const int x0 = cx.bx() * TX;
+    const int yc0 = cx.by() * a.chunk_rows;
+    const int nrows = (H - yc0 < a.chunk_rows) ? H - yc0 : a.chunk_rows;
+    const int S = nrows + 2 * R;       // stream rows: map rows yc0 - R .. yc0 + nrows + R - 1
+    const int nb = (S + B - 1) / B;
+
+    const float* __restrict__ tin = a.tin;
+    const uint32_t* cin32 = static_cast<const uint32_t*>(a.cin);
+    const uint8_t* cin8 = static_cast<const uint8_t*>(a.cin);
+
+    // ---- the pieces this thread stages: (row of the batch, float4 column) are the same for every batch ----
+    int pgx[PER];                      // map column of the piece (folded across the seam); -1: no such piece
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int e = tid + k * NT;
+        pgx[k] = -1;
+        if (e < N4) {
+            const int c4 = e % DC4;
+            int gx = x0 - RA + 4 * c4;
+            if (gx < 0) gx += W; else if (gx >= W) gx -= W;
+            pgx[k] = gx;
+        }
+    }
+    F4 t4[PER];
+    U4 k4[CM == GS_COUNTS ? PER : 1];
+    uint32_t kf[CM == GS_FLAGS ? PER : 1];
+    int pgy[PER];                      // map row of the piece in flight; -1: past the stream (nothing requested)
+
+    auto prefetch = [&](int kb) {
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int e = tid + k * NT;
+            pgy[k] = -1;
+            if (e < N4) {
+                const int s = kb * B + e / DC4;
+                if (s < S) {
+                    int gy = yc0 - R + s;
+                    if (gy < 0) gy += H; else if (gy >= H) gy -= H;
+                    pgy[k] = gy;
+                    const int64_t off = (int64_t)gy * W + pgx[k];
+                    t4[k] = cx.ld4(tin + off);
+                    if (CM == GS_COUNTS) k4[k] = cx.ldu4(cin32 + off);
+                    if (CM == GS_FLAGS) kf[k] = cx.ldu1(reinterpret_cast<const uint32_t*>(cin8 + off));
+                }
+            }
+        }
+    };
+
+    prefetch(0);
+    for (int kb = 0; kb < nb; ++kb) {
+        const int blk = (kb & 1) * B;
+        // ---- stage: registers -> D ring (merge, decay); retire the deposit marks of the cells this CTA owns ----
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int e = tid + k * NT;
+            if (e < N4) {
+                const int r = e / DC4, c4 = e - r * DC4;
+                F4 t;
+                t.x = t.y = t.z = t.w = 0.0f;
+                if (pgy[k] >= 0) {
+                    t = t4[k];
+                    if (CM != GS_NONE) {
+                        if (CM == GS_COUNTS) {
+                            t.x = smd::merge_deposit(t.x, k4[k].x, tc.dep); t.y = smd::merge_deposit(t.y, k4[k].y, tc.dep);
+                            t.z = smd::merge_deposit(t.z, k4[k].z, tc.dep); t.w = smd::merge_deposit(t.w, k4[k].w, tc.dep);
+                        } else {                                         // clamp(t + k*dep, 0, 1) == 1 for dep >= 1, t >= 0
+                            t.x = (kf[k] & 0xffu) ? 1.0f : t.x; t.y = (kf[k] & 0xff00u) ? 1.0f : t.y;
+                            t.z = (kf[k] & 0xff0000u) ? 1.0f : t.z; t.w = (kf[k] & 0xff000000u) ? 1.0f : t.w;
+                        }
+                        const int o = kb * B + r - R;                    // output row (chunk-relative) this stream row is the centre of
+                        const bool own = o >= 0 && o < nrows && 4 * c4 >= RA && 4 * c4 < RA + TX && x0 + (4 * c4 - RA) < W;
+                        if (own) {
+                            const int64_t off = (int64_t)pgy[k] * W + pgx[k];
+                            if (CM == GS_COUNTS) { U4 z; z.x = z.y = z.z = z.w = 0u; *reinterpret_cast<U4*>(static_cast<uint32_t*>(a.czero) + off) = z; }
+                            else *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(a.czero) + off) = 0u;
+                        }
+                    }
+                    t.x = smd::decay_cell(t.x, tc.decay_sub); t.y = smd::decay_cell(t.y, tc.decay_sub);
+                    t.z = smd::decay_cell(t.z, tc.decay_sub); t.w = smd::decay_cell(t.w, tc.decay_sub);
+                }
+                *reinterpret_cast<F4*>(D + (blk + r) * DC + 4 * c4) = t;
+            }
+        }
+        if (kb + 1 < nb) prefetch(kb + 1);          // in flight while this batch is blurred
+        cx.sync();
+
+        // ---- h-blur: Hb[row][xs .. xs+3]; output j taps D columns xs + j + (RA - R) + d, d = 0 .. 2R ----
+        {
+            constexpr int ITEMS = B * (TX / 4), IPT = ITEMS / NT;
+            constexpr int NV = (RA + R + 4 + 3) / 4 * 4, SH = RA - R;
+            static_assert(ITEMS % NT == 0, "items per thread");
+#pragma unroll 1
+            for (int i = 0; i < IPT; ++i) {
+                const int item = tid + i * NT;
+                const int r = item / (TX / 4), xs = (item % (TX / 4)) * 4;
+                float v[NV];
+                const F4* src = reinterpret_cast<const F4*>(D + (blk + r) * DC + xs);
+#pragma unroll
+                for (int q = 0; q < NV / 4; ++q) {
+                    const F4 f = src[q];
+                    v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+                }
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+                for (int d = 0; d <= 2 * R; ++d) {
+                    const float w = gc.w[d];
+                    a0 = smd::fma(w, v[SH + d], a0);
+                    a1 = smd::fma(w, v[SH + d + 1], a1);
+                    a2 = smd::fma(w, v[SH + d + 2], a2);
+                    a3 = smd::fma(w, v[SH + d + 3], a3);
+                }
+                F4 o;
+                o.x = a0; o.y = a1; o.z = a2; o.w = a3;
+                *reinterpret_cast<F4*>(Hb + (blk + r) * TX + xs) = o;
+            }
+        }
+        cx.sync();
+
+        // ---- v-blur: outputs o_first .. o_first + VR - 1 (chunk-relative rows) of columns 4*c4 .. 4*c4+3 ----
+        {
+            constexpr int VR = B / 4;                // TX/4 = 64 column groups x 4 row groups = 256 threads
+            const int c4 = tid & (TX / 4 - 1), rg = tid / (TX / 4);
+            const int o_first = kb * B - 2 * R + rg * VR;
+            const int gx = x0 + 4 * c4;
+            if (o_first + VR > 0 && o_first < nrows && gx < W) {
+                float acc[VR][4];
+#pragma unroll
+                for (int j = 0; j < VR; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+                // stream row o + d holds tap d of output o: rows arrive in tap order, so each accumulator sees d = 0 .. 2R
+#pragma unroll
+                for (int i = 0; i < VR + 2 * R; ++i) {
+                    const F4 h = *reinterpret_cast<const F4*>(Hb + ((o_first + i) & (NR - 1)) * TX + 4 * c4);
+#pragma unroll
+                    for (int j = 0; j < VR; ++j) {
+                        const int d = i - j;
+                        if (d >= 0 && d <= 2 * R) {
+                            const float w = gc.w[d];
+                            acc[j][0] = smd::fma(w, h.x, acc[j][0]);
+                            acc[j][1] = smd::fma(w, h.y, acc[j][1]);
+                            acc[j][2] = smd::fma(w, h.z, acc[j][2]);
+                            acc[j][3] = smd::fma(w, h.w, acc[j][3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < VR; ++j) {
+                    const int o = o_first + j;
+                    if (o >= 0 && o < nrows) {
+                        const F4 c = *reinterpret_cast<const F4*>(D + ((o + R) & (NR - 1)) * DC + RA + 4 * c4);
+                        F4 out;
+                        out.x = smd::mixf_pre(c.x, acc[j][0], tc.rate, tc.one_minus_rate);
+                        out.y = smd::mixf_pre(c.y, acc[j][1], tc.rate, tc.one_minus_rate);
+                        out.z = smd::mixf_pre(c.z, acc[j][2], tc.rate, tc.one_minus_rate);
+                        out.w = smd::mixf_pre(c.w, acc[j][3], tc.rate, tc.one_minus_rate);
+                        const int gy = yc0 + o;
+                        *reinterpret_cast<F4*>(a.tout + (int64_t)gy * W + gx) = out;
+                        if (SURF) cx.surf_write(out, a.surf, gx, gy + a.surf_row0);
+                    }
+                }
+            }
+        }
+        cx.sync();          // the next batch overwrites ring block (kb+1)&1, which this v-blur was still reading
+    }
+}
+
+}  // namespace smk

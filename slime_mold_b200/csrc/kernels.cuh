@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include "agent_core.cuh"
 #include "trail_core.cuh"
+#include "gauss_stream.cuh"
 
 namespace smk {
 
@@ -293,6 +294,7 @@ __device__ __forceinline__ int64_t row_index(int64_t y, const TrailGeom& g)
 
 // Deposit representation seen by the trail pass: none (diffusion only), u32 counts, u8 flags.
 enum { CM_NONE = 0, CM_COUNTS = 1, CM_FLAGS = 2 };
+static_assert(CM_NONE == GS_NONE && CM_COUNTS == GS_COUNTS && CM_FLAGS == GS_FLAGS, "deposit representation tags");
 
 struct RawRow {
     float4 t;
@@ -500,7 +502,7 @@ k_trail_generic(const float* __restrict__ tin, const void* __restrict__ cin_v,
 // Pass 1 (horizontal) fuses merge + decay and writes the decayed field D and the
 // row-blurred field Hb; pass 2 (vertical) mixes D with the column blur of Hb.
 // ---------------------------------------------------------------------------
-struct GaussConsts { int R; float w[17]; };
+// GaussConsts { R, w[17] }: gauss_stream.cuh
 
 template <bool HAS_COUNTS>
 static __global__ void __launch_bounds__(256)
@@ -804,6 +806,29 @@ k_gauss_fused_packed(const float* __restrict__ tin, const uint32_t* __restrict__
             }
         }
     }
+}
+
+// Streaming form (gauss_stream.cuh): the device context of gauss_stream_cta and the kernel around it.
+struct GsDevCtx {
+    __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
+    __device__ __forceinline__ int bx() const { return (int)blockIdx.x; }
+    __device__ __forceinline__ int by() const { return (int)blockIdx.y; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ float4 ld4(const float* p) const { return __ldg(reinterpret_cast<const float4*>(p)); }
+    __device__ __forceinline__ uint4 ldu4(const uint32_t* p) const { return __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ uint32_t ldu1(const uint32_t* p) const { return __ldg(p); }
+    __device__ __forceinline__ void surf_write(float4 v, unsigned long long surf, int x, int y) const
+    {
+        surf2Dwrite(v, (cudaSurfaceObject_t)surf, x * 4, y);
+    }
+};
+
+template <int R, int CM, bool SURF>
+static __global__ void __launch_bounds__(kGsNT, (R <= 4 ? 4 : 3))
+k_gauss_stream(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
+{
+    extern __shared__ __align__(16) float gs_smem[];
+    gauss_stream_cta<R, CM, SURF>(GsDevCtx{}, gs_smem, a, tc, gc);
 }
 
 // ---------------------------------------------------------------------------

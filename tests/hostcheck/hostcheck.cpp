@@ -6,6 +6,11 @@
 #include <cstddef>
 #include "../../slime_mold_b200/csrc/agent_core.cuh"
 #include "../../slime_mold_b200/csrc/trail_core.cuh"
+#include "../../slime_mold_b200/csrc/gauss_stream.cuh"
+#include <pthread.h>
+#include <cstring>
+#include <thread>
+#include <vector>
 
 struct HostLd {
     float operator()(const float* p) const { return *p; }
@@ -101,3 +106,89 @@ void hc_trail_pass(const float* in, uint32_t* counts, float* out, const hc_param
 }
 
 }  // extern "C"
+
+// ---- CTA emulation of the streaming Gaussian kernel (gauss_stream.cuh) -------------------------------------------
+// The kernel body is written against a context; here the context is a host thread per CUDA thread and a pthread
+// barrier per CTA, so the index logic, the ring bookkeeping and the statement order of the very source the GPU runs
+// can be compared with the oracle on a machine without a GPU.
+struct HostGsCtx {
+    int t, bxv, byv;
+    pthread_barrier_t* bar;
+    int surf_w;
+    int tid() const { return t; }
+    int bx() const { return bxv; }
+    int by() const { return byv; }
+    void sync() const { pthread_barrier_wait(bar); }
+    smk::F4 ld4(const float* p) const { smk::F4 v; std::memcpy(&v, p, 16); return v; }
+    smk::U4 ldu4(const uint32_t* p) const { smk::U4 v; std::memcpy(&v, p, 16); return v; }
+    uint32_t ldu1(const uint32_t* p) const { uint32_t v; std::memcpy(&v, p, 4); return v; }
+    void surf_write(smk::F4 v, unsigned long long surf, int x, int y) const
+    {
+        std::memcpy(reinterpret_cast<float*>(surf) + (size_t)y * surf_w + x, &v, 16);
+    }
+};
+
+template <int R, int CM, bool SURF>
+static void run_gauss_stream(const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+{
+    const int gx = (a.W + smk::kGsTX - 1) / smk::kGsTX, gy = (a.H + a.chunk_rows - 1) / a.chunk_rows;
+    const size_t nfl = smk::gs_smem_bytes<R>() / sizeof(float);
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            // "shared memory" starts as NaN: a value that was never staged must not reach a stored output
+            std::vector<float> raw(nfl + 4);
+            float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(raw.data()) + 15) & ~(uintptr_t)15);
+            for (size_t i = 0; i < nfl; ++i) smem[i] = NAN;
+            pthread_barrier_t bar;
+            pthread_barrier_init(&bar, nullptr, smk::kGsNT);
+            std::vector<std::thread> th;
+            th.reserve(smk::kGsNT);
+            for (int t = 0; t < smk::kGsNT; ++t)
+                th.emplace_back([&, t]() {
+                    HostGsCtx cx{t, bx, by, &bar, a.W};
+                    smk::gauss_stream_cta<R, CM, SURF>(cx, smem, a, tc, gc);
+                });
+            for (auto& x : th) x.join();
+            pthread_barrier_destroy(&bar);
+        }
+}
+
+template <int R>
+static void run_gauss_stream_r(int cm, bool surf, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+{
+    if (cm == 0) run_gauss_stream<R, smk::GS_NONE, false>(a, tc, gc);
+    else if (cm == 1) { if (surf) run_gauss_stream<R, smk::GS_COUNTS, true>(a, tc, gc); else run_gauss_stream<R, smk::GS_COUNTS, false>(a, tc, gc); }
+    else { if (surf) run_gauss_stream<R, smk::GS_FLAGS, true>(a, tc, gc); else run_gauss_stream<R, smk::GS_FLAGS, false>(a, tc, gc); }
+}
+
+extern "C" int hc_gauss_stream(const float* tin, const void* cin, void* czero, float* tout, float* surf_out, int W, int H,
+                               int chunk_rows, int R, const float* weights, int cm, const hc_params* p)
+{
+    if (W % 4 != 0 || W < smk::kGsMinW || H < smk::kGsMinRows || R < 1 || R > 8 || chunk_rows < 1) return -1;
+    smd::TrailConsts tc{};
+    tc.dep = p->pheromone_deposition_amount;
+    volatile float d = p->decay_factor * 0.001f;
+    tc.decay_sub = d;
+    tc.rate = fminf(fmaxf(p->diffusion_rate, 0.0f), 1.0f);
+    volatile float om = 1.0f - tc.rate;
+    tc.one_minus_rate = om;
+    smk::GaussConsts gc{};
+    gc.R = R;
+    for (int i = 0; i <= 2 * R; ++i) gc.w[i] = weights[i];
+    smk::GsArgs a{};
+    a.tin = tin; a.cin = cin; a.czero = czero; a.tout = tout;
+    a.W = W; a.H = H; a.chunk_rows = chunk_rows;
+    a.surf = (unsigned long long)reinterpret_cast<uintptr_t>(surf_out); a.surf_row0 = 0;
+    const bool surf = surf_out != nullptr;
+    switch (R) {
+    case 1: run_gauss_stream_r<1>(cm, surf, a, tc, gc); break;
+    case 2: run_gauss_stream_r<2>(cm, surf, a, tc, gc); break;
+    case 3: run_gauss_stream_r<3>(cm, surf, a, tc, gc); break;
+    case 4: run_gauss_stream_r<4>(cm, surf, a, tc, gc); break;
+    case 5: run_gauss_stream_r<5>(cm, surf, a, tc, gc); break;
+    case 6: run_gauss_stream_r<6>(cm, surf, a, tc, gc); break;
+    case 7: run_gauss_stream_r<7>(cm, surf, a, tc, gc); break;
+    default: run_gauss_stream_r<8>(cm, surf, a, tc, gc); break;
+    }
+    return 0;
+}

@@ -209,14 +209,16 @@ def test_gaussian_extension(oracle, engine_lib, R, sigma):
     be.close()
 
 
-@pytest.mark.parametrize("kernel", ["packed", "scalar", "two_pass"])
+@pytest.mark.parametrize("kernel", ["packed", "scalar", "two_pass", "stream"])
 @pytest.mark.parametrize("R,sigma,W,H", [(1, 0.7, 160, 64), (2, 1.0, 416, 200), (3, 1.3, 517, 131), (4, 2.0, 256, 96), (5, 2.5, 1000, 97),
                                          (6, 3.0, 384, 130), (7, 3.5, 772, 65), (8, 4.0, 640, 333)])
 def test_gaussian_extension_fused_and_two_pass(oracle, engine_lib, monkeypatch, R, sigma, W, H, kernel):
-    """EXTENSION: the fused shared-memory kernels (FFMA2-packed and scalar; ragged tiles, wrap on all four sides) and the
+    """EXTENSION: the fused shared-memory kernels (FFMA2-packed and scalar; ragged tiles, wrap on all four sides), the
+    streaming kernel (maps of at least 288 x 64 with W % 4 == 0; smaller ones fall back to the tile kernel) and the
     two-pass form give the oracle's bits, in diffusion-only passes and in full steps (deposit counts merged by the pass)."""
     monkeypatch.setenv("SM_GAUSS_TWO_PASS", "1" if kernel == "two_pass" else "0")
     monkeypatch.setenv("SM_GAUSS_PACKED", "1" if kernel == "packed" else "0")
+    monkeypatch.setenv("SM_GAUSS_KERNEL", "stream" if kernel == "stream" else "tile")
     s = settings_for("Default").clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=0.7, pheromone_deposition_amount=0.4)
     u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
     p = to_oracle_params(oracle, u)
@@ -242,6 +244,51 @@ def test_gaussian_extension_fused_and_two_pass(oracle, engine_lib, monkeypatch, 
     assert bits_equal(be.read_agents(), a), "agents"
     got = be.read_trail()
     assert bits_equal(got, ref), mismatch_report(got, ref, "gauss full step")
+    be.close()
+
+
+@pytest.mark.parametrize("chunk", [0, 40])
+@pytest.mark.parametrize("dep", [1.0, 0.4])
+@pytest.mark.parametrize("R,sigma,W,H", [(1, 0.7, 288, 64), (2, 1.0, 512, 256), (3, 1.3, 516, 131), (4, 2.0, 1024, 96), (6, 3.0, 388, 150),
+                                         (8, 4.0, 1280, 333)])
+def test_gaussian_stream_full_steps(oracle, engine_lib, monkeypatch, R, sigma, W, H, dep, chunk):
+    """EXTENSION, streaming kernel (gauss_stream.cuh): full steps in Gaussian mode -- with dep >= 1 the agents mark u8
+    deposit flags and sense through the texture copy the pass keeps in step (the box-blur step's fast path), with a
+    fractional deposit they count -- against the oracle's phase-split agents + Gaussian pass; CTA chunk heights
+    chosen by the engine and forced to a value that leaves ragged chunks."""
+    monkeypatch.setenv("SM_GAUSS_KERNEL", "stream")
+    monkeypatch.setenv("SM_GAUSS_CHUNK", str(chunk))
+    s = settings_for("Default").clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=0.8, pheromone_deposition_amount=dep)
+    u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
+    p = to_oracle_params(oracle, u)
+    N = 60_000
+    field = random_trail(W, H, seed=10 + R)
+    ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 6)
+    be = sm.CudaBackend.new(W, H, s, agent_count=N, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+    be.write_trail(field)
+    be.write_agents(ag)
+    a, ref = ag.copy(), field
+    counts = np.zeros((H, W), np.uint32)
+    for chunk_steps in (1, 4):
+        be.step(chunk_steps)
+        for _ in range(chunk_steps):
+            oracle.agents_phase_split(a, ref, counts, p)
+            ref = oracle.trail_pass(ref, p, counts=counts, gauss_radius=R, gauss_sigma=sigma)
+        assert bits_equal(be.read_agents(), a), "agents"
+        got = be.read_trail()
+        assert bits_equal(got, ref), mismatch_report(got, ref, "gauss stream full step")
+    # a diffusion-only pass in between (marks the sampler copy stale), then steps again
+    be.diffuse_only(1)
+    ref = oracle.trail_pass(ref, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
+    be.step(2)
+    for _ in range(2):
+        oracle.agents_phase_split(a, ref, counts, p)
+        ref = oracle.trail_pass(ref, p, counts=counts, gauss_radius=R, gauss_sigma=sigma)
+    assert bits_equal(be.read_agents(), a), "agents after the mixed sequence"
+    got = be.read_trail()
+    assert bits_equal(got, ref), mismatch_report(got, ref, "gauss stream mixed sequence")
+    st = be.trail_statistics()
+    assert abs(st.sum - ref.sum(dtype=np.float64)) < 1e-6 * ref.size and st.max == ref.max()
     be.close()
 
 

@@ -1,0 +1,86 @@
+"""The streaming Gaussian kernel (slime_mold_b200/csrc/gauss_stream.cuh) on the CPU: tests/hostcheck runs the kernel
+body -- the very source the GPU compiles -- one host thread per CUDA thread with a pthread barrier per CTA, and the
+result is compared bit for bit with the oracle's definition of the extension.  Covers every radius, all three deposit
+representations, ragged last tiles / chunks, the toroidal seam on all four sides and chunk heights that are not a
+multiple of the batch.  (The device instantiation is checked by tests/test_gpu_parity.py, -m gpu.)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import slime_mold_b200 as sm
+from conftest import bits_equal, mismatch_report
+from presets_util import random_trail, to_oracle_params
+
+
+def P(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=0, counts=None, want_surf=False):
+    H, W = field.shape
+    out = np.full_like(field, np.nan)
+    surf = np.full_like(field, np.nan) if want_surf else None
+    w = oracle.gauss_weights(R, sigma)
+    cin = czero = None
+    if cm == 1:
+        cin = counts.copy()
+        czero = np.full((H, W), 7, np.uint32)             # the pass must retire every cell of the other buffer
+    elif cm == 2:
+        cin = (counts > 0).astype(np.uint8)
+        czero = np.full((H, W), 7, np.uint8)
+    rc = hostcheck.hc_gauss_stream(P(field, C.c_float),
+                                   None if cin is None else cin.ctypes.data_as(C.c_void_p),
+                                   None if czero is None else czero.ctypes.data_as(C.c_void_p),
+                                   P(out, C.c_float), None if surf is None else P(surf, C.c_float),
+                                   C.c_int(W), C.c_int(H), C.c_int(chunk), C.c_int(R), P(w, C.c_float), C.c_int(cm), C.byref(p))
+    assert rc == 0
+    return out, surf, czero
+
+
+def params_for(oracle, W, H, R, sigma, dep, rate=0.7):
+    s = sm.init_preset_manager().get_preset("Default").settings.clone(
+        blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=rate, pheromone_deposition_amount=dep)
+    return to_oracle_params(oracle, sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s))
+
+
+@pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.7, 288, 64, 64), (2, 1.0, 416, 200, 48), (3, 1.3, 516, 131, 40), (4, 2.0, 512, 96, 96),
+                                               (5, 2.5, 1000, 97, 32), (6, 3.0, 384, 130, 56), (7, 3.5, 772, 65, 24), (8, 4.0, 640, 333, 104)])
+def test_stream_diffuse_only_bits(oracle, hostcheck, R, sigma, W, H, chunk):
+    p = params_for(oracle, W, H, R, sigma, dep=1.0)
+    field = np.random.default_rng(R).random((H, W), dtype=np.float32)
+    ref = oracle.trail_pass(field, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
+    got, _, _ = run_stream(hostcheck, oracle, field, p, R, sigma, chunk)
+    assert bits_equal(got, ref), mismatch_report(got, ref, f"stream R={R}")
+
+
+@pytest.mark.parametrize("cm,dep", [(1, 0.4), (1, 2.5), (2, 1.0)])
+@pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.5, 300, 70, 32), (2, 1.0, 292, 64, 64), (4, 2.0, 520, 90, 48), (5, 2.5, 288, 100, 72), (8, 4.0, 548, 77, 40)])
+def test_stream_full_step_bits(oracle, hostcheck, cm, dep, R, sigma, W, H, chunk):
+    """Deposits merged by the pass (u32 counts, or u8 flags when dep >= 1), the other deposit buffer retired,
+    the sampler copy written."""
+    p = params_for(oracle, W, H, R, sigma, dep=dep)
+    rng = np.random.default_rng(100 * R + cm)
+    field = random_trail(W, H, seed=R, density=0.5)
+    counts = (rng.random((H, W)) < 0.2).astype(np.uint32) * rng.integers(1, 4, (H, W)).astype(np.uint32)
+    # deposits on the seams and in the corners
+    counts[0, :5] = 1; counts[-1, -5:] = 2; counts[:3, -1] = 1; counts[-3:, 0] = 3
+    ref = oracle.trail_pass(field, p, counts=counts.copy(), gauss_radius=R, gauss_sigma=sigma)
+    got, surf, czero = run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=cm, counts=counts, want_surf=True)
+    assert bits_equal(got, ref), mismatch_report(got, ref, f"stream full step R={R} cm={cm}")
+    assert bits_equal(surf, ref), "sampler copy differs from the row-major output"
+    assert not czero.any(), "deposit marks of the next step's buffer were not all retired"
+
+
+def test_stream_constant_field_and_mass(oracle, hostcheck):
+    """Size-independent properties: a constant field stays constant under the blur (weights sum to 1 up to rounding),
+    and with decay 0 and rate 1 the mass is conserved up to rounding."""
+    W, H, R, sigma = 512, 128, 8, 4.0
+    s = sm.init_preset_manager().get_preset("Default").settings.clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=1.0)
+    p = to_oracle_params(oracle, sm.SimSizeUniform.new(W, H, 0.0, s))
+    field = np.random.default_rng(0).random((H, W), dtype=np.float32)
+    got, _, _ = run_stream(hostcheck, oracle, field, p, R, sigma, 64)
+    assert abs(got.sum(dtype=np.float64) - field.sum(dtype=np.float64)) < 1e-5 * field.size
+    const = np.full((H, W), 0.625, np.float32)
+    got, _, _ = run_stream(hostcheck, oracle, const, p, R, sigma, 64)
+    assert np.allclose(got, 0.625, rtol=0, atol=2e-7)
