@@ -56,7 +56,19 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--independent", action="store_true", help="diagnostic: N ranks, each an independent single-GPU engine")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = min(steps, 100))")
+    ap.add_argument("--gaussian", type=int, default=0, metavar="R",
+                    help="EXTENSION (BASELINE configs[2] 'large blur radius'): Gaussian blur of radius R (sigma R/2) instead of the "
+                         "reference's 3x3 box; single GPU only")
     return ap.parse_args()
+
+
+def bench_settings(args):
+    """Preset parameters, plus the Gaussian extension's radius / sigma when --gaussian R is given."""
+    import slime_mold_b200 as sm
+    s = sm.init_preset_manager().get_preset(args.preset).settings
+    if args.gaussian:
+        s = s.clone(blur_radius=float(args.gaussian), blur_sigma=args.gaussian / 2.0)
+    return s
 
 
 def hbm_peak():
@@ -122,13 +134,15 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # reference arm: CPU restatement of compute.wgsl on the host cores (oracle/, OpenMP)
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_run(width, height, agents, preset, seed, steps, warmup, budget_s):
+def cpu_reference_run(width, height, agents, preset, seed, steps, warmup, budget_s, gaussian=0):
     """Times the oracle (phase_split, all host threads) on a bounded sample of the workload.
     Returns (agent_steps_per_s, ms_per_step, sample description, cores)."""
     from oracle import slime_oracle as so            # bench.py's cpu_baseline / reference leg only
     import slime_mold_b200 as sm
     so.build()
     s = sm.init_preset_manager().get_preset(preset).settings
+    if gaussian:
+        s = s.clone(blur_radius=float(gaussian), blur_sigma=gaussian / 2.0)
     p = so.make_params(width, height, decay_factor=s.pheromone_decay_factor, agent_jitter=s.agent_jitter,
                        agent_speed_min=s.agent_speed_min, agent_speed_max=s.agent_speed_max,
                        agent_turn_speed=s.agent_turn_speed, agent_sensor_angle=s.agent_sensor_angle,
@@ -137,7 +151,16 @@ def cpu_reference_run(width, height, agents, preset, seed, steps, warmup, budget
     cores = so.max_threads()
     n = agents
     ag = so.init_agents(n, width, height, s.agent_speed_min, s.agent_speed_max, seed)
-    sim = so.Sim(p, ag)
+    Sim = so.Sim
+    if gaussian:
+        class Sim(so.Sim):
+            """Gaussian extension: the oracle's phase-split agents pass followed by its Gaussian trail pass."""
+
+            def step(self, n=1):
+                for _ in range(n):
+                    so.agents_phase_split(self.agents, self.trail, self.counts, self.p)
+                    self.trail = so.trail_pass(self.trail, self.p, counts=self.counts, gauss_radius=gaussian, gauss_sigma=gaussian / 2.0)
+    sim = Sim(p, ag)
     t0 = time.perf_counter()
     sim.step(1)                                       # calibration step (also the first warm-up step)
     t1 = time.perf_counter() - t0
@@ -147,14 +170,15 @@ def cpu_reference_run(width, height, agents, preset, seed, steps, warmup, budget
         # bounded sample: keep the full map (the trail pass is part of every step) and a prefix of the agents
         frac = max(min(1.0, budget_s / (t1 * total)), 1.0 / 64)
         n = max(int(agents * frac), 1)
-        sim = so.Sim(p, ag[:n].copy(), trail=sim.trail)
+        sim = Sim(p, ag[:n].copy(), trail=sim.trail)
     for _ in range(max(warmup - 1, 0)):
         sim.step(1)
     t0 = time.perf_counter()
     sim.step(steps)
     dt = time.perf_counter() - t0
     sample = (f"{n} of {agents} agents ({100.0 * n / agents:.1f}%) on the full {width}x{height} map, {steps} timed steps, "
-              f"seed {seed}, preset {preset}, phase_split semantics, OpenMP {cores} threads")
+              f"seed {seed}, preset {preset}{', Gaussian blur radius %d' % gaussian if gaussian else ''}, phase_split semantics, "
+              f"OpenMP {cores} threads")
     return n * steps / dt, 1e3 * dt / steps, sample, cores
 
 
@@ -165,7 +189,7 @@ def run_reference(args):
     N = max(args.gpus, 1)
     width, height, agents = args.width, args.height * N, args.agents * N
     val, ms, sample, cores = cpu_reference_run(width, height, agents, args.preset, args.seed, args.steps, args.warmup,
-                                               budget_s=150.0)
+                                               budget_s=150.0, gaussian=args.gaussian)
     line = {
         "impl": "reference", "metric": "agent_steps_per_sec", "value": val, "unit": "agent-steps/s", "n_gpus": N,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -198,6 +222,8 @@ def workload_config(args, N):
         "parallelism": f"strips{N}" if N > 1 else "single",
         "exchange": (os.environ.get("SM_EXCHANGE") or "p2p") if N > 1 else None,
         "spinup_steps": args.spinup, "seed": args.seed,
+        "blur": (f"EXTENSION: separable Gaussian, radius {args.gaussian}, sigma {args.gaussian / 2.0} (no reference semantics)"
+                 if args.gaussian else "3x3 box (compute.wgsl:164-195)"),
         "l2": (f"inputs larger than L2: agent state {args.agents * 20 / 1e6:.0f} MB/GPU is streamed every step (no flush between steps)"
                if args.agents * 20 > 126e6 else
                f"working set ({args.agents * 20 / 1e6:.0f} MB of agent state per GPU) fits the 126 MB L2: L2-resident, not a DRAM number; no flush"),
@@ -226,12 +252,15 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     width, height, agents = args.width, args.height * N, args.agents * N
-    settings = sm.init_preset_manager().get_preset(args.preset).settings
+    settings = bench_settings(args)
+    eng_flags = sm.SM_FLAG_GAUSSIAN_BLUR if args.gaussian else 0
+    if args.gaussian and N > 1:
+        raise SystemExit("--gaussian is single-GPU only (the extension is not built for strips)")
     if args.independent:
         width, height, agents = args.width, args.height, args.agents
-        be = sm.CudaBackend.new(width, height, settings, agent_count=agents, device=local_rank)
+        be = sm.CudaBackend.new(width, height, settings, agent_count=agents, device=local_rank, flags=eng_flags)
     else:
-        be = sm.CudaBackend.new(width, height, settings, agent_count=agents, device=local_rank, rank=rank, world_size=N)
+        be = sm.CudaBackend.new(width, height, settings, agent_count=agents, device=local_rank, rank=rank, world_size=N, flags=eng_flags)
     if N > 1 and not args.independent:
         ids = [be.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -350,7 +379,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
         v, ms_cpu, sample, cores = cpu_reference_run(width, height, agents, args.preset, args.seed, steps=3, warmup=1,
-                                                     budget_s=args.cpu_seconds)
+                                                     budget_s=args.cpu_seconds, gaussian=args.gaussian)
         cpu = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms_cpu}
 
     if rank == 0:

@@ -414,7 +414,11 @@ int sm_engine::launch_agents()
             arr_stale = false;
         }
         const smk::FetchTex f{trail_tex, (float)((int32_t)(ghost + pad_rows) - (int32_t)row0 + 1)};
-        if (idx32) launch(f, int32_t{});
+        if (agent_stream_hint && !multi && idx32) {
+            // A/B instantiation: evict-first hints on the agent stream (single GPU, 32-bit offsets, texture sampler)
+            if (flags) smk::k_agents<smk::XM_SINGLE, int32_t, smk::FetchTex, true, true><<<nb, 256, 0, stream>>>(a, id, n_local, f, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            else smk::k_agents<smk::XM_SINGLE, int32_t, smk::FetchTex, false, true><<<nb, 256, 0, stream>>>(a, id, n_local, f, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+        } else if (idx32) launch(f, int32_t{});
         else launch(f, int64_t{});
     } else if (idx32) {
         launch(smd::FetchLinear<int32_t, smk::LdgF32>{trail_ptr(cur), (int32_t)W, (int32_t)row0, smk::LdgF32()}, int32_t{});
@@ -772,6 +776,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         const char* gk = getenv("SM_GAUSS_KERNEL");          // "stream" (gauss_stream.cuh) | "tile" (k_gauss_fused)
         e->gauss_stream = gk ? std::string(gk) == "stream" : false;
     }
+    e->agent_stream_hint = env_int("SM_AGENT_STREAM_HINT", 0);   // 1: evict-first loads / stores of the agent state (A/B)
     e->gauss_chunk = env_int("SM_GAUSS_CHUNK", 0);         // rows per CTA of the streaming kernel (0 = chosen per map)
     e->gauss_packed = env_int("SM_GAUSS_PACKED", 0) != 0;   // measured: no faster than the scalar form (the kernel waits on barriers and loads, not on FMA issue)
 

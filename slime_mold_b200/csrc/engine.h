@@ -78,6 +78,7 @@ struct sm_engine {
     bool no_flags = false;            // SM_NO_DEPOSIT_FLAGS=1: always count deposits (A/B switch)
     int rpc_override = 0;
     bool gauss_packed = false;        // SM_GAUSS_PACKED=1: the FFMA2 form of the fused Gaussian kernel (A/B; measured 3-10 % slower)
+    int agent_stream_hint = 0;        // SM_AGENT_STREAM_HINT=1: the agent kernel streams its state with evict-first hints (A/B)
     bool gauss_stream = false;        // SM_GAUSS_KERNEL=stream: the streaming Gaussian kernel (gauss_stream.cuh) instead of the tile kernel
     int gauss_chunk = 0;              // SM_GAUSS_CHUNK: rows per CTA of the streaming kernel (0 = chosen per map)
     bool gauss_stream_ok() const;

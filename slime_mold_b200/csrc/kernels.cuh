@@ -142,7 +142,7 @@ struct LeaverBufs {
 // FLAGS: deposits are u8 "somebody deposited here" marks written with plain stores instead of u32
 // counts bumped with RED atomics -- exact whenever dep >= 1 and the field is non-negative, because
 // clamp(t + k*dep, 0, 1) == 1 for every k >= 1 (all shipped presets: dep = 1.0).
-template <int XM, class IdxT, class FETCH, bool FLAGS>
+template <int XM, class IdxT, class FETCH, bool FLAGS, bool HINT>
 __device__ __forceinline__ void step_agent_slot(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
                                                 float4 a, uint32_t id, const FETCH& fetch, void* __restrict__ deposits,
                                                 const AgentConsts& c, const LeaverBufs& lv)
@@ -150,7 +150,8 @@ __device__ __forceinline__ void step_agent_slot(float4* __restrict__ agents, uin
     constexpr bool MULTI = XM != XM_SINGLE;
     int32_t cx, cy;
     smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, c, fetch, cx, cy);
-    agents[i] = a;
+    if (HINT) __stcs(agents + i, a);      // evict-first: the agent stream should not push the trail out of L2
+    else agents[i] = a;
     // Fast path (every agent on one GPU, all but the strip-boundary agents otherwise): the new cell is
     // on a row this rank owns -> local deposit, no migration.  One subtract + one unsigned compare.
     int32_t lr = cy - (int32_t)c.row_base;
@@ -222,15 +223,23 @@ static inline int agents_per_thread_for(uint64_t n, int num_sms)
     return apt;
 }
 
+template <bool HINT>
 __device__ __forceinline__ void load_agent_slot(const float4* agents, const uint32_t* ids, uint64_t i, float4& a, uint32_t& id)
 {
     // asm volatile: the loads stay where they are written (ahead of the previous agent's arithmetic) --
     // left to the compiler a plain load is sunk to its first use, which exposes the full DRAM latency
-    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(agents + i));
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(id) : "l"(ids + i));
+    if (HINT) {
+        // .cs (evict-first): 20 B in + 16 B out per agent pass through L2 once per step -- 600 MB at config 2, five times
+        // the L2 -- while the trail copy the gathers hit is 67 MB and worth keeping there (SM_AGENT_STREAM_HINT, A/B)
+        asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(agents + i));
+        asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(id) : "l"(ids + i));
+    } else {
+        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(agents + i));
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(id) : "l"(ids + i));
+    }
 }
 
-template <int XM, class IdxT, class FETCH, bool FLAGS>
+template <int XM, class IdxT, class FETCH, bool FLAGS, bool HINT = false>
 static __global__ void __launch_bounds__(256, SM_AGENTS_MIN_BLOCKS)
 k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
          const FETCH fetch, void* __restrict__ deposits, const AgentConsts c,
@@ -252,16 +261,16 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     if (i >= n) return;
     float4 a_next;
     uint32_t id_next;
-    load_agent_slot(agents, ids, i, a_next, id_next);
+    load_agent_slot<HINT>(agents, ids, i, a_next, id_next);
 #pragma unroll 1
     for (int j = 0; j < agents_per_thread; ++j) {
         float4 a = a_next;
         const uint32_t id = id_next;
         const uint64_t i_next = i + 256u;
         const bool more = (j + 1 < agents_per_thread) && i_next < n;
-        if (more) load_agent_slot(agents, ids, i_next, a_next, id_next);
+        if (more) load_agent_slot<HINT>(agents, ids, i_next, a_next, id_next);
         if (!MULTI || id != kDeadAgent)
-            step_agent_slot<XM, IdxT, FETCH, FLAGS>(agents, ids, i, a, id, fetch, deposits, c, lv);
+            step_agent_slot<XM, IdxT, FETCH, FLAGS, HINT>(agents, ids, i, a, id, fetch, deposits, c, lv);
         if (!more) break;
         i = i_next;
     }

@@ -17,24 +17,49 @@ def P(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+GUARD = 4      # rows of guard band around every array the kernel writes: a store outside the map must show up
+
+
+def guarded(shape, dtype, fill):
+    H, W = shape
+    full = np.full((H + 2 * GUARD, W), fill, dtype)
+    return full, full[GUARD:GUARD + H]
+
+
+def guards_intact(full, fill):
+    g = np.concatenate([full[:GUARD].ravel(), full[-GUARD:].ravel()])
+    return bool(np.all(np.isnan(g))) if isinstance(fill, float) and np.isnan(fill) else bool(np.all(g == fill))
+
+
 def run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=0, counts=None, want_surf=False):
     H, W = field.shape
-    out = np.full_like(field, np.nan)
-    surf = np.full_like(field, np.nan) if want_surf else None
+    # the input sits between NaN guard rows too: a read outside the map would poison an output
+    _, fin = guarded((H, W), np.float32, np.nan)
+    fin[:] = field
+    field = fin
+    out_full, out = guarded((H, W), np.float32, np.nan)
+    surf_full, surf = guarded((H, W), np.float32, np.nan) if want_surf else (None, None)
     w = oracle.gauss_weights(R, sigma)
-    cin = czero = None
+    cin = czero = czero_full = None
     if cm == 1:
-        cin = counts.copy()
-        czero = np.full((H, W), 7, np.uint32)             # the pass must retire every cell of the other buffer
+        _, cin = guarded((H, W), np.uint32, 1)
+        cin[:] = counts
+        czero_full, czero = guarded((H, W), np.uint32, 7)   # the pass must retire every cell of the other buffer, and only those
     elif cm == 2:
-        cin = (counts > 0).astype(np.uint8)
-        czero = np.full((H, W), 7, np.uint8)
+        _, cin = guarded((H, W), np.uint8, 1)
+        cin[:] = counts > 0
+        czero_full, czero = guarded((H, W), np.uint8, 7)
     rc = hostcheck.hc_gauss_stream(P(field, C.c_float),
                                    None if cin is None else cin.ctypes.data_as(C.c_void_p),
                                    None if czero is None else czero.ctypes.data_as(C.c_void_p),
                                    P(out, C.c_float), None if surf is None else P(surf, C.c_float),
                                    C.c_int(W), C.c_int(H), C.c_int(chunk), C.c_int(R), P(w, C.c_float), C.c_int(cm), C.byref(p))
     assert rc == 0
+    assert guards_intact(out_full, np.nan), "the kernel stored outside the output field"
+    if surf_full is not None:
+        assert guards_intact(surf_full, np.nan), "the kernel stored outside the sampler copy"
+    if czero_full is not None:
+        assert guards_intact(czero_full, 7), "the kernel retired deposit marks outside the map"
     return out, surf, czero
 
 
