@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 T0=$(date +%s)
 el() { echo "[t+$(( $(date +%s) - T0 ))s] $*"; }
 el "== parity: Gaussian kernels (tile / packed / two-pass / stream) =="
-timeout 240 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "gaussian" 2>&1 | tail -4 | tee gpurun_out/r8_parity_gauss.log
+timeout 240 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "gaussian" 2>&1 | tail -15 | tee gpurun_out/r8_parity_gauss.log
 el "== sweep: stream vs tile =="
 rm -f gpurun_out/kernel_sweep.jsonl
 timeout 200 python tools/bench_kernels.py gauss_stream 2>&1 | tail -3
