@@ -302,7 +302,7 @@ int sm_engine::setup_tiles()
 bool sm_engine::flag_mode() const
 {
     if (no_flags) return false;
-    if ((cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && !gauss_stream_ok()) return false;   // the tile / two-pass Gaussian kernels only merge counts
+    if ((cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && !(gauss_stream_ok() && world == 1)) return false;   // the tile / two-pass Gaussian kernels only merge counts
     return trail_nonneg && params.pheromone_deposition_amount >= 1.0f;
 }
 
@@ -439,7 +439,7 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     p.g.W = W; p.g.rows = rows; p.g.wrap_y = (world == 1) ? 1 : 0;
     p.g.y_first = 0; p.g.y_last = rows; p.g.chunks1 = 0xFFFFFFFFu; p.g.y_first2 = p.g.y_last2 = 0;
     // the full step keeps the sampler's block-linear copy in step; other passes just mark it stale
-    const bool write_surf = use_tex && has_counts && (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) || gauss_stream_ok());
+    const bool write_surf = use_tex && has_counts && (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) || (gauss_stream_ok() && world == 1));
     p.g.surf = write_surf ? trail_surf : 0;
     p.g.surf_row0 = (int)(ghost + pad_rows);
     if (!write_surf) arr_stale = true;
@@ -536,7 +536,7 @@ int sm_engine::launch_trail(bool has_counts)
 // block-linear copy in step, so a Gaussian full step runs the same agent kernel as the box-blur step.
 bool sm_engine::gauss_stream_ok() const
 {
-    return gauss_stream && !gauss_two_pass && world == 1 && W % 4 == 0 && W >= (uint32_t)smk::kGsMinW && rows >= (uint32_t)smk::kGsMinRows;
+    return gauss_stream && !gauss_two_pass && W % 4 == 0 && W >= (uint32_t)smk::kGsMinW && rows >= (uint32_t)smk::kGsMinRows;
 }
 
 template <int R, int CM, bool SURF>
@@ -575,8 +575,16 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
 {
     const smk::TrailGeom& g = p.g;
     const smd::TrailConsts& tc = p.tc;
-    if (world != 1) return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR is single-GPU only");
     int R = (int)lroundf(params.blur_radius);
+    if (world != 1) {
+        // strips: diffusion-only passes of the streaming kernel (BASELINE config 5 at 2/4/8 GPUs); the R rows of the
+        // neighbours it reads are the ghost rows sm_diffuse_only exchanges after every pass
+        if (has_counts) return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR: full steps are single-GPU only (diffusion-only passes run on strips)");
+        if (!gauss_stream_ok())
+            return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR on strips needs the streaming kernel (SM_GAUSS_KERNEL=stream, W %% 4 == 0, W >= %d, >= %d rows per strip)",
+                           smk::kGsMinW, smk::kGsMinRows);
+        if ((uint32_t)(R < 1 ? 1 : R) > ghost) return sm_fail(SM_ERR_STATE, "strip has %u ghost rows, the blur needs %d", ghost, R);
+    }
     if (R < 1 || R > 8) return sm_fail(SM_ERR_BAD_ARG, "gaussian blur radius must round to 1..8 (got %g)", params.blur_radius);
     if (!(params.blur_sigma > 0.0f)) return sm_fail(SM_ERR_BAD_ARG, "gaussian blur sigma must be > 0");
     smk::GaussConsts gc{};
@@ -595,7 +603,7 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
         // streaming single pass (gauss_stream.cuh): counts or flags merged, sampler copy written in a full step
         smk::GsArgs a{};
         a.tin = p.tin; a.cin = p.cm == smk::CM_NONE ? nullptr : p.cin; a.czero = p.cm == smk::CM_NONE ? nullptr : p.czero; a.tout = p.tout;
-        a.W = (int)W; a.H = (int)rows;
+        a.W = (int)W; a.H = (int)rows; a.wrap_y = g.wrap_y;
         a.surf = (unsigned long long)g.surf; a.surf_row0 = g.surf_row0;
         const bool surf = g.surf != 0;
         auto go = [&](auto r_tag) -> int {

@@ -316,6 +316,11 @@ static int halo_depths(const sm_engine* e, uint32_t* g, uint32_t* m)
     if (!(sd < 60000.0f) || !(mv < 60000.0f)) return sm_fail(SM_ERR_BAD_ARG, "sensor distance / speed too large for strips");
     *g = (uint32_t)ceilf(sd) + 3u;
     *m = (uint32_t)ceilf(mv) + 1u;
+    if (e->cfg.flags & SM_FLAG_GAUSSIAN_BLUR) {          // extension: the blur reads R rows of the neighbours (R <= 8)
+        const float br = e->params.blur_radius;
+        const uint32_t R = (br >= 1.0f && br <= 8.5f) ? (uint32_t)lroundf(br) : 8u;
+        if (*g < R) *g = R;
+    }
     if (*g > e->ghost || *m > e->ghost || *m + 1 > e->rows)
         return sm_fail(SM_ERR_BAD_ARG, "strip of %u rows with %u ghost rows is too thin: sensing needs %u, motion needs %u",
                        e->rows, e->ghost, *g, *m);
@@ -844,6 +849,7 @@ uint32_t sm_engine::overlap_band()
 
 bool sm_engine::overlap_ok()
 {
+    if (cfg.flags & SM_FLAG_GAUSSIAN_BLUR) return false;   // the Gaussian extension runs the serial order (pass, then ghost exchange)
     return overlap_enabled && p2p && !fake_multi && world > 1 && side_stream && overlap_band() > 0;
 }
 

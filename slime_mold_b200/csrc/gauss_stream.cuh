@@ -28,11 +28,18 @@ namespace smk {
 #if defined(__CUDACC__)
 #define SM_KD __device__ __forceinline__
 #define SM_HDC __host__ __device__ constexpr
+// A value the compiler must keep in a register from here on: kernel parameters are otherwise re-read from the constant bank
+// (LDC / LDCU) wherever they are used, and those reads share a scoreboard with the global loads around them -- ncu showed
+// each LDG of the prefetch waiting for the previous one to RETURN because an LDC sat between them.
+#define SM_OPAQUE32(x) asm volatile("" : "+r"(x))
+#define SM_OPAQUE64(p) asm volatile("" : "+l"(p))
 using F4 = float4;
 using U4 = uint4;
 #else
 #define SM_KD inline
 #define SM_HDC constexpr
+#define SM_OPAQUE32(x) ((void)0)
+#define SM_OPAQUE64(p) ((void)0)
 struct alignas(16) F4 { float x, y, z, w; };
 struct alignas(16) U4 { uint32_t x, y, z, w; };
 #endif
@@ -45,7 +52,10 @@ enum { GS_NONE = 0, GS_COUNTS = 1, GS_FLAGS = 2 };
 constexpr int kGsTX = 256;      // output columns per CTA
 constexpr int kGsNT = 256;      // threads per CTA
 template <int R> SM_HDC int gs_ra() { return (R + 3) / 4 * 4; }                  // halo columns staged per side (whole float4s)
-template <int R> SM_HDC int gs_batch() { return R <= 4 ? 8 : 16; }               // rows per batch; 2R <= B
+#ifndef SM_GS_BATCH_SMALL
+#define SM_GS_BATCH_SMALL 16   // rows per batch for radius <= 4 (8: 34 KB of rings, but three barriers per 8 rows -- 29 % of the stall samples at radius 2)
+#endif
+template <int R> SM_HDC int gs_batch() { return R <= 4 ? SM_GS_BATCH_SMALL : 16; }   // rows per batch; 2R <= B
 template <int R> SM_HDC int gs_dc() { return kGsTX + 2 * gs_ra<R>() + 4; }       // row stride of D (floats): 16-byte multiple, +4 against bank conflicts
 template <int R> SM_HDC size_t gs_smem_bytes() { return sizeof(float) * 2 * gs_batch<R>() * (size_t)(gs_dc<R>() + kGsTX); }
 // smallest map the kernel takes: a float4 never straddles the seam, one fold per coordinate is enough
@@ -56,7 +66,9 @@ struct GsArgs {
     const void* cin;        // GS_COUNTS: u32 per cell, GS_FLAGS: u8 per cell (deposits of this step)
     void* czero;            // the other deposit buffer: this pass retires (zeroes) the cells it owns
     float* tout;
-    int W, H;               // row length, rows of the map (rows wrap toroidally: single GPU)
+    int W, H;               // row length, owned rows (the whole map on one GPU, the strip on several)
+    int wrap_y;             // 1: rows wrap toroidally inside the buffer (single GPU); 0: strip with at least R ghost rows
+                            //    above and below the owned rows (filled by the neighbours before the pass)
     int chunk_rows;         // output rows per CTA (blockIdx.y)
     unsigned long long surf;   // block-linear copy of the output for the TEX sampler (SURF instantiations)
     int surf_row0;
@@ -80,45 +92,53 @@ SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs
     const int S = nrows + 2 * R;       // stream rows: map rows yc0 - R .. yc0 + nrows + R - 1
     const int nb = (S + B - 1) / B;
 
-    const float* __restrict__ tin = a.tin;
+    const float* tin = a.tin;
     const uint32_t* cin32 = static_cast<const uint32_t*>(a.cin);
     const uint8_t* cin8 = static_cast<const uint8_t*>(a.cin);
+    int Wq = W, Hq = H;
+    SM_OPAQUE64(tin); SM_OPAQUE64(cin32); SM_OPAQUE64(cin8); SM_OPAQUE32(Wq); SM_OPAQUE32(Hq);
 
     // ---- the pieces this thread stages: (row of the batch, float4 column) are the same for every batch ----
-    int pgx[PER];                      // map column of the piece (folded across the seam); -1: no such piece
+    int pgx[PER];                      // map column of the piece (folded across the seam)
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         const int e = tid + k * NT;
-        pgx[k] = -1;
-        if (e < N4) {
-            const int c4 = e % DC4;
-            int gx = x0 - RA + 4 * c4;
-            if (gx < 0) gx += W; else if (gx >= W) gx -= W;
-            pgx[k] = gx;
-        }
+        const int c4 = (e < N4 ? e : 0) % DC4;
+        int gx = x0 - RA + 4 * c4;
+        if (gx < 0) gx += W; else if (gx >= W) gx -= W;
+        pgx[k] = gx;
     }
     F4 t4[PER];
     U4 k4[CM == GS_COUNTS ? PER : 1];
     uint32_t kf[CM == GS_FLAGS ? PER : 1];
-    int pgy[PER];                      // map row of the piece in flight; -1: past the stream (nothing requested)
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { t4[k].x = t4[k].y = t4[k].z = t4[k].w = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < (CM == GS_COUNTS ? PER : 1); ++k) { k4[k].x = k4[k].y = k4[k].z = k4[k].w = 0u; }
+#pragma unroll
+    for (int k = 0; k < (CM == GS_FLAGS ? PER : 1); ++k) kf[k] = 0u;
+    int pgy[PER];                      // buffer row of the piece in flight (negative / >= H: ghost rows of a strip)
+    constexpr int kNoRow = -0x40000000;   // past the stream: nothing was requested
 
+    // All addresses first, then the loads back to back (predicated, no branch, nothing between them).
     auto prefetch = [&](int kb) {
+        int64_t off[PER];
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const int e = tid + k * NT;
-            pgy[k] = -1;
-            if (e < N4) {
-                const int s = kb * B + e / DC4;
-                if (s < S) {
-                    int gy = yc0 - R + s;
-                    if (gy < 0) gy += H; else if (gy >= H) gy -= H;
-                    pgy[k] = gy;
-                    const int64_t off = (int64_t)gy * W + pgx[k];
-                    t4[k] = cx.ld4(tin + off);
-                    if (CM == GS_COUNTS) k4[k] = cx.ldu4(cin32 + off);
-                    if (CM == GS_FLAGS) kf[k] = cx.ldu1(reinterpret_cast<const uint32_t*>(cin8 + off));
-                }
-            }
+            const int s = kb * B + (e < N4 ? e : 0) / DC4;
+            const bool valid = e < N4 && s < S;
+            int gy = yc0 - R + (s < S ? s : S - 1);   // strips: rows -R .. -1 and H .. H+R-1 are ghost rows of the buffer
+            if (a.wrap_y) { if (gy < 0) gy += Hq; else if (gy >= Hq) gy -= Hq; }
+            pgy[k] = valid ? gy : kNoRow;
+            off[k] = (int64_t)gy * Wq + pgx[k];
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const bool valid = pgy[k] != kNoRow;
+            cx.ld4(t4[k], tin + off[k], valid);
+            if (CM == GS_COUNTS) cx.ldu4(k4[k], cin32 + off[k], valid);
+            if (CM == GS_FLAGS) cx.ldu1(kf[k], reinterpret_cast<const uint32_t*>(cin8 + off[k]), valid);
         }
     };
 
@@ -133,7 +153,7 @@ SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs
                 const int r = e / DC4, c4 = e - r * DC4;
                 F4 t;
                 t.x = t.y = t.z = t.w = 0.0f;
-                if (pgy[k] >= 0) {
+                if (pgy[k] != kNoRow) {
                     t = t4[k];
                     if (CM != GS_NONE) {
                         if (CM == GS_COUNTS) {

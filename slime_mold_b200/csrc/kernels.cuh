@@ -823,9 +823,22 @@ struct GsDevCtx {
     __device__ __forceinline__ int bx() const { return (int)blockIdx.x; }
     __device__ __forceinline__ int by() const { return (int)blockIdx.y; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
-    __device__ __forceinline__ float4 ld4(const float* p) const { return __ldg(reinterpret_cast<const float4*>(p)); }
-    __device__ __forceinline__ uint4 ldu4(const uint32_t* p) const { return __ldg(reinterpret_cast<const uint4*>(p)); }
-    __device__ __forceinline__ uint32_t ldu1(const uint32_t* p) const { return __ldg(p); }
+    // predicated read-only loads as volatile asm: they are issued where they are written, back to back (no branch, no
+    // constant-bank read between them); a piece that is not `valid` keeps its old register contents
+    __device__ __forceinline__ void ld4(float4& v, const float* p, bool valid) const
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+                     : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"((int)valid));
+    }
+    __device__ __forceinline__ void ldu4(uint4& v, const uint32_t* p, bool valid) const
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+                     : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(p), "r"((int)valid));
+    }
+    __device__ __forceinline__ void ldu1(uint32_t& v, const uint32_t* p, bool valid) const
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((int)valid));
+    }
     __device__ __forceinline__ void surf_write(float4 v, unsigned long long surf, int x, int y) const
     {
         surf2Dwrite(v, (cudaSurfaceObject_t)surf, x * 4, y);
@@ -833,7 +846,7 @@ struct GsDevCtx {
 };
 
 template <int R, int CM, bool SURF>
-static __global__ void __launch_bounds__(kGsNT, (R <= 4 ? 4 : 3))
+static __global__ void __launch_bounds__(kGsNT, (gs_batch<R>() == 8 ? 4 : 3))     // rings: 34 KB (batches of 8 rows) / 67 KB (16)
 k_gauss_stream(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
 {
     extern __shared__ __align__(16) float gs_smem[];

@@ -119,9 +119,9 @@ struct HostGsCtx {
     int bx() const { return bxv; }
     int by() const { return byv; }
     void sync() const { pthread_barrier_wait(bar); }
-    smk::F4 ld4(const float* p) const { smk::F4 v; std::memcpy(&v, p, 16); return v; }
-    smk::U4 ldu4(const uint32_t* p) const { smk::U4 v; std::memcpy(&v, p, 16); return v; }
-    uint32_t ldu1(const uint32_t* p) const { uint32_t v; std::memcpy(&v, p, 4); return v; }
+    void ld4(smk::F4& v, const float* p, bool valid) const { if (valid) std::memcpy(&v, p, 16); }
+    void ldu4(smk::U4& v, const uint32_t* p, bool valid) const { if (valid) std::memcpy(&v, p, 16); }
+    void ldu1(uint32_t& v, const uint32_t* p, bool valid) const { if (valid) std::memcpy(&v, p, 4); }
     void surf_write(smk::F4 v, unsigned long long surf, int x, int y) const
     {
         std::memcpy(reinterpret_cast<float*>(surf) + (size_t)y * surf_w + x, &v, 16);
@@ -162,7 +162,7 @@ static void run_gauss_stream_r(int cm, bool surf, const smk::GsArgs& a, const sm
 }
 
 extern "C" int hc_gauss_stream(const float* tin, const void* cin, void* czero, float* tout, float* surf_out, int W, int H,
-                               int chunk_rows, int R, const float* weights, int cm, const hc_params* p)
+                               int chunk_rows, int R, const float* weights, int cm, const hc_params* p, int wrap_y)
 {
     if (W % 4 != 0 || W < smk::kGsMinW || H < smk::kGsMinRows || R < 1 || R > 8 || chunk_rows < 1) return -1;
     smd::TrailConsts tc{};
@@ -177,7 +177,7 @@ extern "C" int hc_gauss_stream(const float* tin, const void* cin, void* czero, f
     for (int i = 0; i <= 2 * R; ++i) gc.w[i] = weights[i];
     smk::GsArgs a{};
     a.tin = tin; a.cin = cin; a.czero = czero; a.tout = tout;
-    a.W = W; a.H = H; a.chunk_rows = chunk_rows;
+    a.W = W; a.H = H; a.chunk_rows = chunk_rows; a.wrap_y = wrap_y;
     a.surf = (unsigned long long)reinterpret_cast<uintptr_t>(surf_out); a.surf_row0 = 0;
     const bool surf = surf_out != nullptr;
     switch (R) {

@@ -53,7 +53,7 @@ def run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=0, counts=None, 
                                    None if cin is None else cin.ctypes.data_as(C.c_void_p),
                                    None if czero is None else czero.ctypes.data_as(C.c_void_p),
                                    P(out, C.c_float), None if surf is None else P(surf, C.c_float),
-                                   C.c_int(W), C.c_int(H), C.c_int(chunk), C.c_int(R), P(w, C.c_float), C.c_int(cm), C.byref(p))
+                                   C.c_int(W), C.c_int(H), C.c_int(chunk), C.c_int(R), P(w, C.c_float), C.c_int(cm), C.byref(p), C.c_int(1))
     assert rc == 0
     assert guards_intact(out_full, np.nan), "the kernel stored outside the output field"
     if surf_full is not None:
@@ -109,3 +109,40 @@ def test_stream_constant_field_and_mass(oracle, hostcheck):
     const = np.full((H, W), 0.625, np.float32)
     got, _, _ = run_stream(hostcheck, oracle, const, p, R, sigma, 64)
     assert np.allclose(got, 0.625, rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("R,sigma,strips", [(2, 1.0, 2), (5, 2.5, 3), (8, 4.0, 4)])
+def test_stream_on_strips_bits(oracle, hostcheck, R, sigma, strips):
+    """Strip mode of the kernel (multi-GPU diffusion-only passes, BASELINE config 5 at 2/4/8 GPUs): every strip runs the
+    pass on its own rows with `ghost` rows of its neighbours above and below (no row wrap inside the buffer; the
+    toroidal seam is the ring exchange), the ghosts are refreshed between passes -- the protocol of
+    sm_diffuse_only on strips -- and the stitched result equals the single-domain oracle bit for bit."""
+    W, H, ghost, passes = 320, 64 * strips, 9, 3
+    p = params_for(oracle, W, H, R, sigma, dep=1.0)
+    field = np.random.default_rng(strips).random((H, W), dtype=np.float32)
+    ref = field
+    for _ in range(passes):
+        ref = oracle.trail_pass(ref, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
+    w = oracle.gauss_weights(R, sigma)
+    rows = H // strips
+    cur = field
+    for _ in range(passes):
+        new = np.empty_like(cur)
+        for r in range(strips):
+            y0 = r * rows
+            buf = np.full((rows + 2 * ghost, W), np.nan, np.float32)      # [ghost | owned | ghost], filled by the "exchange"
+            idx = np.arange(y0 - ghost, y0 + rows + ghost) % H
+            buf[:] = cur[idx]
+            # rows past the R the pass may touch stay poisoned: reading them would show up in the output
+            buf[:ghost - R] = np.nan
+            buf[ghost + rows + R:] = np.nan
+            out = np.full((rows + 2 * ghost, W), np.nan, np.float32)
+            pp = params_for(oracle, W, rows, R, sigma, dep=1.0)
+            rc = hostcheck.hc_gauss_stream(P(buf[ghost:], C.c_float), None, None, P(out[ghost:], C.c_float), None,
+                                           C.c_int(W), C.c_int(rows), C.c_int(40), C.c_int(R), P(w, C.c_float), C.c_int(0),
+                                           C.byref(pp), C.c_int(0))
+            assert rc == 0
+            assert np.all(np.isnan(out[:ghost])) and np.all(np.isnan(out[ghost + rows:])), "stored into the ghost rows"
+            new[y0:y0 + rows] = out[ghost:ghost + rows]
+        cur = new
+    assert bits_equal(cur, ref), mismatch_report(cur, ref, f"strips R={R}")
