@@ -52,10 +52,7 @@ enum { GS_NONE = 0, GS_COUNTS = 1, GS_FLAGS = 2 };
 constexpr int kGsTX = 256;      // output columns per CTA
 constexpr int kGsNT = 256;      // threads per CTA
 template <int R> SM_HDC int gs_ra() { return (R + 3) / 4 * 4; }                  // halo columns staged per side (whole float4s)
-#ifndef SM_GS_BATCH_SMALL
-#define SM_GS_BATCH_SMALL 16   // rows per batch for radius <= 4 (8: 34 KB of rings, but three barriers per 8 rows -- 29 % of the stall samples at radius 2)
-#endif
-template <int R> SM_HDC int gs_batch() { return R <= 4 ? SM_GS_BATCH_SMALL : 16; }   // rows per batch; 2R <= B
+template <int R> SM_HDC int gs_batch() { return 16; }   // rows per batch; 2R <= B (batches of 8 rows for radius <= 4: three barriers per 8 rows were 29 % of the stall samples)
 template <int R> SM_HDC int gs_dc() { return kGsTX + 2 * gs_ra<R>() + 4; }       // row stride of D (floats): 16-byte multiple, +4 against bank conflicts
 template <int R> SM_HDC size_t gs_smem_bytes() { return sizeof(float) * 2 * gs_batch<R>() * (size_t)(gs_dc<R>() + kGsTX); }
 // smallest map the kernel takes: a float4 never straddles the seam, one fold per coordinate is enough
@@ -74,14 +71,20 @@ struct GsArgs {
     int surf_row0;
 };
 
+struct GsFoldYes { static constexpr bool value = true; };      // prefetch instantiations: rows folded across the seam, or not
+struct GsFoldNo { static constexpr bool value = false; };
+
 template <int R, int CM, bool SURF, class Ctx>
 SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs& a, const smd::TrailConsts& tc, const GaussConsts& gc)
 {
     constexpr int TX = kGsTX, NT = kGsNT, B = gs_batch<R>(), RA = gs_ra<R>(), DC = gs_dc<R>();
-    constexpr int DC4 = (TX + 2 * RA) / 4;          // float4 columns staged per row
     constexpr int NR = 2 * B;                       // ring rows (power of two)
-    constexpr int N4 = B * DC4, PER = (N4 + NT - 1) / NT;
-    static_assert(2 * R <= B && (NR & (NR - 1)) == 0, "ring geometry");
+    constexpr int CG = TX / 4;                      // float4 column groups of the tile (64)
+    constexpr int RPK = NT / CG;                    // rows one sweep of the CTA's threads covers (4)
+    constexpr int PC = B / RPK;                     // centre pieces per thread and batch (4): row 4k + tid/64, column group tid%64
+    constexpr int HP = RA / 2;                      // halo float4s per row (left RA/4 + right RA/4)
+    constexpr int PER = PC + 1;                     // + one halo piece for the first B*HP threads: row tid/HP, halo column tid%HP
+    static_assert(2 * R <= B && (NR & (NR - 1)) == 0 && NT % CG == 0 && B % RPK == 0 && B * HP <= NT, "ring / piece geometry");
     float* D = gsm;                    // [NR][DC]  decayed cells; column c <-> map column x0 - RA + c; stream row s in slot s & (NR-1)
     float* Hb = gsm + NR * DC;         // [NR][TX]  row-blurred cells
     const int tid = cx.tid();
@@ -98,99 +101,100 @@ SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs
     int Wq = W, Hq = H;
     SM_OPAQUE64(tin); SM_OPAQUE64(cin32); SM_OPAQUE64(cin8); SM_OPAQUE32(Wq); SM_OPAQUE32(Hq);
 
-    // ---- the pieces this thread stages: (row of the batch, float4 column) are the same for every batch ----
-    int pgx[PER];                      // map column of the piece (folded across the seam)
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int e = tid + k * NT;
-        const int c4 = (e < N4 ? e : 0) % DC4;
-        int gx = x0 - RA + 4 * c4;
-        if (gx < 0) gx += W; else if (gx >= W) gx -= W;
-        pgx[k] = gx;
-    }
+    // ---- the pieces this thread stages are the same for every batch: shifts and masks only, no division ----
+    const int cg = tid & (CG - 1), rsub = tid / CG;
+    const bool own_col = x0 + 4 * cg < W;                      // ragged last tile: columns past the map are staged (as the
+    int gxc = x0 + 4 * cg;                                      // toroidal neighbours they are) but never stored
+    if (gxc >= W) gxc -= W;
+    const bool has_halo = tid < B * HP;
+    const int hrow = tid / HP, hq = tid % HP;                   // HP is 2 or 4
+    const int hcol = hq < HP / 2 ? 4 * hq : RA + TX + 4 * (hq - HP / 2);   // float column of D: left halo | right halo
+    int gxh = x0 - RA + hcol;
+    if (gxh < 0) gxh += W; else if (gxh >= W) gxh -= W;
+
     F4 t4[PER];
     U4 k4[CM == GS_COUNTS ? PER : 1];
     uint32_t kf[CM == GS_FLAGS ? PER : 1];
+    // a piece past the end of the stream is not loaded (predicate): its registers keep whatever they held -- finite
+    // values, zero at first -- and the ring rows they are parked in never reach a stored output
 #pragma unroll
     for (int k = 0; k < PER; ++k) { t4[k].x = t4[k].y = t4[k].z = t4[k].w = 0.0f; }
 #pragma unroll
     for (int k = 0; k < (CM == GS_COUNTS ? PER : 1); ++k) { k4[k].x = k4[k].y = k4[k].z = k4[k].w = 0u; }
 #pragma unroll
     for (int k = 0; k < (CM == GS_FLAGS ? PER : 1); ++k) kf[k] = 0u;
-    int pgy[PER];                      // buffer row of the piece in flight (negative / >= H: ghost rows of a strip)
-    constexpr int kNoRow = -0x40000000;   // past the stream: nothing was requested
+    int pgy[PC];                       // buffer rows of the centre pieces in flight (their deposit marks are retired by the stage)
+
+    // Does this chunk touch the toroidal seam at all?  (Uniform per CTA; all but the first and last chunk of a map do not.)
+    const bool seam = a.wrap_y && (yc0 - R < 0 || yc0 + nrows + R > H);
 
     // All addresses first, then the loads back to back (predicated, no branch, nothing between them).
-    auto prefetch = [&](int kb) {
+    auto prefetch = [&](int kb, auto fold_tag) {
+        constexpr bool FOLD = decltype(fold_tag)::value;
         int64_t off[PER];
+        bool valid[PER];
+        const int nleft = S - kb * B;                 // stream rows left, this batch included
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
-            const int e = tid + k * NT;
-            const int s = kb * B + (e < N4 ? e : 0) / DC4;
-            const bool valid = e < N4 && s < S;
-            int gy = yc0 - R + (s < S ? s : S - 1);   // strips: rows -R .. -1 and H .. H+R-1 are ghost rows of the buffer
-            if (a.wrap_y) { if (gy < 0) gy += Hq; else if (gy >= Hq) gy -= Hq; }
-            pgy[k] = valid ? gy : kNoRow;
-            off[k] = (int64_t)gy * Wq + pgx[k];
+            const int r = k < PC ? RPK * k + rsub : hrow;
+            valid[k] = (k < PC || has_halo) && r < nleft;
+            int gy = yc0 - R + kb * B + r;            // strips: rows -R .. -1 and H .. H+R-1 are ghost rows of the buffer
+            if (FOLD) { if (gy < 0) gy += Hq; else if (gy >= Hq) gy -= Hq; }
+            if (k < PC) pgy[k] = gy;
+            off[k] = (int64_t)gy * Wq + (k < PC ? gxc : gxh);
         }
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
-            const bool valid = pgy[k] != kNoRow;
-            cx.ld4(t4[k], tin + off[k], valid);
-            if (CM == GS_COUNTS) cx.ldu4(k4[k], cin32 + off[k], valid);
-            if (CM == GS_FLAGS) cx.ldu1(kf[k], reinterpret_cast<const uint32_t*>(cin8 + off[k]), valid);
+            cx.ld4(t4[k], tin + off[k], valid[k]);
+            if (CM == GS_COUNTS) cx.ldu4(k4[k], cin32 + off[k], valid[k]);
+            if (CM == GS_FLAGS) cx.ldu1(kf[k], reinterpret_cast<const uint32_t*>(cin8 + off[k]), valid[k]);
         }
     };
 
-    prefetch(0);
+    if (seam) prefetch(0, GsFoldYes{}); else prefetch(0, GsFoldNo{});
     for (int kb = 0; kb < nb; ++kb) {
         const int blk = (kb & 1) * B;
         // ---- stage: registers -> D ring (merge, decay); retire the deposit marks of the cells this CTA owns ----
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
-            const int e = tid + k * NT;
-            if (e < N4) {
-                const int r = e / DC4, c4 = e - r * DC4;
-                F4 t;
-                t.x = t.y = t.z = t.w = 0.0f;
-                if (pgy[k] != kNoRow) {
-                    t = t4[k];
-                    if (CM != GS_NONE) {
-                        if (CM == GS_COUNTS) {
-                            t.x = smd::merge_deposit(t.x, k4[k].x, tc.dep); t.y = smd::merge_deposit(t.y, k4[k].y, tc.dep);
-                            t.z = smd::merge_deposit(t.z, k4[k].z, tc.dep); t.w = smd::merge_deposit(t.w, k4[k].w, tc.dep);
-                        } else {                                         // clamp(t + k*dep, 0, 1) == 1 for dep >= 1, t >= 0
-                            t.x = (kf[k] & 0xffu) ? 1.0f : t.x; t.y = (kf[k] & 0xff00u) ? 1.0f : t.y;
-                            t.z = (kf[k] & 0xff0000u) ? 1.0f : t.z; t.w = (kf[k] & 0xff000000u) ? 1.0f : t.w;
-                        }
-                        const int o = kb * B + r - R;                    // output row (chunk-relative) this stream row is the centre of
-                        const bool own = o >= 0 && o < nrows && 4 * c4 >= RA && 4 * c4 < RA + TX && x0 + (4 * c4 - RA) < W;
-                        if (own) {
-                            const int64_t off = (int64_t)pgy[k] * W + pgx[k];
+            if (k < PC || has_halo) {
+                const int r = k < PC ? RPK * k + rsub : hrow;
+                F4 t = t4[k];
+                if (CM != GS_NONE) {
+                    if (CM == GS_COUNTS) {
+                        t.x = smd::merge_deposit(t.x, k4[k].x, tc.dep); t.y = smd::merge_deposit(t.y, k4[k].y, tc.dep);
+                        t.z = smd::merge_deposit(t.z, k4[k].z, tc.dep); t.w = smd::merge_deposit(t.w, k4[k].w, tc.dep);
+                    } else {                                         // clamp(t + k*dep, 0, 1) == 1 for dep >= 1, t >= 0
+                        t.x = (kf[k] & 0xffu) ? 1.0f : t.x; t.y = (kf[k] & 0xff00u) ? 1.0f : t.y;
+                        t.z = (kf[k] & 0xff0000u) ? 1.0f : t.z; t.w = (kf[k] & 0xff000000u) ? 1.0f : t.w;
+                    }
+                    if (k < PC) {                                    // only centre pieces are cells this CTA owns
+                        const int o = kb * B + r - R;                // output row (chunk-relative) this stream row is the centre of
+                        if (own_col && o >= 0 && o < nrows) {
+                            const int64_t off = (int64_t)pgy[k < PC ? k : 0] * W + gxc;
                             if (CM == GS_COUNTS) { U4 z; z.x = z.y = z.z = z.w = 0u; *reinterpret_cast<U4*>(static_cast<uint32_t*>(a.czero) + off) = z; }
                             else *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(a.czero) + off) = 0u;
                         }
                     }
-                    t.x = smd::decay_cell(t.x, tc.decay_sub); t.y = smd::decay_cell(t.y, tc.decay_sub);
-                    t.z = smd::decay_cell(t.z, tc.decay_sub); t.w = smd::decay_cell(t.w, tc.decay_sub);
                 }
-                *reinterpret_cast<F4*>(D + (blk + r) * DC + 4 * c4) = t;
+                t.x = smd::decay_cell(t.x, tc.decay_sub); t.y = smd::decay_cell(t.y, tc.decay_sub);
+                t.z = smd::decay_cell(t.z, tc.decay_sub); t.w = smd::decay_cell(t.w, tc.decay_sub);
+                *reinterpret_cast<F4*>(D + (blk + r) * DC + (k < PC ? RA + 4 * cg : hcol)) = t;
             }
         }
-        if (kb + 1 < nb) prefetch(kb + 1);          // in flight while this batch is blurred
+        if (kb + 1 < nb) { if (seam) prefetch(kb + 1, GsFoldYes{}); else prefetch(kb + 1, GsFoldNo{}); }   // in flight while this batch is blurred
         cx.sync();
 
         // ---- h-blur: Hb[row][xs .. xs+3]; output j taps D columns xs + j + (RA - R) + d, d = 0 .. 2R ----
         {
-            constexpr int ITEMS = B * (TX / 4), IPT = ITEMS / NT;
             constexpr int NV = (RA + R + 4 + 3) / 4 * 4, SH = RA - R;
-            static_assert(ITEMS % NT == 0, "items per thread");
-#pragma unroll 1
-            for (int i = 0; i < IPT; ++i) {
-                const int item = tid + i * NT;
-                const int r = item / (TX / 4), xs = (item % (TX / 4)) * 4;
+            // item i of a thread: row RPK*i + rsub of the batch, columns 4*cg .. 4*cg+3 -- fixed offsets from one base address
+            const float* dsrc = D + (blk + rsub) * DC + 4 * cg;
+            float* hdst = Hb + (blk + rsub) * TX + 4 * cg;
+#pragma unroll
+            for (int i = 0; i < PC; ++i) {
                 float v[NV];
-                const F4* src = reinterpret_cast<const F4*>(D + (blk + r) * DC + xs);
+                const F4* src = reinterpret_cast<const F4*>(dsrc + i * RPK * DC);
 #pragma unroll
                 for (int q = 0; q < NV / 4; ++q) {
                     const F4 f = src[q];
@@ -207,7 +211,7 @@ SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs
                 }
                 F4 o;
                 o.x = a0; o.y = a1; o.z = a2; o.w = a3;
-                *reinterpret_cast<F4*>(Hb + (blk + r) * TX + xs) = o;
+                *reinterpret_cast<F4*>(hdst + i * RPK * TX) = o;
             }
         }
         cx.sync();
@@ -215,7 +219,7 @@ SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs
         // ---- v-blur: outputs o_first .. o_first + VR - 1 (chunk-relative rows) of columns 4*c4 .. 4*c4+3 ----
         {
             constexpr int VR = B / 4;                // TX/4 = 64 column groups x 4 row groups = 256 threads
-            const int c4 = tid & (TX / 4 - 1), rg = tid / (TX / 4);
+            const int c4 = cg, rg = rsub;
             const int o_first = kb * B - 2 * R + rg * VR;
             const int gx = x0 + 4 * c4;
             if (o_first + VR > 0 && o_first < nrows && gx < W) {
@@ -223,9 +227,13 @@ SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs
 #pragma unroll
                 for (int j = 0; j < VR; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
                 // stream row o + d holds tap d of output o: rows arrive in tap order, so each accumulator sees d = 0 .. 2R
+                // ring slot of stream row o_first + i as a byte offset: one add and one mask per row (TX * 4 bytes per row,
+                // the column offset sits below the row bits and passes through the mask)
+                const uint32_t hoff0 = ((uint32_t)(o_first & (NR - 1)) * TX + 4u * (uint32_t)c4) * 4u;
 #pragma unroll
                 for (int i = 0; i < VR + 2 * R; ++i) {
-                    const F4 h = *reinterpret_cast<const F4*>(Hb + ((o_first + i) & (NR - 1)) * TX + 4 * c4);
+                    const F4 h = *reinterpret_cast<const F4*>(reinterpret_cast<const char*>(Hb) +
+                                                              ((hoff0 + (uint32_t)i * (TX * 4u)) & (uint32_t)(NR * TX * 4 - 1)));
 #pragma unroll
                     for (int j = 0; j < VR; ++j) {
                         const int d = i - j;
