@@ -5,12 +5,23 @@
  * path: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs load this library.
  *
- * PARITY UNPINNED: the reference has no tests, fixtures or golden vectors
+ * PARITY PIN: the reference has no tests, fixtures or golden vectors
  *  and cannot be built or run in this image (no rustc, no
- * Vulkan/lavapipe).  This file therefore *defines* the semantics the CUDA
- * engine is checked against; tests/test_oracle_vs_numpy.py cross-checks its
- * logic against an independent numpy transliteration of the WGSL, and
- * tests/test_oracle_kats.py against hand-derived known answers.
+ * Vulkan/lavapipe), so there is no wgpu run to compare with.  What pins this
+ * file to the reference is the reference's own SHADER SOURCE executed here:
+ * tests/wgsl_interp.py interprets the text of compute.wgsl / display.wgsl,
+ * tests/golden/make_wgsl_golden.py commits its outputs (tests/golden/wgsl_*.npz,
+ * with the SHA-256 of the shader file), and tests/test_wgsl_reference.py
+ * requires this restatement to reproduce them BIT FOR BIT: so_step_sequential
+ * == the shader's invocations run one after another, so_step_phase_split == the
+ * shader with every load of a dispatch served from the dispatch-start buffers
+ * (dep >= 1), so_display == display.wgsl.  The one thing the shader text does
+ * not fix -- the accuracy of sin / cos and of float % -- is the arithmetic spec
+ * of sm_oracle_math.h; against numpy's libm the results
+ * stay within the stated tolerance.  The Gaussian extension has no reference
+ * semantics and stays "parity unpinned".
+ * Also: tests/test_oracle_vs_numpy.py (independent numpy transliteration) and
+ * tests/test_oracle_kats.py (hand-derived known answers).
  *
  * Update semantics offered:
  *   phase_split : all agents sense the step-start field; deposits accumulate as

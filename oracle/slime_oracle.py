@@ -2,10 +2,11 @@
 
 TEST INFRASTRUCTURE -- the checker, never the thing shipped or measured as the
 product.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
-``--impl reference`` legs may import this module.  PARITY UNPINNED (see the
-header of slime_oracle.c): the reference has no golden vectors and cannot run in
-this image, so this restatement of /root/reference/src/compute.wgsl defines the
-semantics the CUDA engine is compared with.
+``--impl reference`` legs may import this module.  Parity pin (see the header of
+slime_oracle.c): the reference has no golden vectors and cannot run in this image;
+this restatement of /root/reference/src/compute.wgsl is pinned bit for bit to the
+shader's own source text executed by tests/wgsl_interp.py (tests/golden/wgsl_*.npz,
+tests/test_wgsl_reference.py), with sin / cos / float % fixed by the arithmetic spec.
 """
 from __future__ import annotations
 

@@ -6,7 +6,8 @@
  * loosely specified (sin/cos: 2^-11 absolute error on [-pi,pi], nothing outside),
  * and the reference has no golden vectors, so this header *defines* the
  * arithmetic the CUDA engine must reproduce bit for bit (DESIGN.md "Arithmetic
- * spec").  PARITY UNPINNED: there is no reference-produced vector for this path.
+ * spec").  WGSL leaves the accuracy of sin / cos to the backend, so no reference-produced vector can pin these bits; everything
+ * around them is pinned to the shader source (tests/test_wgsl_reference.py).
  *
  * Rules: IEEE-754 binary32/binary64, round-to-nearest-even, no contraction
  * (build with -ffp-contract=off), explicit fmaf()/fma() only where written.

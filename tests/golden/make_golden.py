@@ -6,7 +6,8 @@
   after 25 steps on a 96x64 map with 2500 agents, plus a diffusion-only pass.  The
   reference itself cannot run here (no rustc / Vulkan), so these are ORACLE outputs:
   they pin the oracle against drift and give the GPU tests committed vectors, they do
-  not pin the oracle to the reference ("parity unpinned").
+  not pin the oracle to the reference -- tests/golden/make_wgsl_golden.py does that (outputs of the
+  reference's shader source).
 * reference_presets.json : the preset / default values parsed out of
   /root/reference/src/presets.rs and settings.rs (only when /root/reference exists),
   used to check the Python/C++ mirrors of the reference's configuration surface.

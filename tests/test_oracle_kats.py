@@ -1,7 +1,7 @@
 """Hand-derived known answers for the oracle, read directly off
 /root/reference/src/compute.wgsl (line numbers in the comments).  These pin the
 oracle's *logic*; bit-level arithmetic is defined by the oracle itself
-(PARITY UNPINNED: the reference ships no vectors)."""
+(the reference ships no vectors; the pin to its shader source is tests/test_wgsl_reference.py)."""
 import numpy as np
 import pytest
 
