@@ -302,7 +302,7 @@ int sm_engine::setup_tiles()
 bool sm_engine::flag_mode() const
 {
     if (no_flags) return false;
-    if ((cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && !(gauss_stream_ok() && world == 1)) return false;   // the tile / two-pass Gaussian kernels only merge counts
+    if ((cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && !(gauss_fast_ok() && world == 1)) return false;   // the tile / two-pass Gaussian kernels only merge counts
     return trail_nonneg && params.pheromone_deposition_amount >= 1.0f;
 }
 
@@ -439,7 +439,7 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     p.g.W = W; p.g.rows = rows; p.g.wrap_y = (world == 1) ? 1 : 0;
     p.g.y_first = 0; p.g.y_last = rows; p.g.chunks1 = 0xFFFFFFFFu; p.g.y_first2 = p.g.y_last2 = 0;
     // the full step keeps the sampler's block-linear copy in step; other passes just mark it stale
-    const bool write_surf = use_tex && has_counts && (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) || (gauss_stream_ok() && world == 1));
+    const bool write_surf = use_tex && has_counts && (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) || (gauss_fast_ok() && world == 1));
     p.g.surf = write_surf ? trail_surf : 0;
     p.g.surf_row0 = (int)(ghost + pad_rows);
     if (!write_surf) arr_stale = true;
@@ -539,6 +539,44 @@ bool sm_engine::gauss_stream_ok() const
     return gauss_stream && !gauss_two_pass && W % 4 == 0 && W >= (uint32_t)smk::kGsMinW && rows >= (uint32_t)smk::kGsMinRows;
 }
 
+// The register-streaming kernel (gauss_rows.cuh) applies: small radius, W % 4 == 0.  Same capabilities as the streaming
+// kernel (u8 flags, sampler copy, strips with ghost rows).
+bool sm_engine::gauss_rows_ok() const
+{
+    const int R = (int)lroundf(params.blur_radius);
+    return gauss_rows && !gauss_two_pass && R >= 1 && R <= gauss_rows_max_r && R <= smk::kGrMaxR && W % 4 == 0 &&
+           W >= (uint32_t)smk::kGrMinW && rows >= (uint32_t)smk::kGrMinRows;
+}
+
+template <int R, int CM, bool SURF>
+static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+{
+    auto kern = smk::k_gauss_rows<R, CM, SURF>;
+    int per_sm = 0;
+    SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, smk::kGrNT, 0));
+    if (per_sm < 1) per_sm = 1;
+    // chunk height: about 64 rows (2R rows of pipeline fill per chunk), nudged so that the grid is a whole number of
+    // waves of num_sms x resident CTAs
+    smk::GsArgs a = a0;
+    const uint64_t gx = (e->W + smk::kGrCtaCols - 1) / smk::kGrCtaCols;
+    const uint64_t cap = (uint64_t)e->num_sms * per_sm;
+    uint64_t chunk = (uint64_t)e->gauss_chunk;
+    if (chunk == 0) {
+        const double want_chunks = (double)e->rows / 64.0;
+        uint64_t waves = (uint64_t)llround((double)gx * want_chunks / (double)cap);
+        if (waves < 1) waves = 1;
+        uint64_t n_chunks = waves * cap / gx;
+        if (n_chunks < 1) n_chunks = 1;
+        chunk = (e->rows + n_chunks - 1) / n_chunks;
+        if (chunk < 16) chunk = 16;
+    }
+    a.chunk_rows = (int)chunk;
+    dim3 grid((unsigned)gx, (unsigned)((e->rows + chunk - 1) / chunk));
+    kern<<<grid, smk::kGrNT, 0, e->stream>>>(a, tc, gc);
+    SM_CUDA(cudaGetLastError());
+    return SM_OK;
+}
+
 template <int R, int CM, bool SURF>
 static int launch_gauss_stream(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
@@ -580,8 +618,8 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
         // strips: diffusion-only passes of the streaming kernel (BASELINE config 5 at 2/4/8 GPUs); the R rows of the
         // neighbours it reads are the ghost rows sm_diffuse_only exchanges after every pass
         if (has_counts) return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR: full steps are single-GPU only (diffusion-only passes run on strips)");
-        if (!gauss_stream_ok())
-            return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR on strips needs the streaming kernel (SM_GAUSS_KERNEL=stream, W %% 4 == 0, W >= %d, >= %d rows per strip)",
+        if (!gauss_fast_ok())
+            return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR on strips needs the streaming kernel (not SM_GAUSS_KERNEL=tile; W %% 4 == 0, W >= %d, >= %d rows per strip)",
                            smk::kGsMinW, smk::kGsMinRows);
         if ((uint32_t)(R < 1 ? 1 : R) > ghost) return sm_fail(SM_ERR_STATE, "strip has %u ghost rows, the blur needs %d", ghost, R);
     }
@@ -599,13 +637,23 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
     }
     const float* tin0 = trail_ptr(cur);
     float* tout0 = trail_ptr(1 - cur);
-    if (gauss_stream_ok()) {
-        // streaming single pass (gauss_stream.cuh): counts or flags merged, sampler copy written in a full step
+    if (gauss_fast_ok()) {
+        // streaming single pass (gauss_rows.cuh for small radii, gauss_stream.cuh otherwise): counts or flags merged,
+        // sampler copy written in a full step
+        const bool use_rows = gauss_rows_ok();
         smk::GsArgs a{};
         a.tin = p.tin; a.cin = p.cm == smk::CM_NONE ? nullptr : p.cin; a.czero = p.cm == smk::CM_NONE ? nullptr : p.czero; a.tout = p.tout;
         a.W = (int)W; a.H = (int)rows; a.wrap_y = g.wrap_y;
         a.surf = (unsigned long long)g.surf; a.surf_row0 = g.surf_row0;
         const bool surf = g.surf != 0;
+        auto go_rows = [&](auto r_tag) -> int {
+            constexpr int RR = decltype(r_tag)::value;
+            if (p.cm == smk::CM_NONE) return launch_gauss_rows<RR, smk::GS_NONE, false>(this, a, tc, gc);
+            if (p.cm == smk::CM_COUNTS) return surf ? launch_gauss_rows<RR, smk::GS_COUNTS, true>(this, a, tc, gc)
+                                                    : launch_gauss_rows<RR, smk::GS_COUNTS, false>(this, a, tc, gc);
+            return surf ? launch_gauss_rows<RR, smk::GS_FLAGS, true>(this, a, tc, gc)
+                        : launch_gauss_rows<RR, smk::GS_FLAGS, false>(this, a, tc, gc);
+        };
         auto go = [&](auto r_tag) -> int {
             constexpr int RR = decltype(r_tag)::value;
             if (p.cm == smk::CM_NONE) return launch_gauss_stream<RR, smk::GS_NONE, false>(this, a, tc, gc);
@@ -615,6 +663,16 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
                         : launch_gauss_stream<RR, smk::GS_FLAGS, false>(this, a, tc, gc);
         };
         using std::integral_constant;
+        if (use_rows) {
+            switch (R) {
+            case 1: SM_TRY(go_rows(integral_constant<int, 1>{})); break;
+            case 2: SM_TRY(go_rows(integral_constant<int, 2>{})); break;
+            case 3: SM_TRY(go_rows(integral_constant<int, 3>{})); break;
+            default: SM_TRY(go_rows(integral_constant<int, 4>{})); break;
+            }
+            timing.kernel_launches += 1;
+            return SM_OK;
+        }
         switch (R) {
         case 1: SM_TRY(go(integral_constant<int, 1>{})); break;
         case 2: SM_TRY(go(integral_constant<int, 2>{})); break;
@@ -781,8 +839,15 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
     e->gauss_two_pass = env_int("SM_GAUSS_TWO_PASS", 0) != 0;
     {
-        const char* gk = getenv("SM_GAUSS_KERNEL");          // "stream" (gauss_stream.cuh) | "tile" (k_gauss_fused)
-        e->gauss_stream = gk ? std::string(gk) == "stream" : false;
+        // "stream" (gauss_stream.cuh; default wherever it applies: W % 4 == 0, W >= 288, >= 64 rows) | "tile" (k_gauss_fused).
+        // Measured (profiles/): stream is 1.2-1.4x faster at radius 4-8 and lets a Gaussian full step keep the u8 deposit
+        // flags and the sampler copy (6.6e10 vs 4.4e10 agent-steps/s on config 2); the tile kernel is within 5-8 % at radius 2.
+        // "rows" (gauss_rows.cuh, radius <= 4) is the register-streaming kernel: unset = used up to SM_GAUSS_ROWS_MAX_R.
+        const char* gk = getenv("SM_GAUSS_KERNEL");
+        const std::string gks = gk ? gk : "";
+        e->gauss_stream = gks != "tile";
+        e->gauss_rows = gks.empty() || gks == "rows" || gks == "auto";
+        e->gauss_rows_max_r = gks == "rows" ? smk::kGrMaxR : env_int("SM_GAUSS_ROWS_MAX_R", 2);
     }
     e->agent_stream_hint = env_int("SM_AGENT_STREAM_HINT", 0);   // 1: evict-first loads / stores of the agent state (A/B)
     e->gauss_chunk = env_int("SM_GAUSS_CHUNK", 0);         // rows per CTA of the streaming kernel (0 = chosen per map)

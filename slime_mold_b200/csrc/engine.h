@@ -79,9 +79,15 @@ struct sm_engine {
     int rpc_override = 0;
     bool gauss_packed = false;        // SM_GAUSS_PACKED=1: the FFMA2 form of the fused Gaussian kernel (A/B; measured 3-10 % slower)
     int agent_stream_hint = 0;        // SM_AGENT_STREAM_HINT=1: the agent kernel streams its state with evict-first hints (A/B)
-    bool gauss_stream = false;        // SM_GAUSS_KERNEL=stream: the streaming Gaussian kernel (gauss_stream.cuh) instead of the tile kernel
+    bool gauss_stream = true;         // the streaming Gaussian kernel (gauss_stream.cuh) wherever it applies; SM_GAUSS_KERNEL=tile selects the tile kernel
     int gauss_chunk = 0;              // SM_GAUSS_CHUNK: rows per CTA of the streaming kernel (0 = chosen per map)
     bool gauss_stream_ok() const;
+    // the register-streaming kernel for small radii (gauss_rows.cuh): SM_GAUSS_KERNEL=rows forces it for every radius it
+    // takes (1-4), unset = radii up to gauss_rows_max_r (SM_GAUSS_ROWS_MAX_R), stream / tile = never
+    bool gauss_rows = true;
+    int gauss_rows_max_r = 2;
+    bool gauss_rows_ok() const;
+    bool gauss_fast_ok() const { return gauss_rows_ok() || gauss_stream_ok(); }   // kernels that merge u8 flags and write the sampler copy
     bool gauss_two_pass = false;      // SM_GAUSS_TWO_PASS=1: the unfused Gaussian passes (A/B; also used for maps below 160 x 64)
 
     // statistics: accumulator on the device; `stats_fused_valid` = the last thing that changed trail[cur] was a full-step

@@ -7,6 +7,7 @@
 #include "../../slime_mold_b200/csrc/agent_core.cuh"
 #include "../../slime_mold_b200/csrc/trail_core.cuh"
 #include "../../slime_mold_b200/csrc/gauss_stream.cuh"
+#include "../../slime_mold_b200/csrc/gauss_rows.cuh"
 #include <pthread.h>
 #include <cstring>
 #include <thread>
@@ -189,6 +190,83 @@ extern "C" int hc_gauss_stream(const float* tin, const void* cin, void* czero, f
     case 6: run_gauss_stream_r<6>(cm, surf, a, tc, gc); break;
     case 7: run_gauss_stream_r<7>(cm, surf, a, tc, gc); break;
     default: run_gauss_stream_r<8>(cm, surf, a, tc, gc); break;
+    }
+    return 0;
+}
+
+// ---- CTA emulation of the register-streaming Gaussian kernel (gauss_rows.cuh) -------------------------------------
+// Same idea; the warp shuffle becomes an exchange through a per-CTA array between two barriers (all threads of the
+// emulated CTA execute every shuffle: the kernel's control flow is uniform, only its memory operations are predicated).
+struct HostGrCtx : HostGsCtx {
+    smk::F4* xch;
+    bool warp_may_exit() const { return false; }
+    template <int R>
+    void neighbours(const smk::F4& v4, float (&v)[2 * R + 4]) const
+    {
+        xch[t] = v4;
+        sync();
+        const int lane = t & 31;
+        const smk::F4 l = lane > 0 ? xch[t - 1] : v4, r = lane < 31 ? xch[t + 1] : v4;    // SHFL up / down by one lane
+        sync();
+        const float lc[4] = {l.x, l.y, l.z, l.w}, rc[4] = {r.x, r.y, r.z, r.w};
+        for (int i = 0; i < R; ++i) { v[i] = lc[4 - R + i]; v[R + 4 + i] = rc[i]; }
+    }
+};
+
+template <int R, int CM, bool SURF>
+static void run_gauss_rows(const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+{
+    const int gx = (a.W + smk::kGrCtaCols - 1) / smk::kGrCtaCols, gy = (a.H + a.chunk_rows - 1) / a.chunk_rows;
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            std::vector<smk::F4> xch(smk::kGrNT);
+            pthread_barrier_t bar;
+            pthread_barrier_init(&bar, nullptr, smk::kGrNT);
+            std::vector<std::thread> th;
+            th.reserve(smk::kGrNT);
+            for (int t = 0; t < smk::kGrNT; ++t)
+                th.emplace_back([&, t]() {
+                    HostGrCtx cx;
+                    cx.t = t; cx.bxv = bx; cx.byv = by; cx.bar = &bar; cx.surf_w = a.W; cx.xch = xch.data();
+                    smk::gauss_rows_cta<R, CM, SURF>(cx, a, tc, gc);
+                });
+            for (auto& x : th) x.join();
+            pthread_barrier_destroy(&bar);
+        }
+}
+
+template <int R>
+static void run_gauss_rows_r(int cm, bool surf, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+{
+    if (cm == 0) run_gauss_rows<R, smk::GS_NONE, false>(a, tc, gc);
+    else if (cm == 1) { if (surf) run_gauss_rows<R, smk::GS_COUNTS, true>(a, tc, gc); else run_gauss_rows<R, smk::GS_COUNTS, false>(a, tc, gc); }
+    else { if (surf) run_gauss_rows<R, smk::GS_FLAGS, true>(a, tc, gc); else run_gauss_rows<R, smk::GS_FLAGS, false>(a, tc, gc); }
+}
+
+extern "C" int hc_gauss_rows(const float* tin, const void* cin, void* czero, float* tout, float* surf_out, int W, int H,
+                             int chunk_rows, int R, const float* weights, int cm, const hc_params* p, int wrap_y)
+{
+    if (W % 4 != 0 || W < smk::kGrMinW || H < smk::kGrMinRows || R < 1 || R > smk::kGrMaxR || chunk_rows < 1) return -1;
+    smd::TrailConsts tc{};
+    tc.dep = p->pheromone_deposition_amount;
+    volatile float d = p->decay_factor * 0.001f;
+    tc.decay_sub = d;
+    tc.rate = fminf(fmaxf(p->diffusion_rate, 0.0f), 1.0f);
+    volatile float om = 1.0f - tc.rate;
+    tc.one_minus_rate = om;
+    smk::GaussConsts gc{};
+    gc.R = R;
+    for (int i = 0; i <= 2 * R; ++i) gc.w[i] = weights[i];
+    smk::GsArgs a{};
+    a.tin = tin; a.cin = cin; a.czero = czero; a.tout = tout;
+    a.W = W; a.H = H; a.chunk_rows = chunk_rows; a.wrap_y = wrap_y;
+    a.surf = (unsigned long long)reinterpret_cast<uintptr_t>(surf_out); a.surf_row0 = 0;
+    const bool surf = surf_out != nullptr;
+    switch (R) {
+    case 1: run_gauss_rows_r<1>(cm, surf, a, tc, gc); break;
+    case 2: run_gauss_rows_r<2>(cm, surf, a, tc, gc); break;
+    case 3: run_gauss_rows_r<3>(cm, surf, a, tc, gc); break;
+    default: run_gauss_rows_r<4>(cm, surf, a, tc, gc); break;
     }
     return 0;
 }

@@ -31,7 +31,7 @@ def guards_intact(full, fill):
     return bool(np.all(np.isnan(g))) if isinstance(fill, float) and np.isnan(fill) else bool(np.all(g == fill))
 
 
-def run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=0, counts=None, want_surf=False):
+def run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=0, counts=None, want_surf=False, kernel="stream"):
     H, W = field.shape
     # the input sits between NaN guard rows too: a read outside the map would poison an output
     _, fin = guarded((H, W), np.float32, np.nan)
@@ -49,7 +49,8 @@ def run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=0, counts=None, 
         _, cin = guarded((H, W), np.uint8, 1)
         cin[:] = counts > 0
         czero_full, czero = guarded((H, W), np.uint8, 7)
-    rc = hostcheck.hc_gauss_stream(P(field, C.c_float),
+    fn = hostcheck.hc_gauss_rows if kernel == "rows" else hostcheck.hc_gauss_stream
+    rc = fn(P(field, C.c_float),
                                    None if cin is None else cin.ctypes.data_as(C.c_void_p),
                                    None if czero is None else czero.ctypes.data_as(C.c_void_p),
                                    P(out, C.c_float), None if surf is None else P(surf, C.c_float),
@@ -146,3 +147,62 @@ def test_stream_on_strips_bits(oracle, hostcheck, R, sigma, strips):
             new[y0:y0 + rows] = out[ghost:ghost + rows]
         cur = new
     assert bits_equal(cur, ref), mismatch_report(cur, ref, f"strips R={R}")
+
+
+# ---- the register-streaming kernel for small radii (slime_mold_b200/csrc/gauss_rows.cuh), same emulation ----
+# widths: one warp exactly (128), a ragged last warp, several CTAs (> 480 columns), a last output lane next to the seam;
+# chunk heights that are / are not multiples of the batch of 2R+1 rows, a ragged last chunk, one chunk for the whole map
+@pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.7, 128, 16, 16), (1, 0.5, 484, 50, 17), (2, 1.0, 416, 64, 48), (2, 1.3, 1000, 37, 16),
+                                               (3, 1.3, 516, 61, 40), (3, 2.0, 240, 33, 33), (4, 2.0, 512, 48, 25), (4, 2.5, 964, 40, 16)])
+def test_rows_diffuse_only_bits(oracle, hostcheck, R, sigma, W, H, chunk):
+    p = params_for(oracle, W, H, R, sigma, dep=1.0)
+    field = np.random.default_rng(R).random((H, W), dtype=np.float32)
+    ref = oracle.trail_pass(field, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
+    got, _, _ = run_stream(hostcheck, oracle, field, p, R, sigma, chunk, kernel="rows")
+    assert bits_equal(got, ref), mismatch_report(got, ref, f"rows R={R}")
+
+
+@pytest.mark.parametrize("cm,dep", [(1, 0.4), (1, 2.5), (2, 1.0)])
+@pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.5, 300, 40, 32), (2, 1.0, 292, 64, 20), (3, 1.5, 488, 30, 16), (4, 2.0, 520, 45, 45)])
+def test_rows_full_step_bits(oracle, hostcheck, cm, dep, R, sigma, W, H, chunk):
+    p = params_for(oracle, W, H, R, sigma, dep=dep)
+    rng = np.random.default_rng(100 * R + cm)
+    field = random_trail(W, H, seed=R, density=0.5)
+    counts = (rng.random((H, W)) < 0.2).astype(np.uint32) * rng.integers(1, 4, (H, W)).astype(np.uint32)
+    counts[0, :5] = 1; counts[-1, -5:] = 2; counts[:3, -1] = 1; counts[-3:, 0] = 3
+    ref = oracle.trail_pass(field, p, counts=counts.copy(), gauss_radius=R, gauss_sigma=sigma)
+    got, surf, czero = run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=cm, counts=counts, want_surf=True, kernel="rows")
+    assert bits_equal(got, ref), mismatch_report(got, ref, f"rows full step R={R} cm={cm}")
+    assert bits_equal(surf, ref), "sampler copy differs from the row-major output"
+    assert not czero.any(), "deposit marks of the next step's buffer were not all retired"
+
+
+@pytest.mark.parametrize("R,sigma,strips", [(1, 0.8, 2), (2, 1.0, 3), (4, 2.0, 2)])
+def test_rows_on_strips_bits(oracle, hostcheck, R, sigma, strips):
+    """Strip mode (no row wrap, ghost rows filled by the neighbours), as test_stream_on_strips_bits."""
+    W, H, ghost, passes = 256, 32 * strips, 6, 3
+    p = params_for(oracle, W, H, R, sigma, dep=1.0)
+    field = np.random.default_rng(strips).random((H, W), dtype=np.float32)
+    ref = field
+    for _ in range(passes):
+        ref = oracle.trail_pass(ref, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
+    w = oracle.gauss_weights(R, sigma)
+    rows = H // strips
+    cur = field
+    for _ in range(passes):
+        new = np.empty_like(cur)
+        for r in range(strips):
+            y0 = r * rows
+            buf = cur[np.arange(y0 - ghost, y0 + rows + ghost) % H].copy()
+            buf[:ghost - R] = np.nan                                       # rows the pass must not touch stay poisoned
+            buf[ghost + rows + R:] = np.nan
+            out = np.full((rows + 2 * ghost, W), np.nan, np.float32)
+            pp = params_for(oracle, W, rows, R, sigma, dep=1.0)
+            rc = hostcheck.hc_gauss_rows(P(buf[ghost:], C.c_float), None, None, P(out[ghost:], C.c_float), None,
+                                         C.c_int(W), C.c_int(rows), C.c_int(20), C.c_int(R), P(w, C.c_float), C.c_int(0),
+                                         C.byref(pp), C.c_int(0))
+            assert rc == 0
+            assert np.all(np.isnan(out[:ghost])) and np.all(np.isnan(out[ghost + rows:])), "stored into the ghost rows"
+            new[y0:y0 + rows] = out[ghost:ghost + rows]
+        cur = new
+    assert bits_equal(cur, ref), mismatch_report(cur, ref, f"rows on strips R={R}")

@@ -166,6 +166,64 @@ def gauss_stream_sweep():
     os.environ.pop("SM_GAUSS_CHUNK", None)
 
 
+def gauss_rows_sweep():
+    """EXTENSION: the register-streaming Gaussian kernel (gauss_rows.cuh, radius 1-4) against the shared-memory streaming
+    kernel and the tile kernel -- BASELINE config 5's radii 1-8 on 8192^2 and 16384^2, chunk heights, and the full step
+    in Gaussian mode at config-2 size."""
+    for S in (8192, 16384):
+        for R in (1, 2, 3, 4, 5, 6, 7, 8):
+            variants = [("stream", 0)]
+            if R <= 4:
+                variants = [("rows", 0)] + ([("rows", 32), ("rows", 128), ("rows", 256)] if S == 8192 else []) + variants
+            if R in (1, 2, 4, 8) and S == 8192:
+                variants.append(("tile", 0))
+            for kern, chunk in variants:
+                os.environ["SM_GAUSS_KERNEL"] = kern
+                os.environ["SM_GAUSS_CHUNK"] = str(chunk)
+                s = sm.Settings.default().clone(blur_radius=float(R), blur_sigma=R / 2.0)
+                be = sm.CudaBackend.new(S, S, s, agent_count=1, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+                be.write_trail(np.random.default_rng(0).random((256, S), dtype=np.float32), y0=0)
+                passes = max(6, min(60, int(6e9 / (S * S * 8))))
+                be.diffuse_only(3)
+                ms = event_time(be, lambda: be.diffuse_only(passes))
+                gbs = 8.0 * S * S * passes / (ms * 1e-3) / 1e9
+                emit({"sweep": "gauss_rows", "size": S, "radius": R, "kernel": kern, "chunk": chunk, "passes": passes,
+                      "ms_per_pass": ms / passes, "gbs": gbs, "frac_of_measured_peak": gbs / PEAK, "frac_of_8TBs": gbs / 8000.0})
+                be.close()
+    N, W, H = 16_777_216, 4096, 4096
+    for R, kern in ((1, "rows"), (2, "rows"), (2, "stream"), (4, "rows"), (4, "stream"), (8, "stream")):
+        os.environ["SM_GAUSS_KERNEL"] = kern
+        os.environ["SM_GAUSS_CHUNK"] = "0"
+        s = sm.Settings.default().clone(blur_radius=float(R), blur_sigma=R / 2.0)
+        be = sm.CudaBackend.new(W, H, s, agent_count=N, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+        be.init_agents(1)
+        be.step(100)
+        steps = 96
+        ms = event_time(be, lambda: be.step(steps))
+        be.set_timing_enabled(True); be.reset_timing()
+        be.step(48)
+        t = be.timing()
+        emit({"sweep": "gauss_full_step", "radius": R, "kernel": kern, "ms_per_step": ms / steps,
+              "agent_steps_per_s": N * steps / (ms * 1e-3), "agents_ms": t.agents_ms / t.agent_launches,
+              "trail_ms": t.trail_ms / t.trail_launches, "sort_ms_per_step": t.sort_ms / 48})
+        be.close()
+    os.environ.pop("SM_GAUSS_KERNEL", None)
+    os.environ.pop("SM_GAUSS_CHUNK", None)
+
+
+def gauss_rows_ncu_target():
+    """A few passes of the register-streaming kernel at 8192^2 (radius 2, then radius 4): the ncu target."""
+    os.environ["SM_GAUSS_KERNEL"] = "rows"
+    for R in (2, 4):
+        s = sm.Settings.default().clone(blur_radius=float(R), blur_sigma=R / 2.0)
+        be = sm.CudaBackend.new(8192, 8192, s, agent_count=1, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+        be.write_trail(np.random.default_rng(0).random((256, 8192), dtype=np.float32), y0=0)
+        be.diffuse_only(3)
+        be.sync()
+        be.close()
+    os.environ.pop("SM_GAUSS_KERNEL", None)
+
+
 def gauss_ncu_target():
     """A few streaming-kernel passes at 8192^2 (radius 8, then radius 2): the ncu target."""
     os.environ["SM_GAUSS_KERNEL"] = "stream"
@@ -204,6 +262,10 @@ if __name__ == "__main__":
         gauss_sweep()
     if "gauss_stream" in which:
         gauss_stream_sweep()
+    if "gauss_rows" in which:
+        gauss_rows_sweep()
     if "gauss_ncu" in which:
         gauss_ncu_target()
+    if "gauss_rows_ncu" in which:
+        gauss_rows_ncu_target()
     print("sweeps done in", round(time.time() - t0, 1), "s")
