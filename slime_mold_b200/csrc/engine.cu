@@ -548,21 +548,21 @@ bool sm_engine::gauss_rows_ok() const
            W >= (uint32_t)smk::kGrMinW && rows >= (uint32_t)smk::kGrMinRows;
 }
 
-template <int R, int CM, bool SURF>
-static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+template <int R, int CM, bool SURF, bool PK>
+static int launch_gauss_rows_pk(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
-    auto kern = smk::k_gauss_rows<R, CM, SURF>;
+    auto kern = smk::k_gauss_rows<R, CM, SURF, PK>;
     int per_sm = 0;
     SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, smk::kGrNT, 0));
     if (per_sm < 1) per_sm = 1;
-    // chunk height: about 64 rows (2R rows of pipeline fill per chunk), nudged so that the grid is a whole number of
-    // waves of num_sms x resident CTAs
+    // chunk height: about 64 / 128 / 256 rows (2R rows of pipeline fill per chunk), nudged so that the grid is a whole
+    // number of waves of num_sms x resident CTAs
     smk::GsArgs a = a0;
-    const uint64_t gx = (e->W + smk::kGrCtaCols - 1) / smk::kGrCtaCols;
+    const uint64_t gx = (e->W + smk::gr_cta_cols<R>() - 1) / smk::gr_cta_cols<R>();
     const uint64_t cap = (uint64_t)e->num_sms * per_sm;
     uint64_t chunk = (uint64_t)e->gauss_chunk;
     if (chunk == 0) {
-        const double want_chunks = (double)e->rows / 64.0;
+        const double want_chunks = (double)e->rows / (R <= 2 ? 64.0 : R <= 4 ? 128.0 : 256.0);
         uint64_t waves = (uint64_t)llround((double)gx * want_chunks / (double)cap);
         if (waves < 1) waves = 1;
         uint64_t n_chunks = waves * cap / gx;
@@ -575,6 +575,12 @@ static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a0, const smd::Tra
     kern<<<grid, smk::kGrNT, 0, e->stream>>>(a, tc, gc);
     SM_CUDA(cudaGetLastError());
     return SM_OK;
+}
+
+template <int R, int CM, bool SURF>
+static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+{
+    return e->gauss_rows_packed ? launch_gauss_rows_pk<R, CM, SURF, true>(e, a, tc, gc) : launch_gauss_rows_pk<R, CM, SURF, false>(e, a, tc, gc);
 }
 
 template <int R, int CM, bool SURF>
@@ -633,7 +639,7 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
             tmp[d + R] = exp(-(double)(d * d) / (2.0 * (double)params.blur_sigma * (double)params.blur_sigma));
             s += tmp[d + R];
         }
-        for (int d = 0; d <= 2 * R; ++d) gc.w[d] = (float)(tmp[d] / s);
+        for (int d = 0; d <= 2 * R; ++d) gc.set(d, (float)(tmp[d] / s));
     }
     const float* tin0 = trail_ptr(cur);
     float* tout0 = trail_ptr(1 - cur);
@@ -668,7 +674,11 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
             case 1: SM_TRY(go_rows(integral_constant<int, 1>{})); break;
             case 2: SM_TRY(go_rows(integral_constant<int, 2>{})); break;
             case 3: SM_TRY(go_rows(integral_constant<int, 3>{})); break;
-            default: SM_TRY(go_rows(integral_constant<int, 4>{})); break;
+            case 4: SM_TRY(go_rows(integral_constant<int, 4>{})); break;
+            case 5: SM_TRY(go_rows(integral_constant<int, 5>{})); break;
+            case 6: SM_TRY(go_rows(integral_constant<int, 6>{})); break;
+            case 7: SM_TRY(go_rows(integral_constant<int, 7>{})); break;
+            default: SM_TRY(go_rows(integral_constant<int, 8>{})); break;
             }
             timing.kernel_launches += 1;
             return SM_OK;
@@ -847,7 +857,8 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         const std::string gks = gk ? gk : "";
         e->gauss_stream = gks != "tile";
         e->gauss_rows = gks.empty() || gks == "rows" || gks == "auto";
-        e->gauss_rows_max_r = gks == "rows" ? smk::kGrMaxR : env_int("SM_GAUSS_ROWS_MAX_R", 2);
+        e->gauss_rows_max_r = gks == "rows" ? smk::kGrMaxR : env_int("SM_GAUSS_ROWS_MAX_R", 4);
+        e->gauss_rows_packed = env_int("SM_GAUSS_ROWS_PACKED", 0) != 0;    // FFMA2 column taps (A/B)
     }
     e->agent_stream_hint = env_int("SM_AGENT_STREAM_HINT", 0);   // 1: evict-first loads / stores of the agent state (A/B)
     e->gauss_chunk = env_int("SM_GAUSS_CHUNK", 0);         // rows per CTA of the streaming kernel (0 = chosen per map)

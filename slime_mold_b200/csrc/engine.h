@@ -83,9 +83,10 @@ struct sm_engine {
     int gauss_chunk = 0;              // SM_GAUSS_CHUNK: rows per CTA of the streaming kernel (0 = chosen per map)
     bool gauss_stream_ok() const;
     // the register-streaming kernel for small radii (gauss_rows.cuh): SM_GAUSS_KERNEL=rows forces it for every radius it
-    // takes (1-4), unset = radii up to gauss_rows_max_r (SM_GAUSS_ROWS_MAX_R), stream / tile = never
+    // takes (1-8), unset = radii up to gauss_rows_max_r (SM_GAUSS_ROWS_MAX_R), stream / tile = never
     bool gauss_rows = true;
-    int gauss_rows_max_r = 2;
+    int gauss_rows_max_r = 4;         // measured (profiles/): 0.73-0.96 of the HBM peak at radius 1-4 against 0.60-0.69 for the streaming kernel
+    bool gauss_rows_packed = false;   // SM_GAUSS_ROWS_PACKED=1: column taps as FFMA2 on column pairs
     bool gauss_rows_ok() const;
     bool gauss_fast_ok() const { return gauss_rows_ok() || gauss_stream_ok(); }   // kernels that merge u8 flags and write the sampler copy
     bool gauss_two_pass = false;      // SM_GAUSS_TWO_PASS=1: the unfused Gaussian passes (A/B; also used for maps below 160 x 64)

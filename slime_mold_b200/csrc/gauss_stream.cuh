@@ -28,6 +28,7 @@ namespace smk {
 #if defined(__CUDACC__)
 #define SM_KD __device__ __forceinline__
 #define SM_HDC __host__ __device__ constexpr
+#define SM_HDC_INLINE __host__ __device__ inline
 // A value the compiler must keep in a register from here on: kernel parameters are otherwise re-read from the constant bank
 // (LDC / LDCU) wherever they are used, and those reads share a scoreboard with the global loads around them -- ncu showed
 // each LDG of the prefetch waiting for the previous one to RETURN because an LDC sat between them.
@@ -38,13 +39,19 @@ using U4 = uint4;
 #else
 #define SM_KD inline
 #define SM_HDC constexpr
+#define SM_HDC_INLINE inline
 #define SM_OPAQUE32(x) ((void)0)
 #define SM_OPAQUE64(p) ((void)0)
 struct alignas(16) F4 { float x, y, z, w; };
 struct alignas(16) U4 { uint32_t x, y, z, w; };
 #endif
 
-struct GaussConsts { int R; float w[17]; };
+struct GaussConsts {
+    int R;
+    float w[17];
+    smd::f2 w2[17];         // (w[d], w[d]): the FFMA2 operand of the packed column taps (gauss_rows.cuh)
+    SM_HDC_INLINE void set(int d, float v) { w[d] = v; w2[d].lo = v; w2[d].hi = v; }
+};
 
 // deposit representation seen by the pass (same values as CM_* in kernels.cuh)
 enum { GS_NONE = 0, GS_COUNTS = 1, GS_FLAGS = 2 };

@@ -854,28 +854,34 @@ k_gauss_stream(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
     gauss_stream_cta<R, CM, SURF>(GsDevCtx{}, gs_smem, a, tc, gc);
 }
 
-// Register-streaming form for small radii (gauss_rows.cuh): device context and kernel.
+// Register-streaming form (gauss_rows.cuh): device context and kernel.
 struct GrDevCtx : GsDevCtx {
     __device__ __forceinline__ bool warp_may_exit() const { return true; }      // no barriers anywhere in the kernel
-    // v[0 .. R-1] = the last R cells of the lane to the left, v[R+4 .. 2R+3] = the first R cells of the lane to the right
+    // v[0 .. R-1] = the R cells to the left of this thread's four, v[R+4 .. 2R+3] = the R cells to their right: the
+    // nearest four of each side live in the adjacent lane, the rest (R > 4) two lanes away
     template <int R>
     __device__ __forceinline__ void neighbours(const float4& t, float (&v)[2 * R + 4]) const
     {
         const float c[4] = {t.x, t.y, t.z, t.w};
+        constexpr int FAR = R > 4 ? R - 4 : 0, NEAR = R - FAR;
 #pragma unroll
-        for (int i = 0; i < R; ++i) v[i] = __shfl_up_sync(0xffffffffu, c[4 - R + i], 1);
+        for (int i = 0; i < FAR; ++i) v[i] = __shfl_up_sync(0xffffffffu, c[4 - FAR + i], 2);
 #pragma unroll
-        for (int i = 0; i < R; ++i) v[R + 4 + i] = __shfl_down_sync(0xffffffffu, c[i], 1);
+        for (int i = 0; i < NEAR; ++i) v[FAR + i] = __shfl_up_sync(0xffffffffu, c[4 - NEAR + i], 1);
+#pragma unroll
+        for (int i = 0; i < NEAR; ++i) v[R + 4 + i] = __shfl_down_sync(0xffffffffu, c[i], 1);
+#pragma unroll
+        for (int i = 0; i < FAR; ++i) v[R + 4 + NEAR + i] = __shfl_down_sync(0xffffffffu, c[i], 2);
     }
 };
 
-template <int R> constexpr int gr_min_blocks() { return R == 1 ? 8 : R == 2 ? 5 : R == 3 ? 4 : 3; }
+template <int R> constexpr int gr_min_blocks() { return R == 1 ? 8 : R == 2 ? 5 : R == 3 ? 4 : R == 4 ? 3 : 2; }
 
-template <int R, int CM, bool SURF>
+template <int R, int CM, bool SURF, bool PK>
 static __global__ void __launch_bounds__(kGrNT, gr_min_blocks<R>())
 k_gauss_rows(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
 {
-    gauss_rows_cta<R, CM, SURF>(GrDevCtx{}, a, tc, gc);
+    gauss_rows_cta<R, CM, SURF, PK>(GrDevCtx{}, a, tc, gc);
 }
 
 // ---------------------------------------------------------------------------

@@ -175,7 +175,7 @@ extern "C" int hc_gauss_stream(const float* tin, const void* cin, void* czero, f
     tc.one_minus_rate = om;
     smk::GaussConsts gc{};
     gc.R = R;
-    for (int i = 0; i <= 2 * R; ++i) gc.w[i] = weights[i];
+    for (int i = 0; i <= 2 * R; ++i) gc.set(i, weights[i]);
     smk::GsArgs a{};
     a.tin = tin; a.cin = cin; a.czero = czero; a.tout = tout;
     a.W = W; a.H = H; a.chunk_rows = chunk_rows; a.wrap_y = wrap_y;
@@ -206,17 +206,19 @@ struct HostGrCtx : HostGsCtx {
         xch[t] = v4;
         sync();
         const int lane = t & 31;
-        const smk::F4 l = lane > 0 ? xch[t - 1] : v4, r = lane < 31 ? xch[t + 1] : v4;    // SHFL up / down by one lane
+        // SHFL up / down by one and by two lanes (a lane without a source keeps its own value)
+        const smk::F4 l1 = lane > 0 ? xch[t - 1] : v4, r1 = lane < 31 ? xch[t + 1] : v4;
+        const smk::F4 l2 = lane > 1 ? xch[t - 2] : v4, r2 = lane < 30 ? xch[t + 2] : v4;
         sync();
-        const float lc[4] = {l.x, l.y, l.z, l.w}, rc[4] = {r.x, r.y, r.z, r.w};
-        for (int i = 0; i < R; ++i) { v[i] = lc[4 - R + i]; v[R + 4 + i] = rc[i]; }
+        const float lc[8] = {l2.x, l2.y, l2.z, l2.w, l1.x, l1.y, l1.z, l1.w}, rc[8] = {r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+        for (int i = 0; i < R; ++i) { v[i] = lc[8 - R + i]; v[R + 4 + i] = rc[i]; }
     }
 };
 
-template <int R, int CM, bool SURF>
-static void run_gauss_rows(const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+template <int R, int CM, bool SURF, bool PK>
+static void run_gauss_rows_pk(const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
-    const int gx = (a.W + smk::kGrCtaCols - 1) / smk::kGrCtaCols, gy = (a.H + a.chunk_rows - 1) / a.chunk_rows;
+    const int gx = (a.W + smk::gr_cta_cols<R>() - 1) / smk::gr_cta_cols<R>(), gy = (a.H + a.chunk_rows - 1) / a.chunk_rows;
     for (int by = 0; by < gy; ++by)
         for (int bx = 0; bx < gx; ++bx) {
             std::vector<smk::F4> xch(smk::kGrNT);
@@ -228,11 +230,18 @@ static void run_gauss_rows(const smk::GsArgs& a, const smd::TrailConsts& tc, con
                 th.emplace_back([&, t]() {
                     HostGrCtx cx;
                     cx.t = t; cx.bxv = bx; cx.byv = by; cx.bar = &bar; cx.surf_w = a.W; cx.xch = xch.data();
-                    smk::gauss_rows_cta<R, CM, SURF>(cx, a, tc, gc);
+                    smk::gauss_rows_cta<R, CM, SURF, PK>(cx, a, tc, gc);
                 });
             for (auto& x : th) x.join();
             pthread_barrier_destroy(&bar);
         }
+}
+
+static bool g_rows_packed = false;
+template <int R, int CM, bool SURF>
+static void run_gauss_rows(const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+{
+    if (g_rows_packed) run_gauss_rows_pk<R, CM, SURF, true>(a, tc, gc); else run_gauss_rows_pk<R, CM, SURF, false>(a, tc, gc);
 }
 
 template <int R>
@@ -242,6 +251,8 @@ static void run_gauss_rows_r(int cm, bool surf, const smk::GsArgs& a, const smd:
     else if (cm == 1) { if (surf) run_gauss_rows<R, smk::GS_COUNTS, true>(a, tc, gc); else run_gauss_rows<R, smk::GS_COUNTS, false>(a, tc, gc); }
     else { if (surf) run_gauss_rows<R, smk::GS_FLAGS, true>(a, tc, gc); else run_gauss_rows<R, smk::GS_FLAGS, false>(a, tc, gc); }
 }
+
+extern "C" void hc_gauss_rows_set_packed(int on) { g_rows_packed = on != 0; }
 
 extern "C" int hc_gauss_rows(const float* tin, const void* cin, void* czero, float* tout, float* surf_out, int W, int H,
                              int chunk_rows, int R, const float* weights, int cm, const hc_params* p, int wrap_y)
@@ -256,7 +267,7 @@ extern "C" int hc_gauss_rows(const float* tin, const void* cin, void* czero, flo
     tc.one_minus_rate = om;
     smk::GaussConsts gc{};
     gc.R = R;
-    for (int i = 0; i <= 2 * R; ++i) gc.w[i] = weights[i];
+    for (int i = 0; i <= 2 * R; ++i) gc.set(i, weights[i]);
     smk::GsArgs a{};
     a.tin = tin; a.cin = cin; a.czero = czero; a.tout = tout;
     a.W = W; a.H = H; a.chunk_rows = chunk_rows; a.wrap_y = wrap_y;
@@ -266,7 +277,11 @@ extern "C" int hc_gauss_rows(const float* tin, const void* cin, void* czero, flo
     case 1: run_gauss_rows_r<1>(cm, surf, a, tc, gc); break;
     case 2: run_gauss_rows_r<2>(cm, surf, a, tc, gc); break;
     case 3: run_gauss_rows_r<3>(cm, surf, a, tc, gc); break;
-    default: run_gauss_rows_r<4>(cm, surf, a, tc, gc); break;
+    case 4: run_gauss_rows_r<4>(cm, surf, a, tc, gc); break;
+    case 5: run_gauss_rows_r<5>(cm, surf, a, tc, gc); break;
+    case 6: run_gauss_rows_r<6>(cm, surf, a, tc, gc); break;
+    case 7: run_gauss_rows_r<7>(cm, surf, a, tc, gc); break;
+    default: run_gauss_rows_r<8>(cm, surf, a, tc, gc); break;
     }
     return 0;
 }

@@ -149,12 +149,21 @@ def test_stream_on_strips_bits(oracle, hostcheck, R, sigma, strips):
     assert bits_equal(cur, ref), mismatch_report(cur, ref, f"strips R={R}")
 
 
-# ---- the register-streaming kernel for small radii (slime_mold_b200/csrc/gauss_rows.cuh), same emulation ----
+# ---- the register-streaming kernel (slime_mold_b200/csrc/gauss_rows.cuh; one halo lane per side up to radius 4, two above), same emulation ----
 # widths: one warp exactly (128), a ragged last warp, several CTAs (> 480 columns), a last output lane next to the seam;
 # chunk heights that are / are not multiples of the batch of 2R+1 rows, a ragged last chunk, one chunk for the whole map
+@pytest.fixture(params=[0, 1], ids=["scalar", "packed"])
+def rows_packed(request, hostcheck):
+    """Both forms of the column taps: scalar FFMA, and FFMA2 on column pairs (on the host a packed lane IS the scalar fma)."""
+    hostcheck.hc_gauss_rows_set_packed(C.c_int(request.param))
+    yield request.param
+    hostcheck.hc_gauss_rows_set_packed(C.c_int(0))
+
+
 @pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.7, 128, 16, 16), (1, 0.5, 484, 50, 17), (2, 1.0, 416, 64, 48), (2, 1.3, 1000, 37, 16),
-                                               (3, 1.3, 516, 61, 40), (3, 2.0, 240, 33, 33), (4, 2.0, 512, 48, 25), (4, 2.5, 964, 40, 16)])
-def test_rows_diffuse_only_bits(oracle, hostcheck, R, sigma, W, H, chunk):
+                                               (3, 1.3, 516, 61, 40), (3, 2.0, 240, 33, 33), (4, 2.0, 512, 48, 25), (4, 2.5, 964, 40, 16),
+                                               (5, 2.5, 452, 40, 23), (6, 3.0, 448, 61, 61), (7, 3.5, 128, 30, 17), (8, 4.0, 900, 50, 34)])
+def test_rows_diffuse_only_bits(oracle, hostcheck, rows_packed, R, sigma, W, H, chunk):
     p = params_for(oracle, W, H, R, sigma, dep=1.0)
     field = np.random.default_rng(R).random((H, W), dtype=np.float32)
     ref = oracle.trail_pass(field, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
@@ -163,8 +172,9 @@ def test_rows_diffuse_only_bits(oracle, hostcheck, R, sigma, W, H, chunk):
 
 
 @pytest.mark.parametrize("cm,dep", [(1, 0.4), (1, 2.5), (2, 1.0)])
-@pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.5, 300, 40, 32), (2, 1.0, 292, 64, 20), (3, 1.5, 488, 30, 16), (4, 2.0, 520, 45, 45)])
-def test_rows_full_step_bits(oracle, hostcheck, cm, dep, R, sigma, W, H, chunk):
+@pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.5, 300, 40, 32), (2, 1.0, 292, 64, 20), (3, 1.5, 488, 30, 16), (4, 2.0, 520, 45, 45),
+                                               (6, 3.0, 460, 36, 20), (8, 4.0, 448, 40, 40)])
+def test_rows_full_step_bits(oracle, hostcheck, rows_packed, cm, dep, R, sigma, W, H, chunk):
     p = params_for(oracle, W, H, R, sigma, dep=dep)
     rng = np.random.default_rng(100 * R + cm)
     field = random_trail(W, H, seed=R, density=0.5)
@@ -177,10 +187,10 @@ def test_rows_full_step_bits(oracle, hostcheck, cm, dep, R, sigma, W, H, chunk):
     assert not czero.any(), "deposit marks of the next step's buffer were not all retired"
 
 
-@pytest.mark.parametrize("R,sigma,strips", [(1, 0.8, 2), (2, 1.0, 3), (4, 2.0, 2)])
+@pytest.mark.parametrize("R,sigma,strips", [(1, 0.8, 2), (2, 1.0, 3), (4, 2.0, 2), (7, 3.0, 2)])
 def test_rows_on_strips_bits(oracle, hostcheck, R, sigma, strips):
     """Strip mode (no row wrap, ghost rows filled by the neighbours), as test_stream_on_strips_bits."""
-    W, H, ghost, passes = 256, 32 * strips, 6, 3
+    W, H, ghost, passes = 256, 32 * strips, 9, 3
     p = params_for(oracle, W, H, R, sigma, dep=1.0)
     field = np.random.default_rng(strips).random((H, W), dtype=np.float32)
     ref = field

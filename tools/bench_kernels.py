@@ -167,18 +167,19 @@ def gauss_stream_sweep():
 
 
 def gauss_rows_sweep():
-    """EXTENSION: the register-streaming Gaussian kernel (gauss_rows.cuh, radius 1-4) against the shared-memory streaming
-    kernel and the tile kernel -- BASELINE config 5's radii 1-8 on 8192^2 and 16384^2, chunk heights, and the full step
-    in Gaussian mode at config-2 size."""
+    """EXTENSION: the register-streaming Gaussian kernel (gauss_rows.cuh; scalar and FFMA2-packed column taps) against the
+    shared-memory streaming kernel -- BASELINE config 5's radii 1-8 on 8192^2 and 16384^2, chunk heights, and the full
+    step in Gaussian mode at config-2 size."""
     for S in (8192, 16384):
         for R in (1, 2, 3, 4, 5, 6, 7, 8):
-            variants = [("stream", 0)]
-            if R <= 4:
-                variants = [("rows", 0)] + ([("rows", 32), ("rows", 128), ("rows", 256)] if S == 8192 else []) + variants
-            if R in (1, 2, 4, 8) and S == 8192:
-                variants.append(("tile", 0))
+            variants = [("rows", 0), ("rows_packed", 0)]
+            if S == 8192:
+                variants.append(("stream", 0))
+                if R in (2, 5, 8):
+                    variants += [("rows_packed", 64), ("rows_packed", 128), ("rows_packed", 512)]
             for kern, chunk in variants:
-                os.environ["SM_GAUSS_KERNEL"] = kern
+                os.environ["SM_GAUSS_KERNEL"] = "rows" if kern.startswith("rows") else kern
+                os.environ["SM_GAUSS_ROWS_PACKED"] = "1" if kern == "rows_packed" else "0"
                 os.environ["SM_GAUSS_CHUNK"] = str(chunk)
                 s = sm.Settings.default().clone(blur_radius=float(R), blur_sigma=R / 2.0)
                 be = sm.CudaBackend.new(S, S, s, agent_count=1, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
@@ -190,9 +191,11 @@ def gauss_rows_sweep():
                 emit({"sweep": "gauss_rows", "size": S, "radius": R, "kernel": kern, "chunk": chunk, "passes": passes,
                       "ms_per_pass": ms / passes, "gbs": gbs, "frac_of_measured_peak": gbs / PEAK, "frac_of_8TBs": gbs / 8000.0})
                 be.close()
+    os.environ.pop("SM_GAUSS_ROWS_PACKED", None)
     N, W, H = 16_777_216, 4096, 4096
-    for R, kern in ((1, "rows"), (2, "rows"), (2, "stream"), (4, "rows"), (4, "stream"), (8, "stream")):
-        os.environ["SM_GAUSS_KERNEL"] = kern
+    for R, kern in ((2, "rows"), (2, "rows_packed"), (4, "rows_packed"), (8, "rows_packed"), (8, "stream")):
+        os.environ["SM_GAUSS_KERNEL"] = "rows" if kern.startswith("rows") else kern
+        os.environ["SM_GAUSS_ROWS_PACKED"] = "1" if kern == "rows_packed" else "0"
         os.environ["SM_GAUSS_CHUNK"] = "0"
         s = sm.Settings.default().clone(blur_radius=float(R), blur_sigma=R / 2.0)
         be = sm.CudaBackend.new(W, H, s, agent_count=N, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
@@ -209,12 +212,14 @@ def gauss_rows_sweep():
         be.close()
     os.environ.pop("SM_GAUSS_KERNEL", None)
     os.environ.pop("SM_GAUSS_CHUNK", None)
+    os.environ.pop("SM_GAUSS_ROWS_PACKED", None)
 
 
 def gauss_rows_ncu_target():
-    """A few passes of the register-streaming kernel at 8192^2 (radius 2, then radius 4): the ncu target."""
+    """A few passes of the register-streaming kernel at 8192^2 (radius 4, then radius 8; packed column taps): the ncu target."""
     os.environ["SM_GAUSS_KERNEL"] = "rows"
-    for R in (2, 4):
+    os.environ["SM_GAUSS_ROWS_PACKED"] = "1"
+    for R in (4, 8):
         s = sm.Settings.default().clone(blur_radius=float(R), blur_sigma=R / 2.0)
         be = sm.CudaBackend.new(8192, 8192, s, agent_count=1, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
         be.write_trail(np.random.default_rng(0).random((256, 8192), dtype=np.float32), y0=0)
