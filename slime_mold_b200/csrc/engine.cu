@@ -580,7 +580,9 @@ static int launch_gauss_rows_pk(sm_engine* e, const smk::GsArgs& a0, const smd::
 template <int R, int CM, bool SURF>
 static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
-    return e->gauss_rows_packed ? launch_gauss_rows_pk<R, CM, SURF, true>(e, a, tc, gc) : launch_gauss_rows_pk<R, CM, SURF, false>(e, a, tc, gc);
+    // packed column taps: 3-5 % faster at radius 3-4, neutral at 1-2; above 4 the extra registers cost a resident CTA
+    const bool pk = e->gauss_rows_packed < 0 ? R <= 4 : e->gauss_rows_packed != 0;
+    return pk ? launch_gauss_rows_pk<R, CM, SURF, true>(e, a, tc, gc) : launch_gauss_rows_pk<R, CM, SURF, false>(e, a, tc, gc);
 }
 
 template <int R, int CM, bool SURF>
@@ -849,16 +851,17 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
     e->gauss_two_pass = env_int("SM_GAUSS_TWO_PASS", 0) != 0;
     {
-        // "stream" (gauss_stream.cuh; default wherever it applies: W % 4 == 0, W >= 288, >= 64 rows) | "tile" (k_gauss_fused).
-        // Measured (profiles/): stream is 1.2-1.4x faster at radius 4-8 and lets a Gaussian full step keep the u8 deposit
-        // flags and the sampler copy (6.6e10 vs 4.4e10 agent-steps/s on config 2); the tile kernel is within 5-8 % at radius 2.
-        // "rows" (gauss_rows.cuh, radius <= 4) is the register-streaming kernel: unset = used up to SM_GAUSS_ROWS_MAX_R.
+        // Unset: the register-streaming kernel (gauss_rows.cuh) up to radius SM_GAUSS_ROWS_MAX_R (5), the shared-memory streaming
+        // kernel (gauss_stream.cuh) above, the tile kernel (k_gauss_fused) for maps the first two do not take (W % 4 != 0, tiny).
+        // "rows" / "stream" / "tile" force one of them wherever it applies.  Measured on 8192^2-16384^2 (profiles/), fraction of
+        // the HBM peak: rows 0.88-0.95 (R 1-2), 0.77-0.83 (R 3-4), 0.64-0.69 (R 5); stream 0.51-0.69; tile 0.31-0.61.  rows and
+        // stream let a Gaussian full step keep the u8 deposit flags and the sampler copy (6.8e10 vs 4.4e10 agent-steps/s).
         const char* gk = getenv("SM_GAUSS_KERNEL");
         const std::string gks = gk ? gk : "";
         e->gauss_stream = gks != "tile";
         e->gauss_rows = gks.empty() || gks == "rows" || gks == "auto";
-        e->gauss_rows_max_r = gks == "rows" ? smk::kGrMaxR : env_int("SM_GAUSS_ROWS_MAX_R", 4);
-        e->gauss_rows_packed = env_int("SM_GAUSS_ROWS_PACKED", 0) != 0;    // FFMA2 column taps (A/B)
+        e->gauss_rows_max_r = gks == "rows" ? smk::kGrMaxR : env_int("SM_GAUSS_ROWS_MAX_R", 5);
+        e->gauss_rows_packed = env_int("SM_GAUSS_ROWS_PACKED", -1);        // FFMA2 column taps: -1 = where measured faster (radius <= 4)
     }
     e->agent_stream_hint = env_int("SM_AGENT_STREAM_HINT", 0);   // 1: evict-first loads / stores of the agent state (A/B)
     e->gauss_chunk = env_int("SM_GAUSS_CHUNK", 0);         // rows per CTA of the streaming kernel (0 = chosen per map)

@@ -85,8 +85,8 @@ struct sm_engine {
     // the register-streaming kernel for small radii (gauss_rows.cuh): SM_GAUSS_KERNEL=rows forces it for every radius it
     // takes (1-8), unset = radii up to gauss_rows_max_r (SM_GAUSS_ROWS_MAX_R), stream / tile = never
     bool gauss_rows = true;
-    int gauss_rows_max_r = 4;         // measured (profiles/): 0.73-0.96 of the HBM peak at radius 1-4 against 0.60-0.69 for the streaming kernel
-    bool gauss_rows_packed = false;   // SM_GAUSS_ROWS_PACKED=1: column taps as FFMA2 on column pairs
+    int gauss_rows_max_r = 5;         // measured (profiles/): 0.64-0.95 of the HBM peak at radius 1-5 against 0.55-0.69 for the streaming kernel; a tie at 6, behind at 7-8
+    int gauss_rows_packed = -1;       // SM_GAUSS_ROWS_PACKED: column taps as FFMA2 on column pairs (1), scalar (0), where faster (-1: radius <= 4)
     bool gauss_rows_ok() const;
     bool gauss_fast_ok() const { return gauss_rows_ok() || gauss_stream_ok(); }   // kernels that merge u8 flags and write the sampler copy
     bool gauss_two_pass = false;      // SM_GAUSS_TWO_PASS=1: the unfused Gaussian passes (A/B; also used for maps below 160 x 64)

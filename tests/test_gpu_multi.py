@@ -27,7 +27,12 @@ CASES = {
     "diffuse_mix": ("Sponge", 512, 1024, 200_000, 30, False),
     # per-rank snapshot files mid-run, restored into freshly created engines (new communicator), then continued
     "snapshot_mid": ("Waves", 256, 512, 100_000, 40, False),
+    # EXTENSION: Gaussian diffusion-only passes on strips (BASELINE config 5 at 2/4/8 GPUs): the pass reads R ghost rows of
+    # each neighbour, refreshed after every pass; radius 3 runs the register-streaming kernel, radius 6 the shared-memory one
+    "gauss_rows_diffuse": ("Default", 512, 512, 20_000, 6, False),
+    "gauss_stream_diffuse": ("Default", 512, 512, 20_000, 6, False),
 }
+GAUSS = {"gauss_rows_diffuse": (3, 1.5), "gauss_stream_diffuse": (6, 3.0)}
 
 
 def _worker(rank, world, case, out_dir, exchange):
@@ -54,7 +59,10 @@ def _worker(rank, world, case, out_dir, exchange):
             uid = open(idf, "rb").read()
         be.comm_init(uid)
 
-    be = sm.CudaBackend.new(W, H, s, agent_count=N, device=rank, rank=rank, world_size=world)
+    if case in GAUSS:
+        s = s.clone(blur_radius=float(GAUSS[case][0]), blur_sigma=GAUSS[case][1], pheromone_diffusion_rate=0.8)
+    be = sm.CudaBackend.new(W, H, s, agent_count=N, device=rank, rank=rank, world_size=world,
+                            flags=sm.SM_FLAG_GAUSSIAN_BLUR if case in GAUSS else 0)
     connect(be, "a")
     if device_init:
         be.init_agents(seed=11)
@@ -75,6 +83,8 @@ def _worker(rank, world, case, out_dir, exchange):
         connect(be, "b")
         be.load_snapshot(snap)
         be.step(steps - steps // 2)
+    elif case in GAUSS:
+        be.diffuse_only(steps)
     elif case == "diffuse_mix":
         be.step(steps // 3)
         be.diffuse_only(7)
@@ -100,7 +110,7 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
     preset, W, H, N, steps, device_init = CASES[case]
     if H // world < 32:
         pytest.skip("strips too thin for this case")
-    if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips", "diffuse_mix"):
+    if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips", "diffuse_mix", "gauss_rows_diffuse"):
         pytest.skip("NCCL path: three representative cases")
     mp.spawn(_worker, args=(world, case, str(tmp_path), exchange), nprocs=world, join=True)
     u = preset_uniform(preset, W, H)
@@ -113,6 +123,13 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
             ss = s0.clone(pheromone_deposition_amount=dep)
             sim.p = to_oracle_params(oracle, sm2.SimSizeUniform.new(W, H, ss.pheromone_decay_factor, ss))
             sim.step(steps // 5)
+    elif case in GAUSS:
+        import slime_mold_b200 as sm2
+        R, sigma = GAUSS[case]
+        ss = sm2.init_preset_manager().get_preset(preset).settings.clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=0.8)
+        sim.p = to_oracle_params(oracle, sm2.SimSizeUniform.new(W, H, ss.pheromone_decay_factor, ss))
+        for _ in range(steps):
+            sim.trail = oracle.trail_pass(sim.trail, sim.p, counts=None, gauss_radius=R, gauss_sigma=sigma)
     elif case == "diffuse_mix":
         for n_steps, n_passes in ((steps // 3, 7), (steps // 3, 1), (steps // 3, 0)):
             sim.step(n_steps)
