@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libslime_b200.so")
-SOURCES = ["engine.cu", "exchange.cu"]
+SOURCES = ["engine.cu", "gauss.cu", "exchange.cu"]
 HEADERS = ["engine.h", "kernels.cuh", "agent_core.cuh", "trail_core.cuh", "gauss_stream.cuh", "gauss_rows.cuh", "device_math.cuh",
            os.path.join("..", "..", "include", "slime_b200.h")]
 
@@ -47,12 +47,29 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    # the translation units are compiled side by side (the kernel templates make each of them a minute or two of ptxas)
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log, failed = "", False
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        log += " ".join(cmd) + "\n" + out
+        failed |= pr.returncode != 0
+    if not failed:
+        cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-ldl"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        failed = res.returncode != 0
+    for obj in objs:
+        if os.path.exists(obj):
+            os.remove(obj)
     with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+        f.write(log)
+    if failed:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed (see slime_mold_b200/build.log)")
     if verbose:
