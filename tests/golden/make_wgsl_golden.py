@@ -52,29 +52,41 @@ CASES = [
     ("lowdep", "Default", {"pheromone_deposition_amount": 0.3, "agent_jitter": 0.1, "decay_factor": 35.0}),
 ]
 
+# tiny and ragged maps (the engine's generic kernels: W % 4 != 0, fewer cells than a warp, a single cell): short sensors so
+# that some land inside, agents wrap around the map several times
+SMALL = {"agent_sensor_distance": 2.5, "agent_jitter": 0.15}
+SMALL_CASES = [
+    ("tiny_1x1", 1, 1, 6, SMALL),
+    ("tiny_2x3", 2, 3, 12, SMALL),
+    ("ragged_13x7", 13, 7, 60, SMALL),
+    ("ragged_37x5", 37, 5, 80, {"agent_sensor_distance": 1.5, "diffusion_rate": 0.5}),
+]
+SMALL_FRAMES = 4
 
-def case_uniform(preset, over):
-    u = preset_uniform(preset, W, H)
+
+def case_uniform(preset, over, w=W, h=H):
+    u = preset_uniform(preset, w, h)
     for k, v in over.items():
         setattr(u, k, v)
     return u
 
 
-def initial_state(u, seed):
+def initial_state(u, seed, n=N):
+    w, h = int(u.width), int(u.height)
     rng = np.random.default_rng(seed)
-    ag = np.stack([rng.random(N) * W, rng.random(N) * H, rng.random(N) * 6.2831855,
-                   u.agent_speed_min + rng.random(N) * (u.agent_speed_max - u.agent_speed_min)], axis=1).astype(np.float32)
-    return ag, random_trail(W, H, seed=seed + 1, density=0.35)
+    ag = np.stack([rng.random(n) * w, rng.random(n) * h, rng.random(n) * 6.2831855,
+                   u.agent_speed_min + rng.random(n) * (u.agent_speed_max - u.agent_speed_min)], axis=1).astype(np.float32)
+    return ag, random_trail(w, h, seed=seed + 1, density=0.35 if w * h > 100 else 0.8)
 
 
-def make_case(src, tag, preset, over):
-    u = case_uniform(preset, over)
-    ag0, tr0 = initial_state(u, SEED)
-    out = dict(params=np.frombuffer(bytes(u), dtype=np.uint8), agents0=ag0, trail0=tr0, frames=FRAMES,
+def make_case(src, tag, preset, over, w=W, h=H, n=N, frames=FRAMES):
+    u = case_uniform(preset, over, w, h)
+    ag0, tr0 = initial_state(u, SEED, n)
+    out = dict(params=np.frombuffer(bytes(u), dtype=np.uint8), agents0=ag0, trail0=tr0, frames=frames,
                shader_sha256=source_digest(src))
     for sched, key in (("sequential", "seq"), ("lockstep", "lock")):
         sim = ShaderSim(src, u, ag0, tr0, SpecMath(so))
-        for k in range(1, FRAMES + 1):
+        for k in range(1, frames + 1):
             sim.frame(sched)
             out[f"{key}_agents{k}"] = sim.agents.data.copy()
             out[f"{key}_trail{k}"] = sim.trail2d.copy()
@@ -121,10 +133,15 @@ def make_display(src):
 if __name__ == "__main__":
     so.build()
     csrc, dsrc = shader_source("compute.wgsl"), shader_source("display.wgsl")
-    for tag, preset, over in CASES:
+    only_small = "--small" in sys.argv          # the small cases were added later: same generator, same shader files
+    for tag, preset, over in ([] if only_small else CASES):
         t = time.time()
         make_case(csrc, tag, preset, over)
         print(f"wgsl_{tag}.npz  {time.time() - t:.1f} s")
-    make_edge(csrc)
-    make_display(dsrc)
-    print("wgsl_edge.npz, wgsl_display.npz")
+    for tag, w, h, n, over in SMALL_CASES:
+        make_case(csrc, tag, "Default", over, w, h, n, SMALL_FRAMES)
+        print(f"wgsl_{tag}.npz")
+    if not only_small:
+        make_edge(csrc)
+        make_display(dsrc)
+        print("wgsl_edge.npz, wgsl_display.npz")

@@ -13,7 +13,7 @@ from conftest import bits_equal, mismatch_report
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-LOCKSTEP_TAGS = ["default", "sponge", "waves", "snake", "mesh_jitter"]
+LOCKSTEP_TAGS = ["default", "sponge", "waves", "snake", "mesh_jitter", "tiny_1x1", "tiny_2x3", "ragged_13x7", "ragged_37x5"]
 
 
 def load(tag):

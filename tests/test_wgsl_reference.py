@@ -28,8 +28,9 @@ sys.path.insert(0, GOLD)
 import make_wgsl_golden as mk  # noqa: E402
 import wgsl_reference as wr  # noqa: E402
 
-CASE_TAGS = [c[0] for c in mk.CASES]
-LOCKSTEP_TAGS = [c[0] for c in mk.CASES if c[2].get("pheromone_deposition_amount", 1.0) >= 1.0]
+SMALL_TAGS = [c[0] for c in mk.SMALL_CASES]                   # 1x1, 2x3, 13x7, 37x5 maps
+CASE_TAGS = [c[0] for c in mk.CASES] + SMALL_TAGS
+LOCKSTEP_TAGS = [c[0] for c in mk.CASES if c[2].get("pheromone_deposition_amount", 1.0) >= 1.0] + SMALL_TAGS
 
 
 def load(tag):
@@ -108,7 +109,7 @@ def test_oracle_within_tolerance_of_libm_backend(oracle, tag):
     dang = np.minimum(dang, np.abs(dang - np.float32(2 * np.pi)))
     tol = 1e-5 + 0.011 * u.agent_jitter
     ok = dang <= tol
-    assert ok.mean() > 0.97
+    assert ok.mean() > (0.97 if len(ok) > 100 else 0.9)
     move = u.agent_speed_max * 0.016
     dx = np.abs(a[ok, 0] - b[ok, 0])
     dy = np.abs(a[ok, 1] - b[ok, 1])
@@ -130,7 +131,7 @@ def test_fixture_digests_match_the_shader_files():
 
 
 @needs_reference
-@pytest.mark.parametrize("tag", ["default", "mesh_jitter"])
+@pytest.mark.parametrize("tag", ["default", "mesh_jitter", "tiny_1x1", "ragged_13x7"])
 def test_shader_rerun_reproduces_fixture(oracle, tag):
     g = load(tag)
     u = uniform_of(g)
@@ -141,8 +142,7 @@ def test_shader_rerun_reproduces_fixture(oracle, tag):
     sim = wr.ShaderSim(src, u, g["agents0"], g["trail0"], wr.SpecMath(oracle))
     sim.run_agents("sequential")
     sim.run_decay()
-    n = 64                                                      # first agents only see the initial field + earlier deposits
-    assert bits_equal(sim.agents.data[:n], g["seq_agents1"][:n])
+    assert bits_equal(sim.agents.data, g["seq_agents1"])
 
 
 @needs_reference
