@@ -633,6 +633,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         e->gauss_stream = gks != "tile";
         e->gauss_rows = gks.empty() || gks == "rows" || gks == "auto";
         e->gauss_rows_max_r = gks == "rows" ? smk::kGrMaxR : env_int("SM_GAUSS_ROWS_MAX_R", 5);
+        e->gauss_stream_packed = env_int("SM_GAUSS_STREAM_PACKED", 0) != 0;
         e->gauss_rows_packed = env_int("SM_GAUSS_ROWS_PACKED", -1);        // FFMA2 column taps: -1 = where measured faster (radius <= 4)
     }
     e->agent_stream_hint = env_int("SM_AGENT_STREAM_HINT", 0);   // 1: evict-first loads / stores of the agent state (A/B)

@@ -46,7 +46,7 @@ bool sm_engine::gauss_rows_ok() const
            W >= (uint32_t)smk::kGrMinW && rows >= (uint32_t)smk::kGrMinRows;
 }
 
-template <int R, int CM, bool SURF, bool PK>
+template <int R, int CM, bool SURF, int PK>
 static int launch_gauss_rows_pk(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
     auto kern = smk::k_gauss_rows<R, CM, SURF, PK>;
@@ -80,18 +80,33 @@ static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a, const smd::Trai
 {
     // packed column taps: 3-5 % faster at radius 3-4, neutral at 1-2; above 4 the extra registers cost a resident CTA
     // (measured at radius 5-8 too, then dropped from the build: each of those instantiations is 2-3 K instructions)
-    if constexpr (R <= 4) {
-        const bool pk = e->gauss_rows_packed < 0 ? true : e->gauss_rows_packed != 0;
-        return pk ? launch_gauss_rows_pk<R, CM, SURF, true>(e, a, tc, gc) : launch_gauss_rows_pk<R, CM, SURF, false>(e, a, tc, gc);
+    if constexpr (R <= 5) {
+        const int pk = e->gauss_rows_packed < 0 ? (R <= 4 ? 1 : 0) : e->gauss_rows_packed;
+        if (pk >= 2) return launch_gauss_rows_pk<R, CM, SURF, 2>(e, a, tc, gc);
+        if (pk == 1) return launch_gauss_rows_pk<R, CM, SURF, 1>(e, a, tc, gc);
+        return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
     } else {
-        return launch_gauss_rows_pk<R, CM, SURF, false>(e, a, tc, gc);
+        return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
     }
 }
 
+template <int R, int CM, bool SURF, bool PK>
+static int launch_gauss_stream_pk(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc);
+
 template <int R, int CM, bool SURF>
-static int launch_gauss_stream(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+static int launch_gauss_stream(sm_engine* e, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
-    auto kern = smk::k_gauss_stream<R, CM, SURF>;
+    // packed taps (SM_GAUSS_STREAM_PACKED) are built for the radii this kernel is the default for
+    if constexpr (R >= 5) {
+        if (e->gauss_stream_packed) return launch_gauss_stream_pk<R, CM, SURF, true>(e, a, tc, gc);
+    }
+    return launch_gauss_stream_pk<R, CM, SURF, false>(e, a, tc, gc);
+}
+
+template <int R, int CM, bool SURF, bool PK>
+static int launch_gauss_stream_pk(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
+{
+    auto kern = smk::k_gauss_stream<R, CM, SURF, PK>;
     const size_t smem = smk::gs_smem_bytes<R>();
     SM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

@@ -12,8 +12,9 @@
 //   v-blur   a row of h-blurred cells is tap d of the output d rows above it, so the taps of an output arrive in the
 //            oracle's order d = 0 .. 2R: P = 2R+1 live accumulator quads, each finished (mixed with its decayed centre,
 //            stored) and reset once per P rows.  The batch is unrolled P times, so every accumulator's role in every
-//            row is static -- no register is ever moved or indexed dynamically.  PK instantiations run these taps as
-//            FFMA2 on column pairs (the weight pair (w, w) is a uniform-register operand: no per-thread cost).
+//            row is static -- no register is ever moved or indexed dynamically.  PK >= 1 instantiations run these taps
+//            as FFMA2 on column pairs (the weight pair (w, w) is a uniform-register operand: no per-thread cost); PK == 2
+//            also packs the half of the row taps whose operands are aligned pairs.
 //
 // Arithmetic per output: exactly the oracle's statements (acc = 0.0f; acc = fma(w[d], v[d], acc), d = -R..R; rows after
 // columns; mix(decayed centre, acc, rate)) -- a packed lane rounds like the scalar instruction -- so the bits equal the
@@ -36,7 +37,7 @@ template <int R> SM_HDC int gr_warp_cols() { return (32 - 2 * gr_halo_lanes<R>()
 template <int R> SM_HDC int gr_cta_cols() { return (kGrNT / 32) * gr_warp_cols<R>(); }
 template <int R> SM_HDC int gr_load_rows() { return R <= 4 ? 2 * R + 1 : 6; }                 // rows requested at a time
 
-template <int R, int CM, bool SURF, bool PK, class Ctx>
+template <int R, int CM, bool SURF, int PK, class Ctx>
 SM_KD void gauss_rows_cta(const Ctx& cx, const GsArgs& a, const smd::TrailConsts& tc, const GaussConsts& gc)
 {
     static_assert(R >= 1 && R <= kGrMaxR, "radius");
@@ -139,16 +140,36 @@ SM_KD void gauss_rows_cta(const Ctx& cx, const GsArgs& a, const smd::TrailConsts
             cx.template neighbours<R>(t, v);
             v[R] = t.x; v[R + 1] = t.y; v[R + 2] = t.z; v[R + 3] = t.w;
             float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
+            if (PK >= 2) {
+                // the taps with an even offset read the aligned pairs (v[d], v[d+1]), (v[d+2], v[d+3]): one FFMA2 for two
+                // outputs; the odd ones stay scalar.  Every output still sees its taps in the order d = 0 .. 2R.
+                smd::f2 h01 = smd::mk2(0.0f, 0.0f), h23 = smd::mk2(0.0f, 0.0f);
 #pragma unroll
-            for (int d = 0; d < P; ++d) {
-                const float w = gc.w[d];
-                h0 = smd::fma(w, v[d], h0);
-                h1 = smd::fma(w, v[d + 1], h1);
-                h2 = smd::fma(w, v[d + 2], h2);
-                h3 = smd::fma(w, v[d + 3], h3);
+                for (int d = 0; d < P; ++d) {
+                    if (d % 2 == 0) {
+                        h01 = smd::fma2(gc.w2[d], smd::mk2(v[d], v[d + 1]), h01);
+                        h23 = smd::fma2(gc.w2[d], smd::mk2(v[d + 2], v[d + 3]), h23);
+                    } else {
+                        const float w = gc.w[d];
+                        h01.lo = smd::fma(w, v[d], h01.lo);
+                        h01.hi = smd::fma(w, v[d + 1], h01.hi);
+                        h23.lo = smd::fma(w, v[d + 2], h23.lo);
+                        h23.hi = smd::fma(w, v[d + 3], h23.hi);
+                    }
+                }
+                h0 = h01.lo; h1 = h01.hi; h2 = h23.lo; h3 = h23.hi;
+            } else {
+#pragma unroll
+                for (int d = 0; d < P; ++d) {
+                    const float w = gc.w[d];
+                    h0 = smd::fma(w, v[d], h0);
+                    h1 = smd::fma(w, v[d + 1], h1);
+                    h2 = smd::fma(w, v[d + 2], h2);
+                    h3 = smd::fma(w, v[d + 3], h3);
+                }
             }
             // v-blur: this row is tap d of the output d rows above stream row s (chunk-relative output row s - d)
-            if (PK) {
+            if (PK >= 1) {
                 const smd::f2 h01 = smd::mk2(h0, h1), h23 = smd::mk2(h2, h3);
 #pragma unroll
                 for (int d = 0; d < P; ++d) {

@@ -81,7 +81,7 @@ struct GsArgs {
 struct GsFoldYes { static constexpr bool value = true; };      // prefetch instantiations: rows folded across the seam, or not
 struct GsFoldNo { static constexpr bool value = false; };
 
-template <int R, int CM, bool SURF, class Ctx>
+template <int R, int CM, bool SURF, bool PK, class Ctx>
 SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs& a, const smd::TrailConsts& tc, const GaussConsts& gc)
 {
     constexpr int TX = kGsTX, NT = kGsNT, B = gs_batch<R>(), RA = gs_ra<R>(), DC = gs_dc<R>();
@@ -208,13 +208,33 @@ SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs
                     v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
                 }
                 float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                if (PK) {
+                    // taps whose window offset is even read the aligned pairs (v[i], v[i+1]), (v[i+2], v[i+3]) the LDS.128s
+                    // delivered: one FFMA2 (uniform-register weight pair) for two outputs; the others stay scalar
+                    smd::f2 a01 = smd::mk2(0.0f, 0.0f), a23 = smd::mk2(0.0f, 0.0f);
 #pragma unroll
-                for (int d = 0; d <= 2 * R; ++d) {
-                    const float w = gc.w[d];
-                    a0 = smd::fma(w, v[SH + d], a0);
-                    a1 = smd::fma(w, v[SH + d + 1], a1);
-                    a2 = smd::fma(w, v[SH + d + 2], a2);
-                    a3 = smd::fma(w, v[SH + d + 3], a3);
+                    for (int d = 0; d <= 2 * R; ++d) {
+                        if ((SH + d) % 2 == 0) {
+                            a01 = smd::fma2(gc.w2[d], smd::mk2(v[SH + d], v[SH + d + 1]), a01);
+                            a23 = smd::fma2(gc.w2[d], smd::mk2(v[SH + d + 2], v[SH + d + 3]), a23);
+                        } else {
+                            const float w = gc.w[d];
+                            a01.lo = smd::fma(w, v[SH + d], a01.lo);
+                            a01.hi = smd::fma(w, v[SH + d + 1], a01.hi);
+                            a23.lo = smd::fma(w, v[SH + d + 2], a23.lo);
+                            a23.hi = smd::fma(w, v[SH + d + 3], a23.hi);
+                        }
+                    }
+                    a0 = a01.lo; a1 = a01.hi; a2 = a23.lo; a3 = a23.hi;
+                } else {
+#pragma unroll
+                    for (int d = 0; d <= 2 * R; ++d) {
+                        const float w = gc.w[d];
+                        a0 = smd::fma(w, v[SH + d], a0);
+                        a1 = smd::fma(w, v[SH + d + 1], a1);
+                        a2 = smd::fma(w, v[SH + d + 2], a2);
+                        a3 = smd::fma(w, v[SH + d + 3], a3);
+                    }
                 }
                 F4 o;
                 o.x = a0; o.y = a1; o.z = a2; o.w = a3;
@@ -245,11 +265,17 @@ SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs
                     for (int j = 0; j < VR; ++j) {
                         const int d = i - j;
                         if (d >= 0 && d <= 2 * R) {
-                            const float w = gc.w[d];
-                            acc[j][0] = smd::fma(w, h.x, acc[j][0]);
-                            acc[j][1] = smd::fma(w, h.y, acc[j][1]);
-                            acc[j][2] = smd::fma(w, h.z, acc[j][2]);
-                            acc[j][3] = smd::fma(w, h.w, acc[j][3]);
+                            if (PK) {                                // column pairs, weight pair from a uniform register
+                                const smd::f2 p01 = smd::fma2(gc.w2[d], smd::mk2(h.x, h.y), smd::mk2(acc[j][0], acc[j][1]));
+                                const smd::f2 p23 = smd::fma2(gc.w2[d], smd::mk2(h.z, h.w), smd::mk2(acc[j][2], acc[j][3]));
+                                acc[j][0] = p01.lo; acc[j][1] = p01.hi; acc[j][2] = p23.lo; acc[j][3] = p23.hi;
+                            } else {
+                                const float w = gc.w[d];
+                                acc[j][0] = smd::fma(w, h.x, acc[j][0]);
+                                acc[j][1] = smd::fma(w, h.y, acc[j][1]);
+                                acc[j][2] = smd::fma(w, h.z, acc[j][2]);
+                                acc[j][3] = smd::fma(w, h.w, acc[j][3]);
+                            }
                         }
                     }
                 }

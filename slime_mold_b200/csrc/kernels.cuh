@@ -846,12 +846,12 @@ struct GsDevCtx {
     }
 };
 
-template <int R, int CM, bool SURF>
+template <int R, int CM, bool SURF, bool PK = false>
 static __global__ void __launch_bounds__(kGsNT, (gs_batch<R>() == 8 ? 4 : 3))     // rings: 34 KB (batches of 8 rows) / 67 KB (16)
 k_gauss_stream(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
 {
     extern __shared__ __align__(16) float gs_smem[];
-    gauss_stream_cta<R, CM, SURF>(GsDevCtx{}, gs_smem, a, tc, gc);
+    gauss_stream_cta<R, CM, SURF, PK>(GsDevCtx{}, gs_smem, a, tc, gc);
 }
 
 // Register-streaming form (gauss_rows.cuh): device context and kernel.
@@ -877,7 +877,7 @@ struct GrDevCtx : GsDevCtx {
 
 template <int R> constexpr int gr_min_blocks() { return R == 1 ? 8 : R == 2 ? 5 : R == 3 ? 4 : R == 4 ? 3 : 2; }
 
-template <int R, int CM, bool SURF, bool PK>
+template <int R, int CM, bool SURF, int PK>
 static __global__ void __launch_bounds__(kGrNT, gr_min_blocks<R>())
 k_gauss_rows(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
 {

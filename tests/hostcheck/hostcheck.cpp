@@ -112,6 +112,9 @@ void hc_trail_pass(const float* in, uint32_t* counts, float* out, const hc_param
 // The kernel body is written against a context; here the context is a host thread per CUDA thread and a pthread
 // barrier per CTA, so the index logic, the ring bookkeeping and the statement order of the very source the GPU runs
 // can be compared with the oracle on a machine without a GPU.
+static bool g_stream_packed = false;
+extern "C" void hc_gauss_stream_set_packed(int on) { g_stream_packed = on != 0; }
+
 struct HostGsCtx {
     int t, bxv, byv;
     pthread_barrier_t* bar;
@@ -147,7 +150,8 @@ static void run_gauss_stream(const smk::GsArgs& a, const smd::TrailConsts& tc, c
             for (int t = 0; t < smk::kGsNT; ++t)
                 th.emplace_back([&, t]() {
                     HostGsCtx cx{t, bx, by, &bar, a.W};
-                    smk::gauss_stream_cta<R, CM, SURF>(cx, smem, a, tc, gc);
+                    if (g_stream_packed) smk::gauss_stream_cta<R, CM, SURF, true>(cx, smem, a, tc, gc);
+                    else smk::gauss_stream_cta<R, CM, SURF, false>(cx, smem, a, tc, gc);
                 });
             for (auto& x : th) x.join();
             pthread_barrier_destroy(&bar);
@@ -215,7 +219,7 @@ struct HostGrCtx : HostGsCtx {
     }
 };
 
-template <int R, int CM, bool SURF, bool PK>
+template <int R, int CM, bool SURF, int PK>
 static void run_gauss_rows_pk(const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
     const int gx = (a.W + smk::gr_cta_cols<R>() - 1) / smk::gr_cta_cols<R>(), gy = (a.H + a.chunk_rows - 1) / a.chunk_rows;
@@ -237,11 +241,13 @@ static void run_gauss_rows_pk(const smk::GsArgs& a, const smd::TrailConsts& tc, 
         }
 }
 
-static bool g_rows_packed = false;
+static int g_rows_packed = 0;
 template <int R, int CM, bool SURF>
 static void run_gauss_rows(const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
-    if (g_rows_packed) run_gauss_rows_pk<R, CM, SURF, true>(a, tc, gc); else run_gauss_rows_pk<R, CM, SURF, false>(a, tc, gc);
+    if (g_rows_packed >= 2) run_gauss_rows_pk<R, CM, SURF, 2>(a, tc, gc);
+    else if (g_rows_packed == 1) run_gauss_rows_pk<R, CM, SURF, 1>(a, tc, gc);
+    else run_gauss_rows_pk<R, CM, SURF, 0>(a, tc, gc);
 }
 
 template <int R>
@@ -252,7 +258,7 @@ static void run_gauss_rows_r(int cm, bool surf, const smk::GsArgs& a, const smd:
     else { if (surf) run_gauss_rows<R, smk::GS_FLAGS, true>(a, tc, gc); else run_gauss_rows<R, smk::GS_FLAGS, false>(a, tc, gc); }
 }
 
-extern "C" void hc_gauss_rows_set_packed(int on) { g_rows_packed = on != 0; }
+extern "C" void hc_gauss_rows_set_packed(int level) { g_rows_packed = level; }
 
 extern "C" int hc_gauss_rows(const float* tin, const void* cin, void* czero, float* tout, float* surf_out, int W, int H,
                              int chunk_rows, int R, const float* weights, int cm, const hc_params* p, int wrap_y)

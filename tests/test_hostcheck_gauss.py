@@ -64,6 +64,14 @@ def run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=0, counts=None, 
     return out, surf, czero
 
 
+@pytest.fixture(params=[0, 1], ids=["scalar", "packed"])
+def stream_packed(request, hostcheck):
+    """Scalar taps, and the FFMA2 form (column taps on column pairs + the row taps whose operands are aligned pairs)."""
+    hostcheck.hc_gauss_stream_set_packed(C.c_int(request.param))
+    yield request.param
+    hostcheck.hc_gauss_stream_set_packed(C.c_int(0))
+
+
 def params_for(oracle, W, H, R, sigma, dep, rate=0.7):
     s = sm.init_preset_manager().get_preset("Default").settings.clone(
         blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=rate, pheromone_deposition_amount=dep)
@@ -72,7 +80,7 @@ def params_for(oracle, W, H, R, sigma, dep, rate=0.7):
 
 @pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.7, 288, 64, 64), (2, 1.0, 416, 200, 48), (3, 1.3, 516, 131, 40), (4, 2.0, 512, 96, 96),
                                                (5, 2.5, 1000, 97, 32), (6, 3.0, 384, 130, 56), (7, 3.5, 772, 65, 24), (8, 4.0, 640, 333, 104)])
-def test_stream_diffuse_only_bits(oracle, hostcheck, R, sigma, W, H, chunk):
+def test_stream_diffuse_only_bits(oracle, hostcheck, stream_packed, R, sigma, W, H, chunk):
     p = params_for(oracle, W, H, R, sigma, dep=1.0)
     field = np.random.default_rng(R).random((H, W), dtype=np.float32)
     ref = oracle.trail_pass(field, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
@@ -82,7 +90,7 @@ def test_stream_diffuse_only_bits(oracle, hostcheck, R, sigma, W, H, chunk):
 
 @pytest.mark.parametrize("cm,dep", [(1, 0.4), (1, 2.5), (2, 1.0)])
 @pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.5, 300, 70, 32), (2, 1.0, 292, 64, 64), (4, 2.0, 520, 90, 48), (5, 2.5, 288, 100, 72), (8, 4.0, 548, 77, 40)])
-def test_stream_full_step_bits(oracle, hostcheck, cm, dep, R, sigma, W, H, chunk):
+def test_stream_full_step_bits(oracle, hostcheck, stream_packed, cm, dep, R, sigma, W, H, chunk):
     """Deposits merged by the pass (u32 counts, or u8 flags when dep >= 1), the other deposit buffer retired,
     the sampler copy written."""
     p = params_for(oracle, W, H, R, sigma, dep=dep)
@@ -152,9 +160,10 @@ def test_stream_on_strips_bits(oracle, hostcheck, R, sigma, strips):
 # ---- the register-streaming kernel (slime_mold_b200/csrc/gauss_rows.cuh; one halo lane per side up to radius 4, two above), same emulation ----
 # widths: one warp exactly (128), a ragged last warp, several CTAs (> 480 columns), a last output lane next to the seam;
 # chunk heights that are / are not multiples of the batch of 2R+1 rows, a ragged last chunk, one chunk for the whole map
-@pytest.fixture(params=[0, 1], ids=["scalar", "packed"])
+@pytest.fixture(params=[0, 1, 2], ids=["scalar", "packed", "packed2"])
 def rows_packed(request, hostcheck):
-    """Both forms of the column taps: scalar FFMA, and FFMA2 on column pairs (on the host a packed lane IS the scalar fma)."""
+    """The forms of the taps: scalar FFMA; FFMA2 on column pairs for the column taps; that plus FFMA2 for the row taps whose
+    operands are aligned pairs (on the host a packed lane IS the scalar fma: this checks the statement order)."""
     hostcheck.hc_gauss_rows_set_packed(C.c_int(request.param))
     yield request.param
     hostcheck.hc_gauss_rows_set_packed(C.c_int(0))

@@ -215,6 +215,37 @@ def gauss_rows_sweep():
     os.environ.pop("SM_GAUSS_ROWS_PACKED", None)
 
 
+def gauss_packed_sweep():
+    """EXTENSION: A/B of the FFMA2 forms -- rows kernel radius 1-5 with SM_GAUSS_ROWS_PACKED = 0 / 1 / 2, streaming kernel radius
+    5-8 with SM_GAUSS_STREAM_PACKED = 0 / 1 -- diffusion-only passes on 8192^2 (and 16384^2 for the candidates)."""
+    def run(S, R, kern, env, label):
+        os.environ["SM_GAUSS_KERNEL"] = kern
+        os.environ["SM_GAUSS_CHUNK"] = "0"
+        for k, v in env.items():
+            os.environ[k] = v
+        s = sm.Settings.default().clone(blur_radius=float(R), blur_sigma=R / 2.0)
+        be = sm.CudaBackend.new(S, S, s, agent_count=1, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+        be.write_trail(np.random.default_rng(0).random((256, S), dtype=np.float32), y0=0)
+        passes = max(6, min(60, int(6e9 / (S * S * 8))))
+        be.diffuse_only(3)
+        ms = event_time(be, lambda: be.diffuse_only(passes))
+        gbs = 8.0 * S * S * passes / (ms * 1e-3) / 1e9
+        emit({"sweep": "gauss_rows", "size": S, "radius": R, "kernel": label, "chunk": 0, "passes": passes,
+              "ms_per_pass": ms / passes, "gbs": gbs, "frac_of_measured_peak": gbs / PEAK, "frac_of_8TBs": gbs / 8000.0})
+        be.close()
+        for k in env:
+            os.environ.pop(k, None)
+    for S in (8192, 16384):
+        for R in (1, 2, 3, 4, 5):
+            for pk in (0, 1, 2):
+                run(S, R, "rows", {"SM_GAUSS_ROWS_PACKED": str(pk)}, f"rows_pk{pk}")
+        for R in (5, 6, 7, 8):
+            for pk in (0, 1):
+                run(S, R, "stream", {"SM_GAUSS_STREAM_PACKED": str(pk)}, f"stream_pk{pk}")
+    os.environ.pop("SM_GAUSS_KERNEL", None)
+    os.environ.pop("SM_GAUSS_CHUNK", None)
+
+
 def gauss_rows_ncu_target():
     """A few passes of the register-streaming kernel at 8192^2 (radius 4, then radius 8; packed column taps): the ncu target."""
     os.environ["SM_GAUSS_KERNEL"] = "rows"
@@ -269,6 +300,8 @@ if __name__ == "__main__":
         gauss_stream_sweep()
     if "gauss_rows" in which:
         gauss_rows_sweep()
+    if "gauss_packed" in which:
+        gauss_packed_sweep()
     if "gauss_ncu" in which:
         gauss_ncu_target()
     if "gauss_rows_ncu" in which:

@@ -14,7 +14,8 @@ def main(path):
         k = (r["size"], r["radius"], r["kernel"])
         if k not in best or r["ms_per_pass"] < best[k]["ms_per_pass"]:
             best[k] = r
-    kernels = sorted({k[2] for k in best}, key=lambda n: ["rows", "rows_packed", "stream", "tile"].index(n) if n in ("rows", "rows_packed", "stream", "tile") else 9)
+    order = ["rows", "rows_packed", "rows_pk0", "rows_pk1", "rows_pk2", "stream", "stream_pk0", "stream_pk1", "tile"]
+    kernels = sorted({k[2] for k in best}, key=lambda n: order.index(n) if n in order else 99)
     print("| map | radius | " + " | ".join(f"{k}: us/pass, GB/s, of measured peak" for k in kernels) + " |")
     print("|---|---|" + "---|" * len(kernels))
     for size in sorted({k[0] for k in best}):
