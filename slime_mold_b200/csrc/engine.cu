@@ -626,7 +626,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         // Unset: the register-streaming kernel (gauss_rows.cuh) up to radius SM_GAUSS_ROWS_MAX_R (5), the shared-memory streaming
         // kernel (gauss_stream.cuh) above, the tile kernel (k_gauss_fused) for maps the first two do not take (W % 4 != 0, tiny).
         // "rows" / "stream" / "tile" force one of them wherever it applies.  Measured on 8192^2-16384^2 (profiles/), fraction of
-        // the HBM peak: rows 0.88-0.95 (R 1-2), 0.77-0.83 (R 3-4), 0.64-0.69 (R 5); stream 0.51-0.69; tile 0.31-0.61.  rows and
+        // the HBM peak: rows 0.89-0.95 (R 1-2), 0.78-0.85 (R 3-4), 0.65-0.69 (R 5); stream 0.51-0.69; tile 0.31-0.61.  rows and
         // stream let a Gaussian full step keep the u8 deposit flags and the sampler copy (6.8e10 vs 4.4e10 agent-steps/s).
         const char* gk = getenv("SM_GAUSS_KERNEL");
         const std::string gks = gk ? gk : "";
@@ -634,7 +634,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         e->gauss_rows = gks.empty() || gks == "rows" || gks == "auto";
         e->gauss_rows_max_r = gks == "rows" ? smk::kGrMaxR : env_int("SM_GAUSS_ROWS_MAX_R", 5);
         e->gauss_stream_packed = env_int("SM_GAUSS_STREAM_PACKED", 0) != 0;
-        e->gauss_rows_packed = env_int("SM_GAUSS_ROWS_PACKED", -1);        // FFMA2 column taps: -1 = where measured faster (radius <= 4)
+        e->gauss_rows_packed = env_int("SM_GAUSS_ROWS_PACKED", -1);        // FFMA2 taps: -1 = the level measured fastest per radius
     }
     e->agent_stream_hint = env_int("SM_AGENT_STREAM_HINT", 0);   // 1: evict-first loads / stores of the agent state (A/B)
     e->gauss_chunk = env_int("SM_GAUSS_CHUNK", 0);         // rows per CTA of the streaming kernel (0 = chosen per map)

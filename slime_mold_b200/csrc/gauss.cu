@@ -78,10 +78,11 @@ static int launch_gauss_rows_pk(sm_engine* e, const smk::GsArgs& a0, const smd::
 template <int R, int CM, bool SURF>
 static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
-    // packed column taps: 3-5 % faster at radius 3-4, neutral at 1-2; above 4 the extra registers cost a resident CTA
-    // (measured at radius 5-8 too, then dropped from the build: each of those instantiations is 2-3 K instructions)
+    // FFMA2 taps (level 2: column taps + the aligned half of the row taps): 3-6 % faster at radius 3-4, 1-3 % at 1-2; at
+    // radius 5 the extra registers cost a resident CTA (0.60 against 0.65 of the HBM peak), above that they were measured
+    // too and dropped from the build (each of those instantiations is 2-3 K instructions)
     if constexpr (R <= 5) {
-        const int pk = e->gauss_rows_packed < 0 ? (R <= 4 ? 1 : 0) : e->gauss_rows_packed;
+        const int pk = e->gauss_rows_packed < 0 ? (R <= 4 ? 2 : 0) : e->gauss_rows_packed;
         if (pk >= 2) return launch_gauss_rows_pk<R, CM, SURF, 2>(e, a, tc, gc);
         if (pk == 1) return launch_gauss_rows_pk<R, CM, SURF, 1>(e, a, tc, gc);
         return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
@@ -96,7 +97,8 @@ static int launch_gauss_stream_pk(sm_engine* e, const smk::GsArgs& a0, const smd
 template <int R, int CM, bool SURF>
 static int launch_gauss_stream(sm_engine* e, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
-    // packed taps (SM_GAUSS_STREAM_PACKED) are built for the radii this kernel is the default for
+    // packed taps (SM_GAUSS_STREAM_PACKED=1; built for radius >= 5): 16 % fewer instructions, no measurable gain (0.51 ->
+    // 0.52 of the peak at radius 8) -- this kernel waits on its barriers and shared-memory round trips, not on issue slots
     if constexpr (R >= 5) {
         if (e->gauss_stream_packed) return launch_gauss_stream_pk<R, CM, SURF, true>(e, a, tc, gc);
     }
