@@ -60,6 +60,16 @@ typedef struct {
 
 int so_params_size(void) { return (int)sizeof(so_params); }
 
+/* Small problems (tests) run faster on a few threads than on all of them. */
+void so_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int so_max_threads(void)
 {
 #ifdef _OPENMP

@@ -92,6 +92,10 @@ def max_threads() -> int:
     return lib().so_max_threads()
 
 
+def set_threads(n: int) -> None:
+    lib().so_set_threads(C.c_int(n))
+
+
 # ---- arithmetic spec --------------------------------------------------------
 def sincos(x):
     x = _f32(x)
