@@ -288,7 +288,14 @@ int sm_engine::setup_tiles()
     tiles.row_base = (int64_t)row0;
     tiles.tiles_x = (W + (1u << tiles.shift_x) - 1) >> tiles.shift_x;
     tiles.tiles_y = (rows + (1u << tiles.shift_y) - 1) >> tiles.shift_y;
-    n_tiles = (uint64_t)tiles.tiles_x * tiles.tiles_y;
+    {
+        int hb = env_int("SM_SORT_HEADING_BINS", 1);
+        if (hb < 1) hb = 1;
+        if (hb > 64) hb = 64;
+        tiles.heading_bins = (uint32_t)hb;
+        tiles.bin_scale = (float)hb / 6.28318530718f;
+    }
+    n_tiles = (uint64_t)tiles.tiles_x * tiles.tiles_y * tiles.heading_bins;
     if (n_tiles >= (1ull << 31)) return sm_fail(SM_ERR_BAD_ARG, "too many sort tiles");
     n_scan_blocks = (uint32_t)((n_tiles + smk::kScanBlock * smk::kScanItems - 1) / (smk::kScanBlock * smk::kScanItems));
     SM_CUDA(cudaMalloc(&tile_hist, n_tiles * sizeof(uint32_t)));

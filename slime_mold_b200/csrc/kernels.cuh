@@ -893,9 +893,14 @@ struct TileGeom {
     uint32_t W;
     int64_t row_base;            // global row of local row 0
     uint32_t rows;               // owned rows
+    // experiment (SM_SORT_HEADING_BINS, default 1 = off): agents of a tile are further grouped by heading sector, so that
+    // the lanes of a warp sense in the same direction and their three footprints (sensor distance 20-225 cells away
+    // from the tile) fall into fewer texture sectors.  Any permutation gives the same result bits (deposits are order-free).
+    uint32_t heading_bins;
+    float bin_scale;             // heading_bins / 2pi
 };
 
-__device__ __forceinline__ uint32_t tile_key(float x, float y, const TileGeom& t)
+__device__ __forceinline__ uint32_t tile_key(float x, float y, float angle, const TileGeom& t)
 {
     int32_t cx = (int32_t)x;                                   // x in [0, W] (W by rounding)
     int64_t cy = (int64_t)(int32_t)y - t.row_base;
@@ -903,7 +908,12 @@ __device__ __forceinline__ uint32_t tile_key(float x, float y, const TileGeom& t
     if (cx >= (int32_t)t.W) cx = t.W - 1;
     if (cy < 0) cy = 0;
     if (cy >= (int64_t)t.rows) cy = t.rows - 1;
-    return ((uint32_t)cy >> t.shift_y) * t.tiles_x + ((uint32_t)cx >> t.shift_x);
+    uint32_t key = ((uint32_t)cy >> t.shift_y) * t.tiles_x + ((uint32_t)cx >> t.shift_x);
+    if (t.heading_bins > 1u) {
+        const float b = fminf(fmaxf(angle * t.bin_scale, 0.0f), (float)(t.heading_bins - 1u));     // NaN -> sector 0
+        key = key * t.heading_bins + (uint32_t)b;
+    }
+    return key;
 }
 
 // Lanes of a warp that target the same tile are combined into one atomic (the agents are nearly
@@ -927,7 +937,7 @@ k_tile_hist(const float4* __restrict__ agents, const uint32_t* __restrict__ ids,
     uint32_t key = 0xFFFFFFFFu;                                  // invalid / dead lanes group together
     if (i < n && ids[i] != kDeadAgent) {
         float4 a = agents[i];
-        key = tile_key(a.x, a.y, t);
+        key = tile_key(a.x, a.y, a.z, t);
     }
     uint32_t r, sz, gm; bool leader;
     warp_group(key, r, sz, leader, gm);
@@ -1036,7 +1046,7 @@ k_tile_scatter(const float4* __restrict__ agents, const uint32_t* __restrict__ i
         id = ids[i];
         if (id != kDeadAgent) {
             a = agents[i];
-            key = tile_key(a.x, a.y, t);
+            key = tile_key(a.x, a.y, a.z, t);
         }
     }
     uint32_t r, sz, gm; bool leader;

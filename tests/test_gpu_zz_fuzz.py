@@ -28,3 +28,25 @@ def test_engine_equals_oracle_on_random_cases(oracle, engine_lib, seed):
                 a, t = be.read_agents(), be.read_trail()
                 assert bits_equal(a, sim.agents), (case, k, describe(u), mismatch_report(a, sim.agents, "agents"))
                 assert bits_equal(t, sim.trail), (case, k, describe(u), mismatch_report(t, sim.trail, "trail"))
+
+
+@pytest.mark.parametrize("bins", [8, 3])
+def test_heading_sector_sort_changes_no_bit(oracle, engine_lib, monkeypatch, bins):
+    """Experiment switch SM_SORT_HEADING_BINS (agents of a sort tile grouped by heading sector, for gather locality): any
+    storage order gives the oracle's bits -- deposits are order-free and the jitter hash uses the persistent index."""
+    from presets_util import preset_uniform
+    monkeypatch.setenv("SM_SORT_HEADING_BINS", str(bins))
+    W, H, N = 320, 256, 40_000
+    for name in ("Default", "Waves"):
+        s = sm.init_preset_manager().get_preset(name).settings
+        u = preset_uniform(name, W, H)
+        ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 3)
+        sim = oracle.Sim(to_oracle_params(oracle, u), ag)
+        with sm.CudaBackend.new(W, H, s, agent_count=N, sort_interval=2, device=0) as be:
+            be.write_agents(ag)
+            for chunk in (1, 6, 13):
+                sim.step(chunk)
+                be.step(chunk)
+                a, t = be.read_agents(), be.read_trail()
+                assert bits_equal(a, sim.agents), mismatch_report(a, sim.agents, f"{name} agents")
+                assert bits_equal(t, sim.trail), mismatch_report(t, sim.trail, f"{name} trail")

@@ -100,6 +100,30 @@ def presets_sweep():
         be.close()
 
 
+def heading_sort_sweep():
+    """Experiment: SM_SORT_HEADING_BINS -- agents of a sort tile grouped by heading sector (gather locality of the three
+    sensors).  Config 2, steady state, Default (sensor distance 20) and Snake (225)."""
+    N, W, H = 16_777_216, 4096, 4096
+    for preset in ("Default", "Snake"):
+        s = sm.init_preset_manager().get_preset(preset).settings
+        for bins in (1, 2, 4, 8, 16):
+            for interval in (12, 24):
+                os.environ["SM_SORT_HEADING_BINS"] = str(bins)
+                be = sm.CudaBackend.new(W, H, s, agent_count=N, sort_interval=interval)
+                be.init_agents(1)
+                be.step(300)
+                steps = 96
+                ms = event_time(be, lambda: be.step(steps))
+                be.set_timing_enabled(True); be.reset_timing()
+                be.step(48)
+                t = be.timing()
+                emit({"sweep": "heading_sort", "preset": preset, "bins": bins, "sort_interval": interval, "ms_per_step": ms / steps,
+                      "agent_steps_per_s": N * steps / (ms * 1e-3), "agents_ms": t.agents_ms / t.agent_launches,
+                      "trail_ms": t.trail_ms / t.trail_launches, "sort_ms_per_step": t.sort_ms / 48})
+                be.close()
+    os.environ.pop("SM_SORT_HEADING_BINS", None)
+
+
 def gauss_sweep():
     """EXTENSION (no reference semantics): separable Gaussian, radius 2 / 4 / 8, fused shared-memory kernel vs the
     two-pass form (BASELINE config 5 names radii 1-8; radius 1 = the reference's box is the parity mode above)."""
@@ -294,6 +318,8 @@ if __name__ == "__main__":
         agents_sweep()
     if "presets" in which:
         presets_sweep()
+    if "heading_sort" in which:
+        heading_sort_sweep()
     if "gauss" in which:
         gauss_sweep()
     if "gauss_stream" in which:
