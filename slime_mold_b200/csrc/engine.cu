@@ -295,7 +295,16 @@ int sm_engine::setup_tiles()
         tiles.heading_bins = (uint32_t)hb;
         tiles.bin_scale = (float)hb / 6.28318530718f;
     }
-    n_tiles = (uint64_t)tiles.tiles_x * tiles.tiles_y * tiles.heading_bins;
+    n_tiles = (uint64_t)tiles.tiles_x * tiles.tiles_y;
+    {
+        int ss = env_int("SM_SORT_SUPER_SHIFT", 0);
+        if (ss < 0) ss = 0;
+        if (ss > 6) ss = 6;
+        tiles.super_shift = (uint32_t)ss;
+        tiles.super_x = (tiles.tiles_x + (1u << ss) - 1) >> ss;
+        if (ss) n_tiles = ((uint64_t)tiles.super_x * ((tiles.tiles_y + (1u << ss) - 1) >> ss)) << (2 * ss);
+    }
+    n_tiles *= tiles.heading_bins;
     if (n_tiles >= (1ull << 31)) return sm_fail(SM_ERR_BAD_ARG, "too many sort tiles");
     n_scan_blocks = (uint32_t)((n_tiles + smk::kScanBlock * smk::kScanItems - 1) / (smk::kScanBlock * smk::kScanItems));
     SM_CUDA(cudaMalloc(&tile_hist, n_tiles * sizeof(uint32_t)));

@@ -898,6 +898,11 @@ struct TileGeom {
     // from the tile) fall into fewer texture sectors.  Any permutation gives the same result bits (deposits are order-free).
     uint32_t heading_bins;
     float bin_scale;             // heading_bins / 2pi
+    // experiment (SM_SORT_SUPER_SHIFT, default 0 = off): tiles are numbered super-tile by super-tile (2^s x 2^s tiles each)
+    // instead of row by row, so that the ~16 tiles a CTA's 1024 consecutive agents come from form a compact block (32 x 32
+    // cells at s = 2) rather than a 128 x 8 strip: the union of their sensor footprints -- the CTA's L1 working set -- shrinks.
+    uint32_t super_shift;
+    uint32_t super_x;            // super-tiles per row
 };
 
 __device__ __forceinline__ uint32_t tile_key(float x, float y, float angle, const TileGeom& t)
@@ -908,7 +913,12 @@ __device__ __forceinline__ uint32_t tile_key(float x, float y, float angle, cons
     if (cx >= (int32_t)t.W) cx = t.W - 1;
     if (cy < 0) cy = 0;
     if (cy >= (int64_t)t.rows) cy = t.rows - 1;
-    uint32_t key = ((uint32_t)cy >> t.shift_y) * t.tiles_x + ((uint32_t)cx >> t.shift_x);
+    const uint32_t tx = (uint32_t)cx >> t.shift_x, ty = (uint32_t)cy >> t.shift_y;
+    uint32_t key = ty * t.tiles_x + tx;
+    if (t.super_shift) {
+        const uint32_t ss = t.super_shift, m = (1u << ss) - 1u;
+        key = (((ty >> ss) * t.super_x + (tx >> ss)) << (2u * ss)) | ((ty & m) << ss) | (tx & m);
+    }
     if (t.heading_bins > 1u) {
         const float b = fminf(fmaxf(angle * t.bin_scale, 0.0f), (float)(t.heading_bins - 1u));     // NaN -> sector 0
         key = key * t.heading_bins + (uint32_t)b;

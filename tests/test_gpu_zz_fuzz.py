@@ -30,13 +30,15 @@ def test_engine_equals_oracle_on_random_cases(oracle, engine_lib, seed):
                 assert bits_equal(t, sim.trail), (case, k, describe(u), mismatch_report(t, sim.trail, "trail"))
 
 
-@pytest.mark.parametrize("bins", [8, 3])
-def test_heading_sector_sort_changes_no_bit(oracle, engine_lib, monkeypatch, bins):
-    """Experiment switch SM_SORT_HEADING_BINS (agents of a sort tile grouped by heading sector, for gather locality): any
-    storage order gives the oracle's bits -- deposits are order-free and the jitter hash uses the persistent index."""
+@pytest.mark.parametrize("bins,super_shift,W,H", [(8, 0, 320, 256), (3, 2, 320, 256), (1, 2, 300, 77), (1, 1, 37, 23)])
+def test_sort_key_experiments_change_no_bit(oracle, engine_lib, monkeypatch, bins, super_shift, W, H):
+    """Experiment switches SM_SORT_HEADING_BINS (agents of a sort tile grouped by heading sector) and SM_SORT_SUPER_SHIFT
+    (tiles numbered super-tile by super-tile; ragged maps pad the last super-tiles): any storage order gives the oracle's
+    bits -- deposits are order-free and the jitter hash uses the persistent index."""
     from presets_util import preset_uniform
     monkeypatch.setenv("SM_SORT_HEADING_BINS", str(bins))
-    W, H, N = 320, 256, 40_000
+    monkeypatch.setenv("SM_SORT_SUPER_SHIFT", str(super_shift))
+    N = 40_000
     for name in ("Default", "Waves"):
         s = sm.init_preset_manager().get_preset(name).settings
         u = preset_uniform(name, W, H)

@@ -101,14 +101,16 @@ def presets_sweep():
 
 
 def heading_sort_sweep():
-    """Experiment: SM_SORT_HEADING_BINS -- agents of a sort tile grouped by heading sector (gather locality of the three
-    sensors).  Config 2, steady state, Default (sensor distance 20) and Snake (225)."""
+    """Experiments on the sort key: SM_SORT_SUPER_SHIFT (tiles numbered super-tile by super-tile: a CTA's agents come from a
+    compact block of tiles, smaller L1 working set) and SM_SORT_HEADING_BINS (agents of a tile grouped by heading sector).
+    Config 2, steady state, Default (sensor distance 20) and Snake (225)."""
     N, W, H = 16_777_216, 4096, 4096
     for preset in ("Default", "Snake"):
         s = sm.init_preset_manager().get_preset(preset).settings
-        for bins in (1, 2, 4, 8, 16):
+        for bins, sup in ((1, 0), (1, 1), (1, 2), (1, 3), (4, 0), (8, 0), (4, 2)):
             for interval in (12, 24):
                 os.environ["SM_SORT_HEADING_BINS"] = str(bins)
+                os.environ["SM_SORT_SUPER_SHIFT"] = str(sup)
                 be = sm.CudaBackend.new(W, H, s, agent_count=N, sort_interval=interval)
                 be.init_agents(1)
                 be.step(300)
@@ -117,11 +119,12 @@ def heading_sort_sweep():
                 be.set_timing_enabled(True); be.reset_timing()
                 be.step(48)
                 t = be.timing()
-                emit({"sweep": "heading_sort", "preset": preset, "bins": bins, "sort_interval": interval, "ms_per_step": ms / steps,
+                emit({"sweep": "heading_sort", "preset": preset, "bins": bins, "super_shift": sup, "sort_interval": interval, "ms_per_step": ms / steps,
                       "agent_steps_per_s": N * steps / (ms * 1e-3), "agents_ms": t.agents_ms / t.agent_launches,
                       "trail_ms": t.trail_ms / t.trail_launches, "sort_ms_per_step": t.sort_ms / 48})
                 be.close()
     os.environ.pop("SM_SORT_HEADING_BINS", None)
+    os.environ.pop("SM_SORT_SUPER_SHIFT", None)
 
 
 def gauss_sweep():
