@@ -648,6 +648,8 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         const std::string gks = gk ? gk : "";
         e->gauss_stream = gks != "tile";
         e->gauss_rows = gks.empty() || gks == "rows" || gks == "auto";
+        e->gauss_wring = gks == "wring";                 // experiment: radius 5-8 on the private-ring kernel, the rest as by default
+        if (e->gauss_wring) e->gauss_rows = true;
         e->gauss_rows_max_r = gks == "rows" ? smk::kGrMaxR : env_int("SM_GAUSS_ROWS_MAX_R", 5);
         e->gauss_stream_packed = env_int("SM_GAUSS_STREAM_PACKED", 0) != 0;
         e->gauss_rows_packed = env_int("SM_GAUSS_ROWS_PACKED", -1);        // FFMA2 taps: -1 = the level measured fastest per radius

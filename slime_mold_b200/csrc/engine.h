@@ -88,6 +88,7 @@ struct sm_engine {
     int gauss_rows_max_r = 5;         // measured (profiles/): 0.64-0.95 of the HBM peak at radius 1-5 against 0.55-0.69 for the streaming kernel; a tie at 6, behind at 7-8
     int gauss_rows_packed = -1;       // SM_GAUSS_ROWS_PACKED: 0 scalar taps, 1 column taps as FFMA2 on column pairs, 2 also the aligned half of the row taps, -1 = where measured faster (2 for radius <= 4)
     bool gauss_stream_packed = false; // SM_GAUSS_STREAM_PACKED=1: FFMA2 taps in the streaming kernel (radius >= 5; A/B)
+    bool gauss_wring = false;         // SM_GAUSS_KERNEL=wring: experiment, the private-ring kernel (gauss_wring.cuh) for radius 5-8
     bool gauss_rows_ok() const;
     bool gauss_fast_ok() const { return gauss_rows_ok() || gauss_stream_ok(); }   // kernels that merge u8 flags and write the sampler copy
     bool gauss_two_pass = false;      // SM_GAUSS_TWO_PASS=1: the unfused Gaussian passes (A/B; also used for maps below 160 x 64)

@@ -17,6 +17,7 @@
 #include "trail_core.cuh"
 #include "gauss_stream.cuh"
 #include "gauss_rows.cuh"
+#include "gauss_wring.cuh"
 
 namespace smk {
 
@@ -882,6 +883,15 @@ static __global__ void __launch_bounds__(kGrNT, gr_min_blocks<R>())
 k_gauss_rows(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
 {
     gauss_rows_cta<R, CM, SURF, PK>(GrDevCtx{}, a, tc, gc);
+}
+
+// Private-ring form (gauss_wring.cuh; experiment, SM_GAUSS_KERNEL=wring): same device context as the rows kernel.
+template <int R, int CM, bool SURF, int PK>
+static __global__ void __launch_bounds__(kGwNT, 4)
+k_gauss_wring(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
+{
+    extern __shared__ __align__(16) float gw_smem[];
+    gauss_wring_cta<R, CM, SURF, PK>(GrDevCtx{}, gw_smem, a, tc, gc);
 }
 
 // ---------------------------------------------------------------------------

@@ -269,6 +269,7 @@ def gauss_packed_sweep():
         for R in (5, 6, 7, 8):
             for pk in (0, 1):
                 run(S, R, "stream", {"SM_GAUSS_STREAM_PACKED": str(pk)}, f"stream_pk{pk}")
+            run(S, R, "wring", {}, "wring")                    # experiment: private shared-memory ring (gauss_wring.cuh)
     os.environ.pop("SM_GAUSS_KERNEL", None)
     os.environ.pop("SM_GAUSS_CHUNK", None)
 

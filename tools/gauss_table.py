@@ -14,7 +14,7 @@ def main(path):
         k = (r["size"], r["radius"], r["kernel"])
         if k not in best or r["ms_per_pass"] < best[k]["ms_per_pass"]:
             best[k] = r
-    order = ["rows", "rows_packed", "rows_pk0", "rows_pk1", "rows_pk2", "stream", "stream_pk0", "stream_pk1", "tile"]
+    order = ["rows", "rows_packed", "rows_pk0", "rows_pk1", "rows_pk2", "stream", "stream_pk0", "stream_pk1", "wring", "tile"]
     kernels = sorted({k[2] for k in best}, key=lambda n: order.index(n) if n in order else 99)
     print("| map | radius | " + " | ".join(f"{k}: us/pass, GB/s, of measured peak" for k in kernels) + " |")
     print("|---|---|" + "---|" * len(kernels))
