@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--spinup", type=int, default=200, help="untimed steps before warm-up (network formation)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host-state", action="store_true", help="skip the e2e_host_state leg (full state over PCIe every step)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--independent", action="store_true", help="diagnostic: N ranks, each an independent single-GPU engine")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (0 = min(steps, 100))")
@@ -376,6 +377,37 @@ def run_ours(args):
             per[name] = agents * args.steps / (ms_p * 1e-3)
         extras["agent_steps_per_sec_by_preset"] = per
 
+    # ---- the other end of the e2e scale: the HOST owns the whole state (agents + trail uploaded before and read back after
+    #      every step, pinned host memory) -- what a caller pays who treats the engine as a stateless operator.  The reference
+    #      never does this (its buffers live on the GPU, only the 56-byte uniform crosses per frame), so `e2e` above is the
+    #      reference-faithful figure; this one is reported beside it.  Last leg of the run, failures only drop the key.
+    host_state = None
+    if N == 1 and not args.no_host_state:
+        try:
+            n_hs = 3
+            pin_a = torch.empty((agents, 4), dtype=torch.float32, pin_memory=True)
+            pin_t = torch.empty((height, width), dtype=torch.float32, pin_memory=True)
+            a_np, t_np = pin_a.numpy(), pin_t.numpy()
+            be.read_agents(out=a_np)
+            be.read_trail(out=t_np)
+            be.sync()
+            t0 = time.perf_counter()
+            for _ in range(n_hs):
+                be.write_agents(a_np)
+                be.write_trail(t_np)
+                be.write_uniform(uni)
+                be.step(1)
+                be.read_agents(out=a_np)
+                be.read_trail(out=t_np)
+            be.sync()
+            hs_s = time.perf_counter() - t0
+            host_state = {"value": agents * n_hs / hs_s, "unit": "agent-steps/s", "steps": n_hs, "ms_per_step": hs_s / n_hs * 1e3,
+                          "h2d_bytes_per_step": int(a_np.nbytes + t_np.nbytes + 56), "d2h_bytes_per_step": int(a_np.nbytes + t_np.nbytes),
+                          "note": "sm_upload_agents + sm_upload_trail + sm_set_params, sm_step(1), sm_download_agents + "
+                                  "sm_download_trail every step, pinned host buffers: PCIe-bound"}
+        except Exception as exc:      # never lose the headline line over the extra leg
+            host_state = {"error": repr(exc)[:200]}
+
     cpu = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
         v, ms_cpu, sample, cores = cpu_reference_run(width, height, agents, args.preset, args.seed, steps=3, warmup=1,
@@ -392,6 +424,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": 56, "d2h_bytes_per_step": 32,
                     "steps": e2e_steps, "note": "per step: sm_set_params (56-byte uniform from host), sm_step(1), "
                                                 "sm_trail_statistics read back (host sync every step)"},
+            "e2e_host_state": host_state,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
