@@ -305,7 +305,7 @@ __device__ __forceinline__ int64_t row_index(int64_t y, const TrailGeom& g)
 
 // Deposit representation seen by the trail pass: none (diffusion only), u32 counts, u8 flags.
 enum { CM_NONE = 0, CM_COUNTS = 1, CM_FLAGS = 2 };
-static_assert(CM_NONE == GS_NONE && CM_COUNTS == GS_COUNTS && CM_FLAGS == GS_FLAGS, "deposit representation tags");
+static_assert((int)CM_NONE == (int)GS_NONE && (int)CM_COUNTS == (int)GS_COUNTS && (int)CM_FLAGS == (int)GS_FLAGS, "deposit representation tags");
 
 struct RawRow {
     float4 t;
