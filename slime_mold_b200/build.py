@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libslime_b200.so")
-SOURCES = ["engine.cu", "gauss.cu", "exchange.cu"]
+SOURCES = ["engine.cu", "gauss.cu", "gauss_wring.cu", "exchange.cu"]
 HEADERS = ["engine.h", "kernels.cuh", "agent_core.cuh", "trail_core.cuh", "gauss_stream.cuh", "gauss_rows.cuh", "gauss_wring.cuh", "device_math.cuh",
            os.path.join("..", "..", "include", "slime_b200.h")]
 

@@ -9,6 +9,9 @@
 #include "kernels.cuh"
 
 int sm_fail(int code, const char* fmt, ...);
+// gauss_wring.cu (experiment kernel): flags = u8 deposit flags merged (else diffusion-only)
+int sm_gauss_wring_dispatch(struct sm_engine* e, int R, bool flags, bool surf, const smk::GsArgs& a, const smd::TrailConsts& tc,
+                            const smk::GaussConsts& gc);
 
 struct EvPair { cudaEvent_t a, b; int kind; };
 

@@ -91,35 +91,6 @@ static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a, const smd::Trai
     }
 }
 
-// EXPERIMENT (SM_GAUSS_KERNEL=wring, radius 5-8): the rows kernel with its column-tap state in a private shared-memory ring
-template <int R, int CM, bool SURF>
-static int launch_gauss_wring(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
-{
-    auto kern = smk::k_gauss_wring<R, CM, SURF, 2>;
-    const size_t smem = smk::gw_smem_bytes<R>();
-    int per_sm = 0;
-    SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, smk::kGwNT, smem));
-    if (per_sm < 1) per_sm = 1;
-    smk::GsArgs a = a0;
-    const uint64_t gx = (e->W + smk::gr_cta_cols<R>() - 1) / smk::gr_cta_cols<R>();
-    const uint64_t cap = (uint64_t)e->num_sms * per_sm;
-    uint64_t chunk = (uint64_t)e->gauss_chunk;
-    if (chunk == 0) {
-        const double want_chunks = (double)e->rows / 256.0;
-        uint64_t waves = (uint64_t)llround((double)gx * want_chunks / (double)cap);
-        if (waves < 1) waves = 1;
-        uint64_t n_chunks = waves * cap / gx;
-        if (n_chunks < 1) n_chunks = 1;
-        chunk = (e->rows + n_chunks - 1) / n_chunks;
-        if (chunk < 32) chunk = 32;
-    }
-    a.chunk_rows = (int)chunk;
-    dim3 grid((unsigned)gx, (unsigned)((e->rows + chunk - 1) / chunk));
-    kern<<<grid, smk::kGwNT, smem, e->stream>>>(a, tc, gc);
-    SM_CUDA(cudaGetLastError());
-    return SM_OK;
-}
-
 template <int R, int CM, bool SURF, bool PK>
 static int launch_gauss_stream_pk(sm_engine* e, const smk::GsArgs& a0, const smd::TrailConsts& tc, const smk::GaussConsts& gc);
 
@@ -220,20 +191,9 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
                         : launch_gauss_stream<RR, smk::GS_FLAGS, false>(this, a, tc, gc);
         };
         using std::integral_constant;
-        // (u32-count passes stay on the default kernels: the experiment is built for diffusion-only and u8-flag passes)
-        auto go_wring = [&](auto r_tag) -> int {
-            constexpr int RR = decltype(r_tag)::value;
-            if (p.cm == smk::CM_NONE) return launch_gauss_wring<RR, smk::GS_NONE, false>(this, a, tc, gc);
-            return surf ? launch_gauss_wring<RR, smk::GS_FLAGS, true>(this, a, tc, gc)
-                        : launch_gauss_wring<RR, smk::GS_FLAGS, false>(this, a, tc, gc);
-        };
+        // EXPERIMENT (gauss_wring.cu): u32-count passes stay on the default kernels
         if (gauss_wring && p.cm != smk::CM_COUNTS && R >= 5 && W % 4 == 0 && W >= (uint32_t)smk::kGrMinW && rows >= (uint32_t)smk::kGrMinRows) {
-            switch (R) {
-            case 5: SM_TRY(go_wring(integral_constant<int, 5>{})); break;
-            case 6: SM_TRY(go_wring(integral_constant<int, 6>{})); break;
-            case 7: SM_TRY(go_wring(integral_constant<int, 7>{})); break;
-            default: SM_TRY(go_wring(integral_constant<int, 8>{})); break;
-            }
+            SM_TRY(sm_gauss_wring_dispatch(this, R, p.cm == smk::CM_FLAGS, surf, a, tc, gc));
             timing.kernel_launches += 1;
             return SM_OK;
         }
