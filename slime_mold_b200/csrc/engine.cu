@@ -655,6 +655,13 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         e->gauss_rows_packed = env_int("SM_GAUSS_ROWS_PACKED", -1);        // FFMA2 taps: -1 = the level measured fastest per radius
     }
     e->agent_stream_hint = env_int("SM_AGENT_STREAM_HINT", 0);   // 1: evict-first loads / stores of the agent state (A/B)
+    {
+        // experiment (off unless set): DRAM -> L2 fill granularity, 32 / 64 / 128 bytes.  The sensor gathers of maps that do not
+        // fit the L2 (config 3: 8192^2, sensor distance 225) touch one 32-byte sector per footprint row; a smaller fill size
+        // wastes less HBM bandwidth on them, a larger one helps the streaming passes.  Device-wide, so only on request.
+        const int gran = env_int("SM_L2_FETCH_GRANULARITY", 0);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+    }
     e->gauss_chunk = env_int("SM_GAUSS_CHUNK", 0);         // rows per CTA of the streaming kernel (0 = chosen per map)
     e->gauss_packed = env_int("SM_GAUSS_PACKED", 0) != 0;   // measured: no faster than the scalar form (the kernel waits on barriers and loads, not on FMA issue)
 
