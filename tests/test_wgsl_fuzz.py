@@ -86,3 +86,23 @@ def test_engine_arithmetic_on_host_equals_oracle_on_random_cases(oracle, hostche
             t, out = out, t
             assert bits_equal(a, sim.agents), (case, k, describe(u), mismatch_report(a, sim.agents, "agents"))
             assert bits_equal(t, sim.trail), (case, k, describe(u), mismatch_report(t, sim.trail, "trail"))
+
+
+@pytest.mark.skipif(not wr.have_reference(), reason="/root/reference is not present on this machine")
+def test_display_shader_source_equals_oracle_on_random_cases(oracle):
+    """display.wgsl (interpreted) against the oracle's display restatement: random map and texture shapes (both letter-box
+    orientations, magnified and minified), random LUTs, cells at the quantisation edges (k/255 +- half a step), NaN / inf."""
+    src = wr.shader_source("display.wgsl")
+    rng = np.random.default_rng(7)
+    for case in range(24):
+        W, H = int(rng.integers(1, 40)), int(rng.integers(1, 30))
+        tw, th = int(rng.integers(1, 48)), int(rng.integers(1, 40))
+        u = preset_uniform("Default", W, H)
+        tr = (rng.random((H, W)) * 1.6 - 0.3).astype(np.float32)
+        for _ in range(3):
+            tr[rng.integers(0, H), rng.integers(0, W)] = rng.choice([np.nan, np.inf, -np.inf, 1.0, 0.0, 0.99999994, 1.0000001,
+                                                                      0.5 / 255, 254.5 / 255, 255.5 / 255])
+        lut = rng.integers(0, 256, 768, dtype=np.uint8)
+        got = oracle.display(tr, lut, tw, th)
+        ref = wr.run_display(src, u, tr, lut, tw, th)
+        assert np.array_equal(got, ref), (case, W, H, tw, th, int((got != ref).sum()))
