@@ -52,7 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)]
+        ab = ["-DSM_BUILD_AB_VARIANTS=1"] if os.environ.get("SM_BUILD_AB_VARIANTS", "0") == "1" else []   # the A/B-only kernels (gauss.cu)
+        cmd = [nvcc_path(), *NVCC_FLAGS, *ab, "-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log, failed = "", False
     for cmd, pr in procs:

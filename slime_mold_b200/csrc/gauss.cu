@@ -30,6 +30,16 @@
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// The A/B-only instantiations -- rows kernel at radius 6-8 and with packing levels that lost their comparison, the packed forms of
+// the streaming and tile kernels (all measured, none the default anywhere: profiles/NOTES.md) -- are 80 large kernels and half of
+// this file's compile time.  They are built with SM_BUILD_AB_VARIANTS=1 (python -m slime_mold_b200.build reads the environment
+// variable of the same name); without it the switches that select them fall back to the default variant.
+#ifndef SM_BUILD_AB_VARIANTS
+#define SM_BUILD_AB_VARIANTS 0
+#endif
+constexpr bool kAbVariants = SM_BUILD_AB_VARIANTS != 0;
+constexpr int kRowsMaxBuiltR = kAbVariants ? smk::kGrMaxR : 5;
+
 // The streaming Gaussian kernel (gauss_stream.cuh) applies: it also merges u8 deposit flags and keeps the sampler's
 // block-linear copy in step, so a Gaussian full step runs the same agent kernel as the box-blur step.
 bool sm_engine::gauss_stream_ok() const
@@ -42,7 +52,7 @@ bool sm_engine::gauss_stream_ok() const
 bool sm_engine::gauss_rows_ok() const
 {
     const int R = (int)lroundf(params.blur_radius);
-    return gauss_rows && !gauss_two_pass && R >= 1 && R <= gauss_rows_max_r && R <= smk::kGrMaxR && W % 4 == 0 &&
+    return gauss_rows && !gauss_two_pass && R >= 1 && R <= gauss_rows_max_r && R <= kRowsMaxBuiltR && W % 4 == 0 &&
            W >= (uint32_t)smk::kGrMinW && rows >= (uint32_t)smk::kGrMinRows;
 }
 
@@ -81,13 +91,24 @@ static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a, const smd::Trai
     // FFMA2 taps (level 2: column taps + the aligned half of the row taps): 3-6 % faster at radius 3-4, 1-3 % at 1-2; at
     // radius 5 the extra registers cost a resident CTA (0.60 against 0.65 of the HBM peak), above that they were measured
     // too and dropped from the build (each of those instantiations is 2-3 K instructions)
-    if constexpr (R <= 5) {
-        const int pk = e->gauss_rows_packed < 0 ? (R <= 4 ? 2 : 0) : e->gauss_rows_packed;
-        if (pk >= 2) return launch_gauss_rows_pk<R, CM, SURF, 2>(e, a, tc, gc);
-        if (pk == 1) return launch_gauss_rows_pk<R, CM, SURF, 1>(e, a, tc, gc);
+    if constexpr (kAbVariants) {
+        if constexpr (R <= 5) {
+            const int pk = e->gauss_rows_packed < 0 ? (R <= 4 ? 2 : 0) : e->gauss_rows_packed;
+            if (pk >= 2) return launch_gauss_rows_pk<R, CM, SURF, 2>(e, a, tc, gc);
+            if (pk == 1) return launch_gauss_rows_pk<R, CM, SURF, 1>(e, a, tc, gc);
+            return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
+        } else {
+            return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
+        }
+    } else if constexpr (R <= 4) {
+        // default build: level 2 and the scalar form
+        const int pk = e->gauss_rows_packed < 0 ? 2 : e->gauss_rows_packed;
+        if (pk >= 1) return launch_gauss_rows_pk<R, CM, SURF, 2>(e, a, tc, gc);
+        return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
+    } else if constexpr (R == 5) {
         return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
     } else {
-        return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
+        return sm_fail(SM_ERR_STATE, "k_gauss_rows is not built for radius %d (SM_BUILD_AB_VARIANTS=1)", R);   // unreachable: gauss_rows_ok()
     }
 }
 
@@ -99,7 +120,7 @@ static int launch_gauss_stream(sm_engine* e, const smk::GsArgs& a, const smd::Tr
 {
     // packed taps (SM_GAUSS_STREAM_PACKED=1; built for radius >= 5): 16 % fewer instructions, no measurable gain (0.51 ->
     // 0.52 of the peak at radius 8) -- this kernel waits on its barriers and shared-memory round trips, not on issue slots
-    if constexpr (R >= 5) {
+    if constexpr (kAbVariants && R >= 5) {
         if (e->gauss_stream_packed) return launch_gauss_stream_pk<R, CM, SURF, true>(e, a, tc, gc);
     }
     return launch_gauss_stream_pk<R, CM, SURF, false>(e, a, tc, gc);
@@ -230,14 +251,20 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
         auto go = [&](auto r_tag) -> int {
             constexpr int RR = decltype(r_tag)::value;
             const size_t smem = smk::gauss_smem_bytes<RR>();
-            if (gauss_packed) {
-                if (has_counts) {
-                    SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused_packed<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    smk::k_gauss_fused_packed<RR, true><<<grid, 256, smem, stream>>>(tin0, counts_ptr(ccur), counts_ptr(1 - ccur), tout0, g, tc, gc);
-                } else {
-                    SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused_packed<RR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    smk::k_gauss_fused_packed<RR, false><<<grid, 256, smem, stream>>>(tin0, nullptr, nullptr, tout0, g, tc, gc);
+            bool packed_done = false;
+            if constexpr (kAbVariants) {
+                if (gauss_packed) {
+                    packed_done = true;
+                    if (has_counts) {
+                        SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused_packed<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        smk::k_gauss_fused_packed<RR, true><<<grid, 256, smem, stream>>>(tin0, counts_ptr(ccur), counts_ptr(1 - ccur), tout0, g, tc, gc);
+                    } else {
+                        SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused_packed<RR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        smk::k_gauss_fused_packed<RR, false><<<grid, 256, smem, stream>>>(tin0, nullptr, nullptr, tout0, g, tc, gc);
+                    }
                 }
+            }
+            if (packed_done) {
             } else if (has_counts) {
                 SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 smk::k_gauss_fused<RR, true><<<grid, 256, smem, stream>>>(tin0, counts_ptr(ccur), counts_ptr(1 - ccur), tout0, g, tc, gc);

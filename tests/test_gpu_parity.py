@@ -209,6 +209,9 @@ def test_gaussian_extension(oracle, engine_lib, R, sigma):
     be.close()
 
 
+# "packed", "stream_packed", "rows_packed" (level 1) and the rows kernel above radius 5 are A/B-only instantiations: they exist in
+# a library built with SM_BUILD_AB_VARIANTS=1 (python -m slime_mold_b200.build); the default build runs the default variant
+# for those switches, so the cases below always run -- against whichever kernel the library selects.
 @pytest.mark.parametrize("kernel", ["packed", "scalar", "two_pass", "stream", "stream_packed", "rows", "rows_packed", "rows_packed2"])
 @pytest.mark.parametrize("R,sigma,W,H", [(1, 0.7, 160, 64), (2, 1.0, 416, 200), (3, 1.3, 517, 131), (4, 2.0, 256, 96), (5, 2.5, 1000, 97),
                                          (6, 3.0, 384, 130), (7, 3.5, 772, 65), (8, 4.0, 640, 333)])
