@@ -169,9 +169,12 @@ int sm_resize(sm_engine *e, uint32_t width, uint32_t height);
  * verbatim (src/lut_manager.rs:162-186), i.e. LutData.red ++ green ++ blue as main.rs:330-334
  * concatenates them (the reference widens each byte to u32 for its storage buffer).
  * sm_render_rgba8: `rgba` is a caller-owned host buffer of tex_width * tex_height * 4 bytes,
- * row-major, R G B A per texel (the rgba8unorm texture of main.rs:296-314).  The frame shows
- * the trail as it stands after the last completed step (the reference draws between its
- * decay and diffuse dispatches; this engine fuses those two).  Single GPU. */
+ * row-major, R G B A per texel (the rgba8unorm texture of main.rs:296-314).  Like the
+ * reference, which draws between its decay and diffuse dispatches, the frame after an
+ * sm_step() shows the field of the last step after deposits and decay, before the blur
+ * (recomputed per texel from that step's inputs, which are still in device memory); after
+ * anything else that changed the trail (upload, clear, sm_diffuse_only, resize, snapshot
+ * load) it shows the trail as it stands.  Single GPU. */
 int sm_set_lut(sm_engine *e, const uint8_t *lut768);
 int sm_render_rgba8(sm_engine *e, uint32_t tex_width, uint32_t tex_height, uint8_t *rgba);
 

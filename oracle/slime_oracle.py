@@ -41,12 +41,48 @@ class Params(C.Structure):
     ]
 
 
+_FLAVOUR = "gcc -O2 -march=x86-64-v3"
+
+
 def build(force: bool = False) -> str:
-    """Compile the oracle with oracle/Makefile (gcc, -ffp-contract=off, OpenMP)."""
-    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("slime_oracle.c", "sm_oracle_math.h", "Makefile"))
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < src_m:
+    """Compile the oracle with oracle/Makefile (gcc, -ffp-contract=off, OpenMP).  With SM_ORACLE_NATIVE=1 in the
+    environment (bench.py's CPU arm) a second library is built on this very machine at -O3 -march=native and loaded
+    instead; if that build fails the portable one is used."""
+    global _SO, _FLAVOUR, _lib
+    srcs = [os.path.join(_HERE, f) for f in ("slime_oracle.c", "sm_oracle_math.h", "Makefile")]
+    src_m = max(os.path.getmtime(f) for f in srcs)
+    portable = os.path.join(_HERE, "libslime_oracle.so")
+    if force or not os.path.exists(portable) or os.path.getmtime(portable) < src_m:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    if os.environ.get("SM_ORACLE_NATIVE") == "1" and _lib is None:
+        native = os.path.join(_HERE, "libslime_oracle_native.so")
+        stamp = native + ".host"
+        host = _host_id()
+        fresh = os.path.exists(native) and os.path.getmtime(native) >= src_m and os.path.exists(stamp) and open(stamp).read() == host
+        if not fresh:
+            r = subprocess.run(["make", "-C", _HERE, "-s", "-B", "native"], capture_output=True, text=True)
+            fresh = r.returncode == 0 and os.path.exists(native)
+            if fresh:
+                with open(stamp, "w") as f:
+                    f.write(host)
+        if fresh:
+            _SO, _FLAVOUR = native, "gcc -O3 -march=native (built on this host)"
     return _SO
+
+
+def _host_id() -> str:
+    """-march=native code must not travel to another CPU: the native build is tagged with the CPU it was made on."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build_flavour() -> str:
+    return _FLAVOUR
 
 
 _lib = None

@@ -156,9 +156,17 @@ int sm_engine::alloc_trail()
     }
     cur = 0; ccur = 0;
     stats_fused_valid = false;
+    frame_pre_valid = false;
     trail_nonneg = true;
     deposit_mode = 0;
-    if (use_tex) SM_TRY(setup_tex());
+    if (use_tex && setup_tex() != SM_OK) {
+        // no block-linear copy for this map (above the texture-gather size limit, or out of memory for the extra
+        // 4 B/cell): the agent kernel samples the row-major field with LDGs instead -- same bits, still the CUDA path
+        cudaGetLastError();
+        free_tex();
+        use_tex = false;
+        tex_fallback = true;
+    }
     return SM_OK;
 }
 void sm_engine::free_trail()
@@ -236,18 +244,61 @@ static int gather_probe_ok(bool* ok)
     return rc;
 }
 
+static constexpr float kDualSensorDistance = 48.0f;   // presets: 20 (L1 hit rate 74 %: one copy) or 225 (22 %: two copies)
+
+bool sm_engine::want_tex_dual() const
+{
+    if (tex_dual_mode == 1) return false;
+    if (tex_dual_mode == 2) return true;
+    return fabsf(params.agent_sensor_distance) >= kDualSensorDistance;
+}
+
 int sm_engine::setup_tex()
 {
     free_tex();
     const size_t htot = rows + 2 * (size_t)(ghost + pad_rows);
+    int gw = 0, gh = 0;       // cudaArrayTextureGather arrays are limited (32768 x 32768 on sm_100)
+    SM_CUDA(cudaDeviceGetAttribute(&gw, cudaDevAttrMaxTexture2DGatherWidth, device));
+    SM_CUDA(cudaDeviceGetAttribute(&gh, cudaDevAttrMaxTexture2DGatherHeight, device));
+    if ((size_t)W > (size_t)gw || htot > (size_t)gh)
+        return sm_fail(SM_ERR_BAD_ARG, "map %u x %zu exceeds the texture-gather limit %d x %d", W, htot, gw, gh);
+    // second, shifted copy below the first one (same array: one texture object, the lanes of a warp choose per footprint)
+    const size_t hA = (htot + 7) / 8 * 8;
+    size_t aw = W, ah = htot;
+    tex_dual = want_tex_dual() && (size_t)W + 4 <= (size_t)gw && 2 * hA + 2 <= (size_t)gh;
+    tex_b_dy = 0;
+    if (tex_dual) { aw = (size_t)W + 4; ah = 2 * hA + 2; tex_b_dy = (int32_t)hA + 2; }
     cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
-    SM_CUDA(cudaMallocArray(&trail_arr, &fd, W, htot, cudaArraySurfaceLoadStore | cudaArrayTextureGather));
+    SM_CUDA(cudaMallocArray(&trail_arr, &fd, aw, ah, cudaArraySurfaceLoadStore | cudaArrayTextureGather));
     SM_TRY(make_tex(trail_arr, &trail_tex));
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = trail_arr;
     SM_CUDA(cudaCreateSurfaceObject(&trail_surf, &rd));
     arr_stale = true;
+    return SM_OK;
+}
+// The sampling mode follows the sensor distance (sm_set_params can change it between steps): re-create the array when it
+// no longer matches.  Rare (a key press in the reference's UI); the next agent pass refills the array from trail[cur].
+int sm_engine::ensure_tex_mode()
+{
+    if (!use_tex || !trail_arr) return SM_OK;
+    if (want_tex_dual() == tex_dual) return SM_OK;
+    if (want_tex_dual() && !tex_dual) {
+        // asked for, but the doubled array did not fit when it was tried: do not retry on every step
+        const size_t htot = rows + 2 * (size_t)(ghost + pad_rows);
+        int gw = 0, gh = 0;
+        SM_CUDA(cudaDeviceGetAttribute(&gw, cudaDevAttrMaxTexture2DGatherWidth, device));
+        SM_CUDA(cudaDeviceGetAttribute(&gh, cudaDevAttrMaxTexture2DGatherHeight, device));
+        if ((size_t)W + 4 > (size_t)gw || 2 * ((htot + 7) / 8 * 8) + 2 > (size_t)gh) return SM_OK;
+    }
+    SM_CUDA(cudaStreamSynchronize(stream));
+    if (setup_tex() != SM_OK) {
+        cudaGetLastError();
+        free_tex();
+        use_tex = false;
+        tex_fallback = true;
+    }
     return SM_OK;
 }
 void sm_engine::free_tex()
@@ -262,6 +313,9 @@ int sm_engine::refresh_tex(int64_t local_row_begin, int64_t n_rows)
     const int64_t arr_row = local_row_begin + (int64_t)(ghost + pad_rows);
     SM_CUDA(cudaMemcpy2DToArrayAsync(trail_arr, 0, (size_t)arr_row, trail_ptr(cur) + local_row_begin * (int64_t)W,
                                      (size_t)W * 4, (size_t)W * 4, (size_t)n_rows, cudaMemcpyDeviceToDevice, stream));
+    if (tex_dual)     // the shifted copy: (x, r) -> (x + 4, r + tex_b_dy)
+        SM_CUDA(cudaMemcpy2DToArrayAsync(trail_arr, 16, (size_t)(arr_row + tex_b_dy), trail_ptr(cur) + local_row_begin * (int64_t)W,
+                                         (size_t)W * 4, (size_t)W * 4, (size_t)n_rows, cudaMemcpyDeviceToDevice, stream));
     return SM_OK;
 }
 
@@ -271,7 +325,7 @@ int sm_engine::refresh_tex_ghosts(uint32_t g)
     const int32_t off = (int32_t)(ghost + pad_rows);
     const uint64_t total = 2ull * g * W;
     const unsigned nb = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms * 4);
-    smk::k_rows_to_surface<<<nb, 256, 0, stream>>>(trail_base[cur], trail_surf, W, off - (int32_t)g, off + (int32_t)rows, (int32_t)g);
+    smk::k_rows_to_surface<<<nb, 256, 0, stream>>>(trail_base[cur], trail_surf, W, off - (int32_t)g, off + (int32_t)rows, (int32_t)g, tex_dual ? tex_b_dy : 0);
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
     return SM_OK;
@@ -371,12 +425,18 @@ int sm_engine::sort_agents()
 int sm_engine::launch_agents()
 {
     if (world > 1) n_local = n_upper;            // grid bound; the kernel reads the exact count on the device
-    if (n_local == 0) return SM_OK;
+    const bool flags = flag_mode();
+    // Before the early return: the deposit mode of the step is a collective decision (a rank whose strip is empty still
+    // merges what its neighbours deposited into it, and takes part in the barrier of a mode change), and the trail pass
+    // accumulates its statistics from zero whether or not an agent kernel ran
+    SM_TRY(switch_deposit_mode(flags ? 2 : 1));
+    if (n_local == 0) {
+        SM_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(smk::StatsAcc), stream));
+        return SM_OK;
+    }
     SM_TRY(tic(0));
     smk::LeaverBufs lv{};
     const bool idx32 = (uint64_t)field_cells() < (1ull << 31);
-    const bool flags = flag_mode();
-    SM_TRY(switch_deposit_mode(flags ? 2 : 1));
     const int apt = smk::agents_per_thread_for(n_local, num_sms);
     const unsigned nb = blocks_for(n_local, 256u * (unsigned)apt);        // a CTA steps 256 * apt consecutive slots
     float4* a = agents[acur];
@@ -424,13 +484,19 @@ int sm_engine::launch_agents()
             else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         }
     };
+    if (use_tex) SM_TRY(ensure_tex_mode());
     if (use_tex) {
         if (arr_stale) {                                  // the array lost track of trail[cur]: one full copy
             SM_TRY(refresh_tex(-(int64_t)(ghost + pad_rows), (int64_t)rows + 2 * (int64_t)(ghost + pad_rows)));
             arr_stale = false;
         }
-        const smk::FetchTex f{trail_tex, (float)((int32_t)(ghost + pad_rows) - (int32_t)row0 + 1)};
-        if (agent_stream_hint && !multi && idx32) {
+        const int32_t arr_row_of_global0 = (int32_t)(ghost + pad_rows) - (int32_t)row0;
+        const smk::FetchTex f{trail_tex, (float)(arr_row_of_global0 + 1), arr_row_of_global0, 0.0f};
+        if (tex_dual) {
+            const smk::FetchTexDual fd{trail_tex, (float)(arr_row_of_global0 + 1), arr_row_of_global0, (float)tex_b_dy};
+            if (idx32) launch(fd, int32_t{});
+            else launch(fd, int64_t{});
+        } else if (agent_stream_hint && !multi && idx32) {
             // A/B instantiation: evict-first hints on the agent stream (single GPU, 32-bit offsets, texture sampler)
             if (flags) smk::k_agents<smk::XM_SINGLE, int32_t, smk::FetchTex, true, true><<<nb, 256, 0, stream>>>(a, id, n_local, f, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
             else smk::k_agents<smk::XM_SINGLE, int32_t, smk::FetchTex, false, true><<<nb, 256, 0, stream>>>(a, id, n_local, f, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
@@ -458,6 +524,7 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     const bool write_surf = use_tex && has_counts && (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) || (gauss_fast_ok() && world == 1));
     p.g.surf = write_surf ? trail_surf : 0;
     p.g.surf_row0 = (int)(ghost + pad_rows);
+    p.g.surf_b_dy = (write_surf && tex_dual) ? tex_b_dy : 0;
     if (!write_surf) arr_stale = true;
     p.tin = trail_ptr(cur);
     p.tout = trail_ptr(1 - cur);
@@ -470,6 +537,9 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     // 8-16 rows per chunk measured best from 4096^2 to 32768^2 (profiles/README.md): the 2/rpc halo
     // re-reads hit L2; small maps take shorter chunks to keep >= 4 CTAs per SM
     uint64_t rpc = 8;
+    // diffusion-only passes on maps far beyond the L2: 16 rows per chunk measured 4-6 % faster from 16384^2 up (halo rows
+    // are 2/16 instead of 2/8 of the reads, and they no longer hit L2); 32768^2: 0.789 -> 0.835 of nominal 8 TB/s
+    if (!has_counts && (uint64_t)W * rows >= (1ull << 28)) rpc = 16;
     const unsigned bx = blocks_for(W / 4, 128);
     while (rpc > 4 && (uint64_t)bx * ((rows + rpc - 1) / rpc) < (uint64_t)num_sms * 4) rpc /= 2;
     if (rpc_override > 0) rpc = rpc_override;
@@ -492,22 +562,22 @@ int sm_engine::trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t 
     dim3 grid(blocks_for(W / 4, bs), (unsigned)(g.chunks1 + chunks2));
     smk::StatsAcc* acc = (smk::StatsAcc*)stats_dev;
     auto go = [&](auto cm_tag, auto surf_tag, auto stats_tag) {
-        constexpr int CMv = decltype(cm_tag)::value;
-        constexpr bool SURFv = decltype(surf_tag)::value, STATSv = decltype(stats_tag)::value;
+        constexpr int CMv = decltype(cm_tag)::value, SURFv = decltype(surf_tag)::value;
+        constexpr bool STATSv = decltype(stats_tag)::value;
         smk::k_trail_rows<CMv, SURFv, 4, STATSv><<<grid, bs, 0, st>>>(p.tin, CMv == smk::CM_NONE ? nullptr : p.cin,
                                                                        CMv == smk::CM_NONE ? nullptr : p.czero, p.tout, g, p.tc, acc);
     };
     using std::integral_constant;
     using T = std::true_type; using F = std::false_type;
-    if (p.cm == smk::CM_NONE) {
-        go(integral_constant<int, smk::CM_NONE>{}, F{}, F{});
-    } else if (p.cm == smk::CM_COUNTS) {
-        if (g.surf) { if (p.stats) go(integral_constant<int, smk::CM_COUNTS>{}, T{}, T{}); else go(integral_constant<int, smk::CM_COUNTS>{}, T{}, F{}); }
-        else        { if (p.stats) go(integral_constant<int, smk::CM_COUNTS>{}, F{}, T{}); else go(integral_constant<int, smk::CM_COUNTS>{}, F{}, F{}); }
-    } else {
-        if (g.surf) { if (p.stats) go(integral_constant<int, smk::CM_FLAGS>{}, T{}, T{}); else go(integral_constant<int, smk::CM_FLAGS>{}, T{}, F{}); }
-        else        { if (p.stats) go(integral_constant<int, smk::CM_FLAGS>{}, F{}, T{}); else go(integral_constant<int, smk::CM_FLAGS>{}, F{}, F{}); }
-    }
+    using S0 = integral_constant<int, 0>; using S1 = integral_constant<int, 1>; using S2 = integral_constant<int, 2>;
+    auto go_cm = [&](auto cm_tag) {
+        if (!g.surf)           { if (p.stats) go(cm_tag, S0{}, T{}); else go(cm_tag, S0{}, F{}); }
+        else if (!g.surf_b_dy) { if (p.stats) go(cm_tag, S1{}, T{}); else go(cm_tag, S1{}, F{}); }
+        else                   { if (p.stats) go(cm_tag, S2{}, T{}); else go(cm_tag, S2{}, F{}); }
+    };
+    if (p.cm == smk::CM_NONE) go(integral_constant<int, smk::CM_NONE>{}, S0{}, F{});
+    else if (p.cm == smk::CM_COUNTS) go_cm(integral_constant<int, smk::CM_COUNTS>{});
+    else go_cm(integral_constant<int, smk::CM_FLAGS>{});
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
     return SM_OK;
@@ -630,6 +700,8 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     {
         const char* smp = getenv("SM_SAMPLER");
         bool want_tex = !(smp && std::string(smp) == "ldg");
+        if (smp && std::string(smp) == "tex1") e->tex_dual_mode = 1;       // A/B: never / always the shifted second copy
+        if (smp && std::string(smp) == "tex2") e->tex_dual_mode = 2;
         bool probe = false;
         if (want_tex) { int prc = gather_probe_ok(&probe); if (prc != SM_OK) { delete e; return prc; } }
         e->use_tex = want_tex && probe;
@@ -735,7 +807,12 @@ int sm_set_params(sm_engine* e, const sm_params* p)
         if (!(sd + 3.0f <= (float)e->ghost))
             return sm_fail(SM_ERR_BAD_ARG, "sensor distance %g needs %d ghost rows; strips provide %u", sd, (int)ceilf(sd) + 3, e->ghost);
     }
+    const sm_params before = e->params;
     e->params = *p;
+    if (const int rc = e->check_gauss(false); rc != SM_OK) {   // extension: a bad radius / sigma is refused here, not in the middle of a step
+        e->params = before;
+        return rc;
+    }
     return SM_OK;
 }
 
@@ -898,6 +975,7 @@ int sm_clear_trail(sm_engine* e)
     e->arr_stale = true;
     e->trail_nonneg = true;
     e->stats_fused_valid = false;
+    e->frame_pre_valid = false;
     return SM_OK;
 }
 
@@ -917,6 +995,10 @@ int sm_upload_trail(sm_engine* e, const float* src, uint32_t x0, uint32_t y0, ui
     if (!src) return sm_fail(SM_ERR_BAD_ARG, "null source");
     uint32_t ya = 0, yb = 0;
     SM_TRY(clip_rows(e, x0, y0, w, h, pitch, &ya, &yb));
+    // strips: the deposit representation of the next step must be the same on every rank, whichever strips the
+    // rectangle touches -- every rank falls back to counts until the next trail pass (this used to sit
+    // inside the intersection test, so ranks the rectangle missed kept flags and lost cross-strip deposits)
+    if (e->world > 1) e->trail_nonneg = false;
     if (ya < yb && w) {
         if (e->trail_nonneg) {
             bool ok = true;
@@ -927,7 +1009,6 @@ int sm_upload_trail(sm_engine* e, const float* src, uint32_t x0, uint32_t y0, ui
             }
             e->trail_nonneg = ok;
         }
-        if (e->world > 1) e->trail_nonneg = false;   // the decision must be the same on every rank
         float* dst = e->trail_ptr(e->cur) + (size_t)(ya - e->row0) * e->W + x0;
         SM_CUDA(cudaMemcpy2DAsync(dst, (size_t)e->W * 4, src + (size_t)(ya - y0) * pitch, pitch * 4, (size_t)w * 4,
                                   yb - ya, cudaMemcpyHostToDevice, e->stream));
@@ -936,6 +1017,7 @@ int sm_upload_trail(sm_engine* e, const float* src, uint32_t x0, uint32_t y0, ui
     e->ghost_stale = true;
     e->arr_stale = true;
     e->stats_fused_valid = false;
+    e->frame_pre_valid = false;
     return SM_OK;
 }
 
@@ -1074,6 +1156,7 @@ int sm_load_snapshot(sm_engine* e, const char* path)
     e->ghost_stale = true;
     e->arr_stale = true;
     e->stats_fused_valid = false;
+    e->frame_pre_valid = false;
     return SM_OK;
 }
 
@@ -1116,7 +1199,18 @@ int sm_render_rgba8(sm_engine* e, uint32_t tex_width, uint32_t tex_height, uint8
         g.sim_w = sim_w; g.sim_h = sim_h; g.scale = scale; g.off_x = off_x; g.off_y = off_y;
     }
     dim3 grid(blocks_for((tex_width + 3) / 4, 256), tex_height);
-    smk::k_display<<<grid, 256, 0, e->stream>>>(e->trail_ptr(e->cur), e->lut_dev, e->frame_dev, g);
+    smk::DisplaySrc src{};
+    if (e->frame_pre_valid) {
+        // the field the reference draws: decay(merge(T_prev, deposits)) of the last step (trail_done flipped cur / ccur)
+        src.trail = e->trail_ptr(1 - e->cur);
+        src.cm = e->deposit_mode == 2 ? smk::CM_FLAGS : smk::CM_COUNTS;
+        src.dep = src.cm == smk::CM_FLAGS ? (const void*)e->flags_ptr(1 - e->ccur) : (const void*)e->counts_ptr(1 - e->ccur);
+        src.tc = e->frame_tc;
+    } else {
+        src.trail = e->trail_ptr(e->cur);
+        src.cm = smk::CM_NONE;
+    }
+    smk::k_display<<<grid, 256, 0, e->stream>>>(src, e->lut_dev, e->frame_dev, g);
     SM_CUDA(cudaGetLastError());
     e->timing.kernel_launches += 1;
     SM_CUDA(cudaMemcpyAsync(rgba_host, e->frame_dev, texels * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -1138,6 +1232,7 @@ int sm_resize(sm_engine* e, uint32_t width, uint32_t height)
     SM_CUDA(cudaGetLastError());
     SM_CUDA(cudaStreamSynchronize(e->stream));
     e->free_trail();                                   // src/main.rs:999-1015: new zeroed trail
+    if (e->tex_fallback) { e->use_tex = true; e->tex_fallback = false; }   // the new size may fit the gather limits again
     e->W = width; e->H = height;
     e->rows = height; e->row0 = 0;
     e->cfg.width = width; e->cfg.height = height;
@@ -1154,6 +1249,7 @@ int sm_step(sm_engine* e, uint32_t n_steps)
     SM_ENTER(e);
     if (!e->agents_valid) return sm_fail(SM_ERR_STATE, "agents were never initialised or uploaded");
     if (e->world > 1 && !e->comm_ready) return sm_fail(SM_ERR_STATE, "multi-GPU engine: call sm_comm_init first");
+    SM_TRY(e->check_gauss(true));                        // nothing is launched on bad blur parameters
     for (uint32_t s = 0; s < n_steps; ++s) {
         if (e->world > 1 && e->ghost_stale) SM_TRY(e->exchange_trail_ghosts());
         if (e->sort_interval && e->steps_since_sort >= e->sort_interval) {
@@ -1170,6 +1266,8 @@ int sm_step(sm_engine* e, uint32_t n_steps)
         }
         e->steps_since_sort++;
         e->timing.steps++;
+        e->frame_pre_valid = true;
+        e->frame_tc = e->trail_consts();
     }
     return SM_OK;
 }
@@ -1178,6 +1276,8 @@ int sm_diffuse_only(sm_engine* e, uint32_t n_passes)
 {
     SM_ENTER(e);
     if (e->world > 1 && !e->comm_ready) return sm_fail(SM_ERR_STATE, "multi-GPU engine: call sm_comm_init first");
+    SM_TRY(e->check_gauss(false));
+    if (n_passes) e->frame_pre_valid = false;
     for (uint32_t s = 0; s < n_passes; ++s) {
         if (e->world > 1 && e->ghost_stale) SM_TRY(e->exchange_trail_ghosts());
         if (e->world > 1 && e->p2p && e->overlap_ok()) {

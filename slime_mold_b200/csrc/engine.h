@@ -52,6 +52,15 @@ struct sm_engine {
     cudaTextureObject_t trail_tex = 0;
     cudaSurfaceObject_t trail_surf = 0;
     bool use_tex = false;             // SM_SAMPLER=tex (default) and the gather probe passed
+    // "straddle-free" sampling for large sensor distances (kernels.cuh: FetchTexT<true>): the array also holds a copy of the
+    // field shifted by (+4, +tex_b_dy) texels.  tex_dual_mode: 0 = auto (dual when |sensor distance| >= kDualSensorDistance
+    // and the doubled array fits the gather limits), 1 = never, 2 = always (SM_SAMPLER=tex1 / tex2: A/B switch).
+    int tex_dual_mode = 0;
+    bool tex_dual = false;            // the array that exists now holds both copies
+    int32_t tex_b_dy = 0;             // rows between a texel of copy A and the same texel of copy B (multiple of 4, plus 2)
+    bool want_tex_dual() const;
+    int ensure_tex_mode();            // (re-)allocates the array when the sampling mode the parameters ask for changed
+    bool tex_fallback = false;        // use_tex was switched off because this map does not fit a gather array (retried by sm_resize)
     bool arr_stale = true;            // the array does not mirror trail[cur] (upload / clear / diffuse-only ...)
     float* gauss_dec = nullptr;       // extension scratch
     float* gauss_hb = nullptr;
@@ -103,6 +112,10 @@ struct sm_engine {
     bool stats_fused_valid = false;
     uint32_t stats_interest = 0;      // > 0: the host read statistics within the last 64 steps -> passes run the STATS instantiation
 
+    // the frame the reference would draw is the field between decay and diffuse of the last step (main.rs:1202-1217):
+    // recomputed by k_display from the inputs of that step's trail pass while they are still intact
+    bool frame_pre_valid = false;     // the last thing that changed the trail was a full step (its inputs are still in HBM)
+    smd::TrailConsts frame_tc{};      // deposit amount / decay of that step
     // display pass (display.wgsl): LUT and frame buffer, allocated on first use
     uint8_t* lut_dev = nullptr;
     bool lut_set = false;
@@ -197,6 +210,7 @@ struct sm_engine {
     void trail_done(bool has_counts);
     int launch_trail(bool has_counts);
     int launch_gauss(bool has_counts, const TrailPass& p);
+    int check_gauss(bool has_counts) const;   // parameter / geometry checks of the Gaussian extension, before anything is launched
     int restore_identity_order();
     int fill_identity_ids();
 

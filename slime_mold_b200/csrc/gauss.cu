@@ -158,22 +158,33 @@ static int launch_gauss_stream_pk(sm_engine* e, const smk::GsArgs& a0, const smd
     return SM_OK;
 }
 
+// Everything that can make a Gaussian pass fail, checked BEFORE anything is launched (sm_set_params, and the top of
+// sm_step / sm_diffuse_only): a bad radius or sigma must not leave a step half done (agents moved, deposits unmerged).
+int sm_engine::check_gauss(bool has_counts) const
+{
+    if (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR)) return SM_OK;
+    const float br = params.blur_radius;
+    if (!(br >= 0.5f && br < 8.5f)) return sm_fail(SM_ERR_BAD_ARG, "gaussian blur radius must round to 1..8 (got %g)", br);
+    if (!(params.blur_sigma > 0.0f) || !(params.blur_sigma < 1.0e6f)) return sm_fail(SM_ERR_BAD_ARG, "gaussian blur sigma must be > 0 and finite");
+    const int R = (int)lroundf(br);
+    if (world != 1) {
+        // strips: diffusion-only passes (BASELINE config 5 at 2/4/8 GPUs); the R rows of the neighbours a pass reads are the
+        // ghost rows sm_diffuse_only exchanges after every pass
+        if (has_counts) return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR: full steps are single-GPU only (diffusion-only passes run on strips)");
+        if (!gauss_fast_ok())
+            return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR on strips needs the streaming kernels (W %% 4 == 0, W >= %d, >= %d rows per strip)",
+                           smk::kGsMinW, smk::kGsMinRows);
+        if ((uint32_t)R > ghost) return sm_fail(SM_ERR_STATE, "strip has %u ghost rows, the blur needs %d", ghost, R);
+    }
+    return SM_OK;
+}
+
 int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
 {
     const smk::TrailGeom& g = p.g;
     const smd::TrailConsts& tc = p.tc;
-    int R = (int)lroundf(params.blur_radius);
-    if (world != 1) {
-        // strips: diffusion-only passes of the streaming kernel (BASELINE config 5 at 2/4/8 GPUs); the R rows of the
-        // neighbours it reads are the ghost rows sm_diffuse_only exchanges after every pass
-        if (has_counts) return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR: full steps are single-GPU only (diffusion-only passes run on strips)");
-        if (!gauss_fast_ok())
-            return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR on strips needs the streaming kernel (not SM_GAUSS_KERNEL=tile; W %% 4 == 0, W >= %d, >= %d rows per strip)",
-                           smk::kGsMinW, smk::kGsMinRows);
-        if ((uint32_t)(R < 1 ? 1 : R) > ghost) return sm_fail(SM_ERR_STATE, "strip has %u ghost rows, the blur needs %d", ghost, R);
-    }
-    if (R < 1 || R > 8) return sm_fail(SM_ERR_BAD_ARG, "gaussian blur radius must round to 1..8 (got %g)", params.blur_radius);
-    if (!(params.blur_sigma > 0.0f)) return sm_fail(SM_ERR_BAD_ARG, "gaussian blur sigma must be > 0");
+    SM_TRY(check_gauss(has_counts));
+    const int R = (int)lroundf(params.blur_radius);
     smk::GaussConsts gc{};
     gc.R = R;
     {   // weights: exp(-d^2 / 2 sigma^2) in f64, normalised in f64, rounded to f32 (oracle: so_gauss_weights)
@@ -193,7 +204,7 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
         smk::GsArgs a{};
         a.tin = p.tin; a.cin = p.cm == smk::CM_NONE ? nullptr : p.cin; a.czero = p.cm == smk::CM_NONE ? nullptr : p.czero; a.tout = p.tout;
         a.W = (int)W; a.H = (int)rows; a.wrap_y = g.wrap_y;
-        a.surf = (unsigned long long)g.surf; a.surf_row0 = g.surf_row0;
+        a.surf = (unsigned long long)g.surf; a.surf_row0 = g.surf_row0; a.surf_b_dy = g.surf_b_dy;
         const bool surf = g.surf != 0;
         auto go_rows = [&](auto r_tag) -> int {
             constexpr int RR = decltype(r_tag)::value;

@@ -33,38 +33,62 @@ struct LdgF32 {
 // arithmetic).  At (x0 + 1, y0 + 1) -- the common corner of the four texels -- the footprint is
 // {x0, x0+1} x {y0, y0+1}; components come back as (x0,y0+1), (x0+1,y0+1), (x0+1,y0), (x0,y0)
 // (verified at sm_create by k_gather_probe: the engine refuses the TEX path otherwise).
-struct FetchTex {
+//
+// DUAL ("straddle-free" sampling, selected for large sensor distances): at sensor distance 225 the three footprints of an
+// agent are incoherent -- no two lanes of a warp, and no two warps of an SM, touch the same texels -- so every footprint is
+// an L1 miss, and the agent kernel is bound by the one miss request (one 128-byte line = 8 x 4 texels of the block-linear
+// layout) an SM's L1 can send to the crossbar per cycle (ncu: l1tex__m_l1tex2xbar_req_cycles_active 84 %;
+// tools/microbench/gather_rate.cu: 1.44 SM-cycles per footprint anywhere, 1.00 when it lies inside one line).  A 2x2
+// footprint straddles a line when x0 % 8 == 7 or row % 4 == 3: 34 % of them, 1.41 requests on average.  The array
+// therefore holds a SECOND copy of the field shifted by (+4, +2) texels, where exactly those footprints sit in the
+// middle of a line; only the 6 % that straddle in both copies still cost two requests.  Same texels, same bits.
+template <bool DUAL>
+struct FetchTexT {
     cudaTextureObject_t tex;
     float row_off1;          // (array row of global row 0) + 1 = ghost + pad - row_base + 1, exact in f32
+    int32_t row_off;         // array row of global row 0 (DUAL: phase of the 4-row line groups)
+    float b_dy;              // DUAL: copy B holds field(x, array row r) at texel (x + 4, r + b_dy); b_dy % 4 == 2
     __device__ __forceinline__ void operator()(const AgentConsts&, float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
     {
         // fetched whether or not the tap is inside the map (clamped addressing; the caller discards the
         // footprint of an outside tap).  Coordinates stay in float: for an inside tap fx, fy are integral
         // and < 2^17, so the sums are exact
-        float4 g = tex2Dgather<float4>(tex, fx + 1.0f, fy + row_off1, 0);
+        float gx = fx + 1.0f, gy = fy + row_off1;
+        if (DUAL) {
+            // float -> int conversions saturate (NaN -> 0): any value is fine, an outside tap is discarded anyway
+            const uint32_t xi = (uint32_t)(int32_t)fx, ri = (uint32_t)(int32_t)fy + (uint32_t)row_off;
+            const bool straddles = ((xi & 7u) == 7u) || ((ri & 3u) == 3u);
+            gx = straddles ? gx + 4.0f : gx;
+            gy = straddles ? gy + b_dy : gy;
+        }
+        float4 g = tex2Dgather<float4>(tex, gx, gy, 0);
         v01 = g.x; v11 = g.y; v10 = g.z; v00 = g.w;
     }
 };
+using FetchTex = FetchTexT<false>;
+using FetchTexDual = FetchTexT<true>;
 
 // Row-major trail rows -> the block-linear copy the TEX sampler reads (ghost rows after an exchange).
 // A kernel instead of cudaMemcpy2DToArray: it stays on the compute engine (no copy-engine hand-off
 // inside the step loop).  Two row ranges per launch: [r0a, r0a + n) and [r0b, r0b + n) (buffer rows).
 static __global__ void __launch_bounds__(256)
-k_rows_to_surface(const float* __restrict__ base, cudaSurfaceObject_t surf, uint32_t W, int32_t r0a, int32_t r0b, int32_t n)
+k_rows_to_surface(const float* __restrict__ base, cudaSurfaceObject_t surf, uint32_t W, int32_t r0a, int32_t r0b, int32_t n, int32_t b_dy)
 {
     const uint64_t total = 2ull * (uint64_t)n * W;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t x = (uint32_t)(i % W);
         const uint64_t r = i / W;
         const int32_t row = r < (uint64_t)n ? r0a + (int32_t)r : r0b + (int32_t)(r - n);
-        surf2Dwrite(base[(size_t)row * W + x], surf, (int)(x * 4u), row);
+        const float v = base[(size_t)row * W + x];
+        surf2Dwrite(v, surf, (int)(x * 4u), row);
+        if (b_dy) surf2Dwrite(v, surf, (int)((x + 4u) * 4u), row + b_dy);      // the shifted copy (FetchTexT<true>)
     }
 }
 
 // out[0..3] = gather at the corner of texels (1,1),(2,1),(1,2),(2,2) of a probe array holding T[y][x] = 10*y + x
 static __global__ void k_gather_probe(cudaTextureObject_t tex, float* out)
 {
-    FetchTex f{tex, 1.0f};
+    FetchTex f{tex, 1.0f, 0, 0.0f};
     float v00, v10, v01, v11;
     f(AgentConsts{}, 1.0f, 1.0f, v00, v10, v01, v11);
     out[0] = v00; out[1] = v10; out[2] = v01; out[3] = v11;
@@ -292,6 +316,7 @@ struct TrailGeom {
     int wrap_y;          // 1: rows wrap toroidally inside the buffer (single GPU); 0: ghost rows
     cudaSurfaceObject_t surf;   // block-linear copy of the output for the TEX sampler (0 = none)
     int surf_row0;              // array row of owned row 0
+    int surf_b_dy;              // != 0: the array also holds the (+4, +surf_b_dy)-shifted copy (FetchTexT<true>); SURF == 2 instantiations
 };
 
 __device__ __forceinline__ int64_t row_index(int64_t y, const TrailGeom& g)
@@ -329,7 +354,8 @@ __device__ __forceinline__ float trail_cell(float t, uint32_t k, const TrailCons
 //
 // Requirements (checked by the host): W % 4 == 0 and (W / 4) % 32 != 1, so that a lane is never
 // both the left edge (lane 0) and the right edge (last column group) of its warp.
-template <int CM, bool SURF, int UNROLL, bool STATS>
+// SURF: 0 = row-major output only, 1 = also the sampler's block-linear copy, 2 = also its shifted second copy
+template <int CM, int SURF, int UNROLL, bool STATS>
 static __global__ void __launch_bounds__(128, 8)
 k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
              void* __restrict__ czero_v, float* __restrict__ tout,
@@ -445,6 +471,7 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
                 }
                 // keep the block-linear copy the agent kernel gathers from in step (4 B/cell extra)
                 if (SURF) surf2Dwrite(o, g.surf, (int)(x0 * 4u), y + u + g.surf_row0);
+                if (SURF == 2) surf2Dwrite(o, g.surf, (int)((x0 + 4u) * 4u), y + u + g.surf_row0 + g.surf_b_dy);
                 if (CM == CM_COUNTS) *reinterpret_cast<uint4*>(static_cast<uint32_t*>(czero_v) + off) = make_uint4(0u, 0u, 0u, 0u);
                 if (CM == CM_FLAGS) *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(czero_v) + off) = 0u;
             }
@@ -504,6 +531,7 @@ k_trail_generic(const float* __restrict__ tin, const void* __restrict__ cin_v,
     const float o = smd::box9_mix(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], tc);
     tout[off] = o;
     if (g.surf) surf2Dwrite(o, g.surf, (int)(x * 4), (int)y + g.surf_row0);
+    if (g.surf && g.surf_b_dy) surf2Dwrite(o, g.surf, (int)((x + 4) * 4), (int)y + g.surf_row0 + g.surf_b_dy);
     if (CM == CM_COUNTS) static_cast<uint32_t*>(czero_v)[off] = 0u;
     if (CM == CM_FLAGS) static_cast<uint8_t*>(czero_v)[off] = 0;
 }
@@ -1154,13 +1182,28 @@ struct DisplayGeom {
     float scale, off_x, off_y;   // display.wgsl:58-69, computed once on the host with the same f32 operations
 };
 
-__device__ __forceinline__ uint32_t display_texel(const float* __restrict__ trail, const uint8_t* lut, const DisplayGeom& g,
+// What the frame shows.  The reference draws BETWEEN its decay and diffuse dispatches (main.rs:1184-1217): the field
+// D = decay(merge(T_prev, deposits)).  This engine fuses decay + diffuse, so D is never stored -- but after a full step both
+// of its inputs are still in HBM (the ping-pong field the pass read, and the step's deposit buffer, which only the NEXT
+// trail pass retires), and the display pass recomputes D per texel with the very statements of the trail pass
+// (trail_cell<CM>).  cm == CM_NONE: show `trail` as it is (after an upload, a clear, a diffusion-only pass ...).
+struct DisplaySrc {
+    const float* trail;       // cm == CM_NONE: the current field; else the field the last step started from
+    const void* dep;          // the last step's deposits: u32 counts (CM_COUNTS) or u8 flags (CM_FLAGS)
+    int cm;
+    TrailConsts tc;           // deposit amount / decay of that step
+};
+
+__device__ __forceinline__ uint32_t display_texel(const DisplaySrc& src, const uint8_t* lut, const DisplayGeom& g,
                                                   uint32_t px, float fy, bool row_inside)
 {
     const float fx = __fdiv_rn(smd::sub((float)px, g.off_x), g.scale);               // :72
     if (!(row_inside && fx >= 0.0f && fx < g.sim_w)) return 0xFF000000u;             // :83-85 black, alpha 1
     const int32_t x = (int32_t)fx, y = (int32_t)fy;                                  // :77-78
-    const float t = __ldg(trail + (size_t)y * g.W + x);                              // :79
+    const size_t idx = (size_t)y * g.W + x;
+    float t = __ldg(src.trail + idx);                                                // :79
+    if (src.cm == CM_COUNTS) t = trail_cell<CM_COUNTS>(t, __ldg(static_cast<const uint32_t*>(src.dep) + idx), src.tc);
+    else if (src.cm == CM_FLAGS) t = trail_cell<CM_FLAGS>(t, __ldg(static_cast<const uint8_t*>(src.dep) + idx), src.tc);
     const float inten = smd::clampf(smd::clampf(t, 0.0f, 1.0f), 0.0f, 1.0f);         // :80 and :31
     const uint32_t li = (uint32_t)smd::mul(inten, 255.0f);                           // :34
     // :37-39 f32(lut)/255 stored as rgba8unorm = round(v * 255) = the LUT byte itself for every byte value
@@ -1169,7 +1212,7 @@ __device__ __forceinline__ uint32_t display_texel(const float* __restrict__ trai
 }
 
 static __global__ void __launch_bounds__(256)
-k_display(const float* __restrict__ trail, const uint8_t* __restrict__ lut768, uint32_t* __restrict__ rgba, const DisplayGeom g)
+k_display(const DisplaySrc src, const uint8_t* __restrict__ lut768, uint32_t* __restrict__ rgba, const DisplayGeom g)
 {
     __shared__ uint8_t lut[768];
     for (uint32_t i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = lut768[i];
@@ -1182,13 +1225,13 @@ k_display(const float* __restrict__ trail, const uint8_t* __restrict__ lut768, u
     uint32_t* row = rgba + (size_t)py * g.tw;
     if (px0 + 4u <= g.tw && (g.tw & 3u) == 0u) {
         uint4 o;
-        o.x = display_texel(trail, lut, g, px0, fy, row_inside);
-        o.y = display_texel(trail, lut, g, px0 + 1u, fy, row_inside);
-        o.z = display_texel(trail, lut, g, px0 + 2u, fy, row_inside);
-        o.w = display_texel(trail, lut, g, px0 + 3u, fy, row_inside);
+        o.x = display_texel(src, lut, g, px0, fy, row_inside);
+        o.y = display_texel(src, lut, g, px0 + 1u, fy, row_inside);
+        o.z = display_texel(src, lut, g, px0 + 2u, fy, row_inside);
+        o.w = display_texel(src, lut, g, px0 + 3u, fy, row_inside);
         *reinterpret_cast<uint4*>(row + px0) = o;
     } else {
-        for (uint32_t px = px0; px < g.tw && px < px0 + 4u; ++px) row[px] = display_texel(trail, lut, g, px, fy, row_inside);
+        for (uint32_t px = px0; px < g.tw && px < px0 + 4u; ++px) row[px] = display_texel(src, lut, g, px, fy, row_inside);
     }
 }
 

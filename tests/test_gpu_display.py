@@ -39,9 +39,46 @@ def test_display_after_steps_and_lut_data(oracle, engine_lib, tmp_path):
         be.set_lut(lut)                                         # a LutData, as main.rs:156-166 loads it
         frame = be.render(400, 300)
         trail = be.read_trail()
-    assert np.array_equal(frame, oracle.display(trail, lut.combined(), 400, 300))
+        be.diffuse_only(1)                                      # no agent pass: the frame is the field as it stands
+        frame_after = be.render(400, 300)
+        trail_after = be.read_trail()
+    # the reference draws between its decay and diffuse dispatches (main.rs:1184-1217): the field of the last step after
+    # the deposits and the decay, before the blur
+    u = preset_uniform("Default", W, H)
+    p = to_oracle_params(oracle, u)
+    sim = oracle.Sim(p, oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 5))
+    sim.step(steps - 1)
+    oracle.agents_phase_split(sim.agents, sim.trail, sim.counts, p)
+    pre = sim.trail.copy()
+    oracle.deposit_merge(pre, sim.counts, u.pheromone_deposition_amount)
+    oracle.decay(pre, u.decay_factor)
+    assert bits_equal(trail, oracle.diffuse(pre, u.diffusion_rate))                # same step, same state
+    assert np.array_equal(frame, oracle.display(pre, lut.combined(), 400, 300))
+    assert not np.array_equal(frame, oracle.display(trail, lut.combined(), 400, 300))
+    assert np.array_equal(frame_after, oracle.display(trail_after, lut.combined(), 400, 300))
     assert len(np.unique(frame[..., 0])) > 8 and (frame[..., 3] == 255).all()      # something was drawn
     sm.write_png(str(tmp_path / "frame.png"), frame)
+
+
+def test_display_pre_diffuse_frame_with_fractional_deposits(oracle, engine_lib):
+    """u32 deposit counts (deposition amount < 1): the frame recomputes clamp(t + k*dep, 0, 1) and the decay per texel."""
+    W, H, N, steps = 256, 144, 60_000, 7
+    s = sm.init_preset_manager().get_preset("Waves").settings.clone(pheromone_deposition_amount=0.3)
+    lut = np.random.default_rng(3).integers(0, 256, 768).astype(np.uint8)
+    u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
+    p = to_oracle_params(oracle, u)
+    with sm.CudaBackend.new(W, H, s, agent_count=N, device=0) as be:
+        be.init_agents(seed=2)
+        be.step(steps)
+        be.set_lut(lut)
+        frame = be.render(300, 200)
+    sim = oracle.Sim(p, oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 2))
+    sim.step(steps - 1)
+    oracle.agents_phase_split(sim.agents, sim.trail, sim.counts, p)
+    pre = sim.trail.copy()
+    oracle.deposit_merge(pre, sim.counts, u.pheromone_deposition_amount)
+    oracle.decay(pre, u.decay_factor)
+    assert np.array_equal(frame, oracle.display(pre, lut, 300, 200))
 
 
 @pytest.mark.parametrize("preset", ["Default", "Waves"])

@@ -411,3 +411,53 @@ def test_fused_step_statistics(oracle, engine_lib, dep):
     st = check()
     assert st.sum == 0.0 and st.nonzero == 0
     be.close()
+
+
+# ---- straddle-free sampling: the array's shifted second copy (kernels.cuh FetchTexT<true>) ---------------------------------
+@pytest.mark.parametrize("mode", ["tex1", "tex2"])
+@pytest.mark.parametrize("name,W,H", [("Default", 320, 256), ("Snake", 1024, 768), ("Mesh", 520, 300), ("Waves", 100, 36)])
+def test_sampler_copies_forced(oracle, engine_lib, monkeypatch, mode, name, W, H):
+    # tex1: one copy even at sensor distance 225; tex2: two copies even at 20; 100 x 36 takes the generic trail kernel (W/4 % 32 == 25 is
+    # fine, H is not a multiple of the chunk) and 520 the fast one with a ragged last warp
+    monkeypatch.setenv("SM_SAMPLER", mode)
+    run_pair(oracle, name, W, H, 60000, 14, trail=random_trail(W, H, seed=8), check_every=[1, 13])
+
+
+def test_sampler_mode_follows_sensor_distance(oracle, engine_lib):
+    # sm_set_params switches between one and two copies between steps (the array is re-created and refilled)
+    W, H, N = 640, 512, 80000
+    s0 = settings_for("Default")
+    ag = oracle.init_agents(N, W, H, s0.agent_speed_min, s0.agent_speed_max, 21)
+    tr = random_trail(W, H, seed=2)
+    sim = oracle.Sim(to_oracle_params(oracle, preset_uniform("Default", W, H)), ag, trail=tr)
+    be = sm.CudaBackend.new(W, H, s0, agent_count=N)
+    be.write_agents(ag); be.write_trail(tr)
+    for sd in (20.0, 225.0, 47.0, 48.0, 100.0, 20.0):
+        s = s0.clone(agent_sensor_distance=sd, agent_sensor_angle=1.1)
+        be.update_settings(s)
+        sim.p = to_oracle_params(oracle, sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s))
+        sim.step(3); be.step(3)
+        a, t = be.read_agents(), be.read_trail()
+        assert bits_equal(a, sim.agents), f"sd {sd}: " + mismatch_report(a, sim.agents, "agents")
+        assert bits_equal(t, sim.trail), f"sd {sd}: " + mismatch_report(t, sim.trail, "trail")
+    be.close()
+
+
+@pytest.mark.parametrize("R", [2, 7])
+def test_sampler_second_copy_with_gaussian_full_steps(oracle, engine_lib, monkeypatch, R):
+    # the Gaussian kernels (rows: R = 2, stream: R = 7) write both copies too
+    monkeypatch.setenv("SM_SAMPLER", "tex2")
+    W, H, N = 512, 256, 50000
+    s = settings_for("Default").clone(blur_radius=float(R), blur_sigma=R / 2.0, pheromone_diffusion_rate=0.7)
+    u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
+    p = to_oracle_params(oracle, u)
+    ag = oracle.init_agents(N, W, H, s.agent_speed_min, s.agent_speed_max, 5)
+    sim = oracle.Sim(p, ag)
+    be = sm.CudaBackend.new(W, H, s, agent_count=N, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+    be.write_agents(ag)
+    for _ in range(6):
+        oracle.agents_phase_split(sim.agents, sim.trail, sim.counts, p)
+        sim.trail = oracle.trail_pass(sim.trail, p, counts=sim.counts, gauss_radius=R, gauss_sigma=R / 2.0)
+    be.step(6)
+    assert bits_equal(be.read_agents(), sim.agents) and bits_equal(be.read_trail(), sim.trail)
+    be.close()
