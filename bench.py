@@ -38,6 +38,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+T_START = time.perf_counter()
 
 CONFIG3 = dict(agents=100_000_000, width=8192, height=8192, sd=225.0, sa=1.34)     # BASELINE configs[2]
 CONFIG2 = dict(agents=16_777_216, width=4096, height=4096)                          # BASELINE configs[1]
@@ -370,11 +371,17 @@ def kernel_split(be, steps, local_agents, cells_local, peak):
     return kern
 
 
+def note(h, msg):
+    """Progress on stderr (never on stdout: the JSON line stays alone there)."""
+    print(f"[bench rank {h.rank} +{time.perf_counter() - T_START:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def measure(h, name, width, rows_per_gpu, agents_per_gpu, settings, args, steps, spinup, flags=0, want_e2e=False, clocks=None,
             init_steps=24):
     """One workload: initial-state steps, spin-up, warm-up, K timed steps, the per-kernel split (+ the e2e frame loop)."""
     from slime_mold_b200.settings import SimSizeUniform
     N = h.N
+    note(h, f"measure: {name}")
     width, height, agents = width, rows_per_gpu * N, agents_per_gpu * N
     be = h.engine(width, height, settings, agents, flags=flags)
     be.init_agents(args.seed)
@@ -390,8 +397,7 @@ def measure(h, name, width, rows_per_gpu, agents_per_gpu, settings, args, steps,
     be.step(args.warmup)
     be.sync()
     be.reset_timing()
-    if clocks is not None:
-        h.barrier(be)
+    if clocks is not None:          # rank 0 only: no collective in here
         clocks.start()
         clocks.mark("timed_begin")
     ms_total = h.timed(be, lambda: be.step(steps))
@@ -435,6 +441,7 @@ def parity_before_timing(h, args):
     so.build()
     so.set_threads(max(1, min(8, host_cores() // h.N)))
     N = h.N
+    note(h, "parity before timing")
     W, H, n_agents, steps, seed = 512, 192 * N, 300_000, 35, 11
     s = sm.init_preset_manager().get_preset("Default").settings
     be = h.engine(W, H, s, n_agents)
@@ -450,7 +457,6 @@ def parity_before_timing(h, args):
     rows = ~np.isnan(t[:, 0])
     agents_equal = bool(np.array_equal(a[mine].view(np.uint32), sim.agents[mine].view(np.uint32))) and owned == local == int(mine.sum())
     trail_equal = bool(np.array_equal(t[rows].view(np.uint32), sim.trail[rows].view(np.uint32))) and int(rows.sum()) == H // N
-    total_owned = h.max_over_ranks(0)    # placeholder so every rank takes part in the same collectives
     tt = h.torch.tensor([float(owned)], device="cuda", dtype=h.torch.float64)
     h.dist.all_reduce(tt)
     total_owned = int(tt.item())
@@ -472,6 +478,7 @@ def diffusion_block(h, args, size=16384):
     import slime_mold_b200 as sm
     peak, _ = hbm_peak()
     N = h.N
+    note(h, "diffusion block")
     be = h.engine(size, size * N, sm.Settings.default(), 1)
     rng = np.random.default_rng(0)
     band = rng.random((256, size), dtype=np.float32)

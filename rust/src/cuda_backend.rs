@@ -9,10 +9,15 @@
 use std::ffi::{CStr, CString};
 use std::os::raw::c_int;
 
+// Module placement (the reference is a lib crate `slime_mold` -- src/lib.rs:1-3: lut_manager, presets, settings -- plus a
+// bin crate, src/main.rs, which imports the lib as `slime_mold::..` (main.rs:4-6) and defines `SimSizeUniform` privately
+// (main.rs:29-46)).  This file and ffi.rs are modules OF THE BIN CRATE: `mod ffi; mod cuda_backend;` go next to
+// `mod pipeline_manager;` in main.rs (:21-24).  Then `crate::` is the bin crate -- ffi and the private SimSizeUniform of
+// main.rs are visible from this child module -- and the settings / LUT types come from the lib crate.
 use crate::ffi::*;
-use crate::lut_manager::LutData;
-use crate::settings::Settings;
 use crate::SimSizeUniform;
+use slime_mold::lut_manager::LutData;
+use slime_mold::settings::Settings;
 
 fn check(rc: c_int, what: &str) {
     if rc != SM_OK {

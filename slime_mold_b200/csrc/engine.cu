@@ -244,15 +244,6 @@ static int gather_probe_ok(bool* ok)
     return rc;
 }
 
-static constexpr float kDualSensorDistance = 48.0f;   // presets: 20 (L1 hit rate 74 %: one copy) or 225 (22 %: two copies)
-
-bool sm_engine::want_tex_dual() const
-{
-    if (tex_dual_mode == 1) return false;
-    if (tex_dual_mode == 2) return true;
-    return fabsf(params.agent_sensor_distance) >= kDualSensorDistance;
-}
-
 int sm_engine::setup_tex()
 {
     free_tex();
@@ -262,43 +253,14 @@ int sm_engine::setup_tex()
     SM_CUDA(cudaDeviceGetAttribute(&gh, cudaDevAttrMaxTexture2DGatherHeight, device));
     if ((size_t)W > (size_t)gw || htot > (size_t)gh)
         return sm_fail(SM_ERR_BAD_ARG, "map %u x %zu exceeds the texture-gather limit %d x %d", W, htot, gw, gh);
-    // second, shifted copy below the first one (same array: one texture object, the lanes of a warp choose per footprint)
-    const size_t hA = (htot + 7) / 8 * 8;
-    size_t aw = W, ah = htot;
-    tex_dual = want_tex_dual() && (size_t)W + 4 <= (size_t)gw && 2 * hA + 2 <= (size_t)gh;
-    tex_b_dy = 0;
-    if (tex_dual) { aw = (size_t)W + 4; ah = 2 * hA + 2; tex_b_dy = (int32_t)hA + 2; }
     cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
-    SM_CUDA(cudaMallocArray(&trail_arr, &fd, aw, ah, cudaArraySurfaceLoadStore | cudaArrayTextureGather));
+    SM_CUDA(cudaMallocArray(&trail_arr, &fd, W, htot, cudaArraySurfaceLoadStore | cudaArrayTextureGather));
     SM_TRY(make_tex(trail_arr, &trail_tex));
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = trail_arr;
     SM_CUDA(cudaCreateSurfaceObject(&trail_surf, &rd));
     arr_stale = true;
-    return SM_OK;
-}
-// The sampling mode follows the sensor distance (sm_set_params can change it between steps): re-create the array when it
-// no longer matches.  Rare (a key press in the reference's UI); the next agent pass refills the array from trail[cur].
-int sm_engine::ensure_tex_mode()
-{
-    if (!use_tex || !trail_arr) return SM_OK;
-    if (want_tex_dual() == tex_dual) return SM_OK;
-    if (want_tex_dual() && !tex_dual) {
-        // asked for, but the doubled array did not fit when it was tried: do not retry on every step
-        const size_t htot = rows + 2 * (size_t)(ghost + pad_rows);
-        int gw = 0, gh = 0;
-        SM_CUDA(cudaDeviceGetAttribute(&gw, cudaDevAttrMaxTexture2DGatherWidth, device));
-        SM_CUDA(cudaDeviceGetAttribute(&gh, cudaDevAttrMaxTexture2DGatherHeight, device));
-        if ((size_t)W + 4 > (size_t)gw || 2 * ((htot + 7) / 8 * 8) + 2 > (size_t)gh) return SM_OK;
-    }
-    SM_CUDA(cudaStreamSynchronize(stream));
-    if (setup_tex() != SM_OK) {
-        cudaGetLastError();
-        free_tex();
-        use_tex = false;
-        tex_fallback = true;
-    }
     return SM_OK;
 }
 void sm_engine::free_tex()
@@ -313,9 +275,6 @@ int sm_engine::refresh_tex(int64_t local_row_begin, int64_t n_rows)
     const int64_t arr_row = local_row_begin + (int64_t)(ghost + pad_rows);
     SM_CUDA(cudaMemcpy2DToArrayAsync(trail_arr, 0, (size_t)arr_row, trail_ptr(cur) + local_row_begin * (int64_t)W,
                                      (size_t)W * 4, (size_t)W * 4, (size_t)n_rows, cudaMemcpyDeviceToDevice, stream));
-    if (tex_dual)     // the shifted copy: (x, r) -> (x + 4, r + tex_b_dy)
-        SM_CUDA(cudaMemcpy2DToArrayAsync(trail_arr, 16, (size_t)(arr_row + tex_b_dy), trail_ptr(cur) + local_row_begin * (int64_t)W,
-                                         (size_t)W * 4, (size_t)W * 4, (size_t)n_rows, cudaMemcpyDeviceToDevice, stream));
     return SM_OK;
 }
 
@@ -325,7 +284,7 @@ int sm_engine::refresh_tex_ghosts(uint32_t g)
     const int32_t off = (int32_t)(ghost + pad_rows);
     const uint64_t total = 2ull * g * W;
     const unsigned nb = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms * 4);
-    smk::k_rows_to_surface<<<nb, 256, 0, stream>>>(trail_base[cur], trail_surf, W, off - (int32_t)g, off + (int32_t)rows, (int32_t)g, tex_dual ? tex_b_dy : 0);
+    smk::k_rows_to_surface<<<nb, 256, 0, stream>>>(trail_base[cur], trail_surf, W, off - (int32_t)g, off + (int32_t)rows, (int32_t)g);
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
     return SM_OK;
@@ -484,19 +443,13 @@ int sm_engine::launch_agents()
             else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         }
     };
-    if (use_tex) SM_TRY(ensure_tex_mode());
     if (use_tex) {
         if (arr_stale) {                                  // the array lost track of trail[cur]: one full copy
             SM_TRY(refresh_tex(-(int64_t)(ghost + pad_rows), (int64_t)rows + 2 * (int64_t)(ghost + pad_rows)));
             arr_stale = false;
         }
-        const int32_t arr_row_of_global0 = (int32_t)(ghost + pad_rows) - (int32_t)row0;
-        const smk::FetchTex f{trail_tex, (float)(arr_row_of_global0 + 1), arr_row_of_global0, 0.0f};
-        if (tex_dual) {
-            const smk::FetchTexDual fd{trail_tex, (float)(arr_row_of_global0 + 1), arr_row_of_global0, (float)tex_b_dy};
-            if (idx32) launch(fd, int32_t{});
-            else launch(fd, int64_t{});
-        } else if (agent_stream_hint && !multi && idx32) {
+        const smk::FetchTex f{trail_tex, (float)((int32_t)(ghost + pad_rows) - (int32_t)row0 + 1)};
+        if (agent_stream_hint && !multi && idx32) {
             // A/B instantiation: evict-first hints on the agent stream (single GPU, 32-bit offsets, texture sampler)
             if (flags) smk::k_agents<smk::XM_SINGLE, int32_t, smk::FetchTex, true, true><<<nb, 256, 0, stream>>>(a, id, n_local, f, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
             else smk::k_agents<smk::XM_SINGLE, int32_t, smk::FetchTex, false, true><<<nb, 256, 0, stream>>>(a, id, n_local, f, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
@@ -524,7 +477,7 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     const bool write_surf = use_tex && has_counts && (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) || (gauss_fast_ok() && world == 1));
     p.g.surf = write_surf ? trail_surf : 0;
     p.g.surf_row0 = (int)(ghost + pad_rows);
-    p.g.surf_b_dy = (write_surf && tex_dual) ? tex_b_dy : 0;
+    p.g.surf_pairs = surf_pairs ? 1 : 0;
     if (!write_surf) arr_stale = true;
     p.tin = trail_ptr(cur);
     p.tout = trail_ptr(1 - cur);
@@ -562,20 +515,18 @@ int sm_engine::trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t 
     dim3 grid(blocks_for(W / 4, bs), (unsigned)(g.chunks1 + chunks2));
     smk::StatsAcc* acc = (smk::StatsAcc*)stats_dev;
     auto go = [&](auto cm_tag, auto surf_tag, auto stats_tag) {
-        constexpr int CMv = decltype(cm_tag)::value, SURFv = decltype(surf_tag)::value;
-        constexpr bool STATSv = decltype(stats_tag)::value;
+        constexpr int CMv = decltype(cm_tag)::value;
+        constexpr bool SURFv = decltype(surf_tag)::value, STATSv = decltype(stats_tag)::value;
         smk::k_trail_rows<CMv, SURFv, 4, STATSv><<<grid, bs, 0, st>>>(p.tin, CMv == smk::CM_NONE ? nullptr : p.cin,
                                                                        CMv == smk::CM_NONE ? nullptr : p.czero, p.tout, g, p.tc, acc);
     };
     using std::integral_constant;
     using T = std::true_type; using F = std::false_type;
-    using S0 = integral_constant<int, 0>; using S1 = integral_constant<int, 1>; using S2 = integral_constant<int, 2>;
     auto go_cm = [&](auto cm_tag) {
-        if (!g.surf)           { if (p.stats) go(cm_tag, S0{}, T{}); else go(cm_tag, S0{}, F{}); }
-        else if (!g.surf_b_dy) { if (p.stats) go(cm_tag, S1{}, T{}); else go(cm_tag, S1{}, F{}); }
-        else                   { if (p.stats) go(cm_tag, S2{}, T{}); else go(cm_tag, S2{}, F{}); }
+        if (!g.surf) { if (p.stats) go(cm_tag, F{}, T{}); else go(cm_tag, F{}, F{}); }
+        else         { if (p.stats) go(cm_tag, T{}, T{}); else go(cm_tag, T{}, F{}); }
     };
-    if (p.cm == smk::CM_NONE) go(integral_constant<int, smk::CM_NONE>{}, S0{}, F{});
+    if (p.cm == smk::CM_NONE) go(integral_constant<int, smk::CM_NONE>{}, F{}, F{});
     else if (p.cm == smk::CM_COUNTS) go_cm(integral_constant<int, smk::CM_COUNTS>{});
     else go_cm(integral_constant<int, smk::CM_FLAGS>{});
     SM_CUDA(cudaGetLastError());
@@ -615,6 +566,111 @@ int sm_engine::launch_trail(bool has_counts)
     trail_done(has_counts);
     stats_fused_valid = p.stats;
     if (has_counts && stats_interest) --stats_interest;
+    return SM_OK;
+}
+
+// One frame of src/main.rs:1163-1235: (sort) -> agents -> decay + diffuse (+ the strip exchange).
+int sm_engine::step_once()
+{
+    if (world > 1 && ghost_stale) SM_TRY(exchange_trail_ghosts());
+    if (sort_interval && steps_since_sort >= sort_interval) {
+        SM_TRY(sort_agents());
+        steps_since_sort = 0;
+    }
+    SM_TRY(launch_agents());                             // src/main.rs:1164-1181
+    if (world > 1 && p2p && overlap_ok()) {
+        SM_TRY(p2p_trail_overlapped());                  // trail pass with the exchange hidden behind its interior rows
+    } else {
+        if (world > 1) SM_TRY(p2p ? p2p_after_agents() : exchange_counts());
+        SM_TRY(launch_trail(true));                      // src/main.rs:1184-1199 + 1220-1235
+        if (world > 1) SM_TRY(p2p ? p2p_after_trail() : migrate_agents());
+    }
+    steps_since_sort++;
+    timing.steps++;
+    frame_pre_valid = true;
+    frame_tc = trail_consts();
+    return SM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// CUDA-graph replay of whole sort periods (single GPU)
+// ---------------------------------------------------------------------------
+// The reference submits three command buffers per frame (main.rs:1181, 1199, 1235); this engine launches two kernels per
+// step, and on small maps (BASELINE config 1: 1 M agents on 1920 x 1080, both kernels a few microseconds) the step is bound
+// by launch latency, not by the kernels.  sm_step(n) therefore replays a captured graph of one full period of the host
+// state machine -- 2 x sort_interval steps including their two cell sorts (after which the ping-pong indices of the trail,
+// the deposit buffers and the agent arrays are back where they started), or 2 steps when sorting is off -- whenever the
+// engine is in steady state: same parameters, same buffers, nothing pending (no stale sampler copy, no deposit-mode
+// switch, no statistics request, no per-kernel timing).  Anything else runs the ordinary launch path; results are the
+// same launches in the same order either way.
+uint32_t sm_engine::graph_period() const
+{
+    if (!graph_enabled || world != 1 || timing_enabled || stats_interest || (cfg.flags & SM_FLAG_GAUSSIAN_BLUR)) return 0;
+    return sort_interval ? 2u * sort_interval : 2u;
+}
+
+sm_engine::GraphKey sm_engine::graph_key_now() const
+{
+    GraphKey k;
+    memset(&k, 0, sizeof k);                  // compared with memcmp: padding must be defined
+    k.params = params;
+    k.n_local = n_local;
+    k.acur = acur; k.cur = cur; k.ccur = ccur; k.deposit_mode = deposit_mode;
+    k.sort_interval = sort_interval;
+    k.agents0 = agents[0]; k.trail0 = trail_base[0]; k.arr = trail_arr;
+    k.use_tex = use_tex;
+    k.rpc_override = rpc_override; k.force_generic = force_generic; k.no_flags = no_flags;
+    return k;
+}
+
+// Steady state, and aligned with the period (the next step starts with a sort)?
+bool sm_engine::graph_ready()
+{
+    if (n_local == 0 || !agents_valid) return false;
+    if (sort_interval && steps_since_sort < sort_interval) return false;
+    if (use_tex && arr_stale) return false;
+    if (deposit_mode != (flag_mode() ? 2 : 1)) return false;       // the next agent pass would switch (and wipe) buffers
+    return true;
+}
+
+int sm_engine::graph_steps()
+{
+    const uint32_t period = graph_period();
+    const GraphKey now = graph_key_now();
+    if (step_graph && memcmp(&now, &step_graph_key, sizeof now) != 0) {
+        cudaGraphExecDestroy(step_graph);
+        step_graph = nullptr;
+    }
+    if (!step_graph) {
+        // capture = run the ordinary host path once with the stream in capture mode (nothing executes yet)
+        const uint64_t launches0 = timing.kernel_launches;
+        SM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        int rc = SM_OK;
+        for (uint32_t i = 0; i < period && rc == SM_OK; ++i) rc = step_once();
+        cudaGraph_t g = nullptr;
+        const cudaError_t err = cudaStreamEndCapture(stream, &g);
+        if (rc != SM_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
+        if (err != cudaSuccess) { if (g) cudaGraphDestroy(g); return sm_fail(SM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(err)); }
+        const cudaError_t ierr = cudaGraphInstantiate(&step_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ierr != cudaSuccess) { step_graph = nullptr; return sm_fail(SM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ierr)); }
+        step_graph_launches = timing.kernel_launches - launches0;
+        memcpy(&step_graph_key, &now, sizeof now);
+        const GraphKey after = graph_key_now();                     // the period must bring the host state back
+        if (memcmp(&after, &now, sizeof now) != 0 || (sort_interval && steps_since_sort != sort_interval)) {
+            cudaGraphExecDestroy(step_graph);
+            step_graph = nullptr;
+            graph_enabled = false;
+            return sm_fail(SM_ERR_STATE, "internal: a captured period did not restore the engine's launch state");
+        }
+    } else {
+        // replay: the host state after a period equals the state before it; only the counters move
+        timing.steps += period;
+        timing.kernel_launches += step_graph_launches;
+        frame_pre_valid = true;
+        frame_tc = trail_consts();
+    }
+    SM_CUDA(cudaGraphLaunch(step_graph, stream));
     return SM_OK;
 }
 
@@ -700,12 +756,12 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     {
         const char* smp = getenv("SM_SAMPLER");
         bool want_tex = !(smp && std::string(smp) == "ldg");
-        if (smp && std::string(smp) == "tex1") e->tex_dual_mode = 1;       // A/B: never / always the shifted second copy
-        if (smp && std::string(smp) == "tex2") e->tex_dual_mode = 2;
         bool probe = false;
         if (want_tex) { int prc = gather_probe_ok(&probe); if (prc != SM_OK) { delete e; return prc; } }
         e->use_tex = want_tex && probe;
     }
+    e->surf_pairs = env_int("SM_SURF_PAIRS", 1) != 0;
+    e->graph_enabled = env_int("SM_STEP_GRAPH", 1) != 0;       // 0: every step through the ordinary launch path (A/B)
     e->force_generic = env_int("SM_FORCE_GENERIC_TRAIL", 0) != 0;
     e->no_flags = env_int("SM_NO_DEPOSIT_FLAGS", 0) != 0;
     e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
@@ -784,6 +840,7 @@ int sm_destroy(sm_engine* e)
     if (e->stats_host) cudaFreeHost(e->stats_host);
     if (e->lut_dev) cudaFree(e->lut_dev);
     if (e->frame_dev) cudaFree(e->frame_dev);
+    if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
     for (auto& p : e->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1250,24 +1307,16 @@ int sm_step(sm_engine* e, uint32_t n_steps)
     if (!e->agents_valid) return sm_fail(SM_ERR_STATE, "agents were never initialised or uploaded");
     if (e->world > 1 && !e->comm_ready) return sm_fail(SM_ERR_STATE, "multi-GPU engine: call sm_comm_init first");
     SM_TRY(e->check_gauss(true));                        // nothing is launched on bad blur parameters
-    for (uint32_t s = 0; s < n_steps; ++s) {
-        if (e->world > 1 && e->ghost_stale) SM_TRY(e->exchange_trail_ghosts());
-        if (e->sort_interval && e->steps_since_sort >= e->sort_interval) {
-            SM_TRY(e->sort_agents());
-            e->steps_since_sort = 0;
-        }
-        SM_TRY(e->launch_agents());                      // src/main.rs:1164-1181
-        if (e->world > 1 && e->p2p && e->overlap_ok()) {
-            SM_TRY(e->p2p_trail_overlapped());           // trail pass with the exchange hidden behind its interior rows
+    uint32_t s = 0;
+    while (s < n_steps) {
+        const uint32_t period = e->graph_period();
+        if (period && n_steps - s >= period && e->graph_ready()) {
+            SM_TRY(e->graph_steps());                    // one whole sort period (or two steps without sorting) per graph launch
+            s += period;
         } else {
-            if (e->world > 1) SM_TRY(e->p2p ? e->p2p_after_agents() : e->exchange_counts());
-            SM_TRY(e->launch_trail(true));               // src/main.rs:1184-1199 + 1220-1235
-            if (e->world > 1) SM_TRY(e->p2p ? e->p2p_after_trail() : e->migrate_agents());
+            SM_TRY(e->step_once());
+            ++s;
         }
-        e->steps_since_sort++;
-        e->timing.steps++;
-        e->frame_pre_valid = true;
-        e->frame_tc = e->trail_consts();
     }
     return SM_OK;
 }

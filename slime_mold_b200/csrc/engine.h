@@ -52,14 +52,6 @@ struct sm_engine {
     cudaTextureObject_t trail_tex = 0;
     cudaSurfaceObject_t trail_surf = 0;
     bool use_tex = false;             // SM_SAMPLER=tex (default) and the gather probe passed
-    // "straddle-free" sampling for large sensor distances (kernels.cuh: FetchTexT<true>): the array also holds a copy of the
-    // field shifted by (+4, +tex_b_dy) texels.  tex_dual_mode: 0 = auto (dual when |sensor distance| >= kDualSensorDistance
-    // and the doubled array fits the gather limits), 1 = never, 2 = always (SM_SAMPLER=tex1 / tex2: A/B switch).
-    int tex_dual_mode = 0;
-    bool tex_dual = false;            // the array that exists now holds both copies
-    int32_t tex_b_dy = 0;             // rows between a texel of copy A and the same texel of copy B (multiple of 4, plus 2)
-    bool want_tex_dual() const;
-    int ensure_tex_mode();            // (re-)allocates the array when the sampling mode the parameters ask for changed
     bool tex_fallback = false;        // use_tex was switched off because this map does not fit a gather array (retried by sm_resize)
     bool arr_stale = true;            // the array does not mirror trail[cur] (upload / clear / diffuse-only ...)
     float* gauss_dec = nullptr;       // extension scratch
@@ -173,6 +165,22 @@ struct sm_engine {
     int p2p_trail_overlapped();
     int p2p_diffuse_overlapped();
     int p2p_push_ghosts(cudaStream_t st, uint32_t g);
+
+    // CUDA-graph replay of whole sort periods on one GPU (engine.cu: graph_steps)
+    struct GraphKey {
+        sm_params params; uint64_t n_local; int acur, cur, ccur, deposit_mode; uint32_t sort_interval;
+        const void *agents0, *trail0, *arr; bool use_tex, force_generic, no_flags; int rpc_override;
+    };
+    bool surf_pairs = true;           // SM_SURF_PAIRS=0: the trail pass writes the sampler copy row by row (A/B)
+    bool graph_enabled = true;        // SM_STEP_GRAPH=0 switches it off (A/B)
+    cudaGraphExec_t step_graph = nullptr;
+    GraphKey step_graph_key{};
+    uint64_t step_graph_launches = 0;
+    uint32_t graph_period() const;    // steps per graph launch (0 = graphs do not apply)
+    GraphKey graph_key_now() const;
+    bool graph_ready();
+    int graph_steps();
+    int step_once();
 
     smd::AgentConsts agent_consts() const;
     smd::TrailConsts trail_consts() const;

@@ -204,7 +204,7 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
         smk::GsArgs a{};
         a.tin = p.tin; a.cin = p.cm == smk::CM_NONE ? nullptr : p.cin; a.czero = p.cm == smk::CM_NONE ? nullptr : p.czero; a.tout = p.tout;
         a.W = (int)W; a.H = (int)rows; a.wrap_y = g.wrap_y;
-        a.surf = (unsigned long long)g.surf; a.surf_row0 = g.surf_row0; a.surf_b_dy = g.surf_b_dy;
+        a.surf = (unsigned long long)g.surf; a.surf_row0 = g.surf_row0;
         const bool surf = g.surf != 0;
         auto go_rows = [&](auto r_tag) -> int {
             constexpr int RR = decltype(r_tag)::value;

@@ -205,7 +205,6 @@ SM_KD void gauss_rows_cta(const Ctx& cx, const GsArgs& a, const smd::TrailConsts
                     const int gy = y_begin + o;
                     *reinterpret_cast<F4*>(a.tout + (int64_t)gy * W + gx) = out;
                     if (SURF) cx.surf_write(out, a.surf, gx, gy + a.surf_row0);
-                    if (SURF && a.surf_b_dy) cx.surf_write(out, a.surf, gx + 4, gy + a.surf_row0 + a.surf_b_dy);   // shifted second copy
                 }
                 acc[slot].x = acc[slot].y = acc[slot].z = acc[slot].w = 0.0f;
             }

@@ -76,7 +76,6 @@ struct GsArgs {
     int chunk_rows;         // output rows per CTA (blockIdx.y)
     unsigned long long surf;   // block-linear copy of the output for the TEX sampler (SURF instantiations)
     int surf_row0;
-    int surf_b_dy;             // != 0: the array also holds the (+4, +surf_b_dy)-shifted copy (kernels.cuh: FetchTexT<true>)
 };
 
 struct GsFoldYes { static constexpr bool value = true; };      // prefetch instantiations: rows folded across the seam, or not
@@ -293,7 +292,6 @@ SM_KD void gauss_stream_cta(const Ctx& cx, float* __restrict__ gsm, const GsArgs
                         const int gy = yc0 + o;
                         *reinterpret_cast<F4*>(a.tout + (int64_t)gy * W + gx) = out;
                         if (SURF) cx.surf_write(out, a.surf, gx, gy + a.surf_row0);
-                        if (SURF && a.surf_b_dy) cx.surf_write(out, a.surf, gx + 4, gy + a.surf_row0 + a.surf_b_dy);   // shifted second copy
                     }
                 }
             }

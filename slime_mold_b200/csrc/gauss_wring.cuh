@@ -204,7 +204,6 @@ SM_KD void gauss_wring_cta(const Ctx& cx, float* __restrict__ smem, const GsArgs
                             const int64_t offo = (int64_t)gy * W + gx;
                             *reinterpret_cast<F4*>(a.tout + offo) = out;
                             if (SURF) cx.surf_write(out, a.surf, gx, gy + a.surf_row0);
-                            if (SURF && a.surf_b_dy) cx.surf_write(out, a.surf, gx + 4, gy + a.surf_row0 + a.surf_b_dy);   // shifted second copy
                             if (CM == GS_COUNTS) { U4 z; z.x = z.y = z.z = z.w = 0u; *reinterpret_cast<U4*>(static_cast<uint32_t*>(a.czero) + offo) = z; }
                             if (CM == GS_FLAGS) *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(a.czero) + offo) = 0u;
                         }

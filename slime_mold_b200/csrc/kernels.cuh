@@ -33,62 +33,43 @@ struct LdgF32 {
 // arithmetic).  At (x0 + 1, y0 + 1) -- the common corner of the four texels -- the footprint is
 // {x0, x0+1} x {y0, y0+1}; components come back as (x0,y0+1), (x0+1,y0+1), (x0+1,y0), (x0,y0)
 // (verified at sm_create by k_gather_probe: the engine refuses the TEX path otherwise).
-//
-// DUAL ("straddle-free" sampling, selected for large sensor distances): at sensor distance 225 the three footprints of an
-// agent are incoherent -- no two lanes of a warp, and no two warps of an SM, touch the same texels -- so every footprint is
-// an L1 miss, and the agent kernel is bound by the one miss request (one 128-byte line = 8 x 4 texels of the block-linear
-// layout) an SM's L1 can send to the crossbar per cycle (ncu: l1tex__m_l1tex2xbar_req_cycles_active 84 %;
-// tools/microbench/gather_rate.cu: 1.44 SM-cycles per footprint anywhere, 1.00 when it lies inside one line).  A 2x2
-// footprint straddles a line when x0 % 8 == 7 or row % 4 == 3: 34 % of them, 1.41 requests on average.  The array
-// therefore holds a SECOND copy of the field shifted by (+4, +2) texels, where exactly those footprints sit in the
-// middle of a line; only the 6 % that straddle in both copies still cost two requests.  Same texels, same bits.
-template <bool DUAL>
-struct FetchTexT {
+struct FetchTex {
     cudaTextureObject_t tex;
     float row_off1;          // (array row of global row 0) + 1 = ghost + pad - row_base + 1, exact in f32
-    int32_t row_off;         // array row of global row 0 (DUAL: phase of the 4-row line groups)
-    float b_dy;              // DUAL: copy B holds field(x, array row r) at texel (x + 4, r + b_dy); b_dy % 4 == 2
     __device__ __forceinline__ void operator()(const AgentConsts&, float fx, float fy, float& v00, float& v10, float& v01, float& v11) const
     {
         // fetched whether or not the tap is inside the map (clamped addressing; the caller discards the
         // footprint of an outside tap).  Coordinates stay in float: for an inside tap fx, fy are integral
         // and < 2^17, so the sums are exact
-        float gx = fx + 1.0f, gy = fy + row_off1;
-        if (DUAL) {
-            // float -> int conversions saturate (NaN -> 0): any value is fine, an outside tap is discarded anyway
-            const uint32_t xi = (uint32_t)(int32_t)fx, ri = (uint32_t)(int32_t)fy + (uint32_t)row_off;
-            const bool straddles = ((xi & 7u) == 7u) || ((ri & 3u) == 3u);
-            gx = straddles ? gx + 4.0f : gx;
-            gy = straddles ? gy + b_dy : gy;
-        }
-        float4 g = tex2Dgather<float4>(tex, gx, gy, 0);
+        float4 g = tex2Dgather<float4>(tex, fx + 1.0f, fy + row_off1, 0);
         v01 = g.x; v11 = g.y; v10 = g.z; v00 = g.w;
     }
 };
-using FetchTex = FetchTexT<false>;
-using FetchTexDual = FetchTexT<true>;
+// Measured and dropped in round 2 (profiles/README.md, "sensor distance 225"): a second copy of the field shifted by
+// (+4, +2) texels in the same array, read by the footprints that straddle a 128-byte line (8 x 4 texels) of the first
+// copy -- 34 % of them at sensor distance 225, where no two footprints share a line and the kernel is bound by the L1's
+// miss-request port.  tools/microbench/gather_rate.cu: 1.44 -> 1.0 SM-cycles per incoherent footprint; in the kernel:
+// 12 % fewer L2 requests, 1-9 % less time, paid back by the trail pass writing the second copy.
 
 // Row-major trail rows -> the block-linear copy the TEX sampler reads (ghost rows after an exchange).
 // A kernel instead of cudaMemcpy2DToArray: it stays on the compute engine (no copy-engine hand-off
 // inside the step loop).  Two row ranges per launch: [r0a, r0a + n) and [r0b, r0b + n) (buffer rows).
 static __global__ void __launch_bounds__(256)
-k_rows_to_surface(const float* __restrict__ base, cudaSurfaceObject_t surf, uint32_t W, int32_t r0a, int32_t r0b, int32_t n, int32_t b_dy)
+k_rows_to_surface(const float* __restrict__ base, cudaSurfaceObject_t surf, uint32_t W, int32_t r0a, int32_t r0b, int32_t n)
 {
     const uint64_t total = 2ull * (uint64_t)n * W;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t x = (uint32_t)(i % W);
         const uint64_t r = i / W;
         const int32_t row = r < (uint64_t)n ? r0a + (int32_t)r : r0b + (int32_t)(r - n);
-        const float v = base[(size_t)row * W + x];
-        surf2Dwrite(v, surf, (int)(x * 4u), row);
-        if (b_dy) surf2Dwrite(v, surf, (int)((x + 4u) * 4u), row + b_dy);      // the shifted copy (FetchTexT<true>)
+        surf2Dwrite(base[(size_t)row * W + x], surf, (int)(x * 4u), row);
     }
 }
 
 // out[0..3] = gather at the corner of texels (1,1),(2,1),(1,2),(2,2) of a probe array holding T[y][x] = 10*y + x
 static __global__ void k_gather_probe(cudaTextureObject_t tex, float* out)
 {
-    FetchTex f{tex, 1.0f, 0, 0.0f};
+    FetchTex f{tex, 1.0f};
     float v00, v10, v01, v11;
     f(AgentConsts{}, 1.0f, 1.0f, v00, v10, v01, v11);
     out[0] = v00; out[1] = v10; out[2] = v01; out[3] = v11;
@@ -316,7 +297,7 @@ struct TrailGeom {
     int wrap_y;          // 1: rows wrap toroidally inside the buffer (single GPU); 0: ghost rows
     cudaSurfaceObject_t surf;   // block-linear copy of the output for the TEX sampler (0 = none)
     int surf_row0;              // array row of owned row 0
-    int surf_b_dy;              // != 0: the array also holds the (+4, +surf_b_dy)-shifted copy (FetchTexT<true>); SURF == 2 instantiations
+    int surf_pairs;             // 1: surface rows are written in pairs as whole sectors (A/B switch SM_SURF_PAIRS)
 };
 
 __device__ __forceinline__ int64_t row_index(int64_t y, const TrailGeom& g)
@@ -355,8 +336,10 @@ __device__ __forceinline__ float trail_cell(float t, uint32_t k, const TrailCons
 // Requirements (checked by the host): W % 4 == 0 and (W / 4) % 32 != 1, so that a lane is never
 // both the left edge (lane 0) and the right edge (last column group) of its warp.
 // SURF: 0 = row-major output only, 1 = also the sampler's block-linear copy, 2 = also its shifted second copy
+// u32 counts carry four more registers per row in flight than u8 flags: those instantiations run 6 CTAs per SM instead of 8
+// rather than spill (fractional deposits only; every shipped preset deposits 1.0 and takes the flag path)
 template <int CM, int SURF, int UNROLL, bool STATS>
-static __global__ void __launch_bounds__(128, 8)
+static __global__ void __launch_bounds__(128, (CM == CM_COUNTS ? 6 : 8))
 k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
              void* __restrict__ czero_v, float* __restrict__ tout,
              const TrailGeom g, const TrailConsts tc, StatsAcc* __restrict__ stats)
@@ -439,6 +422,33 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
         finish(r0, prev);
         finish(r1, cur);
     }
+    // Surface writes as WHOLE sectors.  A 32-byte sector of the block-linear array is 4 texels x 2 rows, so a warp-wide
+    // SUST.128 along one row touches 32 half sectors -- and costs as much as streaming twice the bytes
+    // (tools/microbench/surfcopy.cu, 8192^2: row-wise 118.6 us per pass, whole sectors 85.0, a plain linear copy 82.6).
+    // Rows are therefore written in pairs: the lower half-warp hands its odd row to the upper one and takes the upper
+    // half-warp's even row (one SHFL.BFLY per component), so that each of the two SUSTs of a pair covers both rows of 16
+    // column groups.  Needs the pair to start on an even ARRAY row (warp-uniform; otherwise rows are written one by one).
+    const bool lo_half = lane < 16u;
+    const int xp = lo_half ? (int)x0 + 64 : (int)x0 - 64;           // first column of the partner lane (lane ^ 16)
+    const bool p_active = (uint32_t)xp < g.W;
+    const bool pair_mode = SURF && g.surf_pairs && (((y_begin + g.surf_row0) & 1) == 0);
+    auto surf_pair = [&](const float4& oa, const float4& ob, int ya, bool va, bool vb) {
+        const float4 send = lo_half ? ob : oa;
+        float4 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+        recv.z = __shfl_xor_sync(0xffffffffu, send.z, 16);
+        recv.w = __shfl_xor_sync(0xffffffffu, send.w, 16);
+        const int row = ya + g.surf_row0;
+        // first SUST: column groups of the lower half-warp, both rows; second: those of the upper half-warp
+        const float4 d1 = lo_half ? oa : recv, d2 = lo_half ? recv : ob;
+        const int x1 = lo_half ? (int)x0 : xp, x2 = lo_half ? xp : (int)x0;
+        const int r1 = lo_half ? row : row + 1;
+        const bool p1 = lo_half ? (active && va) : (p_active && vb), p2 = lo_half ? (p_active && va) : (active && vb);
+        if (p1) surf2Dwrite(d1, g.surf, x1 * 4, r1);
+        if (p2) surf2Dwrite(d2, g.surf, x2 * 4, r1);
+    };
+    static_assert(UNROLL % 2 == 0, "rows are written to the surface in pairs");
     for (int y = y_begin; y < y_end; y += UNROLL) {
         RawRow raw[UNROLL];
 #pragma unroll
@@ -446,11 +456,13 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
             const int yy = y + u + 1;
             issue(yy >= y_end ? y_bot : yy, raw[u]);     // past the chunk: harmless re-load of the halo row
         }
+        float4 o_even = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             finish(raw[u], next);
-            if (y + u < y_end && active) {
-                float4 o;
+            const bool row_ok = y + u < y_end;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok && active) {
                 o.x = smd::box9_mix(prev[0], prev[1], prev[2], cur[0], cur[1], cur[2], next[0], next[1], next[2], tc);
                 o.y = smd::box9_mix(prev[1], prev[2], prev[3], cur[1], cur[2], cur[3], next[1], next[2], next[3], tc);
                 o.z = smd::box9_mix(prev[2], prev[3], prev[4], cur[2], cur[3], cur[4], next[2], next[3], next[4], tc);
@@ -469,11 +481,17 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
                              min(__float_as_uint(o.w), 1u);          // the field is >= +0 here: non-zero <=> any bit set
                     st_m = fmaxf(fmaxf(st_m, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
                 }
-                // keep the block-linear copy the agent kernel gathers from in step (4 B/cell extra)
-                if (SURF) surf2Dwrite(o, g.surf, (int)(x0 * 4u), y + u + g.surf_row0);
-                if (SURF == 2) surf2Dwrite(o, g.surf, (int)((x0 + 4u) * 4u), y + u + g.surf_row0 + g.surf_b_dy);
                 if (CM == CM_COUNTS) *reinterpret_cast<uint4*>(static_cast<uint32_t*>(czero_v) + off) = make_uint4(0u, 0u, 0u, 0u);
                 if (CM == CM_FLAGS) *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(czero_v) + off) = 0u;
+                // keep the block-linear copy the agent kernel gathers from in step (4 B/cell extra)
+                if (SURF && !pair_mode) surf2Dwrite(o, g.surf, (int)(x0 * 4u), y + u + g.surf_row0);
+            }
+            if (SURF && pair_mode) {                     // warp-uniform branch: every lane takes part in the exchange
+                if ((u & 1) == 0) o_even = o;
+                else {
+                    const bool even_ok = y + u - 1 < y_end;
+                    surf_pair(o_even, o, y + u - 1, even_ok, row_ok);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) { prev[j] = cur[j]; cur[j] = next[j]; }
@@ -531,7 +549,6 @@ k_trail_generic(const float* __restrict__ tin, const void* __restrict__ cin_v,
     const float o = smd::box9_mix(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], tc);
     tout[off] = o;
     if (g.surf) surf2Dwrite(o, g.surf, (int)(x * 4), (int)y + g.surf_row0);
-    if (g.surf && g.surf_b_dy) surf2Dwrite(o, g.surf, (int)((x + 4) * 4), (int)y + g.surf_row0 + g.surf_b_dy);
     if (CM == CM_COUNTS) static_cast<uint32_t*>(czero_v)[off] = 0u;
     if (CM == CM_FLAGS) static_cast<uint8_t*>(czero_v)[off] = 0;
 }

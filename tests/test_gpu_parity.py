@@ -413,18 +413,8 @@ def test_fused_step_statistics(oracle, engine_lib, dep):
     be.close()
 
 
-# ---- straddle-free sampling: the array's shifted second copy (kernels.cuh FetchTexT<true>) ---------------------------------
-@pytest.mark.parametrize("mode", ["tex1", "tex2"])
-@pytest.mark.parametrize("name,W,H", [("Default", 320, 256), ("Snake", 1024, 768), ("Mesh", 520, 300), ("Waves", 100, 36)])
-def test_sampler_copies_forced(oracle, engine_lib, monkeypatch, mode, name, W, H):
-    # tex1: one copy even at sensor distance 225; tex2: two copies even at 20; 100 x 36 takes the generic trail kernel (W/4 % 32 == 25 is
-    # fine, H is not a multiple of the chunk) and 520 the fast one with a ragged last warp
-    monkeypatch.setenv("SM_SAMPLER", mode)
-    run_pair(oracle, name, W, H, 60000, 14, trail=random_trail(W, H, seed=8), check_every=[1, 13])
-
-
-def test_sampler_mode_follows_sensor_distance(oracle, engine_lib):
-    # sm_set_params switches between one and two copies between steps (the array is re-created and refilled)
+# ---- parameter changes between steps (sm_set_params: the reference's hold-key + arrow paths, main.rs:407-433) -------------
+def test_sensor_distance_changes_between_steps(oracle, engine_lib):
     W, H, N = 640, 512, 80000
     s0 = settings_for("Default")
     ag = oracle.init_agents(N, W, H, s0.agent_speed_min, s0.agent_speed_max, 21)
@@ -443,21 +433,50 @@ def test_sampler_mode_follows_sensor_distance(oracle, engine_lib):
     be.close()
 
 
-@pytest.mark.parametrize("R", [2, 7])
-def test_sampler_second_copy_with_gaussian_full_steps(oracle, engine_lib, monkeypatch, R):
-    # the Gaussian kernels (rows: R = 2, stream: R = 7) write both copies too
-    monkeypatch.setenv("SM_SAMPLER", "tex2")
-    W, H, N = 512, 256, 50000
-    s = settings_for("Default").clone(blur_radius=float(R), blur_sigma=R / 2.0, pheromone_diffusion_rate=0.7)
-    u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
-    p = to_oracle_params(oracle, u)
-    ag = oracle.init_agents(N, W, H, s.agent_speed_min, s.agent_speed_max, 5)
-    sim = oracle.Sim(p, ag)
-    be = sm.CudaBackend.new(W, H, s, agent_count=N, flags=sm.SM_FLAG_GAUSSIAN_BLUR)
+@pytest.mark.parametrize("pairs", ["0", "1"])
+@pytest.mark.parametrize("W,H", [(520, 300), (8, 1), (256, 7), (136, 33)])
+def test_sampler_copy_written_row_by_row_or_in_pairs(oracle, engine_lib, monkeypatch, pairs, W, H):
+    # the trail pass writes the sampler's block-linear copy as whole sectors (row pairs, SM_SURF_PAIRS=1, default) or row by row;
+    # odd row counts, a single row, a ragged last warp
+    monkeypatch.setenv("SM_SURF_PAIRS", pairs)
+    run_pair(oracle, "Waves", W, H, 3000, 9, trail=random_trail(W, H, seed=8), check_every=[1, 8])
+
+
+# ---- CUDA-graph replay of whole sort periods (engine.cu: graph_steps) ------------------------------------------------------
+@pytest.mark.parametrize("name,sort_interval", [("Default", 0), ("Waves", 5), ("Snake", 7)])
+def test_step_graph_equals_launch_path_and_oracle(oracle, engine_lib, monkeypatch, name, sort_interval):
+    """sm_step(n) replays captured periods (2 x sort_interval steps) when n is large enough; parameter changes, uploads and
+    statistics requests in between fall back to the launch path and re-capture.  Same bits as the oracle throughout, and as
+    an engine with the graphs switched off."""
+    W, H, N = 384, 256, 70000
+    s = settings_for(name)
+    u = preset_uniform(name, W, H)
+    ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 13)
+    sim = oracle.Sim(to_oracle_params(oracle, u), ag)
+    be = sm.CudaBackend.new(W, H, s, agent_count=N, sort_interval=sort_interval)
     be.write_agents(ag)
-    for _ in range(6):
-        oracle.agents_phase_split(sim.agents, sim.trail, sim.counts, p)
-        sim.trail = oracle.trail_pass(sim.trail, p, counts=sim.counts, gauss_radius=R, gauss_sigma=R / 2.0)
-    be.step(6)
-    assert bits_equal(be.read_agents(), sim.agents) and bits_equal(be.read_trail(), sim.trail)
-    be.close()
+    monkeypatch.setenv("SM_STEP_GRAPH", "0")
+    plain = sm.CudaBackend.new(W, H, s, agent_count=N, sort_interval=sort_interval)
+    monkeypatch.delenv("SM_STEP_GRAPH")
+    plain.write_agents(ag)
+    si = sort_interval or 24
+    plan = [3, 2 * si + 1, 4 * si, 1, 6 * si + 7]
+    for k, n in enumerate(plan):
+        if k == 2:                                   # a parameter change between two graph launches
+            s = s.clone(agent_turn_speed=0.9, pheromone_decay_factor=25.0)
+            u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
+            sim.p = to_oracle_params(oracle, u)
+            be.update_settings(s); plain.update_settings(s)
+        if k == 3:
+            be.trail_statistics(); plain.trail_statistics()      # arms the fused statistics: launch path for a while
+        if k == 4:                                   # an upload in between: the sampler copy is stale, the order is reset
+            tr = random_trail(W, H, seed=9)
+            sim.trail = tr.copy(); be.write_trail(tr); plain.write_trail(tr)
+        sim.step(n); be.step(n); plain.step(n)
+        a, t = be.read_agents(), be.read_trail()
+        assert bits_equal(a, sim.agents), f"{name} leg {k}: " + mismatch_report(a, sim.agents, "agents")
+        assert bits_equal(t, sim.trail), f"{name} leg {k}: " + mismatch_report(t, sim.trail, "trail")
+        assert bits_equal(plain.read_agents(), a) and bits_equal(plain.read_trail(), t)
+    tg, tp = be.timing(), plain.timing()
+    assert tg.steps == tp.steps == sum(plan) and tg.kernel_launches == tp.kernel_launches       # replays are counted like launches
+    be.close(); plain.close()

@@ -69,3 +69,60 @@ def test_backend_calls_only_declared_functions():
     for method in ("new", "write_uniform", "init_agents", "write_agents", "read_agents", "reassign_agent_speeds",
                    "set_agent_count", "clear_trail", "resize", "step", "set_lut", "render", "read_trail"):
         assert re.search(r"pub fn " + method + r"\b", BACKEND), method
+
+
+# ---- module paths: every `use` of the shim must resolve against the reference's crate layout --------------------------
+REF_SRC = "/root/reference/src"
+
+
+def _use_paths(src):
+    out = []
+    for m in re.finditer(r"^use\s+([^;]+);", src, re.M):
+        path = m.group(1).strip()
+        g = re.match(r"(.*)::\{(.*)\}$", path, re.S)
+        if g:
+            out += [g.group(1) + "::" + leaf.strip() for leaf in g.group(2).split(",") if leaf.strip()]
+        else:
+            out.append(path)
+    return out
+
+
+def test_use_paths_resolve_against_the_reference_crates():
+    """The reference is a lib crate (src/lib.rs: `pub mod lut_manager; pub mod presets; pub mod settings;`) plus a bin crate
+    (src/main.rs) that imports it as `slime_mold::..` and owns `SimSizeUniform`.  The shim's files are modules of the BIN
+    crate, so: `slime_mold::<m>::<Item>` needs `pub mod <m>` in lib.rs and a `pub` item in src/<m>.rs; `crate::<Item>` needs
+    the item in main.rs; `crate::ffi::*` needs rust/src/ffi.rs (added to main.rs as `mod ffi;`)."""
+    import pytest
+    if not os.path.isdir(REF_SRC):
+        pytest.skip("the reference checkout is not on this machine")
+    lib_rs = open(os.path.join(REF_SRC, "lib.rs")).read()
+    main_rs = open(os.path.join(REF_SRC, "main.rs")).read()
+    cargo = open(os.path.join(os.path.dirname(REF_SRC), "Cargo.toml")).read()
+    crate_name = re.search(r'^name\s*=\s*"([^"]+)"', cargo, re.M).group(1).replace("-", "_")
+    assert crate_name == "slime_mold"
+    own_modules = {"ffi", "cuda_backend"}
+    checked = 0
+    for path in _use_paths(BACKEND) + _use_paths(FFI):
+        parts = path.split("::")
+        if parts[0] == "std":
+            continue
+        if parts[0] == crate_name:                                   # lib crate
+            mod, item = parts[1], parts[2]
+            assert re.search(r"pub mod " + mod + r"\s*;", lib_rs), f"{path}: lib.rs has no `pub mod {mod}`"
+            src = open(os.path.join(REF_SRC, mod + ".rs")).read()
+            assert re.search(r"pub (struct|enum|fn|type|const) " + item + r"\b", src), f"{path}: no pub item {item} in {mod}.rs"
+        elif parts[0] == "crate":                                    # bin crate (main.rs is the crate root)
+            if parts[1] in own_modules:
+                assert os.path.exists(os.path.join(ROOT, "rust", "src", parts[1] + ".rs")), path
+            else:
+                assert len(parts) == 2, f"{path}: nested bin-crate paths are not expected"
+                assert re.search(r"^(pub )?(struct|enum|fn|type|const) " + parts[1] + r"\b", main_rs, re.M), \
+                    f"{path}: main.rs defines no {parts[1]}"
+        else:
+            raise AssertionError(f"{path}: neither std, the lib crate nor the bin crate")
+        checked += 1
+    assert checked >= 4
+    # the methods the shim calls on reference types exist there
+    assert "agent_count" in open(os.path.join(REF_SRC, "settings.rs")).read()
+    for field in re.findall(r"lut\.(\w+)", BACKEND):
+        assert re.search(r"pub " + field + r"\b", open(os.path.join(REF_SRC, "lut_manager.rs")).read()), field
