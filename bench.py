@@ -386,6 +386,8 @@ def measure(h, name, width, rows_per_gpu, agents_per_gpu, settings, args, steps,
     be = h.engine(width, height, settings, agents, flags=flags)
     be.init_agents(args.seed)
     be.set_timing_enabled(False)
+    if clocks is not None:          # rank 0 only (no collective in here); started early: the first NVML calls take tens of ms
+        clocks.start()
     peak, _ = hbm_peak()
     out = {"workload": name, "agents": agents, "width": width, "height": height}
     # initial state: uniform-random agents on an empty map (the first sort is part of it, as in any run)
@@ -397,8 +399,7 @@ def measure(h, name, width, rows_per_gpu, agents_per_gpu, settings, args, steps,
     be.step(args.warmup)
     be.sync()
     be.reset_timing()
-    if clocks is not None:          # rank 0 only: no collective in here
-        clocks.start()
+    if clocks is not None:
         clocks.mark("timed_begin")
     ms_total = h.timed(be, lambda: be.step(steps))
     if clocks is not None:

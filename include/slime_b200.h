@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define SM_VERSION_MAJOR 0
-#define SM_VERSION_MINOR 1
+#define SM_VERSION_MINOR 2
 
 typedef enum sm_status {
     SM_OK = 0,
@@ -70,6 +70,34 @@ enum {
     SM_FLAG_NO_SORT = 1u << 1
 };
 
+/* Measurement switches.  Every field: 0 = the engine's default, which is what profiles/ measured fastest.  None of them
+ * changes a result bit -- they select between kernels / schedules that are tested bit for bit against each other -- and
+ * the library reads NO environment variables for them: a harness that wants A/B runs fills this struct (the Python
+ * binding maps SM_* environment variables onto it for the test and bench scripts, slime_mold_b200/_lib.py). */
+typedef struct sm_tuning {
+    uint32_t sampler;               /* agent kernel's trail sampler: 0 texture gather from a block-linear copy (LDG when the
+                                       map exceeds the gather limits), 1 always LDG from the row-major field */
+    uint32_t tile_shift_x;          /* cell-sort tiles are 2^x by 2^y cells; 0 = 3 (8 x 8) */
+    uint32_t tile_shift_y;
+    uint32_t trail_rows_per_chunk;  /* rows one CTA of the fused decay+diffuse kernel walks; 0 = 8 (16 for large diffusion-only maps) */
+    uint32_t deposit_counts_only;   /* 1: u32 deposit counts even where u8 flags are exact */
+    uint32_t generic_trail_kernel;  /* 1: the one-cell-per-thread trail kernel for every map */
+    uint32_t surface_row_writes;    /* 1: the trail pass writes the sampler copy row by row instead of as whole sectors */
+    uint32_t no_step_graph;         /* 1: sm_step never replays CUDA graphs of whole sort periods */
+    uint32_t gauss_kernel;          /* EXTENSION: 0 auto, 1 register-streaming (rows), 2 shared-memory streaming, 3 tile, 4 two-pass */
+    uint32_t gauss_rows_max_radius; /* largest radius the rows kernel takes in auto mode; 0 = 5 */
+    uint32_t gauss_rows_packing;    /* FFMA2 taps of the rows kernel: 0 auto, 1 scalar, 2 packed */
+    uint32_t gauss_chunk_rows;      /* rows per CTA of the streaming kernels; 0 = chosen per map */
+    uint32_t exchange;              /* strips: 0 direct peer stores over NVLink (CUDA IPC), 1 NCCL send/recv */
+    uint32_t serial_exchange;       /* strips: 1 = no overlap of the exchange with the interior trail rows */
+    uint32_t migrate_capacity;      /* strips: agents per migration message; 0 = 65536 */
+    uint32_t barrier_fence;         /* strips: flag-barrier fences: 0 acq_rel.sys, 1 three sc system fences, 2 device scope */
+    uint32_t debug_single_rank_strip; /* PROFILING ONLY: a world_size > 1 engine that exchanges with itself (results meaningless) */
+    uint32_t debug_side_timing;     /* strips: per-piece CUDA-event times of the side stream, printed at teardown */
+    uint32_t no_boundary_first;     /* strips: 1 = one agent launch per step, exchange overlapped with the interior trail rows only */
+    uint32_t reserved[5];
+} sm_tuning;
+
 typedef struct sm_config {
     uint32_t width;          /* global map width  (cells) */
     uint32_t height;         /* global map height (cells) */
@@ -78,8 +106,9 @@ typedef struct sm_config {
     int32_t rank;            /* strip index 0..world_size-1 (0 for a single GPU) */
     int32_t world_size;      /* number of horizontal strips == GPUs (1 = whole map) */
     uint32_t flags;          /* SM_FLAG_* */
-    uint32_t sort_interval;  /* steps between agent cell sorts; 0 = engine default */
-    uint32_t reserved;
+    uint32_t sort_interval;  /* steps between agent cell sorts; 0 = engine default (24) */
+    uint32_t ghost_rows;     /* strips: ghost rows kept above and below; 0 = 232 (sensor distance 225 + slack) */
+    sm_tuning tuning;
 } sm_config;
 
 typedef struct sm_timing {       /* CUDA-event totals since sm_reset_timing() */
@@ -116,7 +145,9 @@ int sm_destroy(sm_engine *e);
  * sm_comm_unique_id(), the host distributes the 128 bytes out of band (bench.py
  * uses torch.distributed), every rank then calls sm_comm_init().  The engine
  * exchanges halo rows and migrating agents with its two ring neighbours over
- * NCCL (NVLink). */
+ * peer stores over NVLink or NCCL (sm_tuning.exchange).  libnccl.so.2 is resolved at run
+ * time: an already loaded copy (e.g. torch's) is reused; the environment variable
+ * SM_NCCL_LIB names another one -- the only environment variable the library reads. */
 #define SM_COMM_ID_BYTES 128
 int sm_comm_unique_id(uint8_t id[SM_COMM_ID_BYTES]);
 int sm_comm_init(sm_engine *e, const uint8_t id[SM_COMM_ID_BYTES]);

@@ -44,7 +44,8 @@ impl CudaBackend {
             world_size: 1,
             flags: 0,
             sort_interval: 0,
-            reserved: 0,
+            ghost_rows: 0,
+            tuning: sm_tuning::default(),
         };
         let mut e = std::ptr::null_mut();
         check(unsafe { sm_create(&mut e, &cfg) }, "sm_create");

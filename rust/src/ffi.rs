@@ -43,6 +43,32 @@ pub struct sm_params {
     pub _pad: u32,
 }
 
+/// Measurement switches; `Default::default()` (all zero) = the engine's defaults.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct sm_tuning {
+    pub sampler: u32,
+    pub tile_shift_x: u32,
+    pub tile_shift_y: u32,
+    pub trail_rows_per_chunk: u32,
+    pub deposit_counts_only: u32,
+    pub generic_trail_kernel: u32,
+    pub surface_row_writes: u32,
+    pub no_step_graph: u32,
+    pub gauss_kernel: u32,
+    pub gauss_rows_max_radius: u32,
+    pub gauss_rows_packing: u32,
+    pub gauss_chunk_rows: u32,
+    pub exchange: u32,
+    pub serial_exchange: u32,
+    pub migrate_capacity: u32,
+    pub barrier_fence: u32,
+    pub debug_single_rank_strip: u32,
+    pub debug_side_timing: u32,
+    pub no_boundary_first: u32,
+    pub reserved: [u32; 5],
+}
+
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
 pub struct sm_config {
@@ -54,7 +80,8 @@ pub struct sm_config {
     pub world_size: i32,
     pub flags: u32,
     pub sort_interval: u32,
-    pub reserved: u32,
+    pub ghost_rows: u32,
+    pub tuning: sm_tuning,
 }
 
 #[repr(C)]

@@ -28,12 +28,69 @@ class SlimeError(RuntimeError):
         self.code = code
 
 
+class SmTuning(C.Structure):
+    """`sm_tuning` of include/slime_b200.h: measurement switches, all zero = the engine's defaults."""
+
+    _fields_ = [
+        ("sampler", C.c_uint32), ("tile_shift_x", C.c_uint32), ("tile_shift_y", C.c_uint32),
+        ("trail_rows_per_chunk", C.c_uint32), ("deposit_counts_only", C.c_uint32), ("generic_trail_kernel", C.c_uint32),
+        ("surface_row_writes", C.c_uint32), ("no_step_graph", C.c_uint32),
+        ("gauss_kernel", C.c_uint32), ("gauss_rows_max_radius", C.c_uint32), ("gauss_rows_packing", C.c_uint32),
+        ("gauss_chunk_rows", C.c_uint32),
+        ("exchange", C.c_uint32), ("serial_exchange", C.c_uint32), ("migrate_capacity", C.c_uint32), ("barrier_fence", C.c_uint32),
+        ("debug_single_rank_strip", C.c_uint32), ("debug_side_timing", C.c_uint32),
+        ("no_boundary_first", C.c_uint32),
+        ("reserved", C.c_uint32 * 5),
+    ]
+
+
 class SmConfig(C.Structure):
     _fields_ = [
         ("width", C.c_uint32), ("height", C.c_uint32), ("agent_count", C.c_uint64),
         ("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32),
-        ("flags", C.c_uint32), ("sort_interval", C.c_uint32), ("reserved", C.c_uint32),
+        ("flags", C.c_uint32), ("sort_interval", C.c_uint32), ("ghost_rows", C.c_uint32),
+        ("tuning", SmTuning),
     ]
+
+
+_GAUSS_KERNELS = {"": 0, "auto": 0, "rows": 1, "stream": 2, "tile": 3, "two_pass": 4}
+
+
+def tuning_from_env(env=None) -> SmTuning:
+    """The test / bench harness convention: SM_* environment variables select A/B variants.  They are read HERE, by the
+    harness layer, and handed to the library as an explicit `sm_tuning`; libslime_b200.so itself reads no environment
+    variable for them.  Unset = 0 = default."""
+    env = os.environ if env is None else env
+
+    def num(name, dflt=0):
+        v = env.get(name, "")
+        return int(v) if v.strip() else dflt
+
+    t = SmTuning()
+    t.sampler = 1 if env.get("SM_SAMPLER", "") == "ldg" else 0
+    t.tile_shift_x, t.tile_shift_y = num("SM_TILE_SHIFT_X"), num("SM_TILE_SHIFT_Y")
+    t.trail_rows_per_chunk = num("SM_TRAIL_ROWS_PER_CHUNK")
+    t.deposit_counts_only = num("SM_NO_DEPOSIT_FLAGS")
+    t.generic_trail_kernel = num("SM_FORCE_GENERIC_TRAIL")
+    t.surface_row_writes = 0 if num("SM_SURF_PAIRS", 1) else 1
+    t.no_step_graph = 0 if num("SM_STEP_GRAPH", 1) else 1
+    gk = env.get("SM_GAUSS_KERNEL", "")
+    if gk not in _GAUSS_KERNELS:
+        raise ValueError(f"SM_GAUSS_KERNEL={gk!r}: one of {sorted(_GAUSS_KERNELS)}")
+    t.gauss_kernel = 4 if num("SM_GAUSS_TWO_PASS") else _GAUSS_KERNELS[gk]
+    t.gauss_rows_max_radius = num("SM_GAUSS_ROWS_MAX_R")
+    rp = num("SM_GAUSS_ROWS_PACKED", -1)               # -1 auto, 0 scalar taps, >= 1 FFMA2 taps
+    t.gauss_rows_packing = 0 if rp < 0 else (1 if rp == 0 else 2)
+    t.gauss_chunk_rows = num("SM_GAUSS_CHUNK")
+    t.exchange = 1 if env.get("SM_EXCHANGE", "") == "nccl" else 0
+    t.serial_exchange = 0 if num("SM_OVERLAP", 1) else 1
+    t.migrate_capacity = num("SM_MIGRATE_CAP")
+    bf = num("SM_BARRIER_FENCE", 1)                     # historical numbering: 0 sc fences, 1 acq_rel (default), 2 device scope
+    t.barrier_fence = {0: 1, 1: 0, 2: 2}.get(bf, 0)
+    t.debug_single_rank_strip = num("SM_FAKE_MULTI")
+    t.debug_side_timing = num("SM_SIDE_TIMING")
+    t.no_boundary_first = 0 if num("SM_BOUNDARY_FIRST", 1) else 1
+    return t
 
 
 class SmTiming(C.Structure):

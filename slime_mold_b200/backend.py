@@ -17,7 +17,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import SlimeError, SmConfig, SmTiming, SmTrailStats, check
+from ._lib import SlimeError, SmConfig, SmTiming, SmTrailStats, SmTuning, check, tuning_from_env
 from .settings import Settings, SimSizeUniform
 
 
@@ -28,7 +28,9 @@ def _fptr(a: np.ndarray):
 class CudaBackend:
     def __init__(self, width: int, height: int, settings: Optional[Settings] = None, *, agent_count: Optional[int] = None,
                  device: int = 0, rank: int = 0, world_size: int = 1, flags: int = 0, sort_interval: int = 0,
-                 ghost_rows: int = 0):
+                 ghost_rows: int = 0, tuning: Optional[SmTuning] = None):
+        """`tuning`: an explicit `sm_tuning` (measurement switches); None = what the SM_* environment variables of the test /
+        bench harness say (`_lib.tuning_from_env`), all zero when none is set."""
         self._lib = _lib.load()
         self.settings = settings.clone() if settings is not None else Settings.default()
         if agent_count is not None:
@@ -36,7 +38,8 @@ class CudaBackend:
         self.width, self.height = int(width), int(height)
         self.rank, self.world_size = rank, world_size
         cfg = SmConfig(width=self.width, height=self.height, agent_count=self.settings.agent_count, device=device,
-                       rank=rank, world_size=world_size, flags=flags, sort_interval=sort_interval, reserved=ghost_rows)
+                       rank=rank, world_size=world_size, flags=flags, sort_interval=sort_interval, ghost_rows=ghost_rows,
+                       tuning=tuning if tuning is not None else tuning_from_env())
         self._h = C.c_void_p()
         check(self._lib.sm_create(C.byref(self._h), C.byref(cfg)))
         self.update_settings(self.settings)

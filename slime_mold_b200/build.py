@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libslime_b200.so")
-SOURCES = ["engine.cu", "gauss.cu", "gauss_wring.cu", "exchange.cu"]
-HEADERS = ["engine.h", "kernels.cuh", "agent_core.cuh", "trail_core.cuh", "gauss_stream.cuh", "gauss_rows.cuh", "gauss_wring.cuh", "device_math.cuh",
+SOURCES = ["engine.cu", "gauss.cu", "exchange.cu"]
+HEADERS = ["engine.h", "kernels.cuh", "agent_core.cuh", "trail_core.cuh", "gauss_stream.cuh", "gauss_rows.cuh", "device_math.cuh",
            os.path.join("..", "..", "include", "slime_b200.h")]
 
 NVCC_FLAGS = [
@@ -52,8 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
-        ab = ["-DSM_BUILD_AB_VARIANTS=1"] if os.environ.get("SM_BUILD_AB_VARIANTS", "0") == "1" else []   # the A/B-only kernels (gauss.cu)
-        cmd = [nvcc_path(), *NVCC_FLAGS, *ab, "-c", "-o", obj, os.path.join(CSRC, src)]
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log, failed = "", False
     for cmd, pr in procs:

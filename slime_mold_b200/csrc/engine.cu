@@ -48,12 +48,6 @@ int sm_fail(int code, const char* fmt, ...)
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
-static int env_int(const char* name, int dflt)
-{
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 // ---------------------------------------------------------------------------
 // derived constants
 // ---------------------------------------------------------------------------
@@ -294,30 +288,14 @@ int sm_engine::setup_tiles()
 {
     if (tile_hist) { cudaFree(tile_hist); tile_hist = nullptr; }
     if (tile_sums) { cudaFree(tile_sums); tile_sums = nullptr; }
-    tiles.shift_x = (uint32_t)env_int("SM_TILE_SHIFT_X", 3);
-    tiles.shift_y = (uint32_t)env_int("SM_TILE_SHIFT_Y", 3);
+    tiles.shift_x = tuning.tile_shift_x ? std::min(tuning.tile_shift_x, 10u) : 3u;
+    tiles.shift_y = tuning.tile_shift_y ? std::min(tuning.tile_shift_y, 10u) : 3u;
     tiles.W = W;
     tiles.rows = rows;
     tiles.row_base = (int64_t)row0;
     tiles.tiles_x = (W + (1u << tiles.shift_x) - 1) >> tiles.shift_x;
     tiles.tiles_y = (rows + (1u << tiles.shift_y) - 1) >> tiles.shift_y;
-    {
-        int hb = env_int("SM_SORT_HEADING_BINS", 1);
-        if (hb < 1) hb = 1;
-        if (hb > 64) hb = 64;
-        tiles.heading_bins = (uint32_t)hb;
-        tiles.bin_scale = (float)hb / 6.28318530718f;
-    }
     n_tiles = (uint64_t)tiles.tiles_x * tiles.tiles_y;
-    {
-        int ss = env_int("SM_SORT_SUPER_SHIFT", 0);
-        if (ss < 0) ss = 0;
-        if (ss > 6) ss = 6;
-        tiles.super_shift = (uint32_t)ss;
-        tiles.super_x = (tiles.tiles_x + (1u << ss) - 1) >> ss;
-        if (ss) n_tiles = ((uint64_t)tiles.super_x * ((tiles.tiles_y + (1u << ss) - 1) >> ss)) << (2 * ss);
-    }
-    n_tiles *= tiles.heading_bins;
     if (n_tiles >= (1ull << 31)) return sm_fail(SM_ERR_BAD_ARG, "too many sort tiles");
     n_scan_blocks = (uint32_t)((n_tiles + smk::kScanBlock * smk::kScanItems - 1) / (smk::kScanBlock * smk::kScanItems));
     SM_CUDA(cudaMalloc(&tile_hist, n_tiles * sizeof(uint32_t)));
@@ -375,34 +353,96 @@ int sm_engine::sort_agents()
     if (world > 1) {                      // the scatter dropped the dead (migrated-away) slots
         n_local = n_live;
         SM_TRY(mark_tail_dead());
-        SM_TRY(push_counters());
+        SM_TRY(plan_split());             // boundary-first stepping: which slots are "interior" until the next sort
+        SM_TRY(push_counters());          // (synchronises: the two slot offsets plan_split requested have arrived)
+        finish_split();
     }
     SM_TRY(toc());
     return SM_OK;
 }
 
-int sm_engine::launch_agents()
+// Boundary-first stepping on strips (exchange.cu: p2p_step_split).  The sort leaves the agents ordered by tile row, so the
+// agents of the first / last `t` tile rows of the strip are the slots [0, a) and [b, n): a and b are two entries of the
+// scanned tile histogram (after the scatter, tile_hist[k] is the END offset of tile k).  An agent that starts the sort
+// interval at least `margin` rows away from both strip edges can, until the next sort, neither leave the strip, nor
+// deposit outside it or into the boundary bands, nor sense a row of the boundary bands:
+//   margin = band (rows the boundary trail pass rewrites) + g (sensing reach) + drift (rows it can move in sort_interval steps).
+// Those agents are stepped by the single-GPU instantiation on the main stream while the boundary agents, the barriers,
+// the boundary bands and the ghost-row push run beside them on the side stream.
+int sm_engine::plan_split()
+{
+    split_valid = false;
+    split_pending = false;
+    if (!p2p || !overlap_ok() || tuning.serial_exchange || tuning.no_boundary_first) return SM_OK;
+    const uint32_t band = overlap_band();
+    if (band == 0) return SM_OK;
+    const float vmax = fmaxf(fabsf(params.agent_speed_min), fabsf(params.agent_speed_max));
+    const float sd = fabsf(params.agent_sensor_distance);
+    if (!(vmax < 1.0e5f) || !(sd < 6.0e4f)) return SM_OK;
+    const uint32_t drift = (uint32_t)ceilf(vmax * 0.016f * (float)(sort_interval + 1)) + 2u;
+    const uint32_t margin = band + ((uint32_t)ceilf(sd) + 3u) + drift;
+    const uint32_t th = 1u << tiles.shift_y;
+    const uint32_t t = (margin + th - 1) / th;                    // tile rows per side
+    if (2ull * t + 2 > tiles.tiles_y) return SM_OK;               // no interior worth a second launch
+    // END offsets of the last tile of tile row t-1 and of tile row tiles_y-t-1
+    const size_t ia = (size_t)t * tiles.tiles_x - 1, ib = (size_t)(tiles.tiles_y - t) * tiles.tiles_x - 1;
+    SM_CUDA(cudaMemcpyAsync(split_host, tile_hist + ia, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    SM_CUDA(cudaMemcpyAsync(split_host + 1, tile_hist + ib, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    split_pending = true;
+    return SM_OK;
+}
+void sm_engine::finish_split()
+{
+    if (!split_pending) return;
+    split_pending = false;
+    const uint64_t a = ((uint64_t)split_host[0] + 1023) / 1024 * 1024;      // whole CTAs of the boundary launch (kernels.cuh)
+    const uint64_t b = split_host[1];
+    if (b > a && b <= n_local && b - a >= 64 * 1024) {                       // a second launch has to be worth its latency
+        split_a = a; split_b = b;
+        split_valid = true;
+    }
+}
+
+// What has to happen once per step before any agent kernel of the step is launched (main stream).
+int sm_engine::prepare_agents()
 {
     if (world > 1) n_local = n_upper;            // grid bound; the kernel reads the exact count on the device
-    const bool flags = flag_mode();
-    // Before the early return: the deposit mode of the step is a collective decision (a rank whose strip is empty still
-    // merges what its neighbours deposited into it, and takes part in the barrier of a mode change), and the trail pass
-    // accumulates its statistics from zero whether or not an agent kernel ran
-    SM_TRY(switch_deposit_mode(flags ? 2 : 1));
-    if (n_local == 0) {
-        SM_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(smk::StatsAcc), stream));
+    // The deposit mode of the step is a collective decision (a rank whose strip is empty still merges what its
+    // neighbours deposited into it, and takes part in the barrier of a mode change)
+    SM_TRY(switch_deposit_mode(flag_mode() ? 2 : 1));
+    if (use_tex && arr_stale) {                       // the array lost track of trail[cur]: one full copy
+        SM_TRY(refresh_tex(-(int64_t)(ghost + pad_rows), (int64_t)rows + 2 * (int64_t)(ghost + pad_rows)));
+        arr_stale = false;
+    }
+    return SM_OK;
+}
+
+// part 0: every slot (one launch).  Strips, boundary-first stepping (exchange.cu: p2p_step_split):
+// part 1: the interior slots [split_a, split_b) with the single-GPU instantiation -- agents that cannot leave the strip
+//         or deposit outside it before the next sort;  part 2: everything else with the strip instantiation.
+int sm_engine::launch_agents(int part, cudaStream_t st)
+{
+    if (!st) st = stream;
+    if (part == 0) SM_TRY(prepare_agents());
+    const bool flags = deposit_mode == 2;
+    uint64_t first = 0, count = n_local;
+    if (part == 1) { first = split_a; count = split_b - split_a; }
+    if (part == 2) count = split_a + (n_local - split_b);
+    if (count == 0) {
+        // the trail pass accumulates its statistics from zero whether or not an agent kernel ran
+        if (part != 2) SM_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(smk::StatsAcc), st));
         return SM_OK;
     }
-    SM_TRY(tic(0));
+    if (part != 2) SM_TRY(tic(0, st));
     smk::LeaverBufs lv{};
     const bool idx32 = (uint64_t)field_cells() < (1ull << 31);
-    const int apt = smk::agents_per_thread_for(n_local, num_sms);
-    const unsigned nb = blocks_for(n_local, 256u * (unsigned)apt);        // a CTA steps 256 * apt consecutive slots
-    float4* a = agents[acur];
-    uint32_t* id = ids[acur];
+    const int apt = smk::agents_per_thread_for(count, num_sms);
+    const unsigned nb = blocks_for(count, 256u * (unsigned)apt);        // a CTA steps 256 * apt consecutive slots
+    float4* a = agents[acur] + first;
+    uint32_t* id = ids[acur] + first;
     void* dep = flags ? (void*)flags_ptr(ccur) : (void*)counts_ptr(ccur);
     const smd::AgentConsts ac = agent_consts();
-    const bool multi = world > 1;
+    const bool multi = world > 1 && part != 1;
     if (multi && p2p) {
         // leavers and out-of-strip deposits go straight into the neighbours' HBM (CUDA IPC mappings)
         for (int d = 0; d < 2; ++d) {
@@ -429,31 +469,31 @@ int sm_engine::launch_agents()
         lv.slots_in_use = dev_counters;
         lv.cap = (uint32_t)mig_cap;
     }
+    uint64_t n_arg = count;
+    if (part == 2) {
+        // launch indices [0, split_a) are slots [0, split_a); indices beyond map to slots >= split_b.  split_a is a multiple
+        // of 1024 (sort_agents), so no CTA's 256 * apt consecutive indices straddle the skipped range
+        lv.split = split_a;
+        lv.skip = split_b - split_a;
+        n_arg = n_local;                                                   // the kernel compares SLOT numbers with it
+    }
     auto launch = [&](auto fetch, auto idx_tag) {
         using F = decltype(fetch);
         using I = decltype(idx_tag);
         if (multi && p2p) {
-            if (flags) smk::k_agents<smk::XM_P2P, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
-            else smk::k_agents<smk::XM_P2P, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            if (flags) smk::k_agents<smk::XM_P2P, I, F, true><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            else smk::k_agents<smk::XM_P2P, I, F, false><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         } else if (multi) {
-            if (flags) smk::k_agents<smk::XM_NCCL, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
-            else smk::k_agents<smk::XM_NCCL, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            if (flags) smk::k_agents<smk::XM_NCCL, I, F, true><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            else smk::k_agents<smk::XM_NCCL, I, F, false><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         } else {
-            if (flags) smk::k_agents<smk::XM_SINGLE, I, F, true><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
-            else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, stream>>>(a, id, n_local, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            if (flags) smk::k_agents<smk::XM_SINGLE, I, F, true><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         }
     };
     if (use_tex) {
-        if (arr_stale) {                                  // the array lost track of trail[cur]: one full copy
-            SM_TRY(refresh_tex(-(int64_t)(ghost + pad_rows), (int64_t)rows + 2 * (int64_t)(ghost + pad_rows)));
-            arr_stale = false;
-        }
         const smk::FetchTex f{trail_tex, (float)((int32_t)(ghost + pad_rows) - (int32_t)row0 + 1)};
-        if (agent_stream_hint && !multi && idx32) {
-            // A/B instantiation: evict-first hints on the agent stream (single GPU, 32-bit offsets, texture sampler)
-            if (flags) smk::k_agents<smk::XM_SINGLE, int32_t, smk::FetchTex, true, true><<<nb, 256, 0, stream>>>(a, id, n_local, f, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
-            else smk::k_agents<smk::XM_SINGLE, int32_t, smk::FetchTex, false, true><<<nb, 256, 0, stream>>>(a, id, n_local, f, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
-        } else if (idx32) launch(f, int32_t{});
+        if (idx32) launch(f, int32_t{});
         else launch(f, int64_t{});
     } else if (idx32) {
         launch(smd::FetchLinear<int32_t, smk::LdgF32>{trail_ptr(cur), (int32_t)W, (int32_t)row0, smk::LdgF32()}, int32_t{});
@@ -462,7 +502,7 @@ int sm_engine::launch_agents()
     }
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
-    SM_TRY(toc());
+    if (part != 2) SM_TRY(toc(st));
     return SM_OK;
 }
 
@@ -576,6 +616,14 @@ int sm_engine::step_once()
     if (sort_interval && steps_since_sort >= sort_interval) {
         SM_TRY(sort_agents());
         steps_since_sort = 0;
+    }
+    if (world > 1 && p2p && split_valid && overlap_ok()) {
+        SM_TRY(p2p_step_split());                        // boundary agents + exchange beside the interior agents
+        steps_since_sort++;
+        timing.steps++;
+        frame_pre_valid = true;
+        frame_tc = trail_consts();
+        return SM_OK;
     }
     SM_TRY(launch_agents());                             // src/main.rs:1164-1181
     if (world > 1 && p2p && overlap_ok()) {
@@ -744,54 +792,39 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     e->rows = row1 - e->row0;
     e->ghost = 0;
     if (e->world > 1) {
-        uint32_t want = cfg->reserved ? cfg->reserved : 232u;   // >= ceil(225)+2 (Snake/Mesh presets) + slack
+        uint32_t want = cfg->ghost_rows ? cfg->ghost_rows : 232u;   // >= ceil(225)+2 (Snake/Mesh presets) + slack
         uint32_t min_rows = e->H / e->world;                    // thinnest strip
         e->ghost = std::min(want, min_rows);
         e->pad_rows = 16;
     }
     e->n_global = cfg->agent_count;
-    e->sort_interval = cfg->sort_interval ? cfg->sort_interval : (uint32_t)env_int("SM_SORT_INTERVAL", 24);   // config 2: 16 -> 230.1, 24 -> 225.4, 32 -> 225.7, 48 -> 225.1 us/step (agents slow down as order decays)
+    // config 2: 16 -> 230.1, 24 -> 225.4, 32 -> 225.7, 48 -> 225.1 us/step (the agent kernel slows down as the order decays)
+    e->sort_interval = cfg->sort_interval ? cfg->sort_interval : 24u;
     if (cfg->flags & SM_FLAG_NO_SORT) e->sort_interval = 0;
     if (e->world > 1 && e->sort_interval == 0) e->sort_interval = 16;   // strips need the sort to compact migrated-away slots
+    // measurement switches: sm_config.tuning, all zero by default (no environment variable is read here)
+    const sm_tuning& tn = cfg->tuning;
+    e->tuning = tn;
     {
-        const char* smp = getenv("SM_SAMPLER");
-        bool want_tex = !(smp && std::string(smp) == "ldg");
         bool probe = false;
-        if (want_tex) { int prc = gather_probe_ok(&probe); if (prc != SM_OK) { delete e; return prc; } }
-        e->use_tex = want_tex && probe;
+        if (tn.sampler == 0) { int prc = gather_probe_ok(&probe); if (prc != SM_OK) { delete e; return prc; } }
+        e->use_tex = tn.sampler == 0 && probe;
     }
-    e->surf_pairs = env_int("SM_SURF_PAIRS", 1) != 0;
-    e->graph_enabled = env_int("SM_STEP_GRAPH", 1) != 0;       // 0: every step through the ordinary launch path (A/B)
-    e->force_generic = env_int("SM_FORCE_GENERIC_TRAIL", 0) != 0;
-    e->no_flags = env_int("SM_NO_DEPOSIT_FLAGS", 0) != 0;
-    e->rpc_override = env_int("SM_TRAIL_ROWS_PER_CHUNK", 0);
-    e->gauss_two_pass = env_int("SM_GAUSS_TWO_PASS", 0) != 0;
-    {
-        // Unset: the register-streaming kernel (gauss_rows.cuh) up to radius SM_GAUSS_ROWS_MAX_R (5), the shared-memory streaming
-        // kernel (gauss_stream.cuh) above, the tile kernel (k_gauss_fused) for maps the first two do not take (W % 4 != 0, tiny).
-        // "rows" / "stream" / "tile" force one of them wherever it applies.  Measured on 8192^2-16384^2 (profiles/), fraction of
-        // the HBM peak: rows 0.89-0.95 (R 1-2), 0.78-0.85 (R 3-4), 0.65-0.69 (R 5); stream 0.51-0.69; tile 0.31-0.61.  rows and
-        // stream let a Gaussian full step keep the u8 deposit flags and the sampler copy (6.8e10 vs 4.4e10 agent-steps/s).
-        const char* gk = getenv("SM_GAUSS_KERNEL");
-        const std::string gks = gk ? gk : "";
-        e->gauss_stream = gks != "tile";
-        e->gauss_rows = gks.empty() || gks == "rows" || gks == "auto";
-        e->gauss_wring = gks == "wring";                 // experiment: radius 5-8 on the private-ring kernel, the rest as by default
-        if (e->gauss_wring) e->gauss_rows = true;
-        e->gauss_rows_max_r = gks == "rows" ? smk::kGrMaxR : env_int("SM_GAUSS_ROWS_MAX_R", 5);
-        e->gauss_stream_packed = env_int("SM_GAUSS_STREAM_PACKED", 0) != 0;
-        e->gauss_rows_packed = env_int("SM_GAUSS_ROWS_PACKED", -1);        // FFMA2 taps: -1 = the level measured fastest per radius
-    }
-    e->agent_stream_hint = env_int("SM_AGENT_STREAM_HINT", 0);   // 1: evict-first loads / stores of the agent state (A/B)
-    {
-        // experiment (off unless set): DRAM -> L2 fill granularity, 32 / 64 / 128 bytes.  The sensor gathers of maps that do not
-        // fit the L2 (config 3: 8192^2, sensor distance 225) touch one 32-byte sector per footprint row; a smaller fill size
-        // wastes less HBM bandwidth on them, a larger one helps the streaming passes.  Device-wide, so only on request.
-        const int gran = env_int("SM_L2_FETCH_GRANULARITY", 0);
-        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
-    }
-    e->gauss_chunk = env_int("SM_GAUSS_CHUNK", 0);         // rows per CTA of the streaming kernel (0 = chosen per map)
-    e->gauss_packed = env_int("SM_GAUSS_PACKED", 0) != 0;   // measured: no faster than the scalar form (the kernel waits on barriers and loads, not on FMA issue)
+    e->force_generic = tn.generic_trail_kernel != 0;
+    e->no_flags = tn.deposit_counts_only != 0;
+    e->rpc_override = (int)tn.trail_rows_per_chunk;
+    e->surf_pairs = tn.surface_row_writes == 0;
+    e->graph_enabled = tn.no_step_graph == 0;
+    // Gaussian extension: the register-streaming kernel (gauss_rows.cuh) up to radius gauss_rows_max_r (5), the shared-memory
+    // streaming kernel (gauss_stream.cuh) above, the tile kernel (k_gauss_fused) for maps the first two do not take (W % 4 != 0,
+    // tiny).  Measured on 8192^2-16384^2 (profiles/), fraction of the HBM peak: rows 0.89-0.95 (R 1-2), 0.78-0.85 (R 3-4),
+    // 0.65-0.69 (R 5); stream 0.51-0.69; tile 0.31-0.61.  rows and stream let a Gaussian full step keep the u8 deposit flags
+    // and the sampler copy (6.8e10 vs 4.4e10 agent-steps/s).
+    e->gauss_two_pass = tn.gauss_kernel == 4;
+    e->gauss_stream = tn.gauss_kernel != 3 && tn.gauss_kernel != 4;
+    e->gauss_rows = tn.gauss_kernel == 0 || tn.gauss_kernel == 1;
+    e->gauss_rows_max_r = tn.gauss_kernel == 1 ? 5 : (tn.gauss_rows_max_radius ? (int)std::min(tn.gauss_rows_max_radius, 5u) : 5);
+    e->gauss_rows_packing = (int)tn.gauss_rows_packing;
 
     // defaults = Settings::default(), /root/reference/src/settings.rs:8-27
     sm_params p{};
@@ -817,7 +850,7 @@ int sm_create(sm_engine** out, const sm_config* cfg)
         return fail(sm_fail(SM_ERR_OOM, "cudaMalloc(stats) failed"));
     e->n_local = 0;
     e->agents_valid = false;
-    if (e->world > 1 && env_int("SM_FAKE_MULTI", 0)) {
+    if (e->world > 1 && tn.debug_single_rank_strip) {
         if ((rc = e->fake_comm_init()) != SM_OK) return fail(rc);
     }
     if (cudaStreamSynchronize(e->stream) != cudaSuccess)
@@ -866,6 +899,10 @@ int sm_set_params(sm_engine* e, const sm_params* p)
     }
     const sm_params before = e->params;
     e->params = *p;
+    if (e->world > 1 && memcmp(&before, p, sizeof before) != 0) {
+        e->split_valid = false;                          // the interior / boundary split was planned for the old speeds and reach
+        e->steps_since_sort = e->sort_interval;          // (every rank gets the same call: the sort stays collective)
+    }
     if (const int rc = e->check_gauss(false); rc != SM_OK) {   // extension: a bad radius / sigma is refused here, not in the middle of a step
         e->params = before;
         return rc;
@@ -943,6 +980,7 @@ int sm_upload_agents(sm_engine* e, const float* xyas, uint64_t first, uint64_t n
     e->agents_valid = true;
     e->identity_order = false;
     e->steps_since_sort = e->sort_interval;
+    e->split_valid = false;
     return SM_OK;
 }
 
@@ -993,6 +1031,7 @@ int sm_init_agents(sm_engine* e, uint64_t seed)
     }
     e->agents_valid = true;
     e->steps_since_sort = e->sort_interval;
+    e->split_valid = false;
     return SM_OK;
 }
 
@@ -1206,6 +1245,7 @@ int sm_load_snapshot(sm_engine* e, const char* path)
     e->agents_valid = true;
     e->identity_order = false;
     e->steps_since_sort = e->sort_interval;            // sort before the next step
+    e->split_valid = false;
     SM_CUDA(cudaMemcpy(e->trail_ptr(e->cur), t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
     bool nonneg = e->world == 1;                        // strips: the decision must be the same on every rank
     for (size_t i = 0; nonneg && i < t.size(); ++i) nonneg = t[i] >= 0.0f;

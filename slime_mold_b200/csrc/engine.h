@@ -9,9 +9,6 @@
 #include "kernels.cuh"
 
 int sm_fail(int code, const char* fmt, ...);
-// gauss_wring.cu (experiment kernel): flags = u8 deposit flags merged (else diffusion-only)
-int sm_gauss_wring_dispatch(struct sm_engine* e, int R, bool flags, bool surf, const smk::GsArgs& a, const smd::TrailConsts& tc,
-                            const smk::GaussConsts& gc);
 
 struct EvPair { cudaEvent_t a, b; int kind; };
 
@@ -51,7 +48,7 @@ struct sm_engine {
     cudaArray_t trail_arr = nullptr;
     cudaTextureObject_t trail_tex = 0;
     cudaSurfaceObject_t trail_surf = 0;
-    bool use_tex = false;             // SM_SAMPLER=tex (default) and the gather probe passed
+    bool use_tex = false;             // tuning.sampler == 0 and the gather probe passed
     bool tex_fallback = false;        // use_tex was switched off because this map does not fit a gather array (retried by sm_resize)
     bool arr_stale = true;            // the array does not mirror trail[cur] (upload / clear / diffuse-only ...)
     float* gauss_dec = nullptr;       // extension scratch
@@ -77,25 +74,21 @@ struct sm_engine {
     uint32_t* tile_sums = nullptr;
     uint32_t sort_interval = 24, steps_since_sort = 0;
 
-    // tuning overrides (environment, read at sm_create)
+    // measurement switches (sm_config.tuning; 0 = default everywhere) and what sm_create derived from them
+    sm_tuning tuning{};
     bool force_generic = false;
-    bool no_flags = false;            // SM_NO_DEPOSIT_FLAGS=1: always count deposits (A/B switch)
+    bool no_flags = false;            // always count deposits
     int rpc_override = 0;
-    bool gauss_packed = false;        // SM_GAUSS_PACKED=1: the FFMA2 form of the fused Gaussian kernel (A/B; measured 3-10 % slower)
-    int agent_stream_hint = 0;        // SM_AGENT_STREAM_HINT=1: the agent kernel streams its state with evict-first hints (A/B)
-    bool gauss_stream = true;         // the streaming Gaussian kernel (gauss_stream.cuh) wherever it applies; SM_GAUSS_KERNEL=tile selects the tile kernel
-    int gauss_chunk = 0;              // SM_GAUSS_CHUNK: rows per CTA of the streaming kernel (0 = chosen per map)
+    bool gauss_stream = true;         // the streaming Gaussian kernels wherever they apply (gauss_kernel 3 / 4 select the tile / two-pass forms)
     bool gauss_stream_ok() const;
-    // the register-streaming kernel for small radii (gauss_rows.cuh): SM_GAUSS_KERNEL=rows forces it for every radius it
-    // takes (1-8), unset = radii up to gauss_rows_max_r (SM_GAUSS_ROWS_MAX_R), stream / tile = never
+    // the register-streaming kernel for small radii (gauss_rows.cuh): gauss_kernel 1 forces it for every radius it is built
+    // for (1-5), 0 = radii up to gauss_rows_max_r, 2 / 3 / 4 = never
     bool gauss_rows = true;
-    int gauss_rows_max_r = 5;         // measured (profiles/): 0.64-0.95 of the HBM peak at radius 1-5 against 0.55-0.69 for the streaming kernel; a tie at 6, behind at 7-8
-    int gauss_rows_packed = -1;       // SM_GAUSS_ROWS_PACKED: 0 scalar taps, 1 column taps as FFMA2 on column pairs, 2 also the aligned half of the row taps, -1 = where measured faster (2 for radius <= 4)
-    bool gauss_stream_packed = false; // SM_GAUSS_STREAM_PACKED=1: FFMA2 taps in the streaming kernel (radius >= 5; A/B)
-    bool gauss_wring = false;         // SM_GAUSS_KERNEL=wring: experiment, the private-ring kernel (gauss_wring.cuh) for radius 5-8
+    int gauss_rows_max_r = 5;         // measured (profiles/): 0.64-0.95 of the HBM peak at radius 1-5 against 0.55-0.69 for the streaming kernel
+    int gauss_rows_packing = 0;       // 0 auto (FFMA2 taps up to radius 4), 1 scalar taps, 2 packed
     bool gauss_rows_ok() const;
     bool gauss_fast_ok() const { return gauss_rows_ok() || gauss_stream_ok(); }   // kernels that merge u8 flags and write the sampler copy
-    bool gauss_two_pass = false;      // SM_GAUSS_TWO_PASS=1: the unfused Gaussian passes (A/B; also used for maps below 160 x 64)
+    bool gauss_two_pass = false;      // the unfused Gaussian passes (A/B; also used for maps below 160 x 64)
 
     // statistics: accumulator on the device; `stats_fused_valid` = the last thing that changed trail[cur] was a full-step
     // pass of k_trail_rows, which filled it on the way (else sm_trail_statistics runs k_trail_stats)
@@ -143,7 +136,7 @@ struct sm_engine {
         uint32_t rows = 0;                          // rows they own
     };
     bool p2p = false;
-    bool fake_multi = false;          // SM_FAKE_MULTI=1 (profiling only): strip geometry and kernels of a 2-rank run without any exchange
+    bool fake_multi = false;          // tuning.debug_single_rank_strip (profiling only): a strip engine whose two ring neighbours are itself
     int fake_comm_init();
     PeerView peer[2];
     std::vector<void*> ipc_opened;    // every pointer obtained from cudaIpcOpenMemHandle
@@ -151,6 +144,7 @@ struct sm_engine {
     size_t window_arrival_off[2] = {0, 0};          // offset of the arrival buffer filled by up / by down
     uint32_t barrier_seq = 0;
     int setup_p2p();
+    int p2p_streams_init();
     int p2p_barrier();
     int p2p_after_agents(cudaStream_t st = nullptr, bool timed = true);   // barrier 1 + pull of the neighbours' boundary deposit rows
     int p2p_after_trail(cudaStream_t st = nullptr, bool timed = true);    // push trail ghost rows, append arrivals, barrier 2
@@ -159,8 +153,16 @@ struct sm_engine {
     // bands, the ghost-row push, the arrivals and barrier 2 run beside them on `side_stream`.
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool overlap_enabled = true;      // SM_OVERLAP=0 switches back to the serial exchange (A/B)
+    bool overlap_enabled = true;      // tuning.serial_exchange switches back to the serial order (A/B)
     bool overlap_ok();
+    // boundary-first stepping (engine.cu: plan_split, exchange.cu: p2p_step_split)
+    bool split_valid = false, split_pending = false;
+    uint64_t split_a = 0, split_b = 0;      // interior slots [split_a, split_b) until the next sort
+    uint32_t* split_host = nullptr;         // pinned: two slot offsets read back at sort time
+    cudaEvent_t ev_boundary = nullptr;
+    int plan_split();
+    void finish_split();
+    int p2p_step_split();
     uint32_t overlap_band();          // rows of each boundary band (multiple of the chunk height; 0 = strip too thin)
     int p2p_trail_overlapped();
     int p2p_diffuse_overlapped();
@@ -171,8 +173,8 @@ struct sm_engine {
         sm_params params; uint64_t n_local; int acur, cur, ccur, deposit_mode; uint32_t sort_interval;
         const void *agents0, *trail0, *arr; bool use_tex, force_generic, no_flags; int rpc_override;
     };
-    bool surf_pairs = true;           // SM_SURF_PAIRS=0: the trail pass writes the sampler copy row by row (A/B)
-    bool graph_enabled = true;        // SM_STEP_GRAPH=0 switches it off (A/B)
+    bool surf_pairs = true;           // !tuning.surface_row_writes
+    bool graph_enabled = true;        // !tuning.no_step_graph
     cudaGraphExec_t step_graph = nullptr;
     GraphKey step_graph_key{};
     uint64_t step_graph_launches = 0;
@@ -187,7 +189,7 @@ struct sm_engine {
 
     int tic(int kind, cudaStream_t st = nullptr);
     int toc(cudaStream_t st = nullptr);
-    double side_dbg_ms[8] = {0};     // SM_SIDE_TIMING=1: per-piece times of the side stream (printed at comm teardown)
+    double side_dbg_ms[8] = {0};     // tuning.debug_side_timing: per-piece times of the side stream (printed at comm teardown)
     uint64_t side_dbg_n[8] = {0};
     bool side_dbg = false;
     int resolve_timing();
@@ -203,7 +205,8 @@ struct sm_engine {
     int refresh_tex_ghosts(uint32_t g);                         // both ghost bands, by a kernel
 
     int sort_agents();
-    int launch_agents();
+    int prepare_agents();
+    int launch_agents(int part = 0, cudaStream_t st = nullptr);   // part: 0 all slots, 1 interior (single-GPU kernel), 2 boundary
     struct TrailPass {
         smk::TrailGeom g;
         smd::TrailConsts tc;

@@ -356,9 +356,9 @@ extern "C" int sm_comm_init(sm_engine* e, const uint8_t id[SM_COMM_ID_BYTES])
     SM_CUDA(cudaMalloc(&e->counts_xchg, 2 * e->counts_xchg_rows * e->W * sizeof(uint32_t)));
     // Leavers per step and direction ~ density * W * |v_y| * dt (a few thousand at W = 32768); the whole
     // fixed-size message is sent every step, so keep it small: 64 Ki agents (1.3 MB, ~2 us on NVLink),
-    // SM_MIGRATE_CAP overrides.  Overflow is detected on the device and reported at the next sync point.
+    // sm_tuning.migrate_capacity overrides.  Overflow is detected on the device and reported at the next sync point.
     uint64_t cap = 65536;
-    if (const char* v = getenv("SM_MIGRATE_CAP")) cap = std::max<uint64_t>(1024, strtoull(v, nullptr, 10));
+    if (e->tuning.migrate_capacity) cap = std::max<uint64_t>(1024, e->tuning.migrate_capacity);
     cap = (cap + 3) & ~3ull;
     e->mig_cap = cap;
     e->mig_bytes = 16 + cap * (sizeof(float4) + sizeof(uint32_t));
@@ -379,8 +379,11 @@ extern "C" int sm_comm_init(sm_engine* e, const uint8_t id[SM_COMM_ID_BYTES])
     return SM_OK;
 }
 
-// PROFILING ONLY (SM_FAKE_MULTI=1): lets one process run the multi-GPU kernels (strip geometry, leaver
-// staging, ghost rows) under ncu without a peer.  Nothing is exchanged, so results are meaningless.
+// PROFILING ONLY (sm_tuning.debug_single_rank_strip): lets ONE process run the strip kernels and the overlapped exchange
+// under ncu -- k_agents<XM_P2P>, the boundary bands, the flag barriers, the ghost-row push -- by making the engine its own
+// ring neighbour: the "peer" views are its own buffers, so every peer store lands in local HBM and every barrier is
+// satisfied by the flags this rank wrote itself.  The numbers a profiler reads are those of the kernels; the simulation
+// results are meaningless (the agents that leave the strip come back as arrivals in the wrong rows).
 int sm_engine::fake_comm_init()
 {
     counts_xchg_rows = (uint64_t)ghost + 1;
@@ -396,9 +399,21 @@ int sm_engine::fake_comm_init()
     SM_CUDA(cudaMalloc(&dev_counters, 8 * sizeof(unsigned long long)));
     SM_CUDA(cudaMemset(dev_counters, 0, 8 * sizeof(unsigned long long)));
     SM_CUDA(cudaMallocHost(&host_counters, 8 * sizeof(unsigned long long)));
+    const size_t arr_bytes = (mig_bytes + 63) & ~(size_t)63;
+    window_arrival_off[0] = 64;
+    window_arrival_off[1] = 64 + arr_bytes;
+    SM_CUDA(cudaMalloc(&window, 64 + 2 * arr_bytes));
+    SM_CUDA(cudaMemset(window, 0, 64 + 2 * arr_bytes));
+    for (int d = 0; d < 2; ++d) {
+        for (int i = 0; i < 2; ++i) { peer[d].counts[i] = counts_base[i]; peer[d].flags8[i] = flags_base[i]; peer[d].trail[i] = trail_base[i]; }
+        peer[d].window = window;
+        peer[d].rows = rows;
+    }
     fake_multi = true;
     comm_ready = true;
-    p2p = false;
+    p2p = true;
+    barrier_seq = 0;
+    SM_TRY(p2p_streams_init());
     return SM_OK;
 }
 
@@ -416,13 +431,17 @@ void sm_engine::comm_destroy()
     if (window) { cudaFree(window); window = nullptr; }
     if (side_dbg && side_dbg_n[0]) {
         resolve_timing();
-        fprintf(stderr, "[slime_b200 rank %d] side stream per step: barrier1+pull %.2f us, bands %.2f us, push+arrivals+barrier2 %.2f us (%llu steps)\n",
-                rank, 1e3 * side_dbg_ms[0] / side_dbg_n[0], 1e3 * side_dbg_ms[1] / std::max<uint64_t>(1, side_dbg_n[1]),
-                1e3 * side_dbg_ms[2] / std::max<uint64_t>(1, side_dbg_n[2]), (unsigned long long)side_dbg_n[0]);
+        fprintf(stderr, "[slime_b200 rank %d] side stream per step: boundary agents %.2f us, barrier1+pull %.2f us, bands %.2f us, push+arrivals+barrier2 %.2f us (%llu steps)\n",
+                rank, 1e3 * side_dbg_ms[3] / std::max<uint64_t>(1, side_dbg_n[3]), 1e3 * side_dbg_ms[0] / side_dbg_n[0],
+                1e3 * side_dbg_ms[1] / std::max<uint64_t>(1, side_dbg_n[1]), 1e3 * side_dbg_ms[2] / std::max<uint64_t>(1, side_dbg_n[2]),
+                (unsigned long long)side_dbg_n[0]);
     }
     if (side_stream) { cudaStreamDestroy(side_stream); side_stream = nullptr; }
     if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
     if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
+    if (ev_boundary) { cudaEventDestroy(ev_boundary); ev_boundary = nullptr; }
+    if (split_host) { cudaFreeHost(split_host); split_host = nullptr; }
+    split_valid = false;
     p2p = false;
     if (dev_counters) { cudaFree(dev_counters); dev_counters = nullptr; }
     if (host_counters) { cudaFreeHost(host_counters); host_counters = nullptr; }
@@ -590,7 +609,7 @@ int sm_engine::refresh_counters()
     if (host_counters[2] == 3)
         return sm_fail(SM_ERR_STATE, "rank %d: a ring neighbour did not reach the step barrier within 20 s", rank);
     if (host_counters[2])
-        return sm_fail(SM_ERR_OOM, "rank %d: %s overflow (raise SM_MIGRATE_CAP or the agent capacity)", rank,
+        return sm_fail(SM_ERR_OOM, "rank %d: %s overflow (raise sm_tuning.migrate_capacity or the agent capacity)", rank,
                        host_counters[2] == 1 ? "migration message" : "agent array");
     n_local = host_counters[0];
     n_live = host_counters[1];
@@ -619,12 +638,11 @@ struct IpcBundle { cudaIpcMemHandle_t h[7]; uint32_t rows; uint32_t pad[15]; }; 
 
 // Exchanges IPC handles of the deposit fields, trail fields and the window with both ring neighbours
 // (over the NCCL communicator that already exists) and maps them.  Any failure leaves the engine on
-// the NCCL path (p2p = false) -- both are device paths; SM_EXCHANGE=nccl forces it.
+// the NCCL path (p2p = false) -- both are device paths; sm_tuning.exchange = 1 forces it.
 int sm_engine::setup_p2p()
 {
     p2p = false;
-    const char* mode = getenv("SM_EXCHANGE");
-    const bool want = !(mode && std::string(mode) == "nccl");
+    const bool want = tuning.exchange == 0;
     // the decision must be collective: every rank exchanges a bundle even if it will not use it
     const size_t arr_bytes = (mig_bytes + 63) & ~(size_t)63;
     window_arrival_off[0] = 64;
@@ -715,7 +733,14 @@ int sm_engine::setup_p2p()
     }
     p2p = all != 0;
     barrier_seq = 0;
-    if (p2p && !side_stream) {
+    if (p2p) SM_TRY(p2p_streams_init());
+    return SM_OK;
+}
+
+// Side stream, fork / join events and barrier flavour of the overlapped exchange.
+int sm_engine::p2p_streams_init()
+{
+    if (!side_stream) {
         // highest priority: the small exchange kernels must not queue behind the pending CTAs of the
         // interior trail pass (the block scheduler drains grids of equal priority in launch order)
         int prio_lo = 0, prio_hi = 0;
@@ -723,13 +748,14 @@ int sm_engine::setup_p2p()
         SM_CUDA(cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, prio_hi));
         SM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         SM_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-        if (const char* v = getenv("SM_OVERLAP")) overlap_enabled = atoi(v) != 0;
-        if (const char* v = getenv("SM_SIDE_TIMING")) side_dbg = atoi(v) != 0;
-        if (const char* v = getenv("SM_BARRIER_FENCE")) {
-            const int mode = atoi(v);
-            SM_CUDA(cudaMemcpyToSymbol(smk::g_fence_mode, &mode, sizeof mode));
-        }
+        SM_CUDA(cudaEventCreateWithFlags(&ev_boundary, cudaEventDisableTiming));
+        SM_CUDA(cudaMallocHost(&split_host, 2 * sizeof(uint32_t)));
     }
+    overlap_enabled = tuning.serial_exchange == 0;
+    side_dbg = tuning.debug_side_timing != 0;
+    // g_fence_mode: 0 three sequentially-consistent system fences, 1 acq_rel system fences (default), 2 device scope
+    const int mode = tuning.barrier_fence == 1 ? 0 : tuning.barrier_fence == 2 ? 2 : 1;
+    SM_CUDA(cudaMemcpyToSymbol(smk::g_fence_mode, &mode, sizeof mode));
     return SM_OK;
 }
 
@@ -850,7 +876,7 @@ uint32_t sm_engine::overlap_band()
 bool sm_engine::overlap_ok()
 {
     if (cfg.flags & SM_FLAG_GAUSSIAN_BLUR) return false;   // the Gaussian extension runs the serial order (pass, then ghost exchange)
-    return overlap_enabled && p2p && !fake_multi && world > 1 && side_stream && overlap_band() > 0;
+    return overlap_enabled && p2p && world > 1 && side_stream && overlap_band() > 0;
 }
 
 // Diffusion-only pass on strips (sm_diffuse_only): interior rows on the main stream; boundary bands, ghost-row
@@ -922,3 +948,58 @@ int sm_engine::p2p_trail_overlapped()
     return SM_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Boundary-first step (the default on strips with an interior; engine.cu: plan_split)
+// ---------------------------------------------------------------------------
+// "launch boundary-row work first -> start exchange -> interior agents / blur -> wait -> finish edges".
+//   side stream (high priority)                                   main stream
+//   k_agents<XM_P2P> over the boundary slots + arrivals            k_agents<XM_SINGLE> over the interior slots
+//   barrier 1 + deposit-row pull                                       (the long kernel: everything on the left hides behind it)
+//   trail pass over the two boundary bands
+//   ghost-row push, arrivals, barrier 2                            wait(boundary agents) -> trail pass over the interior rows
+//                                                                  wait(side) -> sampler ghost rows
+// Why the two agent launches are independent, and the bands independent of the interior agents: plan_split's margin.
+// The boundary bands are written into the sampler array while the interior agents still gather from it -- rows those
+// agents cannot reach (margin includes the sensing reach).
+int sm_engine::p2p_step_split()
+{
+    const uint32_t band = overlap_band();
+    uint32_t g = 0, m = 0;
+    SM_TRY(halo_depths(this, &g, &m));
+    SM_TRY(prepare_agents());                                      // deposit mode, sampler copy: once, before the fork
+    SM_CUDA(cudaEventRecord(ev_fork, stream));
+    SM_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+    // side: boundary agents first -- their deposits and leavers are what the neighbours wait for
+    if (side_dbg) SM_TRY(tic(13, side_stream));
+    SM_TRY(launch_agents(2, side_stream));
+    if (side_dbg) SM_TRY(toc(side_stream));
+    SM_CUDA(cudaEventRecord(ev_boundary, side_stream));
+    // main: interior agents
+    SM_TRY(launch_agents(1, stream));
+    // side: barrier 1 + pull
+    if (side_dbg) SM_TRY(tic(10, side_stream));
+    SM_TRY(p2p_after_agents(side_stream, false));
+    if (side_dbg) SM_TRY(toc(side_stream));
+    TrailPass p;
+    SM_TRY(trail_plan(true, p));
+    // main: interior rows, once the boundary agents' deposits are in as well
+    SM_CUDA(cudaStreamWaitEvent(stream, ev_boundary, 0));
+    SM_TRY(tic(1));
+    SM_TRY(trail_launch_rows(p, band, rows - band, stream));
+    SM_TRY(toc());
+    // side: the two boundary bands in one launch
+    if (side_dbg) SM_TRY(tic(11, side_stream));
+    SM_TRY(trail_launch_rows(p, 0, band, side_stream, rows - band, rows));
+    if (side_dbg) { SM_TRY(toc(side_stream)); SM_TRY(tic(12, side_stream)); }
+    trail_done(true);
+    stats_fused_valid = p.stats;
+    if (stats_interest) --stats_interest;
+    SM_TRY(p2p_after_trail(side_stream, false));
+    if (side_dbg) SM_TRY(toc(side_stream));
+    SM_CUDA(cudaEventRecord(ev_join, side_stream));
+    SM_TRY(tic(3));
+    SM_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+    SM_TRY(refresh_tex_ghosts(g));
+    SM_TRY(toc());
+    return SM_OK;
+}

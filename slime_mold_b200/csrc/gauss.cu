@@ -30,15 +30,9 @@
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
-// The A/B-only instantiations -- rows kernel at radius 6-8 and with packing levels that lost their comparison, the packed forms of
-// the streaming and tile kernels (all measured, none the default anywhere: profiles/NOTES.md) -- are 80 large kernels and half of
-// this file's compile time.  They are built with SM_BUILD_AB_VARIANTS=1 (python -m slime_mold_b200.build reads the environment
-// variable of the same name); without it the switches that select them fall back to the default variant.
-#ifndef SM_BUILD_AB_VARIANTS
-#define SM_BUILD_AB_VARIANTS 0
-#endif
-constexpr bool kAbVariants = SM_BUILD_AB_VARIANTS != 0;
-constexpr int kRowsMaxBuiltR = kAbVariants ? smk::kGrMaxR : 5;
+// Variants that lost their comparison in round 1 and are no longer built (profiles/README.md has the tables): the rows kernel at
+// radius 6-8 (167+ registers) and with packing level 1, FFMA2 forms of the streaming and tile kernels, the private-ring kernel.
+constexpr int kRowsMaxBuiltR = 5;
 
 // The streaming Gaussian kernel (gauss_stream.cuh) applies: it also merges u8 deposit flags and keeps the sampler's
 // block-linear copy in step, so a Gaussian full step runs the same agent kernel as the box-blur step.
@@ -68,7 +62,7 @@ static int launch_gauss_rows_pk(sm_engine* e, const smk::GsArgs& a0, const smd::
     smk::GsArgs a = a0;
     const uint64_t gx = (e->W + smk::gr_cta_cols<R>() - 1) / smk::gr_cta_cols<R>();
     const uint64_t cap = (uint64_t)e->num_sms * per_sm;
-    uint64_t chunk = (uint64_t)e->gauss_chunk;
+    uint64_t chunk = (uint64_t)e->tuning.gauss_chunk_rows;
     if (chunk == 0) {
         const double want_chunks = (double)e->rows / (R <= 2 ? 64.0 : R <= 4 ? 128.0 : 256.0);
         uint64_t waves = (uint64_t)llround((double)gx * want_chunks / (double)cap);
@@ -89,26 +83,15 @@ template <int R, int CM, bool SURF>
 static int launch_gauss_rows(sm_engine* e, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
     // FFMA2 taps (level 2: column taps + the aligned half of the row taps): 3-6 % faster at radius 3-4, 1-3 % at 1-2; at
-    // radius 5 the extra registers cost a resident CTA (0.60 against 0.65 of the HBM peak), above that they were measured
-    // too and dropped from the build (each of those instantiations is 2-3 K instructions)
-    if constexpr (kAbVariants) {
-        if constexpr (R <= 5) {
-            const int pk = e->gauss_rows_packed < 0 ? (R <= 4 ? 2 : 0) : e->gauss_rows_packed;
-            if (pk >= 2) return launch_gauss_rows_pk<R, CM, SURF, 2>(e, a, tc, gc);
-            if (pk == 1) return launch_gauss_rows_pk<R, CM, SURF, 1>(e, a, tc, gc);
-            return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
-        } else {
-            return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
-        }
-    } else if constexpr (R <= 4) {
-        // default build: level 2 and the scalar form
-        const int pk = e->gauss_rows_packed < 0 ? 2 : e->gauss_rows_packed;
-        if (pk >= 1) return launch_gauss_rows_pk<R, CM, SURF, 2>(e, a, tc, gc);
+    // radius 5 the extra registers cost a resident CTA (0.60 against 0.65 of the HBM peak) and the scalar form is used
+    if constexpr (R <= 4) {
+        const bool packed = e->gauss_rows_packing != 1;              // 0 auto (packed), 1 scalar, 2 packed
+        if (packed) return launch_gauss_rows_pk<R, CM, SURF, 2>(e, a, tc, gc);
         return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
     } else if constexpr (R == 5) {
         return launch_gauss_rows_pk<R, CM, SURF, 0>(e, a, tc, gc);
     } else {
-        return sm_fail(SM_ERR_STATE, "k_gauss_rows is not built for radius %d (SM_BUILD_AB_VARIANTS=1)", R);   // unreachable: gauss_rows_ok()
+        return sm_fail(SM_ERR_STATE, "k_gauss_rows is not built for radius %d", R);   // unreachable: gauss_rows_ok()
     }
 }
 
@@ -118,11 +101,8 @@ static int launch_gauss_stream_pk(sm_engine* e, const smk::GsArgs& a0, const smd
 template <int R, int CM, bool SURF>
 static int launch_gauss_stream(sm_engine* e, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
 {
-    // packed taps (SM_GAUSS_STREAM_PACKED=1; built for radius >= 5): 16 % fewer instructions, no measurable gain (0.51 ->
-    // 0.52 of the peak at radius 8) -- this kernel waits on its barriers and shared-memory round trips, not on issue slots
-    if constexpr (kAbVariants && R >= 5) {
-        if (e->gauss_stream_packed) return launch_gauss_stream_pk<R, CM, SURF, true>(e, a, tc, gc);
-    }
+    // (an FFMA2 form of the taps removed 16 % of the instructions and changed nothing: this kernel waits on its barriers
+    // and shared-memory round trips, not on issue slots)
     return launch_gauss_stream_pk<R, CM, SURF, false>(e, a, tc, gc);
 }
 
@@ -140,7 +120,7 @@ static int launch_gauss_stream_pk(sm_engine* e, const smk::GsArgs& a0, const smd
     smk::GsArgs a = a0;
     const uint64_t gx = (e->W + smk::kGsTX - 1) / smk::kGsTX;
     const uint64_t cap = (uint64_t)e->num_sms * per_sm;
-    uint64_t chunk = (uint64_t)e->gauss_chunk;
+    uint64_t chunk = (uint64_t)e->tuning.gauss_chunk_rows;
     if (chunk == 0) {
         const double want_chunks = (double)e->rows / 256.0;
         uint64_t waves = (uint64_t)llround((double)gx * want_chunks / (double)cap);
@@ -223,12 +203,6 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
                         : launch_gauss_stream<RR, smk::GS_FLAGS, false>(this, a, tc, gc);
         };
         using std::integral_constant;
-        // EXPERIMENT (gauss_wring.cu): u32-count passes stay on the default kernels
-        if (gauss_wring && p.cm != smk::CM_COUNTS && R >= 5 && W % 4 == 0 && W >= (uint32_t)smk::kGrMinW && rows >= (uint32_t)smk::kGrMinRows) {
-            SM_TRY(sm_gauss_wring_dispatch(this, R, p.cm == smk::CM_FLAGS, surf, a, tc, gc));
-            timing.kernel_launches += 1;
-            return SM_OK;
-        }
         if (use_rows) {
             switch (R) {
             case 1: SM_TRY(go_rows(integral_constant<int, 1>{})); break;
@@ -262,21 +236,7 @@ int sm_engine::launch_gauss(bool has_counts, const TrailPass& p)
         auto go = [&](auto r_tag) -> int {
             constexpr int RR = decltype(r_tag)::value;
             const size_t smem = smk::gauss_smem_bytes<RR>();
-            bool packed_done = false;
-            if constexpr (kAbVariants) {
-                if (gauss_packed) {
-                    packed_done = true;
-                    if (has_counts) {
-                        SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused_packed<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        smk::k_gauss_fused_packed<RR, true><<<grid, 256, smem, stream>>>(tin0, counts_ptr(ccur), counts_ptr(1 - ccur), tout0, g, tc, gc);
-                    } else {
-                        SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused_packed<RR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        smk::k_gauss_fused_packed<RR, false><<<grid, 256, smem, stream>>>(tin0, nullptr, nullptr, tout0, g, tc, gc);
-                    }
-                }
-            }
-            if (packed_done) {
-            } else if (has_counts) {
+            if (has_counts) {
                 SM_CUDA(cudaFuncSetAttribute(smk::k_gauss_fused<RR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 smk::k_gauss_fused<RR, true><<<grid, 256, smem, stream>>>(tin0, counts_ptr(ccur), counts_ptr(1 - ccur), tout0, g, tc, gc);
             } else {

@@ -17,7 +17,6 @@
 #include "trail_core.cuh"
 #include "gauss_stream.cuh"
 #include "gauss_rows.cuh"
-#include "gauss_wring.cuh"
 
 namespace smk {
 
@@ -137,6 +136,10 @@ struct LeaverBufs {
     unsigned long long* left_count;      // XM_P2P: how many agents left this rank during the step
     const unsigned long long* slots_in_use;   // device-side count of the slots in use (the grid covers the host's upper bound of it)
     uint32_t cap;
+    // boundary-first stepping on strips (exchange.cu: p2p_step_split): this launch covers the slots [0, split) and
+    // [split + skip, slots in use) -- the agents near the strip edges at the last sort plus the arrivals since --
+    // while the slots in between are stepped by an XM_SINGLE launch beside it.  skip == 0: every slot.
+    unsigned long long split, skip;
     // XM_P2P: deposit fields of the two ring neighbours (pointer to THEIR owned row 0) and the row
     // count of the upper neighbour (a deposit on my row -k lands on its row rows_up - k)
     void* peer_dep[2];
@@ -149,19 +152,66 @@ struct LeaverBufs {
 // FLAGS: deposits are u8 "somebody deposited here" marks written with plain stores instead of u32
 // counts bumped with RED atomics -- exact whenever dep >= 1 and the field is non-negative, because
 // clamp(t + k*dep, 0, 1) == 1 for every k >= 1 (all shipped presets: dep = 1.0).
-template <int XM, class IdxT, class FETCH, bool FLAGS, bool HINT>
-__device__ __forceinline__ void step_agent_slot(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
-                                                float4 a, uint32_t id, const FETCH& fetch, void* __restrict__ deposits,
-                                                const AgentConsts& c, const LeaverBufs& lv)
+// Strips, rare path: the new cell belongs to a ring neighbour (or there is no deposit cell at all).
+// (Not a real call: passing the parameter blocks by reference to a __noinline__ function makes every thread copy them to
+// local memory at kernel entry -- measured 215 -> 292 us.)
+template <int XM, class IdxT, bool FLAGS>
+__device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
+                                                const float4 a, const uint32_t id, const int32_t cx, const int32_t cy,
+                                                void* __restrict__ deposits, const AgentConsts& c, const LeaverBufs& lv)
+{
+    int32_t lr;
+    if (cx >= 0) {
+        lr = smd::local_row(cy, c);                       // folded across the toroidal seam
+        int32_t lrd = lr;
+        void* base = deposits;
+        bool ok = true;
+        if (XM == XM_NCCL) ok = lrd >= -c.ghost && lrd < c.rows_local + c.ghost;
+        if (XM == XM_P2P) {
+            // write into the neighbour's field over NVLink
+            if (lrd < 0) { base = lv.peer_dep[0]; lrd += lv.rows_up; ok = lrd >= 0; }
+            else { base = lv.peer_dep[1]; lrd -= c.rows_local; ok = lrd < c.ghost; }
+        }
+        if (ok) {
+            const IdxT off = (IdxT)lrd * (IdxT)c.W + (IdxT)cx;
+            if (FLAGS) static_cast<uint8_t*>(base)[off] = 1;
+            else if (XM == XM_P2P) atomicAdd_system(static_cast<uint32_t*>(base) + off, 1u);
+            else atomicAdd(static_cast<uint32_t*>(base) + off, 1u);
+        }
+    } else {
+        // no deposit cell (x == W / y == H rounding corner, non-finite state): owner row clamped like the host
+        const int32_t oy = !(a.y >= 0.0f) ? 0 : (a.y >= c.Hf ? (int32_t)c.H - 1 : (int32_t)a.y);
+        lr = smd::local_row(oy, c);
+    }
+    if (lr < 0 || lr >= c.rows_local) {
+        // migration: hand the agent to the neighbour that owns its row
+        // (no dynamic indexing of the parameter arrays: that would force a per-thread local copy)
+        const bool up = lr < 0;
+        unsigned long long* cnt = up ? lv.send_count[0] : lv.send_count[1];
+        float4* sa = up ? lv.send_a[0] : lv.send_a[1];
+        uint32_t* si = up ? lv.send_id[0] : lv.send_id[1];
+        unsigned long long slot = (XM == XM_P2P) ? atomicAdd_system(cnt, 1ull) : atomicAdd(cnt, 1ull);
+        if (slot < lv.cap) {
+            sa[slot] = a;
+            si[slot] = id;
+            ids[i] = kDeadAgent;
+            if (XM == XM_P2P) atomicAdd(lv.left_count, 1ull);
+        } else {
+            atomicExch(lv.overflow, 1ull);       // staging overflow: reported by the host
+        }
+    }
+}
+
+template <int XM, class IdxT, bool FLAGS>
+__device__ __forceinline__ void finish_agent_slot(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
+                                                  const float4 a, const uint32_t id, const int32_t cx, const int32_t cy,
+                                                  void* __restrict__ deposits, const AgentConsts& c, const LeaverBufs& lv)
 {
     constexpr bool MULTI = XM != XM_SINGLE;
-    int32_t cx, cy;
-    smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, c, fetch, cx, cy);
-    if (HINT) __stcs(agents + i, a);      // evict-first: the agent stream should not push the trail out of L2
-    else agents[i] = a;
+    agents[i] = a;
     // Fast path (every agent on one GPU, all but the strip-boundary agents otherwise): the new cell is
     // on a row this rank owns -> local deposit, no migration.  One subtract + one unsigned compare.
-    int32_t lr = cy - (int32_t)c.row_base;
+    const int32_t lr = cy - (int32_t)c.row_base;
     const bool interior = cx >= 0 && (!MULTI || (uint32_t)lr < (uint32_t)c.rows_local);
     if (interior) {
         // deposit: order-free (phase_split form of compute.wgsl:140)
@@ -169,48 +219,7 @@ __device__ __forceinline__ void step_agent_slot(float4* __restrict__ agents, uin
         if (FLAGS) static_cast<uint8_t*>(deposits)[off] = 1;
         else atomicAdd(static_cast<uint32_t*>(deposits) + off, 1u);
     }
-    if (MULTI && !interior) {
-        // Slow path: the cell belongs to a ring neighbour (or there is no deposit cell at all).
-        if (cx >= 0) {
-            lr = smd::local_row(cy, c);                       // folded across the toroidal seam
-            int32_t lrd = lr;
-            void* base = deposits;
-            bool ok = true;
-            if (XM == XM_NCCL) ok = lrd >= -c.ghost && lrd < c.rows_local + c.ghost;
-            if (XM == XM_P2P) {
-                // write into the neighbour's field over NVLink
-                if (lrd < 0) { base = lv.peer_dep[0]; lrd += lv.rows_up; ok = lrd >= 0; }
-                else { base = lv.peer_dep[1]; lrd -= c.rows_local; ok = lrd < c.ghost; }
-            }
-            if (ok) {
-                const IdxT off = (IdxT)lrd * (IdxT)c.W + (IdxT)cx;
-                if (FLAGS) static_cast<uint8_t*>(base)[off] = 1;
-                else if (XM == XM_P2P) atomicAdd_system(static_cast<uint32_t*>(base) + off, 1u);
-                else atomicAdd(static_cast<uint32_t*>(base) + off, 1u);
-            }
-        } else {
-            // no deposit cell (x == W / y == H rounding corner, non-finite state): owner row clamped like the host
-            const int32_t oy = !(a.y >= 0.0f) ? 0 : (a.y >= c.Hf ? (int32_t)c.H - 1 : (int32_t)a.y);
-            lr = smd::local_row(oy, c);
-        }
-        if (lr < 0 || lr >= c.rows_local) {
-            // migration: hand the agent to the neighbour that owns its row
-            // (no dynamic indexing of the parameter arrays: that would force a per-thread local copy)
-            const bool up = lr < 0;
-            unsigned long long* cnt = up ? lv.send_count[0] : lv.send_count[1];
-            float4* sa = up ? lv.send_a[0] : lv.send_a[1];
-            uint32_t* si = up ? lv.send_id[0] : lv.send_id[1];
-            unsigned long long slot = (XM == XM_P2P) ? atomicAdd_system(cnt, 1ull) : atomicAdd(cnt, 1ull);
-            if (slot < lv.cap) {
-                sa[slot] = a;
-                si[slot] = id;
-                ids[i] = kDeadAgent;
-                if (XM == XM_P2P) atomicAdd(lv.left_count, 1ull);
-            } else {
-                atomicExch(lv.overflow, 1ull);       // staging overflow: reported by the host
-            }
-        }
-    }
+    if (MULTI && !interior) agent_leaves_strip<XM, IdxT, FLAGS>(agents, ids, i, a, id, cx, cy, deposits, c, lv);
 }
 
 #ifndef SM_AGENTS_MIN_BLOCKS
@@ -230,24 +239,36 @@ static inline int agents_per_thread_for(uint64_t n, int num_sms)
     return apt;
 }
 
-template <bool HINT>
 __device__ __forceinline__ void load_agent_slot(const float4* agents, const uint32_t* ids, uint64_t i, float4& a, uint32_t& id)
 {
     // asm volatile: the loads stay where they are written (ahead of the previous agent's arithmetic) --
-    // left to the compiler a plain load is sunk to its first use, which exposes the full DRAM latency
-    if (HINT) {
-        // .cs (evict-first): 20 B in + 16 B out per agent pass through L2 once per step -- 600 MB at config 2, five times
-        // the L2 -- while the trail copy the gathers hit is 67 MB and worth keeping there (SM_AGENT_STREAM_HINT, A/B)
-        asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(agents + i));
-        asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(id) : "l"(ids + i));
-    } else {
-        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(agents + i));
-        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(id) : "l"(ids + i));
-    }
+    // left to the compiler a plain load is sunk to its first use, which exposes the full DRAM latency.
+    // (evict-first hints on this stream were measured in rounds 1 and 2 and changed nothing: 1667 vs 1673 us at config 3)
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(agents + i));
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(id) : "l"(ids + i));
 }
 
-template <int XM, class IdxT, class FETCH, bool FLAGS, bool HINT = false>
-static __global__ void __launch_bounds__(256, SM_AGENTS_MIN_BLOCKS)
+template <int XM, class IdxT, class FETCH, bool FLAGS>
+__device__ __forceinline__ void step_agent_slot(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
+                                                float4 a, uint32_t id, const FETCH& fetch, void* __restrict__ deposits,
+                                                const AgentConsts& c, const LeaverBufs& lv)
+{
+    int32_t cx, cy;
+    smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, c, fetch, cx, cy);
+    finish_agent_slot<XM, IdxT, FLAGS>(agents, ids, i, a, id, cx, cy, deposits, c, lv);
+}
+
+// (A software-pipelined form of this kernel -- agent j+1 sensed, its three gathers in flight, while agent j is moved -- was
+// built and measured in round 2: long-scoreboard stalls fell from 6.3 to 4.2 per issue, but the kernel issues 73 % of the
+// time either way, the pipelined loop executed 10 % more instructions and ran at 4 instead of 5 CTAs per SM: 172 -> 198 us
+// at config 2.  The kernel is bound by instruction issue, not by gather latency; profiles/README.md.)
+#ifndef SM_AGENTS_STRIP_MIN_BLOCKS
+#define SM_AGENTS_STRIP_MIN_BLOCKS 5  // the strip instantiations (XM != XM_SINGLE) carry a little more state through the loop: at 48 registers
+                                      // ptxas consumes the first gather before issuing the other two (two exposed latencies per agent); 4 CTAs /
+                                      // 53 registers restores the schedule -- A/B in tools/r2/gpu_14.sh
+#endif
+template <int XM, class IdxT, class FETCH, bool FLAGS>
+static __global__ void __launch_bounds__(256, (XM == XM_SINGLE ? SM_AGENTS_MIN_BLOCKS : SM_AGENTS_STRIP_MIN_BLOCKS))
 k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
          const FETCH fetch, void* __restrict__ deposits, const AgentConsts c,
          const LeaverBufs lv, StatsAcc* __restrict__ stats_to_zero, const int agents_per_thread)
@@ -259,25 +280,33 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
     // The state of the next slot is requested before the current one is stepped, so only the first
     // load of a thread waits for DRAM; consecutive slots are neighbours in the cell-sorted order, so
     // their footprints also reuse this SM's L1.
-    // MULTI: n is the host's upper bound of the slots in use; every slot past the live ones holds
-    // kDeadAgent (kept so by the sort and by k_append_arrivals), so no device-side count is needed here
     uint64_t i = (uint64_t)blockIdx.x * (256u * (uint32_t)agents_per_thread) + threadIdx.x;
-    // MULTI: the host only knows an upper bound of the slots in use between two sorts (it grows by the migration
-    // capacity every step); the exact count lives on the device -- CTAs past it leave without touching HBM
-    if (MULTI) n = min(n, (uint64_t)*lv.slots_in_use);
-    if (i >= n) return;
+    if (MULTI && lv.skip) {
+        // boundary launch: a CTA's 256 * agents_per_thread consecutive indices map to slots on one side of the skipped
+        // range (the host rounds `split` up to a whole CTA), so the slot arithmetic below is unchanged
+        if (i >= lv.split) i += lv.skip;
+    }
+    if (i >= n) return;                      // n: the host's (upper bound of the) slots in use
     float4 a_next;
     uint32_t id_next;
-    load_agent_slot<HINT>(agents, ids, i, a_next, id_next);
+    load_agent_slot(agents, ids, i, a_next, id_next);       // MULTI: possibly past the slots in use, always inside the allocation
+    // MULTI: the host only knows an upper bound of the slots in use between two sorts (it grows by the migration
+    // capacity every step); the exact count lives on the device -- CTAs past it leave without stepping anything.  Read
+    // AFTER the first state load was issued: the two latencies overlap (they used to add up at the start of every CTA).
+    // Every slot past the live ones holds kDeadAgent (kept so by the sort and by k_append_arrivals).
+    if (MULTI) {
+        n = min(n, (uint64_t)*lv.slots_in_use);
+        if (i >= n) return;
+    }
 #pragma unroll 1
     for (int j = 0; j < agents_per_thread; ++j) {
         float4 a = a_next;
         const uint32_t id = id_next;
         const uint64_t i_next = i + 256u;
         const bool more = (j + 1 < agents_per_thread) && i_next < n;
-        if (more) load_agent_slot<HINT>(agents, ids, i_next, a_next, id_next);
+        if (more) load_agent_slot(agents, ids, i_next, a_next, id_next);
         if (!MULTI || id != kDeadAgent)
-            step_agent_slot<XM, IdxT, FETCH, FLAGS, HINT>(agents, ids, i, a, id, fetch, deposits, c, lv);
+            step_agent_slot<XM, IdxT, FETCH, FLAGS>(agents, ids, i, a, id, fetch, deposits, c, lv);
         if (!more) break;
         i = i_next;
     }
@@ -725,145 +754,6 @@ k_gauss_fused(const float* __restrict__ tin, const uint32_t* __restrict__ cin, u
     }
 }
 
-// Packed variant of k_gauss_fused: the tap loops run on FFMA2 (two IEEE binary32 FMAs per issue slot; see the packed
-// pairs of device_math.cuh).  For radius >= 4 the fused kernel is bound by FMA issue and shared-memory reads, not by HBM.
-//   * D is stored row-pair interleaved -- D2[r/2][c] = (D[r][c], D[r+1][c]) -- so one LDS.128 yields two naturally
-//     aligned register pairs and phase 2 computes TWO rows x four columns per thread with every tap an aligned FFMA2;
-//   * phase 3 computes two adjacent columns x eight rows per thread from LDS.64 pairs of Hb.
-// Each lane of a pair is the same FMA sequence as in the scalar kernel: bit-identical results.
-// MEASURED (profiles/README.md): half the tap instructions, yet 3-10 % SLOWER than the scalar kernel at every radius --
-// the fused kernel is bound by its barriers and load latency at 4 CTAs/SM, not by FMA issue.  Kept selectable
-// (SM_GAUSS_PACKED=1) for the record; a pipelined (persistent, double-buffered) tile loop is the next step, not packing.
-template <int R, bool HAS_COUNTS>
-static __global__ void __launch_bounds__(256)
-k_gauss_fused_packed(const float* __restrict__ tin, const uint32_t* __restrict__ cin, uint32_t* __restrict__ czero,
-                     float* __restrict__ tout, const TrailGeom g, const TrailConsts tc, const GaussConsts gc)
-{
-    using smd::f2;
-    constexpr int TX = kGaussTX, TY = kGaussTY, RW = TY + 2 * R, RP = RW / 2, RA = gauss_ra<R>(), DC = gauss_dcols<R>();
-    constexpr int DC4 = (TX + 2 * RA) / 4;
-    static_assert(RW % 2 == 0, "row pairs");
-    extern __shared__ __align__(16) float gsm[];
-    float* D2 = gsm;                   // [RP][DC][2]  (row 2p, row 2p+1) interleaved per column; column c <-> map column x0 - RA + c
-    float* Hb = gsm + RW * DC;         // [RW][TX]
-    const int W = (int)g.W, H = (int)g.rows;
-    const int x0 = (int)blockIdx.x * TX, y0 = (int)blockIdx.y * TY;
-
-    // ---- phase 1: one thread = four columns of a ROW PAIR; all loads requested before any is consumed ----
-    {
-        constexpr int N4 = RP * DC4, PER = (N4 + 255) / 256;
-        float4 ta[PER], tb[PER];
-        uint4 ka[HAS_COUNTS ? PER : 1], kb[HAS_COUNTS ? PER : 1];
-        int64_t oa[PER], ob[PER];
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int e = (int)threadIdx.x + k * 256;
-            if (e < N4) {
-                const int rp = e / DC4, c4 = e - rp * DC4;
-                int gya = y0 - R + 2 * rp, gyb = gya + 1;
-                if (gya < 0) gya += H; else if (gya >= H) gya -= H;
-                if (gyb < 0) gyb += H; else if (gyb >= H) gyb -= H;
-                int gx = x0 - RA + 4 * c4;
-                if (gx < 0) gx += W; else if (gx >= W) gx -= W;
-                oa[k] = (int64_t)gya * W + gx;
-                ob[k] = (int64_t)gyb * W + gx;
-                ta[k] = __ldg(reinterpret_cast<const float4*>(tin + oa[k]));
-                tb[k] = __ldg(reinterpret_cast<const float4*>(tin + ob[k]));
-                if (HAS_COUNTS) {
-                    ka[k] = __ldg(reinterpret_cast<const uint4*>(cin + oa[k]));
-                    kb[k] = __ldg(reinterpret_cast<const uint4*>(cin + ob[k]));
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int e = (int)threadIdx.x + k * 256;
-            if (e < N4) {
-                const int rp = e / DC4, c4 = e - rp * DC4;
-                float4 a = ta[k], b = tb[k];
-                if (HAS_COUNTS) {
-                    a.x = smd::merge_deposit(a.x, ka[k].x, tc.dep); a.y = smd::merge_deposit(a.y, ka[k].y, tc.dep);
-                    a.z = smd::merge_deposit(a.z, ka[k].z, tc.dep); a.w = smd::merge_deposit(a.w, ka[k].w, tc.dep);
-                    b.x = smd::merge_deposit(b.x, kb[k].x, tc.dep); b.y = smd::merge_deposit(b.y, kb[k].y, tc.dep);
-                    b.z = smd::merge_deposit(b.z, kb[k].z, tc.dep); b.w = smd::merge_deposit(b.w, kb[k].w, tc.dep);
-                    const bool own_col = 4 * c4 >= RA && 4 * c4 < RA + TX && x0 + (4 * c4 - RA) < W;
-                    const int ra = 2 * rp, rb = 2 * rp + 1;
-                    if (own_col && ra >= R && ra < R + TY && y0 + (ra - R) < H) *reinterpret_cast<uint4*>(czero + oa[k]) = make_uint4(0u, 0u, 0u, 0u);
-                    if (own_col && rb >= R && rb < R + TY && y0 + (rb - R) < H) *reinterpret_cast<uint4*>(czero + ob[k]) = make_uint4(0u, 0u, 0u, 0u);
-                }
-                a.x = smd::decay_cell(a.x, tc.decay_sub); a.y = smd::decay_cell(a.y, tc.decay_sub);
-                a.z = smd::decay_cell(a.z, tc.decay_sub); a.w = smd::decay_cell(a.w, tc.decay_sub);
-                b.x = smd::decay_cell(b.x, tc.decay_sub); b.y = smd::decay_cell(b.y, tc.decay_sub);
-                b.z = smd::decay_cell(b.z, tc.decay_sub); b.w = smd::decay_cell(b.w, tc.decay_sub);
-                float4* dst = reinterpret_cast<float4*>(D2 + ((size_t)rp * DC + 4 * c4) * 2);
-                dst[0] = make_float4(a.x, b.x, a.y, b.y);
-                dst[1] = make_float4(a.z, b.z, a.w, b.w);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 2: rows (2rp, 2rp+1), outputs xs .. xs+3; output j taps columns xs + j + (RA - R) + d ----
-    for (int item = threadIdx.x; item < RP * (TX / 4); item += 256) {
-        const int rp = item / (TX / 4), xs = (item % (TX / 4)) * 4;
-        constexpr int NV = (4 + RA + R + 1) / 2 * 2, SH = RA - R;     // columns in the window (even count: one LDS.128 = 2 columns)
-        f2 v[NV];
-        const float4* src = reinterpret_cast<const float4*>(D2 + ((size_t)rp * DC + xs) * 2);
-#pragma unroll
-        for (int q = 0; q < NV / 2; ++q) {
-            const float4 f = src[q];
-            v[2 * q] = smd::mk2(f.x, f.y);
-            v[2 * q + 1] = smd::mk2(f.z, f.w);
-        }
-        f2 a0 = smd::splat2(0.0f), a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll
-        for (int d = 0; d <= 2 * R; ++d) {
-            const f2 w = smd::splat2(gc.w[d]);
-            a0 = smd::fma2(w, v[SH + d], a0);
-            a1 = smd::fma2(w, v[SH + d + 1], a1);
-            a2 = smd::fma2(w, v[SH + d + 2], a2);
-            a3 = smd::fma2(w, v[SH + d + 3], a3);
-        }
-        *reinterpret_cast<float4*>(Hb + (2 * rp) * TX + xs) = make_float4(a0.lo, a1.lo, a2.lo, a3.lo);
-        *reinterpret_cast<float4*>(Hb + (2 * rp + 1) * TX + xs) = make_float4(a0.hi, a1.hi, a2.hi, a3.hi);
-    }
-    __syncthreads();
-
-    // ---- phase 3: columns (2cp, 2cp+1), rows [8*rg, 8*rg + 8) ----
-    {
-        const int cp = threadIdx.x & (TX / 2 - 1), rg = threadIdx.x / (TX / 2);
-        constexpr int ROWS = TY / 4;
-        f2 v[ROWS + 2 * R];
-#pragma unroll
-        for (int k = 0; k < ROWS + 2 * R; ++k) {
-            const float2 f = *reinterpret_cast<const float2*>(Hb + (rg * ROWS + k) * TX + 2 * cp);
-            v[k] = smd::mk2(f.x, f.y);
-        }
-        f2 acc[ROWS];
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) acc[j] = smd::splat2(0.0f);
-#pragma unroll
-        for (int d = 0; d <= 2 * R; ++d) {
-            const f2 w = smd::splat2(gc.w[d]);
-#pragma unroll
-            for (int j = 0; j < ROWS; ++j) acc[j] = smd::fma2(w, v[j + d], acc[j]);
-        }
-        const int gx = x0 + 2 * cp;
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-            const int row = rg * ROWS + j + R;                                   // row of D
-            const int gy = y0 + rg * ROWS + j;
-            if (gx < W && gy < H) {
-                const float* dc = D2 + ((size_t)(row >> 1) * DC + 2 * cp + RA) * 2 + (row & 1);
-                float2 o;
-                o.x = smd::mixf_pre(dc[0], acc[j].lo, tc.rate, tc.one_minus_rate);
-                o.y = smd::mixf_pre(dc[2], acc[j].hi, tc.rate, tc.one_minus_rate);
-                *reinterpret_cast<float2*>(tout + (int64_t)gy * W + gx) = o;
-            }
-        }
-    }
-}
-
 // Streaming form (gauss_stream.cuh): the device context of gauss_stream_cta and the kernel around it.
 struct GsDevCtx {
     __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
@@ -930,15 +820,6 @@ k_gauss_rows(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
     gauss_rows_cta<R, CM, SURF, PK>(GrDevCtx{}, a, tc, gc);
 }
 
-// Private-ring form (gauss_wring.cuh; experiment, SM_GAUSS_KERNEL=wring): same device context as the rows kernel.
-template <int R, int CM, bool SURF, int PK>
-static __global__ void __launch_bounds__(kGwNT, 4)
-k_gauss_wring(const GsArgs a, const TrailConsts tc, const GaussConsts gc)
-{
-    extern __shared__ __align__(16) float gw_smem[];
-    gauss_wring_cta<R, CM, SURF, PK>(GrDevCtx{}, gw_smem, a, tc, gc);
-}
-
 // ---------------------------------------------------------------------------
 // periodic cell sort (counting sort by tile key), carries the persistent index
 // ---------------------------------------------------------------------------
@@ -948,19 +829,11 @@ struct TileGeom {
     uint32_t W;
     int64_t row_base;            // global row of local row 0
     uint32_t rows;               // owned rows
-    // experiment (SM_SORT_HEADING_BINS, default 1 = off): agents of a tile are further grouped by heading sector, so that
-    // the lanes of a warp sense in the same direction and their three footprints (sensor distance 20-225 cells away
-    // from the tile) fall into fewer texture sectors.  Any permutation gives the same result bits (deposits are order-free).
-    uint32_t heading_bins;
-    float bin_scale;             // heading_bins / 2pi
-    // experiment (SM_SORT_SUPER_SHIFT, default 0 = off): tiles are numbered super-tile by super-tile (2^s x 2^s tiles each)
-    // instead of row by row, so that the ~16 tiles a CTA's 1024 consecutive agents come from form a compact block (32 x 32
-    // cells at s = 2) rather than a 128 x 8 strip: the union of their sensor footprints -- the CTA's L1 working set -- shrinks.
-    uint32_t super_shift;
-    uint32_t super_x;            // super-tiles per row
 };
 
-__device__ __forceinline__ uint32_t tile_key(float x, float y, float angle, const TileGeom& t)
+// (Sort keys that also group by heading sector, or number the tiles super-tile by super-tile, were measured in round 2 on
+// configs [1] and [2] and changed nothing: gpurun_out/r2 probe, profiles/README.md.)
+__device__ __forceinline__ uint32_t tile_key(float x, float y, const TileGeom& t)
 {
     int32_t cx = (int32_t)x;                                   // x in [0, W] (W by rounding)
     int64_t cy = (int64_t)(int32_t)y - t.row_base;
@@ -969,16 +842,7 @@ __device__ __forceinline__ uint32_t tile_key(float x, float y, float angle, cons
     if (cy < 0) cy = 0;
     if (cy >= (int64_t)t.rows) cy = t.rows - 1;
     const uint32_t tx = (uint32_t)cx >> t.shift_x, ty = (uint32_t)cy >> t.shift_y;
-    uint32_t key = ty * t.tiles_x + tx;
-    if (t.super_shift) {
-        const uint32_t ss = t.super_shift, m = (1u << ss) - 1u;
-        key = (((ty >> ss) * t.super_x + (tx >> ss)) << (2u * ss)) | ((ty & m) << ss) | (tx & m);
-    }
-    if (t.heading_bins > 1u) {
-        const float b = fminf(fmaxf(angle * t.bin_scale, 0.0f), (float)(t.heading_bins - 1u));     // NaN -> sector 0
-        key = key * t.heading_bins + (uint32_t)b;
-    }
-    return key;
+    return ty * t.tiles_x + tx;
 }
 
 // Lanes of a warp that target the same tile are combined into one atomic (the agents are nearly
@@ -1002,7 +866,7 @@ k_tile_hist(const float4* __restrict__ agents, const uint32_t* __restrict__ ids,
     uint32_t key = 0xFFFFFFFFu;                                  // invalid / dead lanes group together
     if (i < n && ids[i] != kDeadAgent) {
         float4 a = agents[i];
-        key = tile_key(a.x, a.y, a.z, t);
+        key = tile_key(a.x, a.y, t);
     }
     uint32_t r, sz, gm; bool leader;
     warp_group(key, r, sz, leader, gm);
@@ -1111,7 +975,7 @@ k_tile_scatter(const float4* __restrict__ agents, const uint32_t* __restrict__ i
         id = ids[i];
         if (id != kDeadAgent) {
             a = agents[i];
-            key = tile_key(a.x, a.y, a.z, t);
+            key = tile_key(a.x, a.y, t);
         }
     }
     uint32_t r, sz, gm; bool leader;

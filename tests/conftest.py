@@ -53,7 +53,7 @@ def hostcheck():
     so_path = os.path.join(d, "libhostcheck.so")
     src = os.path.join(d, "hostcheck.cpp")
     csrc = os.path.join(ROOT, "slime_mold_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("device_math.cuh", "agent_core.cuh", "trail_core.cuh", "gauss_stream.cuh", "gauss_rows.cuh", "gauss_wring.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("device_math.cuh", "agent_core.cuh", "trail_core.cuh", "gauss_stream.cuh", "gauss_rows.cuh")]
     if not os.path.exists(so_path) or any(os.path.getmtime(p) > os.path.getmtime(so_path) for p in deps):
         cxx = "/usr/bin/g++-13" if os.path.exists("/usr/bin/g++-13") else "g++"
         subprocess.run([cxx, "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC",

@@ -8,7 +8,6 @@
 #include "../../slime_mold_b200/csrc/trail_core.cuh"
 #include "../../slime_mold_b200/csrc/gauss_stream.cuh"
 #include "../../slime_mold_b200/csrc/gauss_rows.cuh"
-#include "../../slime_mold_b200/csrc/gauss_wring.cuh"
 #include <pthread.h>
 #include <cstring>
 #include <thread>
@@ -293,77 +292,3 @@ extern "C" int hc_gauss_rows(const float* tin, const void* cin, void* czero, flo
     return 0;
 }
 
-// ---- CTA emulation of the private-ring Gaussian kernel (gauss_wring.cuh): the rows context + a block of "shared memory" ----
-template <int R, int CM, bool SURF, int PK>
-static void run_gauss_wring_pk(const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
-{
-    const int gx = (a.W + smk::gr_cta_cols<R>() - 1) / smk::gr_cta_cols<R>(), gy = (a.H + a.chunk_rows - 1) / a.chunk_rows;
-    const size_t nfl = smk::gw_smem_bytes<R>() / sizeof(float);
-    for (int by = 0; by < gy; ++by)
-        for (int bx = 0; bx < gx; ++bx) {
-            std::vector<float> raw(nfl + 4);
-            float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(raw.data()) + 15) & ~(uintptr_t)15);
-            for (size_t i = 0; i < nfl; ++i) smem[i] = NAN;          // never-written shared memory must not reach an output
-            std::vector<smk::F4> xch(smk::kGwNT);
-            pthread_barrier_t bar;
-            pthread_barrier_init(&bar, nullptr, smk::kGwNT);
-            std::vector<std::thread> th;
-            th.reserve(smk::kGwNT);
-            for (int t = 0; t < smk::kGwNT; ++t)
-                th.emplace_back([&, t]() {
-                    HostGrCtx cx;
-                    cx.t = t; cx.bxv = bx; cx.byv = by; cx.bar = &bar; cx.surf_w = a.W; cx.xch = xch.data();
-                    smk::gauss_wring_cta<R, CM, SURF, PK>(cx, smem, a, tc, gc);
-                });
-            for (auto& x : th) x.join();
-            pthread_barrier_destroy(&bar);
-        }
-}
-
-template <int R, int CM, bool SURF>
-static void run_gauss_wring(const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
-{
-    if (g_rows_packed >= 2) run_gauss_wring_pk<R, CM, SURF, 2>(a, tc, gc);
-    else if (g_rows_packed == 1) run_gauss_wring_pk<R, CM, SURF, 1>(a, tc, gc);
-    else run_gauss_wring_pk<R, CM, SURF, 0>(a, tc, gc);
-}
-
-template <int R>
-static void run_gauss_wring_r(int cm, bool surf, const smk::GsArgs& a, const smd::TrailConsts& tc, const smk::GaussConsts& gc)
-{
-    if (cm == 0) run_gauss_wring<R, smk::GS_NONE, false>(a, tc, gc);
-    else if (cm == 1) { if (surf) run_gauss_wring<R, smk::GS_COUNTS, true>(a, tc, gc); else run_gauss_wring<R, smk::GS_COUNTS, false>(a, tc, gc); }
-    else { if (surf) run_gauss_wring<R, smk::GS_FLAGS, true>(a, tc, gc); else run_gauss_wring<R, smk::GS_FLAGS, false>(a, tc, gc); }
-}
-
-extern "C" int hc_gauss_wring(const float* tin, const void* cin, void* czero, float* tout, float* surf_out, int W, int H,
-                              int chunk_rows, int R, const float* weights, int cm, const hc_params* p, int wrap_y)
-{
-    if (W % 4 != 0 || W < smk::kGrMinW || H < smk::kGrMinRows || R < 1 || R > smk::kGrMaxR || chunk_rows < 1) return -1;
-    smd::TrailConsts tc{};
-    tc.dep = p->pheromone_deposition_amount;
-    volatile float d = p->decay_factor * 0.001f;
-    tc.decay_sub = d;
-    tc.rate = fminf(fmaxf(p->diffusion_rate, 0.0f), 1.0f);
-    volatile float om = 1.0f - tc.rate;
-    tc.one_minus_rate = om;
-    smk::GaussConsts gc{};
-    gc.R = R;
-    for (int i = 0; i <= 2 * R; ++i) gc.set(i, weights[i]);
-    smk::GsArgs a{};
-    a.tin = tin; a.cin = cin; a.czero = czero; a.tout = tout;
-    a.W = W; a.H = H; a.chunk_rows = chunk_rows; a.wrap_y = wrap_y;
-    a.surf = (unsigned long long)reinterpret_cast<uintptr_t>(surf_out); a.surf_row0 = 0;
-    const bool surf = surf_out != nullptr;
-    switch (R) {
-    case 1: run_gauss_wring_r<1>(cm, surf, a, tc, gc); break;
-    case 2: run_gauss_wring_r<2>(cm, surf, a, tc, gc); break;
-    case 3: run_gauss_wring_r<3>(cm, surf, a, tc, gc); break;
-    case 4: run_gauss_wring_r<4>(cm, surf, a, tc, gc); break;
-    case 5: run_gauss_wring_r<5>(cm, surf, a, tc, gc); break;
-    case 6: run_gauss_wring_r<6>(cm, surf, a, tc, gc); break;
-    case 7: run_gauss_wring_r<7>(cm, surf, a, tc, gc); break;
-    default: run_gauss_wring_r<8>(cm, surf, a, tc, gc); break;
-    }
-    return 0;
-}

@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(engine_lib):
 
 def test_struct_layouts_match_header():
     from slime_mold_b200 import SimSizeUniform
-    from slime_mold_b200._lib import SmConfig, SmTiming, SmTrailStats
+    from slime_mold_b200._lib import SmConfig, SmTiming, SmTrailStats, SmTuning
     src = r'''
     #include <stdio.h>
     #include <stddef.h>
@@ -41,6 +41,8 @@ def test_struct_layouts_match_header():
         printf("%zu %zu %zu %zu %zu\n", offsetof(sm_params, decay_factor), offsetof(sm_params, diffusion_rate),
                offsetof(sm_params, pheromone_deposition_amount), offsetof(sm_params, blur_radius), offsetof(sm_params, _pad));
         printf("%zu %zu %zu\n", offsetof(sm_config, agent_count), offsetof(sm_config, device), offsetof(sm_config, sort_interval));
+        printf("%zu %zu %zu %zu %zu\n", sizeof(sm_tuning), offsetof(sm_config, tuning), offsetof(sm_tuning, gauss_kernel),
+               offsetof(sm_tuning, exchange), offsetof(sm_tuning, debug_side_timing));
         return 0;
     }'''
     with tempfile.TemporaryDirectory() as d:
@@ -56,12 +58,38 @@ def test_struct_layouts_match_header():
     # offsets of SURVEY.md 8(a) a6
     assert list(map(int, out[1].split())) == [8, 36, 40, 44, 52]
     assert list(map(int, out[2].split())) == [SmConfig.agent_count.offset, SmConfig.device.offset, SmConfig.sort_interval.offset]
+    assert list(map(int, out[3].split())) == [C.sizeof(SmTuning), SmConfig.tuning.offset, SmTuning.gauss_kernel.offset,
+                                              SmTuning.exchange.offset, SmTuning.debug_side_timing.offset]
+
+
+def test_tuning_fields_match_header_and_library_reads_no_environment():
+    """Every field of the header's sm_tuning, in order, in the ctypes mirror; the SM_* environment convention lives in the
+    Python harness only: the shared library references getenv for SM_NCCL_LIB and nothing else."""
+    import re
+    from slime_mold_b200._lib import SmTuning, tuning_from_env
+    hdr = open(os.path.join(ROOT, "include", "slime_b200.h")).read()
+    body = re.search(r"typedef struct sm_tuning\s*\{(.*?)\}\s*sm_tuning\s*;", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S), re.S).group(1)
+    names = [n.split("[")[0] for n in re.findall(r"uint32_t\s+(\w+(?:\[\d+\])?)\s*;", body)]
+    assert names == [f[0] for f in SmTuning._fields_]
+    t = tuning_from_env({})
+    assert bytes(t) == bytes(C.sizeof(SmTuning))                      # nothing set -> all zero -> engine defaults
+    t = tuning_from_env({"SM_SAMPLER": "ldg", "SM_GAUSS_KERNEL": "stream", "SM_EXCHANGE": "nccl", "SM_STEP_GRAPH": "0",
+                         "SM_SURF_PAIRS": "0", "SM_GAUSS_ROWS_PACKED": "0", "SM_OVERLAP": "0", "SM_TILE_SHIFT_X": "4"})
+    assert (t.sampler, t.gauss_kernel, t.exchange, t.no_step_graph, t.surface_row_writes, t.gauss_rows_packing, t.serial_exchange,
+            t.tile_shift_x) == (1, 2, 1, 1, 1, 1, 1, 4)
+    csrc = os.path.join(ROOT, "slime_mold_b200", "csrc")
+    uses = []
+    for fn in sorted(os.listdir(csrc)):
+        for i, line in enumerate(open(os.path.join(csrc, fn)), 1):
+            if "getenv(" in line:
+                uses.append((fn, i, line.strip()))
+    assert len(uses) == 1 and "SM_NCCL_LIB" in uses[0][2], uses
 
 
 def test_version(engine_lib):
     ma, mi = C.c_int(-1), C.c_int(-1)
     engine_lib.sm_version(C.byref(ma), C.byref(mi))
-    assert (ma.value, mi.value) == (0, 1)
+    assert (ma.value, mi.value) == (0, 2)
 
 
 def test_no_cpu_fallback(engine_lib):

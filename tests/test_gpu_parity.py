@@ -209,10 +209,7 @@ def test_gaussian_extension(oracle, engine_lib, R, sigma):
     be.close()
 
 
-# "packed", "stream_packed", "rows_packed" (level 1) and the rows kernel above radius 5 are A/B-only instantiations: they exist in
-# a library built with SM_BUILD_AB_VARIANTS=1 (python -m slime_mold_b200.build); the default build runs the default variant
-# for those switches, so the cases below always run -- against whichever kernel the library selects.
-@pytest.mark.parametrize("kernel", ["packed", "scalar", "two_pass", "stream", "stream_packed", "rows", "rows_packed", "rows_packed2"])
+@pytest.mark.parametrize("kernel", ["scalar", "two_pass", "stream", "rows", "rows_packed2"])
 @pytest.mark.parametrize("R,sigma,W,H", [(1, 0.7, 160, 64), (2, 1.0, 416, 200), (3, 1.3, 517, 131), (4, 2.0, 256, 96), (5, 2.5, 1000, 97),
                                          (6, 3.0, 384, 130), (7, 3.5, 772, 65), (8, 4.0, 640, 333)])
 def test_gaussian_extension_fused_and_two_pass(oracle, engine_lib, monkeypatch, R, sigma, W, H, kernel):
@@ -220,10 +217,8 @@ def test_gaussian_extension_fused_and_two_pass(oracle, engine_lib, monkeypatch, 
     streaming kernel (maps of at least 288 x 64 with W % 4 == 0; smaller ones fall back to the tile kernel) and the
     two-pass form give the oracle's bits, in diffusion-only passes and in full steps (deposit counts merged by the pass)."""
     monkeypatch.setenv("SM_GAUSS_TWO_PASS", "1" if kernel == "two_pass" else "0")
-    monkeypatch.setenv("SM_GAUSS_PACKED", "1" if kernel == "packed" else "0")
     monkeypatch.setenv("SM_GAUSS_KERNEL", "rows" if kernel.startswith("rows") else "stream" if kernel.startswith("stream") else "tile")
-    monkeypatch.setenv("SM_GAUSS_ROWS_PACKED", {"rows_packed": "1", "rows_packed2": "2"}.get(kernel, "0"))    # FFMA2 forms of the taps
-    monkeypatch.setenv("SM_GAUSS_STREAM_PACKED", "1" if kernel == "stream_packed" else "0")
+    monkeypatch.setenv("SM_GAUSS_ROWS_PACKED", "2" if kernel == "rows_packed2" else "0")    # FFMA2 form of the taps
     s = settings_for("Default").clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=0.7, pheromone_deposition_amount=0.4)
     u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)
     p = to_oracle_params(oracle, u)
@@ -252,7 +247,7 @@ def test_gaussian_extension_fused_and_two_pass(oracle, engine_lib, monkeypatch, 
     be.close()
 
 
-@pytest.mark.parametrize("kernel", ["stream", "stream_packed", "rows", "rows_packed", "rows_packed2"])
+@pytest.mark.parametrize("kernel", ["stream", "rows", "rows_packed2"])
 @pytest.mark.parametrize("chunk", [0, 40])
 @pytest.mark.parametrize("dep", [1.0, 0.4])
 @pytest.mark.parametrize("R,sigma,W,H", [(1, 0.7, 288, 64), (2, 1.0, 512, 256), (3, 1.3, 516, 131), (4, 2.0, 1024, 96), (6, 3.0, 388, 150),
@@ -263,8 +258,7 @@ def test_gaussian_stream_full_steps(oracle, engine_lib, monkeypatch, R, sigma, W
     fractional deposit they count -- against the oracle's phase-split agents + Gaussian pass; CTA chunk heights
     chosen by the engine and forced to a value that leaves ragged chunks."""
     monkeypatch.setenv("SM_GAUSS_KERNEL", "rows" if kernel.startswith("rows") else "stream")
-    monkeypatch.setenv("SM_GAUSS_ROWS_PACKED", {"rows_packed": "1", "rows_packed2": "2"}.get(kernel, "0"))
-    monkeypatch.setenv("SM_GAUSS_STREAM_PACKED", "1" if kernel == "stream_packed" else "0")
+    monkeypatch.setenv("SM_GAUSS_ROWS_PACKED", "2" if kernel == "rows_packed2" else "0")
     monkeypatch.setenv("SM_GAUSS_CHUNK", str(chunk))
     s = settings_for("Default").clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=0.8, pheromone_deposition_amount=dep)
     u = sm.SimSizeUniform.new(W, H, s.pheromone_decay_factor, s)

@@ -49,7 +49,7 @@ def run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=0, counts=None, 
         _, cin = guarded((H, W), np.uint8, 1)
         cin[:] = counts > 0
         czero_full, czero = guarded((H, W), np.uint8, 7)
-    fn = {"rows": hostcheck.hc_gauss_rows, "wring": hostcheck.hc_gauss_wring}.get(kernel, hostcheck.hc_gauss_stream)
+    fn = {"rows": hostcheck.hc_gauss_rows}.get(kernel, hostcheck.hc_gauss_stream)
     rc = fn(P(field, C.c_float),
                                    None if cin is None else cin.ctypes.data_as(C.c_void_p),
                                    None if czero is None else czero.ctypes.data_as(C.c_void_p),
@@ -225,67 +225,3 @@ def test_rows_on_strips_bits(oracle, hostcheck, R, sigma, strips):
             new[y0:y0 + rows] = out[ghost:ghost + rows]
         cur = new
     assert bits_equal(cur, ref), mismatch_report(cur, ref, f"rows on strips R={R}")
-
-
-# ---- the private-ring kernel (slime_mold_b200/csrc/gauss_wring.cuh; experiment for radius 5-8), same emulation ----
-@pytest.fixture(params=[0, 2], ids=["scalar", "packed2"])
-def wring_packed(request, hostcheck):
-    hostcheck.hc_gauss_rows_set_packed(C.c_int(request.param))
-    yield request.param
-    hostcheck.hc_gauss_rows_set_packed(C.c_int(0))
-
-
-@pytest.mark.parametrize("R,sigma,W,H,chunk", [(1, 0.7, 128, 16, 16), (2, 1.0, 416, 64, 48), (3, 1.3, 516, 61, 40), (4, 2.0, 512, 48, 25),
-                                               (5, 2.5, 452, 40, 23), (6, 3.0, 448, 61, 61), (7, 3.5, 128, 30, 17), (8, 4.0, 900, 50, 34),
-                                               (8, 3.0, 240, 37, 16)])
-def test_wring_diffuse_only_bits(oracle, hostcheck, wring_packed, R, sigma, W, H, chunk):
-    p = params_for(oracle, W, H, R, sigma, dep=1.0)
-    field = np.random.default_rng(R).random((H, W), dtype=np.float32)
-    ref = oracle.trail_pass(field, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
-    got, _, _ = run_stream(hostcheck, oracle, field, p, R, sigma, chunk, kernel="wring")
-    assert bits_equal(got, ref), mismatch_report(got, ref, f"wring R={R}")
-
-
-@pytest.mark.parametrize("cm,dep", [(1, 0.4), (1, 2.5), (2, 1.0)])
-@pytest.mark.parametrize("R,sigma,W,H,chunk", [(2, 1.0, 292, 64, 20), (5, 2.5, 300, 45, 45), (6, 3.0, 460, 36, 20), (8, 4.0, 448, 40, 40)])
-def test_wring_full_step_bits(oracle, hostcheck, wring_packed, cm, dep, R, sigma, W, H, chunk):
-    p = params_for(oracle, W, H, R, sigma, dep=dep)
-    rng = np.random.default_rng(100 * R + cm)
-    field = random_trail(W, H, seed=R, density=0.5)
-    counts = (rng.random((H, W)) < 0.2).astype(np.uint32) * rng.integers(1, 4, (H, W)).astype(np.uint32)
-    counts[0, :5] = 1; counts[-1, -5:] = 2; counts[:3, -1] = 1; counts[-3:, 0] = 3
-    ref = oracle.trail_pass(field, p, counts=counts.copy(), gauss_radius=R, gauss_sigma=sigma)
-    got, surf, czero = run_stream(hostcheck, oracle, field, p, R, sigma, chunk, cm=cm, counts=counts, want_surf=True, kernel="wring")
-    assert bits_equal(got, ref), mismatch_report(got, ref, f"wring full step R={R} cm={cm}")
-    assert bits_equal(surf, ref), "sampler copy differs from the row-major output"
-    assert not czero.any(), "deposit marks of the next step's buffer were not all retired"
-
-
-@pytest.mark.parametrize("R,sigma,strips", [(6, 3.0, 2), (8, 4.0, 3)])
-def test_wring_on_strips_bits(oracle, hostcheck, R, sigma, strips):
-    W, H, ghost, passes = 256, 32 * strips, 9, 2
-    p = params_for(oracle, W, H, R, sigma, dep=1.0)
-    field = np.random.default_rng(strips).random((H, W), dtype=np.float32)
-    ref = field
-    for _ in range(passes):
-        ref = oracle.trail_pass(ref, p, counts=None, gauss_radius=R, gauss_sigma=sigma)
-    w = oracle.gauss_weights(R, sigma)
-    rows = H // strips
-    cur = field
-    for _ in range(passes):
-        new = np.empty_like(cur)
-        for r in range(strips):
-            y0 = r * rows
-            buf = cur[np.arange(y0 - ghost, y0 + rows + ghost) % H].copy()
-            buf[:ghost - R] = np.nan
-            buf[ghost + rows + R:] = np.nan
-            out = np.full((rows + 2 * ghost, W), np.nan, np.float32)
-            pp = params_for(oracle, W, rows, R, sigma, dep=1.0)
-            rc = hostcheck.hc_gauss_wring(P(buf[ghost:], C.c_float), None, None, P(out[ghost:], C.c_float), None,
-                                          C.c_int(W), C.c_int(rows), C.c_int(20), C.c_int(R), P(w, C.c_float), C.c_int(0),
-                                          C.byref(pp), C.c_int(0))
-            assert rc == 0
-            assert np.all(np.isnan(out[:ghost])) and np.all(np.isnan(out[ghost + rows:])), "stored into the ghost rows"
-            new[y0:y0 + rows] = out[ghost:ghost + rows]
-        cur = new
-    assert bits_equal(cur, ref), mismatch_report(cur, ref, f"wring on strips R={R}")

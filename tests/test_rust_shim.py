@@ -37,18 +37,36 @@ def test_every_header_function_is_declared_with_the_same_arity():
 def c_struct(name):
     body = re.search(r"typedef struct " + name + r"\s*\{(.*?)\}\s*" + name + r"\s*;", HEADER, re.S).group(1)
     out = []
-    for ty, names in re.findall(r"(uint32_t|int32_t|uint64_t|float|double)\s+([^;]+);", body):
-        out += [(n.strip(), C_WIDTH[ty]) for n in names.split(",")]
+    for ty, names in re.findall(r"(uint32_t|int32_t|uint64_t|float|double|sm_tuning)\s+([^;]+);", body):
+        for n in names.split(","):
+            n = n.strip()
+            arr = re.match(r"(\w+)\[(\d+)\]$", n)
+            if ty == "sm_tuning":
+                out.append((n, sum(w for _, w in c_struct("sm_tuning"))))
+            elif arr:
+                out.append((arr.group(1), C_WIDTH[ty] * int(arr.group(2))))
+            else:
+                out.append((n, C_WIDTH[ty]))
     return out
 
 
 def rust_struct(name):
     body = re.search(r"pub struct " + name + r"\s*\{(.*?)\}", FFI, re.S).group(1)
-    return [(n, RS_WIDTH[t]) for n, t in re.findall(r"pub (\w+):\s*(\w+),", body)]
+    out = []
+    for n, t in re.findall(r"pub (\w+):\s*([^,\n]+),", body):
+        t = t.strip()
+        arr = re.match(r"\[(\w+);\s*(\d+)\]$", t)
+        if t == "sm_tuning":
+            out.append((n, sum(w for _, w in rust_struct("sm_tuning"))))
+        elif arr:
+            out.append((n, RS_WIDTH[arr.group(1)] * int(arr.group(2))))
+        else:
+            out.append((n, RS_WIDTH[t]))
+    return out
 
 
 def test_repr_c_structs_mirror_the_header():
-    for name in ("sm_params", "sm_config", "sm_timing", "sm_trail_stats"):
+    for name in ("sm_params", "sm_tuning", "sm_config", "sm_timing", "sm_trail_stats"):
         assert c_struct(name) == rust_struct(name), name
         assert re.search(r"#\[repr\(C\)\]\s*(#\[derive[^\]]*\]\s*)?pub struct " + name, FFI), name
     assert sum(w for _, w in c_struct("sm_params")) == 56          # SimSizeUniform, src/main.rs:29-46

@@ -100,33 +100,6 @@ def presets_sweep():
         be.close()
 
 
-def heading_sort_sweep():
-    """Experiments on the sort key: SM_SORT_SUPER_SHIFT (tiles numbered super-tile by super-tile: a CTA's agents come from a
-    compact block of tiles, smaller L1 working set) and SM_SORT_HEADING_BINS (agents of a tile grouped by heading sector).
-    Config 2, steady state, Default (sensor distance 20) and Snake (225)."""
-    N, W, H = 16_777_216, 4096, 4096
-    for preset in ("Default", "Snake"):
-        s = sm.init_preset_manager().get_preset(preset).settings
-        for bins, sup in ((1, 0), (1, 1), (1, 2), (1, 3), (4, 0), (8, 0), (4, 2)):
-            for interval in (12, 24):
-                os.environ["SM_SORT_HEADING_BINS"] = str(bins)
-                os.environ["SM_SORT_SUPER_SHIFT"] = str(sup)
-                be = sm.CudaBackend.new(W, H, s, agent_count=N, sort_interval=interval)
-                be.init_agents(1)
-                be.step(300)
-                steps = 96
-                ms = event_time(be, lambda: be.step(steps))
-                be.set_timing_enabled(True); be.reset_timing()
-                be.step(48)
-                t = be.timing()
-                emit({"sweep": "heading_sort", "preset": preset, "bins": bins, "super_shift": sup, "sort_interval": interval, "ms_per_step": ms / steps,
-                      "agent_steps_per_s": N * steps / (ms * 1e-3), "agents_ms": t.agents_ms / t.agent_launches,
-                      "trail_ms": t.trail_ms / t.trail_launches, "sort_ms_per_step": t.sort_ms / 48})
-                be.close()
-    os.environ.pop("SM_SORT_HEADING_BINS", None)
-    os.environ.pop("SM_SORT_SUPER_SHIFT", None)
-
-
 def gauss_sweep():
     """EXTENSION (no reference semantics): separable Gaussian, radius 2 / 4 / 8, fused shared-memory kernel vs the
     two-pass form (BASELINE config 5 names radii 1-8; radius 1 = the reference's box is the parity mode above)."""
@@ -269,7 +242,6 @@ def gauss_packed_sweep():
         for R in (5, 6, 7, 8):
             for pk in (0, 1):
                 run(S, R, "stream", {"SM_GAUSS_STREAM_PACKED": str(pk)}, f"stream_pk{pk}")
-            run(S, R, "wring", {}, "wring")                    # experiment: private shared-memory ring (gauss_wring.cuh)
     os.environ.pop("SM_GAUSS_KERNEL", None)
     os.environ.pop("SM_GAUSS_CHUNK", None)
 
@@ -322,8 +294,6 @@ if __name__ == "__main__":
         agents_sweep()
     if "presets" in which:
         presets_sweep()
-    if "heading_sort" in which:
-        heading_sort_sweep()
     if "gauss" in which:
         gauss_sweep()
     if "gauss_stream" in which:

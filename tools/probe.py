@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--tag", default="")
     ap.add_argument("--no-kernel-split", action="store_true")
+    ap.add_argument("--fake-strips", type=int, default=0, metavar="N",
+                    help="PROFILING ONLY: rank 0 of an N-strip engine that exchanges with itself (sm_tuning.debug_single_rank_strip): "
+                         "the strip kernels and the overlapped exchange in one process, e.g. under ncu; results are meaningless")
     a = ap.parse_args()
 
     s = sm.init_preset_manager().get_preset(a.preset).settings
@@ -46,8 +49,13 @@ def main():
     if a.jitter is not None: ch["agent_jitter"] = a.jitter
     if a.gaussian: ch.update(blur_radius=float(a.gaussian), blur_sigma=a.gaussian / 2.0)
     s = s.clone(**ch)
-    be = sm.CudaBackend.new(a.width, a.height, s, agent_count=a.agents, sort_interval=a.sort_interval,
-                            flags=sm.SM_FLAG_GAUSSIAN_BLUR if a.gaussian else 0)
+    if a.fake_strips > 1:
+        os.environ["SM_FAKE_MULTI"] = "1"
+        be = sm.CudaBackend.new(a.width, a.height * a.fake_strips, s, agent_count=a.agents * a.fake_strips, sort_interval=a.sort_interval,
+                                rank=0, world_size=a.fake_strips)
+    else:
+        be = sm.CudaBackend.new(a.width, a.height, s, agent_count=a.agents, sort_interval=a.sort_interval,
+                                flags=sm.SM_FLAG_GAUSSIAN_BLUR if a.gaussian else 0)
     be.init_agents(a.seed)
     stream = torch.cuda.ExternalStream(be.stream_handle)
 
