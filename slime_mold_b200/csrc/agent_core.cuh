@@ -19,6 +19,7 @@ struct AgentConsts {
     float sensor_angle, sensor_distance;
     float jitter;
     float neg_zero;            // -0.0f, opaque to the compiler (see mul2_nofuse)
+    uint32_t zero_bits;        // 0u, opaque to the compiler (see the gather fence in agent_update_impl)
     // strip of the trail this kernel may read (multi-GPU): global rows
     // [row0 - halo, row0 + rows + halo) live at trail + (row - row_base) * W
     int64_t row_base;
@@ -177,9 +178,17 @@ SM_HD void agent_update_impl(float& x, float& y, float& angle, float& speed, int
     const float pxC = add(x, mul(sd, cC)), pyC = add(y, mul(sd, sC));      // :87-90
     const float fxC = ::floorf(pxC), fyC = ::floorf(pyC);
     // all three footprints are requested before any of them is consumed: one exposed memory latency, not three
-    const Footprint qL = fetch_footprint(c, fxLR.lo, fyLR.lo, fetch);      // :93
-    const Footprint qR = fetch_footprint(c, fxLR.hi, fyLR.hi, fetch);      // :94
-    const Footprint qC = fetch_footprint(c, fxC, fyC, fetch);              // :95
+    Footprint qL = fetch_footprint(c, fxLR.lo, fyLR.lo, fetch);            // :93
+    Footprint qR = fetch_footprint(c, fxLR.hi, fyLR.hi, fetch);            // :94
+    Footprint qC = fetch_footprint(c, fxC, fyC, fetch);                    // :95
+#ifdef __CUDA_ARCH__
+    // Scheduling fence, bit-neutral: OR-ing (last gather's word & 0) into one word of the first two footprints makes their
+    // consumers depend on the LAST gather, so ptxas cannot consume the first footprint before the other two gathers are
+    // issued.  Short of registers it does exactly that in the strip and unrolled instantiations (seen in SASS and in
+    // ncu: two or three exposed gather latencies per agent instead of one).  zero_bits is 0 from the parameter block.
+    qL.v00 = u2f(f2u(qL.v00) | (f2u(qC.v11) & c.zero_bits));
+    qR.v00 = u2f(f2u(qR.v00) | (f2u(qC.v11) & c.zero_bits));
+#endif
     const f2 dxLR = sub2(pxLR, fxLR), dyLR = sub2(pyLR, fyLR);             // :18-19
     const f2 mxLR = sub2(one2, dxLR), myLR = sub2(one2, dyLR);             // the (1 - t) of mix()
     const float dxC = sub(pxC, fxC), dyC = sub(pyC, fyC);

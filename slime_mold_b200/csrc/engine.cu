@@ -58,6 +58,7 @@ smd::AgentConsts sm_engine::agent_consts() const
     c.Wf = (float)W; c.Hf = (float)H;
     c.rcpW = 1.0f / c.Wf; c.rcpH = 1.0f / c.Hf;
     c.neg_zero = -0.0f;
+    c.zero_bits = 0u;
     c.xmax = (float)W - 2.0f; c.ymax = (float)H - 2.0f;
     c.speed_min = params.agent_speed_min; c.speed_max = params.agent_speed_max;
     c.turn_speed = params.agent_turn_speed;
@@ -842,7 +843,9 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     int rc;
     if ((rc = e->alloc_trail()) != SM_OK) return fail(rc);
     uint64_t cap = e->n_global;
-    if (e->world > 1) cap = std::min<uint64_t>(e->n_global, 2 * ((e->n_global + e->world - 1) / e->world) + (1u << 20));
+    // strips: twice the even share plus slack; never more than every agent plus slack -- the slack is what arrivals need
+    // between two sorts even on a rank that already holds everybody (slots of departed agents are only reclaimed by the sort)
+    if (e->world > 1) cap = std::min<uint64_t>(e->n_global, 2 * ((e->n_global + e->world - 1) / e->world)) + (1u << 20);
     if ((rc = e->alloc_agents(cap)) != SM_OK) return fail(rc);
     if ((rc = e->setup_tiles()) != SM_OK) return fail(rc);
     if (cudaMalloc(&e->stats_dev, sizeof(smk::StatsAcc)) != cudaSuccess ||
@@ -1044,7 +1047,7 @@ int sm_set_agent_count(sm_engine* e, uint64_t n, uint64_t seed)
     e->n_global = n;
     e->cfg.agent_count = n;
     uint64_t cap = n;
-    if (e->world > 1) cap = std::min<uint64_t>(n, 2 * ((n + e->world - 1) / e->world) + (1u << 20));
+    if (e->world > 1) cap = std::min<uint64_t>(n, 2 * ((n + e->world - 1) / e->world)) + (1u << 20);
     if (cap > e->cap_local) SM_TRY(e->alloc_agents(cap));
     e->agents_valid = false;
     return sm_init_agents(e, seed);

@@ -202,7 +202,14 @@ __device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, 
     }
 }
 
-template <int XM, class IdxT, bool FLAGS>
+#ifndef SM_DEPOSIT_MATCH_ANY
+#define SM_DEPOSIT_MATCH_ANY 0        // 1: __match_any_sync-aggregated counts.  Measured in round 2 (tools/r2/gpu_17.sh, deposit 0.3): the plain
+                                      // RED is FASTER -- config 2: k_agents 181 us (RED) vs 214 us (match_any); config 3: 1597 vs 1628.  After the
+                                      // cell sort a warp's 32 agents hit ~25 distinct cells, so a group rarely has more than one or two lanes, and
+                                      // MATCH.ANY costs more issue slots than the fire-and-forget REDs it saves; L2 atomic throughput is not a limit
+                                      // here (the sort's histogram, where a warp shares one or two keys, is where aggregation pays)
+#endif
+template <int XM, class IdxT, bool FLAGS, bool AGG = (SM_DEPOSIT_MATCH_ANY != 0)>
 __device__ __forceinline__ void finish_agent_slot(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
                                                   const float4 a, const uint32_t id, const int32_t cx, const int32_t cy,
                                                   void* __restrict__ deposits, const AgentConsts& c, const LeaverBufs& lv)
@@ -217,6 +224,13 @@ __device__ __forceinline__ void finish_agent_slot(float4* __restrict__ agents, u
         // deposit: order-free (phase_split form of compute.wgsl:140)
         const IdxT off = (IdxT)lr * (IdxT)c.W + (IdxT)cx;
         if (FLAGS) static_cast<uint8_t*>(deposits)[off] = 1;
+        else if (AGG) {
+            // warp-aggregated count (fractional deposits): the lanes of the warp that hit the same cell elect a leader that adds
+            // the size of the group -- after the cell sort the lanes of a warp share a few tiles, at one or more agents per cell
+            const uint32_t active = __activemask();
+            const uint32_t group = __match_any_sync(active, (unsigned long long)off);
+            if ((threadIdx.x & 31u) == (uint32_t)(__ffs(group) - 1)) atomicAdd(static_cast<uint32_t*>(deposits) + off, (uint32_t)__popc(group));
+        }
         else atomicAdd(static_cast<uint32_t*>(deposits) + off, 1u);
     }
     if (MULTI && !interior) agent_leaves_strip<XM, IdxT, FLAGS>(agents, ids, i, a, id, cx, cy, deposits, c, lv);
@@ -311,6 +325,11 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
         i = i_next;
     }
 }
+
+// (A fully unrolled form of this kernel -- four agents per thread, one base address per array with immediate offsets, 32-bit
+// slot numbers, no register moves between iterations, the generic heading path as a real call -- was built and measured in
+// round 2: 8.6 % fewer warp instructions (132.9 M vs 145.3 M at config 2), and the same time to within 1 %: the issue rate
+// fell from 72 % to 63-66 % (longer gather stalls, instruction-cache misses of the four bodies).  profiles/README.md.)
 
 // ---------------------------------------------------------------------------
 // trail: merge deposits -> decay -> 3x3 toroidal mean -> mix, out of place

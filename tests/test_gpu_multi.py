@@ -23,6 +23,11 @@ CASES = {
     "thin_strips": ("Default", 256, 128, 30_000, 40, False),
     "firecracker_devinit": ("Firecracker Trees", 1024, 1024, 1_000_000, 33, True),
     "mode_switch": ("Default", 256, 512, 150_000, 40, False),
+    # a trail rectangle that touches only SOME strips, uploaded mid-run, followed by steps -- the deposit
+    # representation of the next step must be the same collective decision on every rank
+    "partial_upload": ("Default", 256, 512, 150_000, 30, False),
+    # a strip with no agents at all (everything starts in the upper half of the map) still merges its neighbours' deposits
+    "empty_strip": ("Default", 256, 512, 80_000, 30, False),
     # steps, diffusion-only passes (sm_diffuse_only on strips: overlapped ghost push + one barrier per pass), steps
     "diffuse_mix": ("Sponge", 512, 1024, 200_000, 30, False),
     # per-rank snapshot files mid-run, restored into freshly created engines (new communicator), then continued
@@ -39,6 +44,7 @@ def _worker(rank, world, case, out_dir, exchange):
     os.environ["SM_EXCHANGE"] = exchange
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
     import torch  # noqa: F401  (first, so the process ends up with torch's libnccl)
     import slime_mold_b200 as sm
     from oracle import slime_oracle as so
@@ -69,7 +75,17 @@ def _worker(rank, world, case, out_dir, exchange):
     else:
         be.write_agents(so.init_agents(N, W, H, s.agent_speed_min, s.agent_speed_max, 11))
         be.write_trail(random_trail(W, H, seed=4))
-    if case == "mode_switch":
+    if case == "partial_upload":
+        be.step(steps // 2)
+        rect = random_trail(64, 40, seed=77) - np.float32(0.25)          # some negative cells: counts mode until the next pass
+        be.write_trail(rect, x0=100, y0=20)                              # rows 20..59: the first strip only
+        be.step(steps - steps // 2)
+    elif case == "empty_strip":
+        a0 = so.init_agents(N, W, H, s.agent_speed_min, s.agent_speed_max, 11)
+        a0[:, 1] *= np.float32(0.45)                                     # nobody starts in the lower strips
+        be.write_agents(a0)
+        be.step(steps)
+    elif case == "mode_switch":
         # deposit representation changes mid-run (flags <-> counts) on every rank at the same step
         for dep in (1.0, 0.3, 2.0, 0.05, 1.0):
             be.update_settings(s.clone(pheromone_deposition_amount=dep))
@@ -110,13 +126,23 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
     preset, W, H, N, steps, device_init = CASES[case]
     if H // world < 32:
         pytest.skip("strips too thin for this case")
-    if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips", "diffuse_mix", "gauss_rows_diffuse"):
+    if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips", "diffuse_mix", "gauss_rows_diffuse", "partial_upload"):
         pytest.skip("NCCL path: three representative cases")
     mp.spawn(_worker, args=(world, case, str(tmp_path), exchange), nprocs=world, join=True)
     u = preset_uniform(preset, W, H)
     ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 11)
     sim = oracle.Sim(to_oracle_params(oracle, u), ag, trail=None if device_init else random_trail(W, H, seed=4))
-    if case == "mode_switch":
+    if case == "partial_upload":
+        sim.step(steps // 2)
+        rect = random_trail(64, 40, seed=77) - np.float32(0.25)
+        sim.trail[20:60, 100:164] = rect
+        sim.step(steps - steps // 2)
+    elif case == "empty_strip":
+        a0 = ag.copy()
+        a0[:, 1] *= np.float32(0.45)
+        sim = oracle.Sim(to_oracle_params(oracle, u), a0, trail=random_trail(W, H, seed=4))
+        sim.step(steps)
+    elif case == "mode_switch":
         import slime_mold_b200 as sm2
         s0 = sm2.init_preset_manager().get_preset(preset).settings
         for dep in (1.0, 0.3, 2.0, 0.05, 1.0):
