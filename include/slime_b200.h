@@ -205,7 +205,9 @@ int sm_resize(sm_engine *e, uint32_t width, uint32_t height);
  * sm_step() shows the field of the last step after deposits and decay, before the blur
  * (recomputed per texel from that step's inputs, which are still in device memory); after
  * anything else that changed the trail (upload, clear, sm_diffuse_only, resize, snapshot
- * load) it shows the trail as it stands.  Single GPU. */
+ * load) it shows the trail as it stands.  On strips every rank writes the frame rows that
+ * show its own map rows (the bars above / below the map belong to the first / last strip)
+ * and leaves the rest of `rgba` untouched: the ranks' frames tile the whole frame. */
 int sm_set_lut(sm_engine *e, const uint8_t *lut768);
 int sm_render_rgba8(sm_engine *e, uint32_t tex_width, uint32_t tex_height, uint8_t *rgba);
 

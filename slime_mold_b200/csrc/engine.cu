@@ -310,7 +310,7 @@ int sm_engine::setup_tiles()
 bool sm_engine::flag_mode() const
 {
     if (no_flags) return false;
-    if ((cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && !(gauss_fast_ok() && world == 1)) return false;   // the tile / two-pass Gaussian kernels only merge counts
+    if ((cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && !gauss_fast_ok()) return false;   // the tile / two-pass Gaussian kernels only merge counts
     return trail_nonneg && params.pheromone_deposition_amount >= 1.0f;
 }
 
@@ -515,7 +515,7 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     p.g.W = W; p.g.rows = rows; p.g.wrap_y = (world == 1) ? 1 : 0;
     p.g.y_first = 0; p.g.y_last = rows; p.g.chunks1 = 0xFFFFFFFFu; p.g.y_first2 = p.g.y_last2 = 0;
     // the full step keeps the sampler's block-linear copy in step; other passes just mark it stale
-    const bool write_surf = use_tex && has_counts && (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) || (gauss_fast_ok() && world == 1));
+    const bool write_surf = use_tex && has_counts && (!(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) || gauss_fast_ok());
     p.g.surf = write_surf ? trail_surf : 0;
     p.g.surf_row0 = (int)(ghost + pad_rows);
     p.g.surf_pairs = surf_pairs ? 1 : 0;
@@ -1275,11 +1275,10 @@ int sm_set_lut(sm_engine* e, const uint8_t* lut768)
 int sm_render_rgba8(sm_engine* e, uint32_t tex_width, uint32_t tex_height, uint8_t* rgba_host)
 {
     SM_ENTER(e);
-    if (e->world != 1) return sm_fail(SM_ERR_STATE, "sm_render_rgba8 is single-GPU only (download the strips instead)");
     if (!e->lut_set) return sm_fail(SM_ERR_STATE, "no LUT: call sm_set_lut first");
     if (!rgba_host) return sm_fail(SM_ERR_BAD_ARG, "null frame buffer");
     if (tex_width == 0 || tex_height == 0 || tex_width > 65536 || tex_height > 65535) return sm_fail(SM_ERR_BAD_ARG, "bad frame size");
-    const size_t texels = (size_t)tex_width * tex_height;
+    size_t texels = (size_t)tex_width * tex_height;
     if (texels > e->frame_cap) {
         if (e->frame_dev) { cudaFree(e->frame_dev); e->frame_dev = nullptr; e->frame_cap = 0; }
         SM_CUDA(cudaMalloc(&e->frame_dev, texels * 4));
@@ -1298,7 +1297,30 @@ int sm_render_rgba8(sm_engine* e, uint32_t tex_width, uint32_t tex_height, uint8
         }
         g.sim_w = sim_w; g.sim_h = sim_h; g.scale = scale; g.off_x = off_x; g.off_y = off_y;
     }
-    dim3 grid(blocks_for((tex_width + 3) / 4, 256), tex_height);
+    // Strips: this rank draws the frame rows that show its map rows -- fy = (py - off_y) / scale is monotone in py, so they are
+    // one contiguous range; the letter-box bars above the map belong to the first strip, those below it to the last.  The
+    // other rows of the caller's buffer are left untouched (like sm_download_agents / sm_download_trail on strips).
+    uint32_t py0 = 0, py1 = tex_height;
+    if (e->world > 1) {
+        auto owner_is_me = [&](uint32_t py) {
+            volatile float d = (float)py - g.off_y;
+            volatile float fy = d / g.scale;                            // display.wgsl:73, the kernel's f32 operations
+            const float v = fy;
+            uint32_t row;
+            if (!(v >= 0.0f)) row = 0;                                  // bar above the map (or NaN)
+            else if (!(v < g.sim_h)) row = e->H - 1;                    // bar below
+            else row = (uint32_t)v;
+            return row >= e->row0 && row < e->row0 + e->rows;
+        };
+        while (py0 < tex_height && !owner_is_me(py0)) ++py0;
+        py1 = py0;
+        while (py1 < tex_height && owner_is_me(py1)) ++py1;
+    }
+    g.row_base = e->row0;
+    g.py_first = py0;
+    if (py1 == py0) return SM_OK;                                       // a frame smaller than the strip count: nothing of it is mine
+    texels = (size_t)tex_width * (py1 - py0);
+    dim3 grid(blocks_for((tex_width + 3) / 4, 256), py1 - py0);
     smk::DisplaySrc src{};
     if (e->frame_pre_valid) {
         // the field the reference draws: decay(merge(T_prev, deposits)) of the last step (trail_done flipped cur / ccur)
@@ -1313,7 +1335,7 @@ int sm_render_rgba8(sm_engine* e, uint32_t tex_width, uint32_t tex_height, uint8
     smk::k_display<<<grid, 256, 0, e->stream>>>(src, e->lut_dev, e->frame_dev, g);
     SM_CUDA(cudaGetLastError());
     e->timing.kernel_launches += 1;
-    SM_CUDA(cudaMemcpyAsync(rgba_host, e->frame_dev, texels * 4, cudaMemcpyDeviceToHost, e->stream));
+    SM_CUDA(cudaMemcpyAsync(rgba_host + (size_t)py0 * tex_width * 4, e->frame_dev, texels * 4, cudaMemcpyDeviceToHost, e->stream));
     SM_CUDA(cudaStreamSynchronize(e->stream));
     return SM_OK;
 }

@@ -781,21 +781,26 @@ int sm_engine::p2p_after_agents(cudaStream_t st, bool timed)
     uint32_t* wu = reinterpret_cast<uint32_t*>(peer[0].window);
     uint32_t* wd = reinterpret_cast<uint32_t*>(peer[1].window);
     const size_t row0_off = (size_t)(ghost + pad_rows) * W;
-    // one 16-byte element per thread and row (flags: W bytes per row, counts: 4 W)
-    const uint64_t pull_elems = ((uint64_t)W * (deposit_mode == 2 ? 1 : 4) + 15) / 16;
+    // rows of each neighbour's deposit field the trail pass of my edge rows reads: one for the 3x3 box, R for the Gaussian
+    // extension (its full steps on strips run the serial order: pull, pass, push)
+    uint32_t pr = 1;
+    if (cfg.flags & SM_FLAG_GAUSSIAN_BLUR) pr = (uint32_t)std::max(1l, lroundf(params.blur_radius));
+    const uint32_t pw = pr * W;                      // contiguous: `pr` whole rows
+    // one 16-byte element per thread (flags: 1 byte per cell, counts: 4)
+    const uint64_t pull_elems = ((uint64_t)pw * (deposit_mode == 2 ? 1 : 4) + 15) / 16;
     const unsigned pull_blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(256, (pull_elems + 127) / 128));
     if (deposit_mode == 2) {
         uint8_t* f = flags_ptr(ccur);
-        const uint8_t* up_last = peer[0].flags8[ccur] + row0_off + (size_t)(peer[0].rows - 1) * W;
+        const uint8_t* up_last = peer[0].flags8[ccur] + row0_off + (size_t)(peer[0].rows - pr) * W;
         const uint8_t* down_first = peer[1].flags8[ccur] + row0_off;
-        smk::k_barrier_pull<uint8_t><<<pull_blocks, 128, 0, st>>>(w, wu, wd, barrier_seq, dev_counters + 2, f - (int64_t)W, up_last,
-                                                            f + (int64_t)rows * W, down_first, W);
+        smk::k_barrier_pull<uint8_t><<<pull_blocks, 128, 0, st>>>(w, wu, wd, barrier_seq, dev_counters + 2, f - (int64_t)pr * W, up_last,
+                                                            f + (int64_t)rows * W, down_first, pw);
     } else {
         uint32_t* cn = counts_ptr(ccur);
-        const uint32_t* up_last = peer[0].counts[ccur] + row0_off + (size_t)(peer[0].rows - 1) * W;
+        const uint32_t* up_last = peer[0].counts[ccur] + row0_off + (size_t)(peer[0].rows - pr) * W;
         const uint32_t* down_first = peer[1].counts[ccur] + row0_off;
-        smk::k_barrier_pull<uint32_t><<<pull_blocks, 128, 0, st>>>(w, wu, wd, barrier_seq, dev_counters + 2, cn - (int64_t)W, up_last,
-                                                             cn + (int64_t)rows * W, down_first, W);
+        smk::k_barrier_pull<uint32_t><<<pull_blocks, 128, 0, st>>>(w, wu, wd, barrier_seq, dev_counters + 2, cn - (int64_t)pr * W, up_last,
+                                                             cn + (int64_t)rows * W, down_first, pw);
     }
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;

@@ -150,7 +150,10 @@ int sm_engine::check_gauss(bool has_counts) const
     if (world != 1) {
         // strips: diffusion-only passes (BASELINE config 5 at 2/4/8 GPUs); the R rows of the neighbours a pass reads are the
         // ghost rows sm_diffuse_only exchanges after every pass
-        if (has_counts) return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR: full steps are single-GPU only (diffusion-only passes run on strips)");
+        // full steps on strips (round 2): the pass also reads R deposit rows of each neighbour, pulled over NVLink after barrier 1
+        // (exchange.cu: p2p_after_agents); peer-store exchange only
+        if (has_counts && comm_ready && !p2p)
+            return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR: full steps on strips need the peer-store exchange (sm_tuning.exchange = 0)");
         if (!gauss_fast_ok())
             return sm_fail(SM_ERR_STATE, "SM_FLAG_GAUSSIAN_BLUR on strips needs the streaming kernels (W %% 4 == 0, W >= %d, >= %d rows per strip)",
                            smk::kGsMinW, smk::kGsMinRows);

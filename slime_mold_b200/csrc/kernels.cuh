@@ -1076,8 +1076,10 @@ k_trail_stats(const float* __restrict__ t, uint64_t cells, StatsAcc* __restrict_
 // 4 B/cell read + 4 B/texel written; HBM-bound.
 // ---------------------------------------------------------------------------
 struct DisplayGeom {
-    uint32_t W, H;            // simulation size (this engine's strip is the whole map: single GPU only)
+    uint32_t W, H;            // simulation size (global)
     uint32_t tw, th;          // frame size
+    uint32_t row_base;        // global row of row 0 of `trail` / `dep` (strips; 0 on one GPU)
+    uint32_t py_first;        // frame row of blockIdx.y == 0 (strips render the frame rows that show their map rows)
     float sim_w, sim_h;       // f32(W), f32(H)                    display.wgsl:48-49
     float scale, off_x, off_y;   // display.wgsl:58-69, computed once on the host with the same f32 operations
 };
@@ -1100,7 +1102,7 @@ __device__ __forceinline__ uint32_t display_texel(const DisplaySrc& src, const u
     const float fx = __fdiv_rn(smd::sub((float)px, g.off_x), g.scale);               // :72
     if (!(row_inside && fx >= 0.0f && fx < g.sim_w)) return 0xFF000000u;             // :83-85 black, alpha 1
     const int32_t x = (int32_t)fx, y = (int32_t)fy;                                  // :77-78
-    const size_t idx = (size_t)y * g.W + x;
+    const size_t idx = (size_t)(y - (int32_t)g.row_base) * g.W + x;
     float t = __ldg(src.trail + idx);                                                // :79
     if (src.cm == CM_COUNTS) t = trail_cell<CM_COUNTS>(t, __ldg(static_cast<const uint32_t*>(src.dep) + idx), src.tc);
     else if (src.cm == CM_FLAGS) t = trail_cell<CM_FLAGS>(t, __ldg(static_cast<const uint8_t*>(src.dep) + idx), src.tc);
@@ -1117,12 +1119,12 @@ k_display(const DisplaySrc src, const uint8_t* __restrict__ lut768, uint32_t* __
     __shared__ uint8_t lut[768];
     for (uint32_t i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = lut768[i];
     __syncthreads();
-    const uint32_t py = blockIdx.y;
+    const uint32_t py = g.py_first + blockIdx.y;
     const float fy = __fdiv_rn(smd::sub((float)py, g.off_y), g.scale);               // :73
     const bool row_inside = fy >= 0.0f && fy < g.sim_h;                              // :76
     const uint32_t px0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
     if (px0 >= g.tw) return;
-    uint32_t* row = rgba + (size_t)py * g.tw;
+    uint32_t* row = rgba + (size_t)blockIdx.y * g.tw;
     if (px0 + 4u <= g.tw && (g.tw & 3u) == 0u) {
         uint4 o;
         o.x = display_texel(src, lut, g, px0, fy, row_inside);

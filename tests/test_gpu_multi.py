@@ -38,6 +38,15 @@ CASES = {
     "gauss_stream_diffuse": ("Default", 512, 512, 20_000, 6, False),
 }
 GAUSS = {"gauss_rows_diffuse": (3, 1.5), "gauss_stream_diffuse": (6, 3.0)}
+# EXTENSION, round 2: FULL steps in Gaussian mode on strips (the pass pulls R deposit rows of each neighbour); u8 flags with the
+# rows kernel, u32 counts (deposit 0.4) with the streaming kernel
+GAUSS_FULL = {"gauss_rows_full": (3, 1.5, 1.0), "gauss_stream_full": (6, 3.0, 0.4)}
+CASES.update({
+    "gauss_rows_full": ("Default", 512, 512, 120_000, 12, False),
+    "gauss_stream_full": ("Default", 512, 512, 120_000, 12, False),
+    # the display pass on strips: every rank draws the frame rows that show its map rows; together they are the reference's frame
+    "render": ("Waves", 256, 512, 100_000, 9, False),
+})
 
 
 def _worker(rank, world, case, out_dir, exchange):
@@ -67,8 +76,11 @@ def _worker(rank, world, case, out_dir, exchange):
 
     if case in GAUSS:
         s = s.clone(blur_radius=float(GAUSS[case][0]), blur_sigma=GAUSS[case][1], pheromone_diffusion_rate=0.8)
+    if case in GAUSS_FULL:
+        s = s.clone(blur_radius=float(GAUSS_FULL[case][0]), blur_sigma=GAUSS_FULL[case][1], pheromone_diffusion_rate=0.8,
+                    pheromone_deposition_amount=GAUSS_FULL[case][2])
     be = sm.CudaBackend.new(W, H, s, agent_count=N, device=rank, rank=rank, world_size=world,
-                            flags=sm.SM_FLAG_GAUSSIAN_BLUR if case in GAUSS else 0)
+                            flags=sm.SM_FLAG_GAUSSIAN_BLUR if (case in GAUSS or case in GAUSS_FULL) else 0)
     connect(be, "a")
     if device_init:
         be.init_agents(seed=11)
@@ -111,7 +123,13 @@ def _worker(rank, world, case, out_dir, exchange):
         be.step(steps)
     a = be.read_agents()
     t = be.read_trail()
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), agents=a, trail=t, owned=be.last_owned, local=be.local_agent_count)
+    frame = np.zeros((1, 1, 4), np.uint8)
+    if case == "render":
+        lut = np.random.default_rng(3).integers(0, 256, 768).astype(np.uint8)
+        be.set_lut(lut)
+        frame = np.zeros((200, 333, 4), np.uint8)            # alpha 0 = "not written by this rank"
+        be.render(333, 200, out=frame)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), agents=a, trail=t, owned=be.last_owned, local=be.local_agent_count, frame=frame)
     be.close()
 
 
@@ -126,6 +144,8 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
     preset, W, H, N, steps, device_init = CASES[case]
     if H // world < 32:
         pytest.skip("strips too thin for this case")
+    if exchange == "nccl" and (case in GAUSS_FULL or case == "render"):
+        pytest.skip("peer-store exchange only")
     if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips", "diffuse_mix", "gauss_rows_diffuse", "partial_upload"):
         pytest.skip("NCCL path: three representative cases")
     mp.spawn(_worker, args=(world, case, str(tmp_path), exchange), nprocs=world, join=True)
@@ -149,6 +169,31 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
             ss = s0.clone(pheromone_deposition_amount=dep)
             sim.p = to_oracle_params(oracle, sm2.SimSizeUniform.new(W, H, ss.pheromone_decay_factor, ss))
             sim.step(steps // 5)
+    elif case in GAUSS_FULL:
+        import slime_mold_b200 as sm2
+        R, sigma, dep = GAUSS_FULL[case]
+        ss = sm2.init_preset_manager().get_preset(preset).settings.clone(blur_radius=float(R), blur_sigma=sigma, pheromone_diffusion_rate=0.8,
+                                                                         pheromone_deposition_amount=dep)
+        sim.p = to_oracle_params(oracle, sm2.SimSizeUniform.new(W, H, ss.pheromone_decay_factor, ss))
+        for _ in range(steps):
+            oracle.agents_phase_split(sim.agents, sim.trail, sim.counts, sim.p)
+            sim.trail = oracle.trail_pass(sim.trail, sim.p, counts=sim.counts, gauss_radius=R, gauss_sigma=sigma)
+    elif case == "render":
+        sim.step(steps - 1)
+        oracle.agents_phase_split(sim.agents, sim.trail, sim.counts, sim.p)
+        pre = sim.trail.copy()
+        oracle.deposit_merge(pre, sim.counts, u.pheromone_deposition_amount)      # (clears the counts)
+        oracle.decay(pre, u.decay_factor)
+        sim.trail = oracle.diffuse(pre, u.diffusion_rate)
+        lut = np.random.default_rng(3).integers(0, 256, 768).astype(np.uint8)
+        want = oracle.display(pre, lut, 333, 200)                               # the frame between decay and diffuse (main.rs:1202-1217)
+        got = np.zeros_like(want)
+        for r in range(world):
+            f = np.load(tmp_path / f"rank{r}.npz")["frame"]
+            mine = f[..., 3] != 0
+            assert not (mine & (got[..., 3] != 0)).any(), "a frame row was drawn by two strips"
+            got[mine] = f[mine]
+        assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} frame bytes differ"
     elif case in GAUSS:
         import slime_mold_b200 as sm2
         R, sigma = GAUSS[case]
