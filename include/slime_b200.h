@@ -67,7 +67,14 @@ enum {
      * reference semantics ("parity unpinned"). */
     SM_FLAG_GAUSSIAN_BLUR = 1u << 0,
     /* Never re-order agents in memory (disables the periodic cell sort). */
-    SM_FLAG_NO_SORT = 1u << 1
+    SM_FLAG_NO_SORT = 1u << 1,
+    /* The reference's own RACY semantics instead of the deterministic phase_split: agents sense and deposit on ONE live
+     * buffer with the shader's non-atomic read-modify-write (compute.wgsl:93-95, 136-141), decay and diffuse run in place
+     * (:148-195, a cell may read neighbours the same dispatch already rewrote).  Results depend on the GPU's scheduling and
+     * differ from run to run, exactly like the reference's: this mode cannot be checked bit for bit against anything and is
+     * validated by field statistics only (tests/test_gpu_statistics.py).  Single GPU, 3x3 box only; slower than the default
+     * path (three passes, LDG sampling).  Opt-in. */
+    SM_FLAG_SEM_INPLACE = 1u << 2
 };
 
 /* Measurement switches.  Every field: 0 = the engine's default, which is what profiles/ measured fastest.  None of them

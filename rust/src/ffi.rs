@@ -14,6 +14,7 @@ pub const SM_ERR_STATE: c_int = -6;
 
 pub const SM_FLAG_GAUSSIAN_BLUR: u32 = 1 << 0;
 pub const SM_FLAG_NO_SORT: u32 = 1 << 1;
+pub const SM_FLAG_SEM_INPLACE: u32 = 1 << 2;
 pub const SM_COMM_ID_BYTES: usize = 128;
 
 /// Opaque engine handle.

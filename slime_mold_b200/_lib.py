@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("SM_LIB_PATH") or os.path.join(_HERE, "libslime_b200.s
 
 SM_FLAG_GAUSSIAN_BLUR = 1 << 0
 SM_FLAG_NO_SORT = 1 << 1
+SM_FLAG_SEM_INPLACE = 1 << 2
 SM_COMM_ID_BYTES = 128
 
 STATUS_NAMES = {0: "SM_OK", -1: "SM_ERR_BAD_ARG", -2: "SM_ERR_CUDA", -3: "SM_ERR_NCCL", -4: "SM_ERR_OOM",

@@ -610,9 +610,46 @@ int sm_engine::launch_trail(bool has_counts)
     return SM_OK;
 }
 
+// SM_FLAG_SEM_INPLACE: the reference's three dispatches on one live buffer (header: opt-in, statistics-only parity).
+int sm_engine::step_inplace()
+{
+    float* t = trail_ptr(cur);
+    const smd::AgentConsts ac = agent_consts();
+    const smd::TrailConsts tc = trail_consts();
+    if (n_local) {
+        SM_TRY(tic(0));
+        if ((uint64_t)field_cells() < (1ull << 31))
+            smk::k_agents_inplace<int32_t><<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, t, ac, tc.dep);
+        else
+            smk::k_agents_inplace<int64_t><<<blocks_for(n_local, 256), 256, 0, stream>>>(agents[acur], ids[acur], n_local, t, ac, tc.dep);
+        SM_TRY(toc());
+    }
+    SM_TRY(tic(1));
+    const uint64_t cells = (uint64_t)rows * W;
+    smk::k_decay_inplace<<<(unsigned)std::min<uint64_t>((cells + 255) / 256, (uint64_t)num_sms * 32), 256, 0, stream>>>(t, cells, tc.decay_sub);
+    smk::k_diffuse_inplace<<<dim3(blocks_for(W, 16), blocks_for(rows, 16)), 256, 0, stream>>>(t, W, rows, tc);
+    SM_CUDA(cudaGetLastError());
+    SM_TRY(toc());
+    timing.kernel_launches += n_local ? 3 : 2;
+    arr_stale = true;                   // this mode never samples the block-linear copy
+    stats_fused_valid = false;
+    trail_nonneg = true;
+    frame_pre_valid = false;            // the frame shows the field as it stands
+    steps_since_sort++;
+    timing.steps++;
+    return SM_OK;
+}
+
 // One frame of src/main.rs:1163-1235: (sort) -> agents -> decay + diffuse (+ the strip exchange).
 int sm_engine::step_once()
 {
+    if (cfg.flags & SM_FLAG_SEM_INPLACE) {
+        if (sort_interval && steps_since_sort >= sort_interval) {
+            SM_TRY(sort_agents());        // locality only: the jitter hash uses the persistent index
+            steps_since_sort = 0;
+        }
+        return step_inplace();
+    }
     if (world > 1 && ghost_stale) SM_TRY(exchange_trail_ghosts());
     if (sort_interval && steps_since_sort >= sort_interval) {
         SM_TRY(sort_agents());
@@ -654,7 +691,7 @@ int sm_engine::step_once()
 // same launches in the same order either way.
 uint32_t sm_engine::graph_period() const
 {
-    if (!graph_enabled || world != 1 || timing_enabled || stats_interest || (cfg.flags & SM_FLAG_GAUSSIAN_BLUR)) return 0;
+    if (!graph_enabled || world != 1 || timing_enabled || stats_interest || (cfg.flags & (SM_FLAG_GAUSSIAN_BLUR | SM_FLAG_SEM_INPLACE))) return 0;
     return sort_interval ? 2u * sort_interval : 2u;
 }
 
@@ -778,6 +815,8 @@ int sm_create(sm_engine** out, const sm_config* cfg)
     if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
         return sm_fail(SM_ERR_BAD_ARG, "bad rank/world_size %d/%d", cfg->rank, cfg->world_size);
     if ((uint32_t)cfg->world_size > cfg->height) return sm_fail(SM_ERR_BAD_ARG, "more strips than rows");
+    if ((cfg->flags & SM_FLAG_SEM_INPLACE) && (cfg->world_size != 1 || (cfg->flags & SM_FLAG_GAUSSIAN_BLUR)))
+        return sm_fail(SM_ERR_BAD_ARG, "SM_FLAG_SEM_INPLACE is single-GPU, 3x3 box only");
     int num_sms = 0;
     SM_TRY(check_device(cfg->device, &num_sms));
 

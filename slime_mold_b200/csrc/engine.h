@@ -183,6 +183,7 @@ struct sm_engine {
     bool graph_ready();
     int graph_steps();
     int step_once();
+    int step_inplace();               // SM_FLAG_SEM_INPLACE
 
     smd::AgentConsts agent_consts() const;
     smd::TrailConsts trail_consts() const;

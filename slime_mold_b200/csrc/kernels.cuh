@@ -332,6 +332,60 @@ k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
 // fell from 72 % to 63-66 % (longer gather stalls, instruction-cache misses of the four bodies).  profiles/README.md.)
 
 // ---------------------------------------------------------------------------
+// SM_FLAG_SEM_INPLACE: the reference's racy passes, statement for statement, on ONE live buffer
+// ---------------------------------------------------------------------------
+// Volatile loads: every sensor tap and every deposit read sees whatever the buffer holds at that moment (no L1-stale
+// copies beyond what the hardware's own races produce) -- the point of this mode is the race, not its speed.
+struct LdLive {
+    __device__ __forceinline__ float operator()(const float* p) const { return *reinterpret_cast<const volatile float*>(p); }
+};
+
+// compute.wgsl:57-145 as written: sense the live map, move, then `trail[i] = clamp(trail[i] + dep, 0, 1)` NON-atomically.
+template <class IdxT>
+static __global__ void __launch_bounds__(256)
+k_agents_inplace(float4* __restrict__ agents, const uint32_t* __restrict__ ids, uint64_t n, float* trail, const AgentConsts c, const float dep)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = agents[i];
+    const uint32_t id = ids[i];
+    int32_t cx, cy;
+    const smd::FetchLinear<IdxT, LdLive> fetch{trail, (IdxT)c.W, (IdxT)0, LdLive()};
+    smd::agent_update(a.x, a.y, a.z, a.w, (int32_t)id, c, fetch, cx, cy);
+    agents[i] = a;
+    if (cx >= 0) {
+        volatile float* cell = trail + ((IdxT)cy * (IdxT)c.W + (IdxT)cx);
+        const float cur = *cell;                                           // :140 read ...
+        *cell = smd::clampf(smd::add(cur, dep), 0.0f, 1.0f);               // ... modify, write: the reference's race
+    }
+}
+
+// compute.wgsl:148-161, in place (element-wise: no race)
+static __global__ void __launch_bounds__(256)
+k_decay_inplace(float* trail, uint64_t cells, const float decay_sub)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (uint64_t)gridDim.x * blockDim.x)
+        trail[i] = smd::decay_cell(trail[i], decay_sub);
+}
+
+// compute.wgsl:164-195, in place: the nine taps come from the live buffer (some of them already rewritten by other
+// invocations of this very dispatch), workgroups of 16 x 16 like the reference's
+static __global__ void __launch_bounds__(256)
+k_diffuse_inplace(float* trail, const uint32_t W, const uint32_t H, const TrailConsts tc)
+{
+    const uint32_t x = blockIdx.x * 16u + (threadIdx.x & 15u), y = blockIdx.y * 16u + (threadIdx.x >> 4);
+    if (x >= W || y >= H) return;
+    const volatile float* t = trail;
+    float v[9];
+    int j = 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+        const size_t ry = (size_t)((y + H + dy) % H);
+        for (int dx = -1; dx <= 1; ++dx) v[j++] = t[ry * W + (size_t)((x + W + dx) % W)];
+    }
+    trail[(size_t)y * W + x] = smd::box9_mix(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], tc);
+}
+
+// ---------------------------------------------------------------------------
 // trail: merge deposits -> decay -> 3x3 toroidal mean -> mix, out of place
 // ---------------------------------------------------------------------------
 struct TrailGeom {

@@ -30,8 +30,34 @@ def field_stats(t):
             "nonzero": float((t != 0).mean()), "max": float(t.max())}
 
 
+def quarter():
+    """Quarter-scale companion (960 x 540, 250,000 agents, 300 steps, 3 seeds): the corridor the engine's opt-in racy mode
+    (SM_FLAG_SEM_INPLACE) has to stay in -- tests/test_gpu_statistics.py::test_inplace_mode_stays_inside_the_family."""
+    Wq, Hq, Nq, seeds, marks = 960, 540, 250_000, (1, 2, 3), (10, 150, 300)
+    p = so.make_params(Wq, Hq)
+    out = {"config": {"width": Wq, "height": Hq, "agents": Nq, "preset": "Default", "seeds": list(seeds), "marks": list(marks)}, "modes": {}}
+    for mode, stepper in (("sequential_inplace", lambda sim, n: sim.step_sequential(n, inplace_diffuse=True)),
+                          ("phase_split", lambda sim, n: sim.step(n))):
+        rows = []
+        for seed in seeds:
+            sim = so.Sim(p, so.init_agents(Nq, Wq, Hq, 30.0, 50.0, seed))
+            done, per_mark = 0, []
+            for m in marks:
+                stepper(sim, m - done)
+                done = m
+                per_mark.append(field_stats(sim.trail))
+            rows.append(per_mark)
+            print(f"quarter {mode} seed {seed}: mean@{marks[-1]} {per_mark[-1]['mean']:.4f}", flush=True)
+        out["modes"][mode] = rows
+    with open(os.path.join(ROOT, "tests", "golden", "statistics_quarter.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
     so.build()
+    if "--quarter" in sys.argv:
+        quarter()
+        return
     p = so.make_params(W, H)            # Settings::default()
     out = {"config": {"width": W, "height": H, "agents": N, "preset": "Default", "seeds": list(SEEDS), "marks": list(MARKS)},
            "modes": {}}

@@ -113,3 +113,44 @@ def test_table(gold, engine_stats, capsys):
                     cells.append(f"{b[:, j].mean():.4f} +- {b[:, j].std(ddof=1):.4f}")
                     gs.append(f"{abs(a[:, j].mean() - b[:, j].mean()) / max(sigma, 1e-12):.2f}")
                 print(f"{key} | {t} | " + " | ".join(cells) + " | " + ", ".join(gs))
+
+
+# ---- SM_FLAG_SEM_INPLACE: the reference's racy semantics as an opt-in mode, validated by statistics only ---------------------
+QUARTER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "statistics_quarter.json")
+
+
+def test_inplace_mode_stays_inside_the_family(engine_lib):
+    """The racy mode (agents sense and deposit on one live buffer, decay and diffuse in place -- compute.wgsl as written) has no
+    bit-exact reference: two runs of it differ.  What can be asserted: its field statistics stay inside the corridor spanned by the
+    two deterministic members of the same family -- phase_split (nobody sees a deposit of the same frame) and the order-fixed
+    sequential run (everybody sees all earlier ones) -- widened by three seed sigmas and 2 % of the value; and two runs from the
+    same seed are close but, in general, not equal.  960 x 540, 250,000 agents, 300 steps, 3 seeds (goldens:
+    tests/golden/make_statistics_golden.py --quarter)."""
+    if not os.path.exists(QUARTER):
+        pytest.skip("tests/golden/statistics_quarter.json not generated")
+    g = json.load(open(QUARTER))
+    c = g["config"]
+    W, H, N = c["width"], c["height"], c["agents"]
+    s = sm.init_preset_manager().get_preset(c["preset"]).settings
+    rows = []
+    for seed in c["seeds"]:
+        with sm.CudaBackend.new(W, H, s, agent_count=N, device=0, flags=sm.SM_FLAG_SEM_INPLACE) as be:
+            be.init_agents(seed)
+            done, per_mark = 0, []
+            for m in c["marks"]:
+                be.step(m - done)
+                done = m
+                t = be.read_trail()
+                assert np.isfinite(t).all() and t.min() >= 0.0 and t.max() <= 1.0
+                per_mark.append({"mean": float(t.astype(np.float64).mean()), "occupancy": float((t > 0.05).mean())})
+            a = be.read_agents()
+            assert np.isfinite(a).all() and a[:, 0].min() >= 0 and a[:, 0].max() <= W and a[:, 1].min() >= 0 and a[:, 1].max() <= H
+            rows.append(per_mark)
+    for key in ("mean", "occupancy"):
+        e = _arr(rows, key)
+        ps, sq = _arr(g["modes"]["phase_split"], key), _arr(g["modes"]["sequential_inplace"], key)
+        for j, t in enumerate(c["marks"]):
+            lo, hi = min(ps[:, j].mean(), sq[:, j].mean()), max(ps[:, j].mean(), sq[:, j].mean())
+            sigma = max(ps[:, j].std(ddof=1), sq[:, j].std(ddof=1), e[:, j].std(ddof=1))
+            slack = 3.0 * sigma + 0.02 * hi
+            assert lo - slack <= e[:, j].mean() <= hi + slack, (key, t, e[:, j].mean(), lo, hi, sigma)
