@@ -477,6 +477,11 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
     const uint32_t* cin = static_cast<const uint32_t*>(cin_v);
     const uint8_t* fin = static_cast<const uint8_t*>(cin_v);
 
+    // Addressing, measured (round 2, tools/r2/gpu_27.sh, profiles/r2_probe_trail_addressing.jsonl): ~100 of this kernel's 214
+    // warp instructions per 128-cell row compute addresses (a 64-bit multiply per load, the halo row re-derived).  Deriving
+    // every address from one running per-thread cell index instead cut the loop to 182 instructions per row and made the
+    // pass SLOWER -- 4096^2: 49.7 -> 53.9 us at 64 registers (48 B spilled), 55.4 us at 7 CTAs per SM without spills; 8192^2:
+    // 170 -> 184 us.  The kernel is bound by memory-level parallelism, not issue: ptxas hoists this form's loads further.
     auto issue = [&](int y, RawRow& r) {
         const ptrdiff_t off = (ptrdiff_t)y * (ptrdiff_t)W;
         r.t = make_float4(0.f, 0.f, 0.f, 0.f);
