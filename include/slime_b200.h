@@ -196,7 +196,10 @@ int sm_download_trail(sm_engine *e, float *dst, uint32_t x0, uint32_t y0,
 int sm_trail_statistics(sm_engine *e, sm_trail_stats *out);
 
 /* Window resize, src/main.rs:954-1015: agent positions scaled by new/old size,
- * trail replaced by a zeroed map of the new size.  Single GPU only. */
+ * trail replaced by a zeroed map of the new size.  On strips the call is collective (every
+ * rank, same arguments): the strip boundaries move with the new height, agents that now
+ * belong to another strip are handed over (host-mediated -- a window event, not a hot path),
+ * and the peer-memory exchange is set up again over the existing communicator. */
 int sm_resize(sm_engine *e, uint32_t width, uint32_t height);
 
 /* ---- display pass -------------------------------------------------

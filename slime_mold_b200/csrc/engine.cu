@@ -968,12 +968,6 @@ uint64_t sm_local_agent_count(sm_engine* e)
     return e->n_local;
 }
 
-static inline uint32_t owner_row(float y, uint32_t H)
-{
-    if (!(y >= 0.0f)) return 0;                 // negative / NaN
-    if (y >= (float)H) return H - 1;
-    return (uint32_t)y;
-}
 
 int sm_upload_agents(sm_engine* e, const float* xyas, uint64_t first, uint64_t n)
 {
@@ -1382,8 +1376,8 @@ int sm_render_rgba8(sm_engine* e, uint32_t tex_width, uint32_t tex_height, uint8
 int sm_resize(sm_engine* e, uint32_t width, uint32_t height)
 {
     SM_ENTER(e);
-    if (e->world != 1) return sm_fail(SM_ERR_STATE, "sm_resize is single-GPU only");
     if (width == 0 || height == 0 || width > 65536 || height > 65536) return sm_fail(SM_ERR_BAD_ARG, "bad map size");
+    if (e->world != 1) return e->resize_strips(width, height);      // collective: every rank calls it
     SM_CUDA(cudaStreamSynchronize(e->stream));
     // src/main.rs:985-989: x *= new_w as f32 / old_w as f32
     volatile float fx = (float)width / (float)e->W;

@@ -12,6 +12,14 @@ int sm_fail(int code, const char* fmt, ...);
 
 struct EvPair { cudaEvent_t a, b; int kind; };
 
+// the row that owns an agent at height y (out-of-range and NaN clamp as in the agent kernel's own row rule)
+static inline uint32_t owner_row(float y, uint32_t H)
+{
+    if (!(y >= 0.0f)) return 0;                 // negative / NaN
+    if (y >= (float)H) return H - 1;
+    return (uint32_t)y;
+}
+
 // Per-direction migration message (multi-GPU): [u64 count][u64 pad][float4 a[cap]][u32 id[cap]]
 struct MigrateBuf {
     uint8_t* send = nullptr;   // filled by k_agents<true>, sent to the ring neighbour after the trail pass
@@ -231,6 +239,7 @@ struct sm_engine {
     int exchange_counts();
     int exchange_trail_ghosts();
     int migrate_agents();
+    int resize_strips(uint32_t width, uint32_t height);   // sm_resize on strips (collective, host-mediated)
     int refresh_counters();           // multi-GPU: sync and read the device counters into n_local / n_live
     int push_counters();              // multi-GPU: write n_local / n_live to the device counters
     int mark_tail_dead();             // multi-GPU: ids[n_local .. bound) = kDeadAgent (slots the grid may cover before the next sort)

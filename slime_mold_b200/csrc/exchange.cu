@@ -42,6 +42,7 @@ struct NcclApi {
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -63,7 +64,7 @@ int nccl_load()
 #define SM_SYM(name)                                                                    \
     g_nccl.name = reinterpret_cast<decltype(g_nccl.name)>(dlsym(h, "nccl" #name));      \
     if (!g_nccl.name) return sm_fail(SM_ERR_NCCL, "libnccl.so.2 lacks nccl" #name)
-    SM_SYM(GetUniqueId); SM_SYM(CommInitRank); SM_SYM(CommDestroy); SM_SYM(Send); SM_SYM(Recv);
+    SM_SYM(GetUniqueId); SM_SYM(CommInitRank); SM_SYM(CommDestroy); SM_SYM(Send); SM_SYM(Recv); SM_SYM(AllGather);
     SM_SYM(GroupStart); SM_SYM(GroupEnd); SM_SYM(GetErrorString);
 #undef SM_SYM
     g_nccl.ok = true;
@@ -75,6 +76,7 @@ int nccl_load()
 #define ncclCommDestroy g_nccl.CommDestroy
 #define ncclSend g_nccl.Send
 #define ncclRecv g_nccl.Recv
+#define ncclAllGather g_nccl.AllGather
 #define ncclGroupStart g_nccl.GroupStart
 #define ncclGroupEnd g_nccl.GroupEnd
 #define ncclGetErrorString g_nccl.GetErrorString
@@ -586,6 +588,125 @@ int sm_engine::migrate_agents()
     timing.kernel_launches += 2;
     SM_TRY(toc());
     n_upper = std::min<uint64_t>(cap_local, n_upper + 2 * mig_cap);
+    return SM_OK;
+}
+
+// sm_resize on strips (collective; /root/reference/src/main.rs:954-1015 is a window event, so this is host-mediated and makes
+// no attempt to be fast): every rank rescales its live agents exactly as k_rescale_agents does (one IEEE multiply per
+// coordinate), keeps those that fall into its NEW strip, and hands the others -- rounding at the strip edges, or rows that
+// moved because H' / world does not divide like H / world did -- to everybody through one all-gather; each rank adopts
+// what is now its own.  Peer mappings are closed before any buffer is freed (the all-gathers are the barriers), the fields are
+// reallocated zeroed at the new size, and the peer-memory path is set up again over the communicator that already exists.
+int sm_engine::resize_strips(uint32_t width, uint32_t height)
+{
+    if (!comm_ready) return sm_fail(SM_ERR_STATE, "multi-GPU engine: call sm_comm_init first");
+    if (fake_multi) return sm_fail(SM_ERR_STATE, "sm_resize: not in the single-rank profiling mode");
+    if ((uint32_t)world > height) return sm_fail(SM_ERR_BAD_ARG, "more strips than rows");
+    const uint32_t n_row0 = (uint32_t)(((uint64_t)rank * height) / world);
+    const uint32_t n_rows = (uint32_t)(((uint64_t)(rank + 1) * height) / world) - n_row0;
+    const uint32_t n_ghost = std::min(cfg.ghost_rows ? cfg.ghost_rows : 232u, height / (uint32_t)world);
+    {   // the same rule as halo_depths(), on the new geometry, before anything is torn down (every rank decides alike)
+        uint32_t g = 0, m = 0;
+        SM_TRY(halo_depths(this, &g, &m));
+        if (g > n_ghost || m > n_ghost || m + 1 > height / (uint32_t)world)
+            return sm_fail(SM_ERR_BAD_ARG, "sm_resize: strips of %u rows are too thin (sensing needs %u ghost rows, motion %u)",
+                           height / (uint32_t)world, g, m);
+    }
+    SM_CUDA(cudaStreamSynchronize(stream));
+    if (side_stream) SM_CUDA(cudaStreamSynchronize(side_stream));
+    volatile float fx = (float)width / (float)W;         // src/main.rs:985-989
+    volatile float fy = (float)height / (float)H;
+
+    std::vector<float> keep, orphan;
+    std::vector<uint32_t> keep_ids, orphan_ids;
+    if (agents_valid) {
+        SM_TRY(refresh_counters());
+        std::vector<float> a((size_t)n_local * 4);
+        std::vector<uint32_t> id((size_t)n_local);
+        SM_CUDA(cudaMemcpy(a.data(), agents[acur], n_local * sizeof(float4), cudaMemcpyDeviceToHost));
+        SM_CUDA(cudaMemcpy(id.data(), ids[acur], n_local * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < n_local; ++i) {
+            if (id[i] == smk::kDeadAgent) continue;
+            volatile float x = a[4 * i] * fx, y = a[4 * i + 1] * fy;
+            float v[4] = {x, y, a[4 * i + 2], a[4 * i + 3]};
+            const uint32_t r = owner_row(y, height);
+            const bool mine = r >= n_row0 && r < n_row0 + n_rows;
+            (mine ? keep : orphan).insert((mine ? keep : orphan).end(), v, v + 4);
+            (mine ? keep_ids : orphan_ids).push_back(id[i]);
+        }
+    }
+    // orphans: counts first (also the barrier "every rank has stopped touching its neighbours' buffers") ...
+    ncclComm_t c = (ncclComm_t)comm;
+    unsigned long long* d_cnt = nullptr;
+    SM_CUDA(cudaMalloc(&d_cnt, (size_t)(world + 1) * sizeof(unsigned long long)));
+    unsigned long long mine_n = orphan_ids.size();
+    SM_CUDA(cudaMemcpy(d_cnt + world, &mine_n, sizeof mine_n, cudaMemcpyHostToDevice));
+    SM_NCCL(ncclAllGather(d_cnt + world, d_cnt, sizeof(unsigned long long), ncclUint8, c, stream));
+    SM_CUDA(cudaStreamSynchronize(stream));
+    std::vector<unsigned long long> cnt((size_t)world);
+    SM_CUDA(cudaMemcpy(cnt.data(), d_cnt, (size_t)world * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_cnt);
+    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+    ipc_opened.clear();
+    p2p = false;
+    // ... then the payloads, padded to the largest count (also the barrier "every mapping is closed")
+    const size_t slot = std::max<size_t>(1, (size_t)*std::max_element(cnt.begin(), cnt.end())) * 20;     // 16 B agent + 4 B id
+    uint8_t* d_all = nullptr;
+    SM_CUDA(cudaMalloc(&d_all, slot * (size_t)(world + 1)));
+    std::vector<uint8_t> msg(slot, 0);
+    if (mine_n) {
+        memcpy(msg.data(), orphan.data(), (size_t)mine_n * 16);
+        memcpy(msg.data() + (size_t)mine_n * 16, orphan_ids.data(), (size_t)mine_n * 4);
+    }
+    SM_CUDA(cudaMemcpy(d_all + slot * world, msg.data(), slot, cudaMemcpyHostToDevice));
+    SM_NCCL(ncclAllGather(d_all + slot * world, d_all, slot, ncclUint8, c, stream));
+    SM_CUDA(cudaStreamSynchronize(stream));
+    std::vector<uint8_t> all(slot * (size_t)world);
+    SM_CUDA(cudaMemcpy(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        const float* pa = reinterpret_cast<const float*>(all.data() + slot * r);
+        const uint32_t* pi = reinterpret_cast<const uint32_t*>(all.data() + slot * r + (size_t)cnt[r] * 16);
+        for (uint64_t i = 0; i < cnt[r]; ++i) {
+            const uint32_t row = owner_row(pa[4 * i + 1], height);
+            if (row >= n_row0 && row < n_row0 + n_rows) {
+                keep.insert(keep.end(), pa + 4 * i, pa + 4 * i + 4);
+                keep_ids.push_back(pi[i]);
+            }
+        }
+    }
+    const uint64_t m = keep_ids.size();
+    if (m > cap_local) return sm_fail(SM_ERR_OOM, "sm_resize: strip %d would own %llu agents, capacity %llu", rank,
+                                      (unsigned long long)m, (unsigned long long)cap_local);
+
+    // new fields (zeroed: src/main.rs:999-1015), new tiles, new exchange buffers, peer memory mapped again
+    if (window) { cudaFree(window); window = nullptr; }
+    if (counts_xchg) { cudaFree(counts_xchg); counts_xchg = nullptr; }
+    free_trail();
+    if (tex_fallback) { use_tex = true; tex_fallback = false; }
+    W = width; H = height; row0 = n_row0; rows = n_rows; ghost = n_ghost;
+    cfg.width = width; cfg.height = height;
+    params.width = width; params.height = height;
+    SM_TRY(alloc_trail());
+    SM_TRY(setup_tiles());
+    counts_xchg_rows = (uint64_t)ghost + 1;
+    SM_CUDA(cudaMalloc(&counts_xchg, 2 * counts_xchg_rows * W * sizeof(uint32_t)));
+    SM_TRY(setup_p2p());
+    if (m) {
+        SM_CUDA(cudaMemcpy(agents[acur], keep.data(), m * sizeof(float4), cudaMemcpyHostToDevice));
+        SM_CUDA(cudaMemcpy(ids[acur], keep_ids.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    if (agents_valid) {
+        n_local = n_live = m;
+        SM_TRY(mark_tail_dead());
+        SM_TRY(push_counters());
+        identity_order = false;
+    }
+    steps_since_sort = sort_interval;
+    split_valid = false;
+    ghost_stale = true;
+    SM_CUDA(cudaStreamSynchronize(stream));
     return SM_OK;
 }
 

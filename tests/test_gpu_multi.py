@@ -46,7 +46,11 @@ CASES.update({
     "gauss_stream_full": ("Default", 512, 512, 120_000, 12, False),
     # the display pass on strips: every rank draws the frame rows that show its map rows; together they are the reference's frame
     "render": ("Waves", 256, 512, 100_000, 9, False),
+    # sm_resize on strips (main.rs:954-1015): agents rescaled, zeroed fields of the new size, new strip boundaries (405 rows do
+    # not divide evenly, so agents change owner), peer memory mapped again -- then more steps
+    "resize": ("Default", 256, 512, 100_000, 24, False),
 })
+RESIZE_TO = (320, 405)
 
 
 def _worker(rank, world, case, out_dir, exchange):
@@ -113,6 +117,10 @@ def _worker(rank, world, case, out_dir, exchange):
         be.step(steps - steps // 2)
     elif case in GAUSS:
         be.diffuse_only(steps)
+    elif case == "resize":
+        be.step(steps // 2)
+        be.resize(*RESIZE_TO)
+        be.step(steps - steps // 2)
     elif case == "diffuse_mix":
         be.step(steps // 3)
         be.diffuse_only(7)
@@ -146,7 +154,7 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
         pytest.skip("strips too thin for this case")
     if exchange == "nccl" and (case in GAUSS_FULL or case == "render"):
         pytest.skip("peer-store exchange only")
-    if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips", "diffuse_mix", "gauss_rows_diffuse", "partial_upload"):
+    if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips", "diffuse_mix", "gauss_rows_diffuse", "partial_upload", "resize"):
         pytest.skip("NCCL path: three representative cases")
     mp.spawn(_worker, args=(world, case, str(tmp_path), exchange), nprocs=world, join=True)
     u = preset_uniform(preset, W, H)
@@ -201,6 +209,15 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
         sim.p = to_oracle_params(oracle, sm2.SimSizeUniform.new(W, H, ss.pheromone_decay_factor, ss))
         for _ in range(steps):
             sim.trail = oracle.trail_pass(sim.trail, sim.p, counts=None, gauss_radius=R, gauss_sigma=sigma)
+    elif case == "resize":
+        sim.step(steps // 2)
+        W2, H2 = RESIZE_TO
+        a1 = sim.agents.copy()
+        a1[:, 0] *= np.float32(W2) / np.float32(W)                  # main.rs:985-989
+        a1[:, 1] *= np.float32(H2) / np.float32(H)
+        W, H = W2, H2
+        sim = oracle.Sim(to_oracle_params(oracle, preset_uniform(preset, W, H)), a1)
+        sim.step(steps - steps // 2)
     elif case == "diffuse_mix":
         for n_steps, n_passes in ((steps // 3, 7), (steps // 3, 1), (steps // 3, 0)):
             sim.step(n_steps)
