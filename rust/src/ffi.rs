@@ -67,7 +67,8 @@ pub struct sm_tuning {
     pub debug_single_rank_strip: u32,
     pub debug_side_timing: u32,
     pub no_boundary_first: u32,
-    pub reserved: [u32; 5],
+    pub deposit_flag_layout: u32,
+    pub reserved: [u32; 4],
 }
 
 #[repr(C)]

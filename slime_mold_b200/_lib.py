@@ -41,7 +41,8 @@ class SmTuning(C.Structure):
         ("exchange", C.c_uint32), ("serial_exchange", C.c_uint32), ("migrate_capacity", C.c_uint32), ("barrier_fence", C.c_uint32),
         ("debug_single_rank_strip", C.c_uint32), ("debug_side_timing", C.c_uint32),
         ("no_boundary_first", C.c_uint32),
-        ("reserved", C.c_uint32 * 5),
+        ("deposit_flag_layout", C.c_uint32),
+        ("reserved", C.c_uint32 * 4),
     ]
 
 
@@ -91,6 +92,7 @@ def tuning_from_env(env=None) -> SmTuning:
     t.debug_single_rank_strip = num("SM_FAKE_MULTI")
     t.debug_side_timing = num("SM_SIDE_TIMING")
     t.no_boundary_first = 0 if num("SM_BOUNDARY_FIRST", 1) else 1
+    t.deposit_flag_layout = {"": 0, "auto": 0, "linear": 1, "tiled": 2}[env.get("SM_FLAG_LAYOUT", "")]
     return t
 
 

@@ -488,7 +488,8 @@ int sm_engine::launch_agents(int part, cudaStream_t st)
             if (flags) smk::k_agents<smk::XM_NCCL, I, F, true><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
             else smk::k_agents<smk::XM_NCCL, I, F, false><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         } else {
-            if (flags) smk::k_agents<smk::XM_SINGLE, I, F, true><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            if (flags && flags_tiled()) smk::k_agents<smk::XM_SINGLE, I, F, 2><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            else if (flags) smk::k_agents<smk::XM_SINGLE, I, F, true><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
             else smk::k_agents<smk::XM_SINGLE, I, F, false><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         }
     };
@@ -523,11 +524,18 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     p.tin = trail_ptr(cur);
     p.tout = trail_ptr(1 - cur);
     // deposit representation the agents pass of this step used (none for diffusion-only)
-    p.cm = !has_counts ? smk::CM_NONE : (deposit_mode == 2 ? smk::CM_FLAGS : smk::CM_COUNTS);
-    p.cin = p.cm == smk::CM_FLAGS ? (const void*)flags_ptr(ccur) : (const void*)counts_ptr(ccur);
-    p.czero = p.cm == smk::CM_FLAGS ? (void*)flags_ptr(1 - ccur) : (void*)counts_ptr(1 - ccur);
-    p.fast = !(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && W % 4 == 0 && W >= 8 && (W / 4) % 32 != 1 && !force_generic;
+    p.cm = !has_counts ? smk::CM_NONE : (deposit_mode == 2 ? (flags_tiled() ? smk::CM_FLAGS_TILED : smk::CM_FLAGS) : smk::CM_COUNTS);
+    const bool cm_flags = p.cm == smk::CM_FLAGS || p.cm == smk::CM_FLAGS_TILED;
+    p.cin = cm_flags ? (const void*)flags_ptr(ccur) : (const void*)counts_ptr(ccur);
+    p.czero = cm_flags ? (void*)flags_ptr(1 - ccur) : (void*)counts_ptr(1 - ccur);
+    p.fast = trail_rows_kernel_ok();
     p.stats = has_counts && p.fast && stats_interest > 0;   // fused statistics only while the host keeps asking for them
+    p.g.rows_per_chunk = p.fast ? trail_rows_per_chunk(has_counts) : 1u;
+    return SM_OK;
+}
+
+uint32_t sm_engine::trail_rows_per_chunk(bool has_counts) const
+{
     // 8-16 rows per chunk measured best from 4096^2 to 32768^2 (profiles/README.md): the 2/rpc halo
     // re-reads hit L2; small maps take shorter chunks to keep >= 4 CTAs per SM
     uint64_t rpc = 8;
@@ -537,8 +545,7 @@ int sm_engine::trail_plan(bool has_counts, TrailPass& p)
     const unsigned bx = blocks_for(W / 4, 128);
     while (rpc > 4 && (uint64_t)bx * ((rows + rpc - 1) / rpc) < (uint64_t)num_sms * 4) rpc /= 2;
     if (rpc_override > 0) rpc = rpc_override;
-    p.g.rows_per_chunk = p.fast ? (uint32_t)rpc : 1u;
-    return SM_OK;
+    return (uint32_t)rpc;
 }
 
 // Rows [y_first, y_last) of the pass on stream `st` (fast kernel only).
@@ -554,6 +561,8 @@ int sm_engine::trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t 
     g.y_first2 = y_first2; g.y_last2 = y_last2;
     const uint32_t chunks2 = y_last2 > y_first2 ? (y_last2 - y_first2 + rpc - 1) / rpc : 0u;
     dim3 grid(blocks_for(W / 4, bs), (unsigned)(g.chunks1 + chunks2));
+    if (p.cm == smk::CM_FLAGS_TILED && !((rpc == 4 || rpc == 8) && y_first == 0 && y_last == rows && chunks2 == 0 && rows % rpc == 0))
+        return sm_fail(SM_ERR_STATE, "internal: tiled deposit flags need whole chunks of 4 or 8 rows");
     smk::StatsAcc* acc = (smk::StatsAcc*)stats_dev;
     auto go = [&](auto cm_tag, auto surf_tag, auto stats_tag) {
         constexpr int CMv = decltype(cm_tag)::value;
@@ -569,6 +578,7 @@ int sm_engine::trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t 
     };
     if (p.cm == smk::CM_NONE) go(integral_constant<int, smk::CM_NONE>{}, F{}, F{});
     else if (p.cm == smk::CM_COUNTS) go_cm(integral_constant<int, smk::CM_COUNTS>{});
+    else if (p.cm == smk::CM_FLAGS_TILED) go_cm(integral_constant<int, smk::CM_FLAGS_TILED>{});
     else go_cm(integral_constant<int, smk::CM_FLAGS>{});
     SM_CUDA(cudaGetLastError());
     timing.kernel_launches += 1;
@@ -1358,8 +1368,8 @@ int sm_render_rgba8(sm_engine* e, uint32_t tex_width, uint32_t tex_height, uint8
     if (e->frame_pre_valid) {
         // the field the reference draws: decay(merge(T_prev, deposits)) of the last step (trail_done flipped cur / ccur)
         src.trail = e->trail_ptr(1 - e->cur);
-        src.cm = e->deposit_mode == 2 ? smk::CM_FLAGS : smk::CM_COUNTS;
-        src.dep = src.cm == smk::CM_FLAGS ? (const void*)e->flags_ptr(1 - e->ccur) : (const void*)e->counts_ptr(1 - e->ccur);
+        src.cm = e->deposit_mode == 2 ? (e->flags_tiled() ? smk::CM_FLAGS_TILED : smk::CM_FLAGS) : smk::CM_COUNTS;
+        src.dep = e->deposit_mode == 2 ? (const void*)e->flags_ptr(1 - e->ccur) : (const void*)e->counts_ptr(1 - e->ccur);
         src.tc = e->frame_tc;
     } else {
         src.trail = e->trail_ptr(e->cur);

@@ -50,6 +50,20 @@ struct sm_engine {
     int deposit_mode = 0;             // mode of the most recent agents pass: 1 counts, 2 flags
     uint8_t* flags_ptr(int i) const { return flags_base[i] + (size_t)(ghost + pad_rows) * W; }
     bool flag_mode() const;
+    bool trail_rows_kernel_ok() const { return !(cfg.flags & SM_FLAG_GAUSSIAN_BLUR) && W % 4 == 0 && W >= 8 && (W / 4) % 32 != 1 && !force_generic; }
+    // u8 flags stored in 8 x 8-cell tiles (kernels.cuh: flag_tile_offset): one GPU, whole tiles, the streaming trail kernel.
+    // Fixed for the lifetime of a map size, so the two flag buffers never mix layouts.
+    uint32_t trail_rows_per_chunk(bool has_counts) const;
+    bool flags_tiled() const
+    {
+        // (measured, tools/r2/gpu_32.sh: configs[2] 1807 -> 1679 us/step, configs[1] 222.9 -> 221.3, Snake at configs[1] 388 -> 361;
+        // the L2-resident configs[0] loses 1 % -- 20.4 -> 20.6 us -- so maps below 2^23 cells keep the row-major field)
+        if (!(world == 1 && tuning.deposit_flag_layout != 1 && trail_rows_kernel_ok() && W % 8 == 0 && H % 8 == 0 &&
+              ((uint64_t)W * H >= (1ull << 23) || tuning.deposit_flag_layout == 2) && !(cfg.flags & SM_FLAG_SEM_INPLACE)))
+            return false;
+        const uint32_t rpc = trail_rows_per_chunk(true);      // the full-step pass must run whole chunks of 4 or 8 rows
+        return rpc == 4 || rpc == 8;
+    }
     int switch_deposit_mode(int mode);
     bool ghost_stale = true;          // ghost rows of trail[cur] need a (re-)exchange
     // block-linear copy of trail[cur] for the texture-gather sampler of the agent kernel

@@ -209,7 +209,23 @@ __device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, 
                                       // MATCH.ANY costs more issue slots than the fire-and-forget REDs it saves; L2 atomic throughput is not a limit
                                       // here (the sort's histogram, where a warp shares one or two keys, is where aggregation pays)
 #endif
-template <int XM, class IdxT, bool FLAGS, bool AGG = (SM_DEPOSIT_MATCH_ANY != 0)>
+// u8 deposit flags in 8 x 8-cell tiles of 64 bytes (FLAGS == 2 / CM_FLAGS_TILED; single GPU, W % 8 == 0 and H % 8 == 0).
+// Why: between two cell sorts the agents of a warp drift apart by a dozen pixels, and in a row-major field every lane's
+// flag then lies in its own 32-byte sector -- the byte store costs k_agents 255 us of 1550 at BASELINE configs[2] and 17 of
+// 174 at configs[1] (A/B builds with a second, dummy store: tools/r2/gpu_31.sh, profiles/r2_probe_deposit_layout.jsonl).
+// In tiles a 3 x 3-tile neighbourhood is 18 sectors instead of 24 rows x lanes.
+// Layout: with y' = (y - 1) mod H, tile (y' >> 3, x >> 3) starts at ((y' >> 3) * W/8 + (x >> 3)) * 64 and holds cell (x, y) at
+// byte (y' & 7) * 8 + (x & 7).  The row grid is shifted by one because the trail pass requests rows y+1 .. y+4 per batch
+// (the window's NEXT rows): with the shift those are one aligned 32-byte sector per tile -- 4 rows x 8 columns -- which a lane
+// pair fetches with one 16-byte load each and splits by SHFL (k_trail_rows), at the sector efficiency of the row-major field.
+template <class IdxT>
+__host__ __device__ __forceinline__ IdxT flag_tile_offset(IdxT x, IdxT y, IdxT W, IdxT H)
+{
+    const IdxT yp = y == 0 ? H - 1 : y - 1;
+    return (((yp >> 3) * W + (yp & 7)) << 3) + ((x >> 3) << 6) + (x & 7);
+}
+
+template <int XM, class IdxT, int FLAGS, bool AGG = (SM_DEPOSIT_MATCH_ANY != 0)>
 __device__ __forceinline__ void finish_agent_slot(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
                                                   const float4 a, const uint32_t id, const int32_t cx, const int32_t cy,
                                                   void* __restrict__ deposits, const AgentConsts& c, const LeaverBufs& lv)
@@ -223,7 +239,8 @@ __device__ __forceinline__ void finish_agent_slot(float4* __restrict__ agents, u
     if (interior) {
         // deposit: order-free (phase_split form of compute.wgsl:140)
         const IdxT off = (IdxT)lr * (IdxT)c.W + (IdxT)cx;
-        if (FLAGS) static_cast<uint8_t*>(deposits)[off] = 1;
+        if (FLAGS == 2) static_cast<uint8_t*>(deposits)[flag_tile_offset<IdxT>((IdxT)cx, (IdxT)lr, (IdxT)c.W, (IdxT)c.rows_local)] = 1;
+        else if (FLAGS) static_cast<uint8_t*>(deposits)[off] = 1;
         else if (AGG) {
             // warp-aggregated count (fractional deposits): the lanes of the warp that hit the same cell elect a leader that adds
             // the size of the group -- after the cell sort the lanes of a warp share a few tiles, at one or more agents per cell
@@ -233,7 +250,7 @@ __device__ __forceinline__ void finish_agent_slot(float4* __restrict__ agents, u
         }
         else atomicAdd(static_cast<uint32_t*>(deposits) + off, 1u);
     }
-    if (MULTI && !interior) agent_leaves_strip<XM, IdxT, FLAGS>(agents, ids, i, a, id, cx, cy, deposits, c, lv);
+    if (MULTI && !interior) agent_leaves_strip<XM, IdxT, (FLAGS != 0)>(agents, ids, i, a, id, cx, cy, deposits, c, lv);
 }
 
 #ifndef SM_AGENTS_MIN_BLOCKS
@@ -262,7 +279,7 @@ __device__ __forceinline__ void load_agent_slot(const float4* agents, const uint
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(id) : "l"(ids + i));
 }
 
-template <int XM, class IdxT, class FETCH, bool FLAGS>
+template <int XM, class IdxT, class FETCH, int FLAGS>
 __device__ __forceinline__ void step_agent_slot(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
                                                 float4 a, uint32_t id, const FETCH& fetch, void* __restrict__ deposits,
                                                 const AgentConsts& c, const LeaverBufs& lv)
@@ -281,7 +298,7 @@ __device__ __forceinline__ void step_agent_slot(float4* __restrict__ agents, uin
                                       // ptxas consumes the first gather before issuing the other two (two exposed latencies per agent); 4 CTAs /
                                       // 53 registers restores the schedule -- A/B in tools/r2/gpu_14.sh
 #endif
-template <int XM, class IdxT, class FETCH, bool FLAGS>
+template <int XM, class IdxT, class FETCH, int FLAGS>
 static __global__ void __launch_bounds__(256, (XM == XM_SINGLE ? SM_AGENTS_MIN_BLOCKS : SM_AGENTS_STRIP_MIN_BLOCKS))
 k_agents(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t n,
          const FETCH fetch, void* __restrict__ deposits, const AgentConsts c,
@@ -412,7 +429,7 @@ __device__ __forceinline__ int64_t row_index(int64_t y, const TrailGeom& g)
 }
 
 // Deposit representation seen by the trail pass: none (diffusion only), u32 counts, u8 flags.
-enum { CM_NONE = 0, CM_COUNTS = 1, CM_FLAGS = 2 };
+enum { CM_NONE = 0, CM_COUNTS = 1, CM_FLAGS = 2, CM_FLAGS_TILED = 3 };   // CM_FLAGS_TILED: flag_tile_offset() layout (k_trail_rows, k_display)
 static_assert((int)CM_NONE == (int)GS_NONE && (int)CM_COUNTS == (int)GS_COUNTS && (int)CM_FLAGS == (int)GS_FLAGS, "deposit representation tags");
 
 struct RawRow {
@@ -426,7 +443,7 @@ template <int CM>
 __device__ __forceinline__ float trail_cell(float t, uint32_t k, const TrailConsts& tc)
 {
     if (CM == CM_COUNTS) t = smd::merge_deposit(t, k, tc.dep);
-    if (CM == CM_FLAGS) t = k ? 1.0f : t;          // clamp(t + k*dep, 0, 1) with dep >= 1, t >= 0
+    if (CM == CM_FLAGS || CM == CM_FLAGS_TILED) t = k ? 1.0f : t;          // clamp(t + k*dep, 0, 1) with dep >= 1, t >= 0
     return smd::decay_cell(t, tc.decay_sub);
 }
 
@@ -476,6 +493,24 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
     const float* te = tin + xe;
     const uint32_t* cin = static_cast<const uint32_t*>(cin_v);
     const uint8_t* fin = static_cast<const uint8_t*>(cin_v);
+    constexpr bool TILED = CM == CM_FLAGS_TILED;
+    // tiled flags (flag_tile_offset): byte offset of a cell = row part (CTA-uniform per row) + column part (per thread, fixed)
+    const uint32_t ftile0 = (x0 >> 3) << 6, fcole = ((xe >> 3) << 6) + (xe & 7u);
+    const bool odd = (lane & 1u) != 0u;        // lanes 2j and 2j+1 own the two halves of one tile's columns
+    auto frow_p = [&](int yp) { return (((ptrdiff_t)(yp >> 3) * (ptrdiff_t)W + (ptrdiff_t)(yp & 7)) << 3); };   // yp = (y - 1) mod H
+    // CM_FLAGS_TILED launches consist of chunks of 4 or 8 rows that start on a multiple of their size: the four rows a batch
+    // requests are one sector per tile, and the chunk's share of the OTHER flag buffer is zeroed with whole-sector stores
+    // up front instead of four bytes per row
+    // (a property of the whole launch, guaranteed by the host -- sm_engine::flags_tiled() -- because the bulk zeroing covers
+    // rows y_begin+1 .. y_begin+n, which only tiles the field if every chunk does it)
+    static_assert(!TILED || UNROLL == 4, "tiled flags: a batch is one sector of four rows");
+    const int n_rows = y_end - y_begin;
+    if (TILED && active) {
+        // yp rows [y_begin, y_begin + n_rows) of this thread's tile: n_rows * 8 bytes, this lane's half of them
+        uint8_t* z = static_cast<uint8_t*>(czero_v) + frow_p(y_begin) + ftile0 + (lane & 1u) * (uint32_t)(n_rows * 4);
+        *reinterpret_cast<uint4*>(z) = make_uint4(0u, 0u, 0u, 0u);
+        if (n_rows == 8) *reinterpret_cast<uint4*>(z + 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
 
     // Addressing, measured (round 2, tools/r2/gpu_27.sh, profiles/r2_probe_trail_addressing.jsonl): ~100 of this kernel's 214
     // warp instructions per 128-cell row compute addresses (a 64-bit multiply per load, the halo row re-derived).  Deriving
@@ -503,7 +538,7 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
     };
     // d[0] = column x0-1, d[1..4] = own columns, d[5] = column x0+4 (all decayed)
     auto finish = [&](const RawRow& r, float (&d)[6]) {
-        if (CM == CM_FLAGS) {
+        if (CM == CM_FLAGS || TILED) {
             d[1] = trail_cell<CM>(r.t.x, r.k.x & 0xffu, tc);
             d[2] = trail_cell<CM>(r.t.y, r.k.x & 0xff00u, tc);
             d[3] = trail_cell<CM>(r.t.z, r.k.x & 0xff0000u, tc);
@@ -526,6 +561,19 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
         RawRow r0, r1;
         issue(y_top, r0);
         issue(y_begin, r1);
+        if (TILED) {
+            // y' of y_top and y_begin: the last two rows of the sector above the chunk's first one (of the last sector of the
+            // field when the chunk starts at row 0) -- its second half, fetched by both lanes of a pair
+            const ptrdiff_t pb = frow_p((y_begin == 0 ? (int)g.rows : y_begin) - 4) + 16;
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (active) q = __ldg(reinterpret_cast<const uint4*>(fin + pb + ftile0));
+            r0.k.x = odd ? q.y : q.x;
+            r1.k.x = odd ? q.w : q.z;
+            if (edge) {
+                r0.ke = __ldg(fin + pb + fcole);
+                r1.ke = __ldg(fin + pb + 8 + fcole);
+            }
+        }
         finish(r0, prev);
         finish(r1, cur);
     }
@@ -562,6 +610,24 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
         for (int u = 0; u < UNROLL; ++u) {
             const int yy = y + u + 1;
             issue(yy >= y_end ? y_bot : yy, raw[u]);     // past the chunk: harmless re-load of the halo row
+        }
+        if (TILED) {
+            // rows y+1 .. y+4 are rows y' = y .. y+3 of the tiled flags (also across the wrap: y_bot = 0 <-> y' = H - 1): one
+            // 32-byte sector per tile.  The even lane of a pair fetches its first half (two rows x 8 columns), the odd lane
+            // the second; each keeps its own four columns and hands the neighbour's over.
+            const ptrdiff_t gbase = frow_p(y);
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (active) q = __ldg(reinterpret_cast<const uint4*>(fin + gbase + ftile0 + ((lane & 1u) << 4)));
+            const uint32_t ra = __shfl_xor_sync(0xffffffffu, odd ? q.x : q.y, 1);
+            const uint32_t rb = __shfl_xor_sync(0xffffffffu, odd ? q.z : q.w, 1);
+            raw[0].k.x = odd ? ra : q.x;
+            raw[1].k.x = odd ? rb : q.z;
+            raw[2 % UNROLL].k.x = odd ? q.y : ra;
+            raw[3 % UNROLL].k.x = odd ? q.w : rb;
+            if (edge) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) raw[u].ke = __ldg(fin + gbase + u * 8 + fcole);
+            }
         }
         float4 o_even = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -1150,7 +1216,7 @@ struct DisplayGeom {
 // (trail_cell<CM>).  cm == CM_NONE: show `trail` as it is (after an upload, a clear, a diffusion-only pass ...).
 struct DisplaySrc {
     const float* trail;       // cm == CM_NONE: the current field; else the field the last step started from
-    const void* dep;          // the last step's deposits: u32 counts (CM_COUNTS) or u8 flags (CM_FLAGS)
+    const void* dep;          // the last step's deposits: u32 counts (CM_COUNTS) or u8 flags (CM_FLAGS, CM_FLAGS_TILED)
     int cm;
     TrailConsts tc;           // deposit amount / decay of that step
 };
@@ -1165,6 +1231,8 @@ __device__ __forceinline__ uint32_t display_texel(const DisplaySrc& src, const u
     float t = __ldg(src.trail + idx);                                                // :79
     if (src.cm == CM_COUNTS) t = trail_cell<CM_COUNTS>(t, __ldg(static_cast<const uint32_t*>(src.dep) + idx), src.tc);
     else if (src.cm == CM_FLAGS) t = trail_cell<CM_FLAGS>(t, __ldg(static_cast<const uint8_t*>(src.dep) + idx), src.tc);
+    else if (src.cm == CM_FLAGS_TILED)                                               // single GPU only: row_base == 0
+        t = trail_cell<CM_FLAGS>(t, __ldg(static_cast<const uint8_t*>(src.dep) + flag_tile_offset<size_t>((size_t)x, (size_t)y, (size_t)g.W, (size_t)g.H)), src.tc);
     const float inten = smd::clampf(smd::clampf(t, 0.0f, 1.0f), 0.0f, 1.0f);         // :80 and :31
     const uint32_t li = (uint32_t)smd::mul(inten, 255.0f);                           // :34
     // :37-39 f32(lut)/255 stored as rgba8unorm = round(v * 255) = the LUT byte itself for every byte value

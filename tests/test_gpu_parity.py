@@ -41,9 +41,12 @@ def run_pair(oracle, name, W, H, N, steps, seed=3, trail=None, check_every=None,
     be.close()
 
 
+@pytest.mark.parametrize("layout", ["auto", "tiled"])
 @pytest.mark.parametrize("name", PRESET_NAMES)
-def test_preset_one_and_many_steps(oracle, engine_lib, name):
-    # 320x256 map, 40k agents: fast kernel (W % 4 == 0), sort every 16 steps (default)
+def test_preset_one_and_many_steps(oracle, engine_lib, monkeypatch, name, layout):
+    # 320x256 map, 40k agents: fast kernel (W % 4 == 0), sort every 16 steps (default); u8 deposit flags row-major (what a map
+    # of this size gets) and in 8x8 tiles (what maps from 2^23 cells up get)
+    monkeypatch.setenv("SM_FLAG_LAYOUT", layout)
     run_pair(oracle, name, 320, 256, 40000, 60, check_every=[1, 1, 18, 40])
 
 
@@ -436,6 +439,48 @@ def test_sampler_copy_written_row_by_row_or_in_pairs(oracle, engine_lib, monkeyp
     run_pair(oracle, "Waves", W, H, 3000, 9, trail=random_trail(W, H, seed=8), check_every=[1, 8])
 
 
+# ---- u8 deposit flags: 8 x 8-cell tiles (default on one GPU from 2^23 cells up, forced here on small maps) or row-major --------------------
+@pytest.mark.parametrize("layout", ["tiled", "linear"])
+@pytest.mark.parametrize("name,W,H", [("Default", 512, 264), ("Waves", 8, 8), ("Firecracker Trees", 1032, 16), ("Curls", 136, 40),
+                                      ("Default", 260, 136), ("Default", 256, 100)])
+def test_deposit_flag_layouts(oracle, engine_lib, monkeypatch, layout, name, W, H):
+    """kernels.cuh flag_tile_offset: the agent kernel marks cells in 64-byte tiles, the trail pass and the display pass read
+    them back; the last two shapes are not whole tiles and stay row-major.  Includes a deposit-mode change (flags -> counts
+    -> flags) and a frame drawn from the step's flags."""
+    monkeypatch.setenv("SM_FLAG_LAYOUT", layout)
+    N = max(64, W * H // 3)
+    s = settings_for(name)
+    u = preset_uniform(name, W, H)
+    ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 21)
+    tr = random_trail(W, H, seed=6)
+    sim = oracle.Sim(to_oracle_params(oracle, u), ag, trail=tr)
+    be = sm.CudaBackend.new(W, H, s, agent_count=N, sort_interval=5)
+    be.write_agents(ag)
+    be.write_trail(tr)
+    for dep, n in ((None, 7), (0.4, 3), (None, 6)):
+        ss = s if dep is None else s.clone(pheromone_deposition_amount=dep)
+        be.update_settings(ss)
+        uu = sm.SimSizeUniform.new(W, H, ss.pheromone_decay_factor, ss)
+        sim.p = to_oracle_params(oracle, uu)
+        sim.step(n - 1); be.step(n - 1)
+        # the last step of the leg by hand, for the frame the reference draws between decay and diffuse
+        oracle.agents_phase_split(sim.agents, sim.trail, sim.counts, sim.p)
+        pre = sim.trail.copy()
+        oracle.deposit_merge(pre, sim.counts, ss.pheromone_deposition_amount)
+        oracle.decay(pre, uu.decay_factor)
+        sim.trail = oracle.diffuse(pre, uu.diffusion_rate)
+        be.step(1)
+        lut = np.random.default_rng(2).integers(0, 256, 768).astype(np.uint8)
+        be.set_lut(lut)
+        frame = be.render(W + 9, H + 5)
+        want = oracle.display(pre, lut, W + 9, H + 5)
+        assert np.array_equal(frame, want), f"dep {dep}: {np.count_nonzero(frame != want)} frame bytes differ"
+        a, t = be.read_agents(), be.read_trail()
+        assert bits_equal(a, sim.agents), f"dep {dep}: " + mismatch_report(a, sim.agents, "agents")
+        assert bits_equal(t, sim.trail), f"dep {dep}: " + mismatch_report(t, sim.trail, "trail")
+    be.close()
+
+
 # ---- CUDA-graph replay of whole sort periods (engine.cu: graph_steps) ------------------------------------------------------
 @pytest.mark.parametrize("name,sort_interval", [("Default", 0), ("Waves", 5), ("Snake", 7)])
 def test_step_graph_equals_launch_path_and_oracle(oracle, engine_lib, monkeypatch, name, sort_interval):
@@ -443,6 +488,8 @@ def test_step_graph_equals_launch_path_and_oracle(oracle, engine_lib, monkeypatc
     statistics requests in between fall back to the launch path and re-capture.  Same bits as the oracle throughout, and as
     an engine with the graphs switched off."""
     W, H, N = 384, 256, 70000
+    if name == "Waves":
+        monkeypatch.setenv("SM_FLAG_LAYOUT", "tiled")     # the captured kernels include the tiled-flag instantiations
     s = settings_for(name)
     u = preset_uniform(name, W, H)
     ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 13)
