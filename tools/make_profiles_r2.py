@@ -120,6 +120,9 @@ def main():
         "r2_prof_agents_p2p": "k_agents<XM_P2P> (strip instantiation) in one process, self-peer (sm_tuning.debug_single_rank_strip); tools/r2/gpu_11.sh",
         "r2_prof_trail_8192": "k_trail_rows full step at 8192^2, row-by-row surface writes (before the whole-sector form); tools/r2/gpu_01.sh",
         "r2_prof_trail_4096_pairs": "k_trail_rows full step at 4096^2, whole-sector surface writes; tools/r2/gpu_06.sh",
+        "r2_prof_agents_sd225_tiled": "k_agents at BASELINE configs[2] with the u8 deposit flags in 8x8 tiles (final tree); tools/r2/gpu_34.sh",
+        "r2_prof_trail_8192_tiled": "k_trail_rows full step at 8192^2, tiled flags: one sector per tile and batch, bulk zeroing (final tree); tools/r2/gpu_34.sh",
+        "r2_prof_agents_c2_tiled": "k_agents at BASELINE configs[1] with tiled flags (final tree); tools/r2/gpu_34.sh",
     }
     traffic = {}
     for name, note in reps.items():
@@ -132,7 +135,9 @@ def main():
     tj = os.path.join(P, "roofline_traffic.json")
     t = json.load(open(tj)) if os.path.exists(tj) else {}
     for key, name in (("agents_sd225", "r2_prof_agents_sd225"), ("agents", "r2_prof_agents_c2"), ("trail", "r2_prof_trail_4096_pairs"),
-                      ("trail_8192_rowwise", "r2_prof_trail_8192")):
+                      ("trail_8192_rowwise", "r2_prof_trail_8192"),
+                      # final tree (tiled flag field): these replace the entries above where both exist
+                      ("agents_sd225", "r2_prof_agents_sd225_tiled"), ("agents", "r2_prof_agents_c2_tiled"), ("trail_8192", "r2_prof_trail_8192_tiled")):
         if name in traffic:
             t[key] = {"dram_bytes_per_launch": traffic[name][0], "launches": traffic[name][1], "source": name}
     json.dump(t, open(tj, "w"), indent=1)
