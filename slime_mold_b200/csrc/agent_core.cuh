@@ -26,6 +26,7 @@ struct AgentConsts {
     int32_t rows_local;        // rows this rank owns (== H on a single GPU)
     int32_t ghost;             // ghost rows kept above and below the strip (0 on a single GPU)
     int32_t fold_hi, fold_lo;  // seam folding thresholds of local_row()
+    int32_t flag_wrap;         // tiled deposit flags (kernels.cuh flag_tile_offset): H on one GPU (row -1 is row H-1), 0 on strips (ghost rows)
 };
 
 // Local row (relative to the strip's first owned row) of global row `gy`, folded across the

@@ -71,6 +71,7 @@ smd::AgentConsts sm_engine::agent_consts() const
     const int32_t spare = (int32_t)H - (int32_t)rows;
     c.fold_hi = (int32_t)rows + (spare + 1) / 2;
     c.fold_lo = -(spare / 2);
+    c.flag_wrap = world == 1 ? (int32_t)H : 0;
     return c;
 }
 
@@ -482,7 +483,8 @@ int sm_engine::launch_agents(int part, cudaStream_t st)
         using F = decltype(fetch);
         using I = decltype(idx_tag);
         if (multi && p2p) {
-            if (flags) smk::k_agents<smk::XM_P2P, I, F, true><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            if (flags && flags_tiled()) smk::k_agents<smk::XM_P2P, I, F, 2><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
+            else if (flags) smk::k_agents<smk::XM_P2P, I, F, true><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
             else smk::k_agents<smk::XM_P2P, I, F, false><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
         } else if (multi) {
             if (flags) smk::k_agents<smk::XM_NCCL, I, F, true><<<nb, 256, 0, st>>>(a, id, n_arg, fetch, dep, ac, lv, (smk::StatsAcc*)stats_dev, apt);
@@ -561,7 +563,8 @@ int sm_engine::trail_launch_rows(const TrailPass& p, uint32_t y_first, uint32_t 
     g.y_first2 = y_first2; g.y_last2 = y_last2;
     const uint32_t chunks2 = y_last2 > y_first2 ? (y_last2 - y_first2 + rpc - 1) / rpc : 0u;
     dim3 grid(blocks_for(W / 4, bs), (unsigned)(g.chunks1 + chunks2));
-    if (p.cm == smk::CM_FLAGS_TILED && !((rpc == 4 || rpc == 8) && y_first == 0 && y_last == rows && chunks2 == 0 && rows % rpc == 0))
+    if (p.cm == smk::CM_FLAGS_TILED && !((rpc == 4 || rpc == 8) && y_first % rpc == 0 && y_last % rpc == 0 &&
+                                         (chunks2 == 0 || (y_first2 % rpc == 0 && y_last2 % rpc == 0))))
         return sm_fail(SM_ERR_STATE, "internal: tiled deposit flags need whole chunks of 4 or 8 rows");
     smk::StatsAcc* acc = (smk::StatsAcc*)stats_dev;
     auto go = [&](auto cm_tag, auto surf_tag, auto stats_tag) {
@@ -1370,6 +1373,7 @@ int sm_render_rgba8(sm_engine* e, uint32_t tex_width, uint32_t tex_height, uint8
         src.trail = e->trail_ptr(1 - e->cur);
         src.cm = e->deposit_mode == 2 ? (e->flags_tiled() ? smk::CM_FLAGS_TILED : smk::CM_FLAGS) : smk::CM_COUNTS;
         src.dep = e->deposit_mode == 2 ? (const void*)e->flags_ptr(1 - e->ccur) : (const void*)e->counts_ptr(1 - e->ccur);
+        src.flag_wrap = e->world == 1 ? (int)e->H : 0;
         src.tc = e->frame_tc;
     } else {
         src.trail = e->trail_ptr(e->cur);

@@ -58,9 +58,12 @@ struct sm_engine {
     {
         // (measured, tools/r2/gpu_32.sh: configs[2] 1807 -> 1679 us/step, configs[1] 222.9 -> 221.3, Snake at configs[1] 388 -> 361;
         // the L2-resident configs[0] loses 1 % -- 20.4 -> 20.6 us -- so maps below 2^23 cells keep the row-major field)
-        if (!(world == 1 && tuning.deposit_flag_layout != 1 && trail_rows_kernel_ok() && W % 8 == 0 && H % 8 == 0 &&
-              ((uint64_t)W * H >= (1ull << 23) || tuning.deposit_flag_layout == 2) && !(cfg.flags & SM_FLAG_SEM_INPLACE)))
+        if (tuning.deposit_flag_layout == 1 || !trail_rows_kernel_ok() || W % 8 != 0 || rows % 8 != 0 ||
+            (cfg.flags & SM_FLAG_SEM_INPLACE))
             return false;
+        if ((uint64_t)W * rows < (1ull << 23) && tuning.deposit_flag_layout != 2) return false;
+        // strips: the peer-store exchange only (NCCL ships whole rows), equal strips whose owned row 0 starts a tile row
+        if (world > 1 && !(p2p && H % (8u * (uint32_t)world) == 0 && (ghost + pad_rows) % 8 == 0)) return false;
         const uint32_t rpc = trail_rows_per_chunk(true);      // the full-step pass must run whole chunks of 4 or 8 rows
         return rpc == 4 || rpc == 8;
     }

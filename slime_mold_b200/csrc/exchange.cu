@@ -243,6 +243,25 @@ k_barrier_pull(uint32_t* window, uint32_t* up_window, uint32_t* down_window, uin
     }
 }
 
+// The same for u8 flags stored in 8 x 8-cell tiles (kernels.cuh flag_tile_offset): a row is W / 8 pieces of 8 bytes, 64 bytes apart.
+static __global__ void __launch_bounds__(128)
+k_barrier_pull_tiled(uint32_t* window, uint32_t* up_window, uint32_t* down_window, uint32_t seq, unsigned long long* err,
+                     uint8_t* my_row_above, const uint8_t* up_last_row, uint8_t* my_row_below, const uint8_t* down_first_row, uint32_t pieces)
+{
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) ring_barrier(window, up_window + 1, down_window + 0, seq, err);
+        else ring_wait(window, seq, err);
+    }
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pieces; i += gridDim.x * blockDim.x) {
+        const size_t o = (size_t)i * 64u;
+        const uint2 a = *reinterpret_cast<const uint2*>(up_last_row + o);
+        const uint2 b = *reinterpret_cast<const uint2*>(down_first_row + o);
+        *reinterpret_cast<uint2*>(my_row_above + o) = a;
+        *reinterpret_cast<uint2*>(my_row_below + o) = b;
+    }
+}
+
 static __global__ void k_barrier_only(uint32_t* window, uint32_t* up_window, uint32_t* down_window, uint32_t seq,
                                       unsigned long long* err)
 {
@@ -910,7 +929,17 @@ int sm_engine::p2p_after_agents(cudaStream_t st, bool timed)
     // one 16-byte element per thread (flags: 1 byte per cell, counts: 4)
     const uint64_t pull_elems = ((uint64_t)pw * (deposit_mode == 2 ? 1 : 4) + 15) / 16;
     const unsigned pull_blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(256, (pull_elems + 127) / 128));
-    if (deposit_mode == 2) {
+    if (deposit_mode == 2 && flags_tiled()) {
+        // row y of a strip starts at byte ((y' >> 3) * W + (y' & 7)) * 8 past its owned row 0, y' = y - 1 (signed: ghost rows)
+        auto row_at = [&](int64_t y) { const int64_t yp = y - 1; return ((yp >> 3) * (int64_t)W + (yp & 7)) * 8; };
+        uint8_t* f = flags_ptr(ccur);
+        const uint8_t* up_last = peer[0].flags8[ccur] + row0_off + row_at((int64_t)peer[0].rows - 1);
+        const uint8_t* down_first = peer[1].flags8[ccur] + row0_off + row_at(0);
+        const uint32_t pieces = W / 8;
+        const unsigned nb = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>(256, (pieces + 127) / 128));
+        smk::k_barrier_pull_tiled<<<nb, 128, 0, st>>>(w, wu, wd, barrier_seq, dev_counters + 2, f + row_at(-1), up_last,
+                                                      f + row_at((int64_t)rows), down_first, pieces);
+    } else if (deposit_mode == 2) {
         uint8_t* f = flags_ptr(ccur);
         const uint8_t* up_last = peer[0].flags8[ccur] + row0_off + (size_t)(peer[0].rows - pr) * W;
         const uint8_t* down_first = peer[1].flags8[ccur] + row0_off;

@@ -155,7 +155,9 @@ struct LeaverBufs {
 // Strips, rare path: the new cell belongs to a ring neighbour (or there is no deposit cell at all).
 // (Not a real call: passing the parameter blocks by reference to a __noinline__ function makes every thread copy them to
 // local memory at kernel entry -- measured 215 -> 292 us.)
-template <int XM, class IdxT, bool FLAGS>
+template <class IdxT> __host__ __device__ __forceinline__ IdxT flag_tile_offset(IdxT x, IdxT y, IdxT W, IdxT wrap);
+
+template <int XM, class IdxT, int FLAGS>
 __device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
                                                 const float4 a, const uint32_t id, const int32_t cx, const int32_t cy,
                                                 void* __restrict__ deposits, const AgentConsts& c, const LeaverBufs& lv)
@@ -174,7 +176,9 @@ __device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, 
         }
         if (ok) {
             const IdxT off = (IdxT)lrd * (IdxT)c.W + (IdxT)cx;
-            if (FLAGS) static_cast<uint8_t*>(base)[off] = 1;
+            // (tiled flags: lrd is relative to owned row 0 of whichever strip `base` addresses -- every strip has the same geometry)
+            if (FLAGS == 2) static_cast<uint8_t*>(base)[flag_tile_offset<IdxT>((IdxT)cx, (IdxT)lrd, (IdxT)c.W, (IdxT)0)] = 1;
+            else if (FLAGS) static_cast<uint8_t*>(base)[off] = 1;
             else if (XM == XM_P2P) atomicAdd_system(static_cast<uint32_t*>(base) + off, 1u);
             else atomicAdd(static_cast<uint32_t*>(base) + off, 1u);
         }
@@ -209,7 +213,7 @@ __device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, 
                                       // MATCH.ANY costs more issue slots than the fire-and-forget REDs it saves; L2 atomic throughput is not a limit
                                       // here (the sort's histogram, where a warp shares one or two keys, is where aggregation pays)
 #endif
-// u8 deposit flags in 8 x 8-cell tiles of 64 bytes (FLAGS == 2 / CM_FLAGS_TILED; single GPU, W % 8 == 0 and H % 8 == 0).
+// u8 deposit flags in 8 x 8-cell tiles of 64 bytes (FLAGS == 2 / CM_FLAGS_TILED; W % 8 == 0, owned rows % 8 == 0; strips: peer-store path).
 // Why: between two cell sorts the agents of a warp drift apart by a dozen pixels, and in a row-major field every lane's
 // flag then lies in its own 32-byte sector -- the byte store costs k_agents 255 us of 1550 at BASELINE configs[2] and 17 of
 // 174 at configs[1] (A/B builds with a second, dummy store: tools/r2/gpu_31.sh, profiles/r2_probe_deposit_layout.jsonl).
@@ -218,11 +222,15 @@ __device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, 
 // byte (y' & 7) * 8 + (x & 7).  The row grid is shifted by one because the trail pass requests rows y+1 .. y+4 per batch
 // (the window's NEXT rows): with the shift those are one aligned 32-byte sector per tile -- 4 rows x 8 columns -- which a lane
 // pair fetches with one 16-byte load each and splits by SHFL (k_trail_rows), at the sector efficiency of the row-major field.
+// y is relative to the owned row 0 the base pointer addresses.  wrap = H on one GPU (row -1 is row H - 1); 0 on strips, where
+// y' = -1 and the rows beyond are ghost rows of the same buffer (the strip's ghost + pad depth is a multiple of 8, so owned row 0
+// starts a tile row there too): IdxT is signed, >> and & floor.
 template <class IdxT>
-__host__ __device__ __forceinline__ IdxT flag_tile_offset(IdxT x, IdxT y, IdxT W, IdxT H)
+__host__ __device__ __forceinline__ IdxT flag_tile_offset(IdxT x, IdxT y, IdxT W, IdxT wrap)
 {
-    const IdxT yp = y == 0 ? H - 1 : y - 1;
-    return (((yp >> 3) * W + (yp & 7)) << 3) + ((x >> 3) << 6) + (x & 7);
+    IdxT yp = y - 1;
+    if (yp < 0) yp += wrap;
+    return ((yp >> 3) * W + (yp & 7)) * 8 + (x >> 3) * 64 + (x & 7);
 }
 
 template <int XM, class IdxT, int FLAGS, bool AGG = (SM_DEPOSIT_MATCH_ANY != 0)>
@@ -239,7 +247,7 @@ __device__ __forceinline__ void finish_agent_slot(float4* __restrict__ agents, u
     if (interior) {
         // deposit: order-free (phase_split form of compute.wgsl:140)
         const IdxT off = (IdxT)lr * (IdxT)c.W + (IdxT)cx;
-        if (FLAGS == 2) static_cast<uint8_t*>(deposits)[flag_tile_offset<IdxT>((IdxT)cx, (IdxT)lr, (IdxT)c.W, (IdxT)c.rows_local)] = 1;
+        if (FLAGS == 2) static_cast<uint8_t*>(deposits)[flag_tile_offset<IdxT>((IdxT)cx, (IdxT)lr, (IdxT)c.W, (IdxT)c.flag_wrap)] = 1;
         else if (FLAGS) static_cast<uint8_t*>(deposits)[off] = 1;
         else if (AGG) {
             // warp-aggregated count (fractional deposits): the lanes of the warp that hit the same cell elect a leader that adds
@@ -250,7 +258,7 @@ __device__ __forceinline__ void finish_agent_slot(float4* __restrict__ agents, u
         }
         else atomicAdd(static_cast<uint32_t*>(deposits) + off, 1u);
     }
-    if (MULTI && !interior) agent_leaves_strip<XM, IdxT, (FLAGS != 0)>(agents, ids, i, a, id, cx, cy, deposits, c, lv);
+    if (MULTI && !interior) agent_leaves_strip<XM, IdxT, FLAGS>(agents, ids, i, a, id, cx, cy, deposits, c, lv);
 }
 
 #ifndef SM_AGENTS_MIN_BLOCKS
@@ -497,7 +505,7 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
     // tiled flags (flag_tile_offset): byte offset of a cell = row part (CTA-uniform per row) + column part (per thread, fixed)
     const uint32_t ftile0 = (x0 >> 3) << 6, fcole = ((xe >> 3) << 6) + (xe & 7u);
     const bool odd = (lane & 1u) != 0u;        // lanes 2j and 2j+1 own the two halves of one tile's columns
-    auto frow_p = [&](int yp) { return (((ptrdiff_t)(yp >> 3) * (ptrdiff_t)W + (ptrdiff_t)(yp & 7)) << 3); };   // yp = (y - 1) mod H
+    auto frow_p = [&](int yp) { return ((ptrdiff_t)(yp >> 3) * (ptrdiff_t)W + (ptrdiff_t)(yp & 7)) * 8; };   // yp = y - 1 (mod H on one GPU)
     // CM_FLAGS_TILED launches consist of chunks of 4 or 8 rows that start on a multiple of their size: the four rows a batch
     // requests are one sector per tile, and the chunk's share of the OTHER flag buffer is zeroed with whole-sector stores
     // up front instead of four bytes per row
@@ -510,6 +518,9 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
         uint8_t* z = static_cast<uint8_t*>(czero_v) + frow_p(y_begin) + ftile0 + (lane & 1u) * (uint32_t)(n_rows * 4);
         *reinterpret_cast<uint4*>(z) = make_uint4(0u, 0u, 0u, 0u);
         if (n_rows == 8) *reinterpret_cast<uint4*>(z + 16) = make_uint4(0u, 0u, 0u, 0u);
+        // strips: y' = -1 (owned row 0) is no chunk's share -- on one GPU it is row H - 1's place, here a ghost tile row
+        if (!g.wrap_y && y_begin == 0)
+            *reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(czero_v) + frow_p(-1) + ftile0 + (x0 & 7u)) = 0u;
     }
 
     // Addressing, measured (round 2, tools/r2/gpu_27.sh, profiles/r2_probe_trail_addressing.jsonl): ~100 of this kernel's 214
@@ -564,7 +575,7 @@ k_trail_rows(const float* __restrict__ tin, const void* __restrict__ cin_v,
         if (TILED) {
             // y' of y_top and y_begin: the last two rows of the sector above the chunk's first one (of the last sector of the
             // field when the chunk starts at row 0) -- its second half, fetched by both lanes of a pair
-            const ptrdiff_t pb = frow_p((y_begin == 0 ? (int)g.rows : y_begin) - 4) + 16;
+            const ptrdiff_t pb = frow_p(((g.wrap_y && y_begin == 0) ? (int)g.rows : y_begin) - 4) + 16;
             uint4 q = make_uint4(0u, 0u, 0u, 0u);
             if (active) q = __ldg(reinterpret_cast<const uint4*>(fin + pb + ftile0));
             r0.k.x = odd ? q.y : q.x;
@@ -1218,6 +1229,7 @@ struct DisplaySrc {
     const float* trail;       // cm == CM_NONE: the current field; else the field the last step started from
     const void* dep;          // the last step's deposits: u32 counts (CM_COUNTS) or u8 flags (CM_FLAGS, CM_FLAGS_TILED)
     int cm;
+    int flag_wrap;            // CM_FLAGS_TILED: as AgentConsts::flag_wrap
     TrailConsts tc;           // deposit amount / decay of that step
 };
 
@@ -1231,8 +1243,9 @@ __device__ __forceinline__ uint32_t display_texel(const DisplaySrc& src, const u
     float t = __ldg(src.trail + idx);                                                // :79
     if (src.cm == CM_COUNTS) t = trail_cell<CM_COUNTS>(t, __ldg(static_cast<const uint32_t*>(src.dep) + idx), src.tc);
     else if (src.cm == CM_FLAGS) t = trail_cell<CM_FLAGS>(t, __ldg(static_cast<const uint8_t*>(src.dep) + idx), src.tc);
-    else if (src.cm == CM_FLAGS_TILED)                                               // single GPU only: row_base == 0
-        t = trail_cell<CM_FLAGS>(t, __ldg(static_cast<const uint8_t*>(src.dep) + flag_tile_offset<size_t>((size_t)x, (size_t)y, (size_t)g.W, (size_t)g.H)), src.tc);
+    else if (src.cm == CM_FLAGS_TILED)
+        t = trail_cell<CM_FLAGS>(t, __ldg(static_cast<const uint8_t*>(src.dep) +
+                                          flag_tile_offset<ptrdiff_t>((ptrdiff_t)x, (ptrdiff_t)y - (ptrdiff_t)g.row_base, (ptrdiff_t)g.W, (ptrdiff_t)src.flag_wrap)), src.tc);
     const float inten = smd::clampf(smd::clampf(t, 0.0f, 1.0f), 0.0f, 1.0f);         // :80 and :31
     const uint32_t li = (uint32_t)smd::mul(inten, 255.0f);                           // :34
     // :37-39 f32(lut)/255 stored as rgba8unorm = round(v * 255) = the LUT byte itself for every byte value

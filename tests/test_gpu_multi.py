@@ -51,6 +51,11 @@ CASES.update({
     "resize": ("Default", 256, 512, 100_000, 24, False),
 })
 RESIZE_TO = (320, 405)
+# u8 deposit flags in 8x8 tiles on strips (kernels.cuh flag_tile_offset; what strips of 2^23 cells and more get by default, forced
+# here): peer stores into the neighbours' tiled fields, the tiled pull of the halo deposit rows, the boundary bands, the display pass,
+# a deposit-mode change, an empty strip, thin strips (ghost depth == strip height)
+for _c in ("default_devinit", "waves_upload", "thin_strips", "mode_switch", "empty_strip", "render", "firecracker_devinit"):
+    CASES["tiled_" + _c] = CASES[_c]
 
 
 def _worker(rank, world, case, out_dir, exchange):
@@ -62,6 +67,9 @@ def _worker(rank, world, case, out_dir, exchange):
     import slime_mold_b200 as sm
     from oracle import slime_oracle as so
     preset, W, H, N, steps, device_init = CASES[case]
+    if case.startswith("tiled_"):
+        os.environ["SM_FLAG_LAYOUT"] = "tiled"
+        case = case[len("tiled_"):]
     s = sm.init_preset_manager().get_preset(preset).settings
     def connect(be, tag):
         idf = os.path.join(out_dir, f"nccl_id_{tag}.bin")
@@ -152,11 +160,13 @@ def test_strips_on_gpus_equal_oracle(oracle, engine_lib, tmp_path, case, world, 
     preset, W, H, N, steps, device_init = CASES[case]
     if H // world < 32:
         pytest.skip("strips too thin for this case")
-    if exchange == "nccl" and (case in GAUSS_FULL or case == "render"):
+    if exchange == "nccl" and (case in GAUSS_FULL or case == "render" or case.startswith("tiled_")):
         pytest.skip("peer-store exchange only")
     if exchange == "nccl" and case not in ("waves_upload", "mode_switch", "thin_strips", "diffuse_mix", "gauss_rows_diffuse", "partial_upload", "resize"):
         pytest.skip("NCCL path: three representative cases")
     mp.spawn(_worker, args=(world, case, str(tmp_path), exchange), nprocs=world, join=True)
+    if case.startswith("tiled_"):
+        case = case[len("tiled_"):]
     u = preset_uniform(preset, W, H)
     ag = oracle.init_agents(N, W, H, u.agent_speed_min, u.agent_speed_max, 11)
     sim = oracle.Sim(to_oracle_params(oracle, u), ag, trail=None if device_init else random_trail(W, H, seed=4))
