@@ -445,25 +445,34 @@ def parity_before_timing(h, args):
     note(h, "parity before timing")
     W, H, n_agents, steps, seed = 512, 192 * N, 300_000, 35, 11
     s = sm.init_preset_manager().get_preset("Default").settings
-    be = h.engine(W, H, s, n_agents)
-    be.init_agents(seed)
-    be.step(steps)
-    a = be.read_agents()
-    owned, local = be.last_owned, be.local_agent_count
-    t = be.read_trail()
-    be.close()
     sim = so.Sim(oracle_params(so, W, H, s), so.init_agents(n_agents, W, H, s.agent_speed_min, s.agent_speed_max, seed))
     sim.step(steps)
-    mine = ~np.isnan(a[:, 0])
-    rows = ~np.isnan(t[:, 0])
-    agents_equal = bool(np.array_equal(a[mine].view(np.uint32), sim.agents[mine].view(np.uint32))) and owned == local == int(mine.sum())
-    trail_equal = bool(np.array_equal(t[rows].view(np.uint32), sim.trail[rows].view(np.uint32))) and int(rows.sum()) == H // N
-    tt = h.torch.tensor([float(owned)], device="cuda", dtype=h.torch.float64)
-    h.dist.all_reduce(tt)
-    total_owned = int(tt.item())
+    from slime_mold_b200._lib import tuning_from_env
+    agents_equal = trail_equal = True
+    total_owned = n_agents
+    # twice: with the u8 deposit flags row-major (what a map of this size gets) and in 8x8 tiles (what the timed workloads get)
+    for layout in (1, 2):
+        tn = tuning_from_env()
+        tn.deposit_flag_layout = layout
+        be = h.engine(W, H, s, n_agents, tuning=tn)
+        be.init_agents(seed)
+        be.step(steps)
+        a = be.read_agents()
+        owned, local = be.last_owned, be.local_agent_count
+        t = be.read_trail()
+        be.close()
+        mine = ~np.isnan(a[:, 0])
+        rows = ~np.isnan(t[:, 0])
+        agents_equal &= bool(np.array_equal(a[mine].view(np.uint32), sim.agents[mine].view(np.uint32))) and owned == local == int(mine.sum())
+        trail_equal &= bool(np.array_equal(t[rows].view(np.uint32), sim.trail[rows].view(np.uint32))) and int(rows.sum()) == H // N
+        tt = h.torch.tensor([float(owned)], device="cuda", dtype=h.torch.float64)
+        h.dist.all_reduce(tt)
+        if int(tt.item()) != n_agents:
+            total_owned = int(tt.item())          # reported (and fatal below)
     res = {"ranks": N, "agents_equal": h.min_over_ranks(1.0 if agents_equal else 0.0) == 1.0,
            "trail_equal": h.min_over_ranks(1.0 if trail_equal else 0.0) == 1.0, "agents_owned_total": total_owned, "agents": n_agents,
-           "case": f"{W}x{H} map in {N} strips, {n_agents} agents, {steps} steps, Default preset, device-side init seed {seed}, P2P exchange; "
+           "case": f"{W}x{H} map in {N} strips, {n_agents} agents, {steps} steps, Default preset, device-side init seed {seed}, P2P exchange, "
+                   f"run twice (u8 deposit flags row-major and in 8x8 tiles); "
                    f"every rank compares the agents and trail rows it owns with the single-domain oracle bit for bit"}
     res["agents_equal"] = res["agents_equal"] and total_owned == n_agents
     if not (res["agents_equal"] and res["trail_equal"]):
