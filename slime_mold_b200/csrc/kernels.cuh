@@ -155,8 +155,6 @@ struct LeaverBufs {
 // Strips, rare path: the new cell belongs to a ring neighbour (or there is no deposit cell at all).
 // (Not a real call: passing the parameter blocks by reference to a __noinline__ function makes every thread copy them to
 // local memory at kernel entry -- measured 215 -> 292 us.)
-template <class IdxT> __host__ __device__ __forceinline__ IdxT flag_tile_offset(IdxT x, IdxT y, IdxT W, IdxT wrap);
-
 template <int XM, class IdxT, int FLAGS>
 __device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,
                                                 const float4 a, const uint32_t id, const int32_t cx, const int32_t cy,
@@ -177,7 +175,7 @@ __device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, 
         if (ok) {
             const IdxT off = (IdxT)lrd * (IdxT)c.W + (IdxT)cx;
             // (tiled flags: lrd is relative to owned row 0 of whichever strip `base` addresses -- every strip has the same geometry)
-            if (FLAGS == 2) static_cast<uint8_t*>(base)[flag_tile_offset<IdxT>((IdxT)cx, (IdxT)lrd, (IdxT)c.W, (IdxT)0)] = 1;
+            if (FLAGS == 2) static_cast<uint8_t*>(base)[smd::flag_tile_offset<IdxT>((IdxT)cx, (IdxT)lrd, (IdxT)c.W, (IdxT)0)] = 1;
             else if (FLAGS) static_cast<uint8_t*>(base)[off] = 1;
             else if (XM == XM_P2P) atomicAdd_system(static_cast<uint32_t*>(base) + off, 1u);
             else atomicAdd(static_cast<uint32_t*>(base) + off, 1u);
@@ -213,25 +211,7 @@ __device__ __forceinline__ void agent_leaves_strip(float4* __restrict__ agents, 
                                       // MATCH.ANY costs more issue slots than the fire-and-forget REDs it saves; L2 atomic throughput is not a limit
                                       // here (the sort's histogram, where a warp shares one or two keys, is where aggregation pays)
 #endif
-// u8 deposit flags in 8 x 8-cell tiles of 64 bytes (FLAGS == 2 / CM_FLAGS_TILED; W % 8 == 0, owned rows % 8 == 0; strips: peer-store path).
-// Why: between two cell sorts the agents of a warp drift apart by a dozen pixels, and in a row-major field every lane's
-// flag then lies in its own 32-byte sector -- the byte store costs k_agents 255 us of 1550 at BASELINE configs[2] and 17 of
-// 174 at configs[1] (A/B builds with a second, dummy store: tools/r2/gpu_31.sh, profiles/r2_probe_deposit_layout.jsonl).
-// In tiles a 3 x 3-tile neighbourhood is 18 sectors instead of 24 rows x lanes.
-// Layout: with y' = (y - 1) mod H, tile (y' >> 3, x >> 3) starts at ((y' >> 3) * W/8 + (x >> 3)) * 64 and holds cell (x, y) at
-// byte (y' & 7) * 8 + (x & 7).  The row grid is shifted by one because the trail pass requests rows y+1 .. y+4 per batch
-// (the window's NEXT rows): with the shift those are one aligned 32-byte sector per tile -- 4 rows x 8 columns -- which a lane
-// pair fetches with one 16-byte load each and splits by SHFL (k_trail_rows), at the sector efficiency of the row-major field.
-// y is relative to the owned row 0 the base pointer addresses.  wrap = H on one GPU (row -1 is row H - 1); 0 on strips, where
-// y' = -1 and the rows beyond are ghost rows of the same buffer (the strip's ghost + pad depth is a multiple of 8, so owned row 0
-// starts a tile row there too): IdxT is signed, >> and & floor.
-template <class IdxT>
-__host__ __device__ __forceinline__ IdxT flag_tile_offset(IdxT x, IdxT y, IdxT W, IdxT wrap)
-{
-    IdxT yp = y - 1;
-    if (yp < 0) yp += wrap;
-    return ((yp >> 3) * W + (yp & 7)) * 8 + (x >> 3) * 64 + (x & 7);
-}
+using smd::flag_tile_offset;     // trail_core.cuh: u8 deposit flags in 8 x 8-cell tiles (FLAGS == 2 / CM_FLAGS_TILED)
 
 template <int XM, class IdxT, int FLAGS, bool AGG = (SM_DEPOSIT_MATCH_ANY != 0)>
 __device__ __forceinline__ void finish_agent_slot(float4* __restrict__ agents, uint32_t* __restrict__ ids, uint64_t i,

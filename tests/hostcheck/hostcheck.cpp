@@ -292,3 +292,10 @@ extern "C" int hc_gauss_rows(const float* tin, const void* cin, void* czero, flo
     return 0;
 }
 
+
+// u8 deposit flags in 8 x 8-cell tiles: the offset function the agent kernel, the trail pass and the display pass share
+// (trail_core.cuh), for tests/test_hostcheck.py's layout checks.  out[i] = byte offset of cell (x[i], y[i]) relative to owned row 0.
+extern "C" void hc_flag_tile_offsets(const int64_t* x, const int64_t* y, int64_t* out, uint64_t n, int64_t W, int64_t wrap)
+{
+    for (uint64_t i = 0; i < n; ++i) out[i] = smd::flag_tile_offset<int64_t>(x[i], y[i], W, wrap);
+}

@@ -106,3 +106,72 @@ def test_edge_agents_bits(oracle, hostcheck, name):
     hostcheck.hc_agents_phase_split(P(a1, C.c_float), None, C.c_uint64(len(ag)), P(trail, C.c_float), P(c1, C.c_uint32), C.byref(p))
     assert bits_equal(a0, a1), [(i, ag[i], a0[i], a1[i]) for i in range(len(ag)) if not bits_equal(a0[i], a1[i])][:4]
     assert np.array_equal(c0, c1)
+
+
+# ---- u8 deposit flags in 8 x 8-cell tiles (trail_core.cuh flag_tile_offset) -------------------------
+def _tile_offsets(hostcheck, W, ys, wrap):
+    xs = np.arange(W, dtype=np.int64)
+    X, Y = np.meshgrid(xs, np.asarray(ys, dtype=np.int64))
+    x, y = np.ascontiguousarray(X.ravel()), np.ascontiguousarray(Y.ravel())
+    out = np.empty_like(x)
+    hostcheck.hc_flag_tile_offsets(P(x, C.c_int64), P(y, C.c_int64), P(out, C.c_int64), C.c_uint64(x.size), C.c_int64(W), C.c_int64(wrap))
+    return out.reshape(len(ys), W)
+
+
+@pytest.mark.parametrize("W,H", [(8, 8), (64, 24), (520, 40), (1032, 16)])
+def test_flag_tiles_one_gpu_layout(hostcheck, W, H):
+    """One GPU (wrap = H): a permutation of the W*H bytes; the four rows a batch of the trail pass requests (y+1 .. y+4 with
+    y % 4 == 0, across the toroidal seam too) are ONE aligned 32-byte sector per tile, row r of the batch at bytes 8r .. 8r+7 --
+    what the lane-pair load of k_trail_rows assumes; the two prologue rows are the second half of the sector above; the
+    region a chunk of 4 / 8 rows zeroes up front is the cells of rows y_begin+1 .. y_begin+n."""
+    off = _tile_offsets(hostcheck, W, range(H), H)
+    assert np.array_equal(np.sort(off.ravel()), np.arange(W * H))
+    for y in range(0, H, 4):
+        rows = [(y + 1 + u) % H for u in range(4)]
+        for tx in range(W // 8):
+            o = off[rows, tx * 8:(tx + 1) * 8]
+            base = int(o.min())
+            assert base % 32 == 0 and np.array_equal(o - base, np.arange(32).reshape(4, 8))
+        # prologue of a chunk that starts at y (rows y-1 and y): second half of the sector that starts at y' = y - 4
+        pro = off[[(y - 1) % H, y % H], :8]
+        sector_start = int(off[(y - 3) % H, 0])              # row y-3 has y' = y - 4: first row of that sector
+        assert sector_start % 32 == 0 and np.array_equal(pro - sector_start - 16, np.arange(16).reshape(2, 8))
+    for n in (4, 8):
+        for y0 in range(0, H, n):
+            want = np.sort(off[[(y0 + 1 + u) % H for u in range(n)], :].ravel())
+            # per tile: n*8 contiguous bytes from the tile's start + (y0 & 7) * 8
+            tiles = (y0 >> 3) * W * 8 + np.arange(W // 8)[:, None] * 64 + (y0 & 7) * 8 + np.arange(n * 8)[None, :]
+            assert np.array_equal(want, np.sort(tiles.ravel()))
+
+
+@pytest.mark.parametrize("W,rows,G", [(64, 32, 48), (256, 64, 80), (16, 8, 8)])
+def test_flag_tiles_strip_layout(hostcheck, W, rows, G):
+    """Strips (wrap = 0): rows [-G, rows + G) relative to owned row 0 (G = ghost + pad, a multiple of 8) land inside the strip's
+    buffer without collisions; owned row 0 sits at y' = -1, in the ghost tile row above; the rows barrier 1 pulls (-1 and `rows`)
+    are W/8 eight-byte pieces 64 bytes apart (k_barrier_pull_tiled)."""
+    ys = list(range(-G + 1, rows + G))                       # row -G itself would need y' = -G-1 (outside); nothing addresses it
+    off = _tile_offsets(hostcheck, W, ys, 0)
+    assert off.min() >= -G * W and off.max() < (rows + G) * W
+    assert np.unique(off).size == off.size
+    row = {y: off[i] for i, y in enumerate(ys)}
+    assert row[0].max() < 0 and row[1].min() >= 0            # owned row 0 in the ghost tile row, row 1 opens the owned tiles
+    for y in (-1, rows):
+        r = row[y]
+        assert np.array_equal(r.reshape(W // 8, 8) - r[0], np.arange(W // 8)[:, None] * 64 + np.arange(8)[None, :])
+
+
+def test_flag_tiles_lane_pair_exchange():
+    """The SHFL exchange of k_trail_rows' tiled path, restated: lanes 2j / 2j+1 own columns 0-3 / 4-7 of a tile, fetch the first /
+    second 16 bytes of the batch's sector and must end up with their own four columns of each of the four rows."""
+    rng = np.random.default_rng(4)
+    sector = rng.integers(0, 2, 32).astype(np.uint8)          # 4 rows x 8 columns
+    rows = sector.reshape(4, 8)
+    q = {0: sector[:16].view(np.uint32), 1: sector[16:].view(np.uint32)}       # q.x .. q.w of the even / odd lane
+    send = {lane: ((q[lane][0], q[lane][2]) if lane else (q[lane][1], q[lane][3])) for lane in (0, 1)}
+    got = {}
+    for lane in (0, 1):
+        ra, rb = send[1 - lane]
+        got[lane] = [ra, rb, q[lane][1], q[lane][3]] if lane else [q[lane][0], q[lane][2], ra, rb]
+    for lane in (0, 1):
+        for r in range(4):
+            assert got[lane][r] == rows[r, 4 * lane:4 * lane + 4].view(np.uint32)[0]
