@@ -654,21 +654,24 @@ int sm_engine::resize_strips(uint32_t width, uint32_t height)
             (mine ? keep_ids : orphan_ids).push_back(id[i]);
         }
     }
-    // orphans: counts first (also the barrier "every rank has stopped touching its neighbours' buffers") ...
+    // one u64 from every rank (also serves as a barrier)
     ncclComm_t c = (ncclComm_t)comm;
-    unsigned long long* d_cnt = nullptr;
-    SM_CUDA(cudaMalloc(&d_cnt, (size_t)(world + 1) * sizeof(unsigned long long)));
-    unsigned long long mine_n = orphan_ids.size();
-    SM_CUDA(cudaMemcpy(d_cnt + world, &mine_n, sizeof mine_n, cudaMemcpyHostToDevice));
-    SM_NCCL(ncclAllGather(d_cnt + world, d_cnt, sizeof(unsigned long long), ncclUint8, c, stream));
-    SM_CUDA(cudaStreamSynchronize(stream));
-    std::vector<unsigned long long> cnt((size_t)world);
-    SM_CUDA(cudaMemcpy(cnt.data(), d_cnt, (size_t)world * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    cudaFree(d_cnt);
-    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
-    ipc_opened.clear();
-    p2p = false;
-    // ... then the payloads, padded to the largest count (also the barrier "every mapping is closed")
+    auto gather_u64 = [&](unsigned long long v, std::vector<unsigned long long>& out) -> int {
+        unsigned long long* d = nullptr;
+        SM_CUDA(cudaMalloc(&d, (size_t)(world + 1) * sizeof(unsigned long long)));
+        SM_CUDA(cudaMemcpy(d + world, &v, sizeof v, cudaMemcpyHostToDevice));
+        SM_NCCL(ncclAllGather(d + world, d, sizeof(unsigned long long), ncclUint8, c, stream));
+        SM_CUDA(cudaStreamSynchronize(stream));
+        out.resize((size_t)world);
+        SM_CUDA(cudaMemcpy(out.data(), d, (size_t)world * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        return SM_OK;
+    };
+    // orphans: counts first (also the barrier "every rank has finished its last step") ...
+    const unsigned long long mine_n = orphan_ids.size();
+    std::vector<unsigned long long> cnt;
+    SM_TRY(gather_u64(mine_n, cnt));
+    // ... then the payloads, padded to the largest count
     const size_t slot = std::max<size_t>(1, (size_t)*std::max_element(cnt.begin(), cnt.end())) * 20;     // 16 B agent + 4 B id
     uint8_t* d_all = nullptr;
     SM_CUDA(cudaMalloc(&d_all, slot * (size_t)(world + 1)));
@@ -696,8 +699,17 @@ int sm_engine::resize_strips(uint32_t width, uint32_t height)
         }
     }
     const uint64_t m = keep_ids.size();
-    if (m > cap_local) return sm_fail(SM_ERR_OOM, "sm_resize: strip %d would own %llu agents, capacity %llu", rank,
-                                      (unsigned long long)m, (unsigned long long)cap_local);
+    // a strip that cannot hold its share fails the call on EVERY rank, before anything has been changed
+    std::vector<unsigned long long> fits;
+    SM_TRY(gather_u64(m <= cap_local ? 1ull : 0ull, fits));
+    for (int r = 0; r < world; ++r)
+        if (!fits[r]) return sm_fail(SM_ERR_OOM, "sm_resize: strip %d would own more agents than its capacity (%llu on this rank, capacity %llu)",
+                                     r, (unsigned long long)m, (unsigned long long)cap_local);
+    // peer mappings are closed before any buffer they point into is freed (the gather is the barrier "every mapping is closed")
+    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+    ipc_opened.clear();
+    p2p = false;
+    SM_TRY(gather_u64(1ull, fits));
 
     // new fields (zeroed: src/main.rs:999-1015), new tiles, new exchange buffers, peer memory mapped again
     if (window) { cudaFree(window); window = nullptr; }
