@@ -102,8 +102,9 @@ typedef struct sm_tuning {
     uint32_t debug_single_rank_strip; /* PROFILING ONLY: a world_size > 1 engine that exchanges with itself (results meaningless) */
     uint32_t debug_side_timing;     /* strips: per-piece CUDA-event times of the side stream, printed at teardown */
     uint32_t no_boundary_first;     /* strips: 1 = one agent launch per step, exchange overlapped with the interior trail rows only */
-    uint32_t deposit_flag_layout;   /* u8 deposit flags: 0 auto (one GPU, >= 2^23 cells, whole 8 x 8 tiles: tiled; else row-major),
-                                       1 always row-major, 2 tiled wherever the map is whole tiles */
+    uint32_t deposit_flag_layout;   /* u8 deposit flags: 0 auto (>= 2^23 cells per GPU, whole 8 x 8-cell tiles, on strips the peer-store
+                                       exchange: tiled; else row-major), 1 always row-major, 2 tiled wherever the geometry allows
+                                       (never changes a result bit) */
     uint32_t reserved[4];
 } sm_tuning;
 
