@@ -158,7 +158,7 @@ def main():
                     (c["FFMA2"] + c["FADD2"] + c["FMUL2"], c["TLD4"], c["SUST"], c["SHFL"]))
 
     for fn in sorted(os.listdir(G)):
-        if re.match(r"r2_(micro_.*\.log|probe_.*\.jsonl|bench_.*\.log|parity_.*\.log|statistics_.*\.log|gauss_wring_sweep\.jsonl|launches_config1\.csv)$", fn):
+        if re.match(r"r2_(micro_.*\.log|probe_.*\.jsonl|bench_.*\.log|parity_.*\.log|statistics_.*\.log|gauss_wring_sweep\.jsonl|launches_(config1|headline)\.csv)$", fn):
             shutil.copy(os.path.join(G, fn), os.path.join(P, fn))
     print("profiles/ updated:", len([f for f in os.listdir(P) if f.startswith("r2_")]), "round-2 files")
 
